@@ -1,0 +1,844 @@
+/*
+ * stark.c — the caller of the hot path: input parsers, R1CS -> trace arrangement, the STARK
+ * prover and verifier and the proof.json writer, restating
+ *   /root/reference/packages/circom2bellman_core/src/reader.rs:4-89
+ *   /root/reference/packages/r1cs-stark/src/reader.rs:7-42
+ *   /root/reference/packages/r1cs-stark/src/run.rs:109-452, 528-625
+ *   /root/reference/packages/r1cs-stark/src/prove.rs:14-378
+ *   /root/reference/packages/r1cs-stark/src/utils.rs:14-57, 122-524
+ *   /root/reference/packages/r1cs-stark/src/verify.rs:13-258
+ * ORACLE / TEST INFRASTRUCTURE — see oracle.h.
+ */
+#include "oracle.h"
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#define EXTENSION_FACTOR 8            /* utils.rs:135 */
+#define LOG_EXTENSION_FACTOR 3        /* utils.rs:134 */
+#define SPOT_CHECK_SECURITY_FACTOR 80 /* utils.rs:136 */
+
+/* helpers exported by fri.c */
+void orc__buf_puts(orc_buf *b, const char *s);
+void orc__buf_bytes(orc_buf *b, const uint8_t *d, size_t n);
+void orc__branches_json(orc_buf *b, const orc_branch *br, size_t n);
+orc_branch *orc__gen_branches(const uint8_t *leaves, size_t leaf_bytes, size_t n,
+                              const size_t *idx, size_t n_idx, uint8_t root[32]);
+void orc__branches_free(orc_branch *br, size_t n);
+int orc__verify_multi_branch(const uint8_t root[32], const size_t *idx, const orc_branch *br, size_t n);
+
+__thread double orc_stage_s[4];
+
+static double now_s(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+/* ---- little-endian readers ------------------------------------------------------------------ */
+typedef struct { const uint8_t *p; size_t left; int err; } rd_t;
+static uint32_t rd_u32(rd_t *r) {
+    if (r->left < 4) { r->err = 1; return 0; }
+    uint32_t v = (uint32_t)r->p[0] | ((uint32_t)r->p[1] << 8) | ((uint32_t)r->p[2] << 16) | ((uint32_t)r->p[3] << 24);
+    r->p += 4; r->left -= 4;
+    return v;
+}
+static uint64_t rd_u64(rd_t *r) {
+    uint64_t lo = rd_u32(r), hi = rd_u32(r);
+    return lo | (hi << 32);
+}
+static void rd_bytes(rd_t *r, uint8_t *out, size_t n) {
+    if (r->left < n) { r->err = 1; memset(out, 0, n); return; }
+    memcpy(out, r->p, n);
+    r->p += n; r->left -= n;
+}
+
+/* circom2bellman_core/src/reader.rs:4-89 */
+int orc_read_r1cs(orc_r1cs *out, const uint8_t *bytes, size_t len) {
+    memset(out, 0, sizeof *out);
+    rd_t r = {bytes, len, 0};
+    if (rd_u32(&r) != 0x73633172u) return -1; /* "r1cs" */
+    if (rd_u32(&r) != 1) return -2;            /* version */
+    if (rd_u32(&r) != 3) return -3;            /* n_section */
+    if (rd_u32(&r) != 1) return -4;            /* HeaderSection first */
+    (void)rd_u64(&r);
+    out->field_size = rd_u32(&r);
+    rd_bytes(&r, out->prime, 32);
+    out->n_wires = rd_u32(&r);
+    out->n_pub_out = rd_u32(&r);
+    out->n_pub_in = rd_u32(&r);
+    out->n_priv_in = rd_u32(&r);
+    out->n_labels = rd_u64(&r);
+    out->n_constraints = rd_u32(&r);
+    if (rd_u32(&r) != 2) return -5;            /* ConstraintSection */
+    (void)rd_u64(&r);
+    if (r.err) return -6;
+    size_t nc = out->n_constraints;
+    out->off = (size_t *)malloc((3 * nc + 1) * sizeof(size_t));
+    size_t cap = 1024, cnt = 0;
+    out->wire_id = (uint32_t *)malloc(cap * sizeof(uint32_t));
+    out->value = (uint8_t *)malloc(cap * 32);
+    for (size_t c = 0; c < 3 * nc; c++) {
+        out->off[c] = cnt;
+        uint32_t n = rd_u32(&r);
+        for (uint32_t i = 0; i < n; i++) {
+            if (cnt == cap) {
+                cap *= 2;
+                out->wire_id = (uint32_t *)realloc(out->wire_id, cap * sizeof(uint32_t));
+                out->value = (uint8_t *)realloc(out->value, cap * 32);
+            }
+            out->wire_id[cnt] = rd_u32(&r);
+            rd_bytes(&r, out->value + 32 * cnt, 32);
+            cnt++;
+        }
+        if (r.err) return -7;
+    }
+    out->off[3 * nc] = cnt;
+    return 0;
+}
+
+void orc_r1cs_free(orc_r1cs *r) {
+    free(r->off);
+    free(r->wire_id);
+    free(r->value);
+    memset(r, 0, sizeof *r);
+}
+
+/* r1cs-stark/src/reader.rs:7-42 */
+fp_t *orc_read_witness(const uint8_t *bytes, size_t len, size_t *n_wires_out) {
+    rd_t r = {bytes, len, 0};
+    if (rd_u32(&r) != 1936618615u) return NULL; /* "wtns" */
+    for (int i = 0; i < 5; i++) (void)rd_u32(&r);
+    uint32_t field_size = rd_u32(&r);
+    if (field_size > 64 || field_size % 4) return NULL;
+    uint8_t tmp[64];
+    rd_bytes(&r, tmp, field_size); /* prime */
+    uint32_t n_wires = rd_u32(&r);
+    (void)rd_u32(&r);
+    (void)rd_u32(&r);
+    (void)rd_u32(&r);
+    if (r.err) return NULL;
+    fp_t *w = (fp_t *)malloc((size_t)n_wires * sizeof(fp_t));
+    for (uint32_t i = 0; i < n_wires; i++) {
+        rd_bytes(&r, tmp, field_size);
+        fp_from_bytes_le(&w[i], tmp, field_size); /* run.rs:354-357 */
+    }
+    if (r.err) { free(w); return NULL; }
+    *n_wires_out = n_wires;
+    return w;
+}
+
+/* ---- run.rs:109-308, 390-419 ---------------------------------------------------------------- */
+typedef struct { uint8_t k; size_t v; } use_t;
+typedef struct { use_t *u; size_t n, cap; } use_list;
+static void use_push(use_list *l, uint8_t k, size_t v) {
+    if (l->n == l->cap) {
+        l->cap = l->cap ? 2 * l->cap : 4;
+        l->u = (use_t *)realloc(l->u, l->cap * sizeof(use_t));
+    }
+    l->u[l->n].k = k;
+    l->u[l->n].v = v;
+    l->n++;
+}
+
+void orc_build_trace(orc_trace *t, const orc_r1cs *r, const fp_t *witness, int with_witness) {
+    memset(t, 0, sizeof *t);
+    const size_t nc = r->n_constraints, n_wires = r->n_wires;
+    size_t a_len = 0;
+    for (size_t c = 0; c < nc; c++) {
+        size_t n = 0;
+        for (int k = 0; k < 3; k++) {
+            size_t nk = r->off[3 * c + k + 1] - r->off[3 * c + k];
+            if (nk > n) n = nk;
+        }
+        a_len += n;
+    }
+    const size_t os = 3 * a_len;
+    t->original_steps = os;
+    t->n_constraints = nc;
+    t->n_wires = n_wires;
+    t->coefficients = (fp_t *)calloc(os ? os : 1, sizeof(fp_t));
+    t->witness_trace = (fp_t *)calloc(os ? os : 1, sizeof(fp_t));
+    t->computational_trace = (fp_t *)calloc(os ? os : 1, sizeof(fp_t));
+    use_list *uses = (use_list *)calloc(n_wires, sizeof(use_list));
+    size_t *last_coeff = (size_t *)malloc((nc ? nc : 1) * sizeof(size_t));
+    size_t acc = 0;
+    for (size_t c = 0; c < nc; c++) {
+        size_t n = 0;
+        for (int k = 0; k < 3; k++) {
+            size_t nk = r->off[3 * c + k + 1] - r->off[3 * c + k];
+            if (nk > n) n = nk;
+        }
+        for (int k = 0; k < 3; k++) {
+            size_t base = r->off[3 * c + k], nk = r->off[3 * c + k + 1] - base;
+            fp_t tsum = FP_ZERO;
+            for (size_t i = 0; i < n; i++) {
+                size_t pos = (size_t)k * a_len + acc + i; /* index inside A||B||C */
+                size_t wire;
+                fp_t coef;
+                if (i < nk) {
+                    wire = r->wire_id[base + i];
+                    fp_from_bytes_le(&coef, r->value + 32 * (base + i), 32);
+                } else {
+                    wire = n_wires - 1; /* run.rs:165 padding row */
+                    coef = FP_ZERO;
+                }
+                use_push(&uses[wire], (uint8_t)k, acc + i);
+                t->coefficients[pos] = coef;
+                if (with_witness) {
+                    if (i < nk) {
+                        fp_t prod;
+                        fp_mul(&prod, &coef, &witness[wire]);
+                        fp_add(&tsum, &tsum, &prod);
+                    }
+                    t->witness_trace[pos] = witness[wire];
+                    t->computational_trace[pos] = tsum;
+                }
+            }
+        }
+        acc += n;
+        last_coeff[c] = acc - 1;
+    }
+    /* run.rs:283-308 flags */
+    t->flag0 = (fp_t *)malloc((os ? os : 1) * sizeof(fp_t));
+    t->flag1 = (fp_t *)malloc((os ? os : 1) * sizeof(fp_t));
+    t->flag2 = (fp_t *)calloc(os ? os : 1, sizeof(fp_t));
+    for (size_t i = 0; i < os; i++) t->flag0[i] = t->flag1[i] = FP_ONE;
+    for (size_t c = 0; c < nc; c++) {
+        size_t f = (last_coeff[c] + 1) % a_len;
+        t->flag1[f] = t->flag1[f + a_len] = t->flag1[f + 2 * a_len] = FP_ZERO;
+        t->flag2[last_coeff[c]] = FP_ONE;
+    }
+    /* run.rs:390-401 copy permutation */
+    t->permuted_indices = (size_t *)calloc(os ? os : 1, sizeof(size_t));
+    for (size_t w = 0; w < n_wires; w++) {
+        use_list *l = &uses[w];
+        if (!l->n) continue;
+        size_t old_w = a_len * l->u[l->n - 1].k + l->u[l->n - 1].v;
+        for (size_t i = 0; i < l->n; i++) {
+            size_t cur = a_len * l->u[i].k + l->u[i].v;
+            t->permuted_indices[cur] = old_w;
+            old_w = cur;
+        }
+    }
+    /* run.rs:359-360, 413-419 */
+    t->n_public = 1 + (size_t)r->n_pub_in + r->n_pub_out;
+    t->public_wires = (fp_t *)malloc(t->n_public * sizeof(fp_t));
+    t->pfi_k = (size_t *)malloc(t->n_public * sizeof(size_t));
+    t->pfi_w = (size_t *)malloc(t->n_public * sizeof(size_t));
+    for (size_t w = 0; w < t->n_public; w++) {
+        if (witness) t->public_wires[w] = witness[w];
+        if (uses[w].n) {
+            t->pfi_k[t->n_pfi] = w;
+            t->pfi_w[t->n_pfi] = a_len * uses[w].u[0].k + uses[w].u[0].v;
+            t->n_pfi++;
+        }
+    }
+    for (size_t w = 0; w < n_wires; w++) free(uses[w].u);
+    free(uses);
+    free(last_coeff);
+}
+
+void orc_trace_free(orc_trace *t) {
+    free(t->witness_trace); free(t->computational_trace); free(t->coefficients);
+    free(t->flag0); free(t->flag1); free(t->flag2);
+    free(t->permuted_indices); free(t->public_wires); free(t->pfi_k); free(t->pfi_w);
+    memset(t, 0, sizeof *t);
+}
+
+/* ---- utils.rs helpers ----------------------------------------------------------------------- */
+static uint32_t log2_ceil_quirk(size_t value) { /* utils.rs:14-23: really floor(log2 v)+1 */
+    uint32_t l = 1;
+    while (value > 1) { value /= 2; l++; }
+    return l;
+}
+
+/* utils.rs:272-290 */
+static void get_random_ff_values(fp_t *out, const uint8_t *seed, uint32_t modulus, size_t size, uint32_t excl) {
+    uint32_t *idx = (uint32_t *)malloc(size * 8 * sizeof(uint32_t));
+    orc_get_pseudorandom_indices(idx, seed, 32, modulus, size * 8, excl);
+    for (size_t i = 0; i < size; i++) {
+        uint8_t b[32];
+        for (int j = 0; j < 8; j++) { /* utils.rs:29-38 u32 big-endian bytes */
+            uint32_t v = idx[i * 8 + j];
+            b[4 * j] = (uint8_t)(v >> 24); b[4 * j + 1] = (uint8_t)(v >> 16);
+            b[4 * j + 2] = (uint8_t)(v >> 8); b[4 * j + 3] = (uint8_t)v;
+        }
+        fp_from_bytes_le(&out[i], b, 32);
+    }
+    free(idx);
+}
+
+/* prove.rs:274-283: k[i] = from_str(decimal(BE(blake(m_root || i)))) */
+static void derive_k(fp_t k[11], const uint8_t m_root[32]) {
+    k[0] = FP_ONE;
+    for (int i = 1; i < 11; i++) {
+        uint8_t msg[33], h[32];
+        memcpy(msg, m_root, 32);
+        msg[32] = (uint8_t)i;
+        orc_blake2s(h, msg, 33);
+        fp_from_bytes_be(&k[i], h, 32);
+    }
+}
+
+/* inv_best_fft(col, g1) then best_fft(., g2): prove.rs:100-124 */
+static fp_t *lde(const fp_t *col, size_t len_in, size_t steps, size_t precision,
+                 const fp_t *g1, const fp_t *g2, uint32_t log_s, uint32_t log_n, unsigned cpus, fp_t **poly_out) {
+    fp_t *buf = (fp_t *)malloc(precision * sizeof(fp_t));
+    memcpy(buf, col, len_in * sizeof(fp_t));
+    orc_inv_best_fft(buf, len_in, g1, log_s, cpus);
+    if (poly_out) {
+        *poly_out = (fp_t *)malloc(steps * sizeof(fp_t));
+        memcpy(*poly_out, buf, steps * sizeof(fp_t));
+    }
+    orc_best_fft(buf, steps, g2, log_n, cpus);
+    return buf;
+}
+
+static fp_t *dup_fp(const fp_t *src, size_t n) {
+    fp_t *d = (fp_t *)malloc(n * sizeof(fp_t));
+    memcpy(d, src, n * sizeof(fp_t));
+    return d;
+}
+
+typedef struct {
+    size_t original_steps, steps, precision, skips;
+    uint32_t log_steps, log_precision;
+    fp_t g1, g2;
+    fp_t *xs;
+} domain_t;
+
+static void make_domain(domain_t *d, size_t original_steps) {
+    d->original_steps = original_steps;
+    d->log_steps = log2_ceil_quirk(original_steps - 1);       /* prove.rs:37 */
+    d->steps = (size_t)1 << d->log_steps;
+    if (d->steps < 8) d->steps = 8;                            /* prove.rs:39-41 (log_steps NOT updated) */
+    d->precision = d->steps * EXTENSION_FACTOR;
+    d->log_precision = d->log_steps + LOG_EXTENSION_FACTOR;    /* prove.rs:50 */
+    if (d->log_precision > 28) abort();                        /* prove.rs:51-53 two-adicity */
+    uint32_t log_n = 0;
+    while (((size_t)1 << log_n) < d->precision) log_n++;
+    fp_root_of_unity(&d->g2, log_n);                           /* prove.rs:71-82 */
+    d->xs = (fp_t *)malloc(d->precision * sizeof(fp_t));
+    size_t order = orc_expand_root_of_unity(d->xs, d->precision, &d->g2); /* :84 */
+    if (order != d->precision) abort();
+    d->skips = d->precision / d->steps;
+    d->g1 = d->xs[d->skips];                                   /* :92 */
+}
+
+void orc_prove_taps_free(orc_prove_taps *t) {
+    for (int i = 0; i < 9; i++) free(t->lde[i]);
+    for (int i = 0; i < 8; i++) free(t->tree_cols[i]);
+    free(t->l_evals);
+    memset(t, 0, sizeof *t);
+}
+
+/* prove.rs:14-378 */
+void orc_mk_r1cs_proof(orc_stark_proof *out, const orc_trace *t, unsigned cpus, orc_prove_taps *taps) {
+    memset(out, 0, sizeof *out);
+    for (int i = 0; i < 4; i++) orc_stage_s[i] = 0;
+    double t_all = now_s(), t0;
+    const size_t os = t->original_steps;
+    if (os % 3 != 0 || os == 0) abort();
+    domain_t D;
+    make_domain(&D, os);
+    const size_t S = D.steps, N = D.precision, sk = D.skips;
+    const uint32_t lS = D.log_steps, lN = D.log_precision;
+    if (os > S) abort();
+
+    /* :55-68 padding */
+    size_t *perm = (size_t *)malloc(S * sizeof(size_t));
+    memcpy(perm, t->permuted_indices, os * sizeof(size_t));
+    for (size_t i = os; i < S; i++) perm[i] = i;
+    fp_t *coeffs = (fp_t *)calloc(S, sizeof(fp_t));
+    fp_t *wit = (fp_t *)calloc(S, sizeof(fp_t));
+    fp_t *comp = (fp_t *)calloc(S, sizeof(fp_t));
+    memcpy(coeffs, t->coefficients, os * sizeof(fp_t));
+    memcpy(wit, t->witness_trace, os * sizeof(fp_t));
+    memcpy(comp, t->computational_trace, os * sizeof(fp_t));
+
+    /* :100-129 */
+    t0 = now_s();
+    fp_t *k_ev = lde(coeffs, S, S, N, &D.g1, &D.g2, lS, lN, cpus, NULL);
+    fp_t *f0_ev = lde(t->flag0, os, S, N, &D.g1, &D.g2, lS, lN, cpus, NULL);
+    fp_t *f1_ev = lde(t->flag1, os, S, N, &D.g1, &D.g2, lS, lN, cpus, NULL);
+    fp_t *f2_ev = lde(t->flag2, os, S, N, &D.g1, &D.g2, lS, lN, cpus, NULL);
+    fp_t *s_ev = lde(wit, S, S, N, &D.g1, &D.g2, lS, lN, cpus, NULL);
+    fp_t *p_ev = lde(comp, S, S, N, &D.g1, &D.g2, lS, lN, cpus, NULL);
+    fp_t *z_ev = (fp_t *)calloc(N, sizeof(fp_t)); /* utils.rs:173-178 */
+    fp_neg(&z_ev[0], &FP_ONE);
+    z_ev[S] = FP_ONE;
+    orc_best_fft(z_ev, S + 1, &D.g2, lN, cpus);
+    orc_stage_s[0] += now_s() - t0;
+
+    /* utils.rs:181-248 */
+    fp_t *q1 = (fp_t *)malloc(N * sizeof(fp_t)), *q2 = (fp_t *)malloc(N * sizeof(fp_t));
+    const size_t o3 = os / 3;
+    for (size_t j = 0; j < N; j++) {
+        fp_t a, b;
+        fp_mul(&a, &f1_ev[j], &p_ev[(j + N - sk) % N]);
+        fp_mul(&b, &k_ev[j], &s_ev[j]);
+        fp_sub(&a, &p_ev[j], &a);
+        fp_sub(&a, &a, &b);
+        fp_mul(&q1[j], &f0_ev[j], &a);
+        size_t j2 = (j + o3 * sk) % N, j3 = (j + o3 * 2 * sk) % N;
+        fp_mul(&a, &p_ev[j], &p_ev[j2]);
+        fp_sub(&a, &p_ev[j3], &a);
+        fp_mul(&q2[j], &f2_ev[j], &a);
+    }
+
+    /* :160-167 index columns */
+    t0 = now_s();
+    fp_t *tmpcol = (fp_t *)malloc(S * sizeof(fp_t));
+    for (size_t i = 0; i < S; i++) fp_from_u64(&tmpcol[i], (uint64_t)i);
+    fp_t *idx_ev = lde(tmpcol, S, S, N, &D.g1, &D.g2, lS, lN, cpus, NULL);
+    for (size_t i = 0; i < S; i++) fp_from_u64(&tmpcol[i], (uint64_t)perm[i]);
+    fp_t *pidx_ev = lde(tmpcol, S, S, N, &D.g1, &D.g2, lS, lN, cpus, NULL);
+    orc_stage_s[0] += now_s() - t0;
+
+    /* :171 utils.rs:250-270 accumulator tree */
+    t0 = now_s();
+    {
+        uint8_t *leaves = (uint8_t *)malloc(S * 40);
+        for (size_t j = 0; j < S; j++) {
+            uint64_t pv = (uint64_t)perm[j];
+            for (int b = 0; b < 8; b++) leaves[40 * j + b] = (uint8_t)(pv >> (8 * b));
+            fp_to_bytes_le(leaves + 40 * j + 8, &wit[j]);
+        }
+        orc_merkle_gen_proofs(leaves, 40, S, NULL, 0, out->a_root, NULL);
+        free(leaves);
+    }
+    orc_stage_s[1] += now_s() - t0;
+    fp_t r[3];
+    get_random_ff_values(r, out->a_root, (uint32_t)N, 3, 0); /* :172 */
+
+    /* utils.rs:293-339 */
+    fp_t *a_mini = (fp_t *)malloc(S * sizeof(fp_t));
+    {
+        fp_t *nmr = (fp_t *)malloc(S * sizeof(fp_t)), *dnm = (fp_t *)malloc(S * sizeof(fp_t));
+        fp_t *inv_dnm = (fp_t *)malloc(S * sizeof(fp_t));
+        fp_t acc_n = FP_ONE, acc_d = FP_ONE;
+        for (size_t j = 0; j < S; j++) {
+            fp_t vn, vd, t1, t2;
+            fp_mul(&t1, &r[1], &idx_ev[j * sk]);
+            fp_mul(&t2, &r[2], &wit[j]);
+            fp_add(&vn, &r[0], &t1);
+            fp_add(&vn, &vn, &t2);
+            fp_mul(&t1, &r[1], &pidx_ev[j * sk]);
+            fp_add(&vd, &r[0], &t1);
+            fp_add(&vd, &vd, &t2);
+            fp_mul(&acc_n, &vn, &acc_n);
+            fp_mul(&acc_d, &vd, &acc_d);
+            nmr[j] = acc_n;
+            dnm[j] = acc_d;
+        }
+        orc_multi_inv(inv_dnm, dnm, S);
+        for (size_t j = 0; j < S; j++) fp_mul(&a_mini[j], &nmr[j], &inv_dnm[j]);
+        free(nmr); free(dnm); free(inv_dnm);
+    }
+    t0 = now_s();
+    fp_t *a_ev = lde(a_mini, S, S, N, &D.g1, &D.g2, lS, lN, cpus, NULL); /* :183-184 */
+    orc_stage_s[0] += now_s() - t0;
+
+    /* utils.rs:344-376 */
+    fp_t *q3 = (fp_t *)malloc(N * sizeof(fp_t));
+    for (size_t j = 0; j < N; j++) {
+        fp_t vn, vd, t1, t2, u, v;
+        fp_mul(&t2, &r[2], &s_ev[j]);
+        fp_mul(&t1, &r[1], &idx_ev[j]);
+        fp_add(&vn, &r[0], &t1);
+        fp_add(&vn, &vn, &t2);
+        fp_mul(&t1, &r[1], &pidx_ev[j]);
+        fp_add(&vd, &r[0], &t1);
+        fp_add(&vd, &vd, &t2);
+        fp_mul(&u, &a_ev[j], &vd);
+        fp_mul(&v, &a_ev[(j + N - sk) % N], &vn);
+        fp_sub(&q3[j], &u, &v);
+    }
+
+    /* :203-214 */
+    fp_t *inv_z = (fp_t *)malloc(N * sizeof(fp_t));
+    orc_multi_inv(inv_z, z_ev, N);
+    fp_t *d1 = (fp_t *)malloc(N * sizeof(fp_t)), *d2 = (fp_t *)malloc(N * sizeof(fp_t)), *d3 = (fp_t *)malloc(N * sizeof(fp_t));
+    for (size_t j = 0; j < N; j++) {
+        if (fp_is_zero(&inv_z[j]) && !(fp_is_zero(&q1[j]) && fp_is_zero(&q2[j]) && fp_is_zero(&q3[j]))) {
+            fprintf(stderr, "oracle: invalid D1/D2/D3 at %zu (utils.rs:379-418): witness does not satisfy the circuit\n", j);
+            abort();
+        }
+        fp_mul(&d1[j], &q1[j], &inv_z[j]);
+        fp_mul(&d2[j], &q2[j], &inv_z[j]);
+        fp_mul(&d3[j], &q3[j], &inv_z[j]);
+    }
+
+    /* :216-232 boundary quotients */
+    fp_t *b2 = (fp_t *)malloc(N * sizeof(fp_t)), *b3 = (fp_t *)malloc(N * sizeof(fp_t));
+    {
+        const size_t np = t->n_pfi;
+        fp_t *xv = (fp_t *)malloc((np ? np : 1) * sizeof(fp_t)), *yv = (fp_t *)malloc((np ? np : 1) * sizeof(fp_t));
+        fp_t *interp2 = (fp_t *)malloc((np ? np : 1) * sizeof(fp_t));
+        for (size_t i = 0; i < np; i++) { /* utils.rs:421-435 */
+            xv[i] = D.xs[sk * t->pfi_w[i]];
+            yv[i] = t->public_wires[t->pfi_k[i]];
+        }
+        orc_lagrange_interp(interp2, xv, yv, np);
+        fp_t *zb2 = (fp_t *)malloc(N * sizeof(fp_t)), *i2 = (fp_t *)malloc(N * sizeof(fp_t));
+        fp_t *zb3 = (fp_t *)malloc(N * sizeof(fp_t)), *inv = (fp_t *)malloc(N * sizeof(fp_t));
+        const fp_t x_last = D.xs[N - sk]; /* utils.rs:459,467 */
+        for (size_t j = 0; j < N; j++) {
+            orc_eval_poly_at(&i2[j], interp2, np, &D.xs[j]); /* prove.rs:217 */
+            fp_t acc = FP_ONE, df;
+            for (size_t i = 0; i < np; i++) { /* utils.rs:438-455 */
+                fp_sub(&df, &D.xs[j], &xv[i]);
+                fp_mul(&acc, &acc, &df);
+            }
+            zb2[j] = acc;
+            fp_sub(&zb3[j], &D.xs[j], &x_last); /* utils.rs:466-474 (1 * (x - x_last)) */
+        }
+        orc_multi_inv(inv, zb2, N);
+        for (size_t j = 0; j < N; j++) { /* utils.rs:477-499 */
+            fp_t df;
+            fp_sub(&df, &s_ev[j], &i2[j]);
+            if (fp_is_zero(&inv[j]) && !fp_is_zero(&df)) {
+                fprintf(stderr, "oracle: invalid B2 at %zu (utils.rs:489)\n", j);
+                abort();
+            }
+            fp_mul(&b2[j], &df, &inv[j]);
+        }
+        orc_multi_inv(inv, zb3, N);
+        for (size_t j = 0; j < N; j++) { /* utils.rs:502-524; I3 == 1 everywhere */
+            fp_t df;
+            fp_sub(&df, &a_ev[j], &FP_ONE);
+            if (fp_is_zero(&inv[j]) && !fp_is_zero(&df)) {
+                fprintf(stderr, "oracle: invalid B3 at %zu (utils.rs:514)\n", j);
+                abort();
+            }
+            fp_mul(&b3[j], &df, &inv[j]);
+        }
+        free(xv); free(yv); free(interp2); free(zb2); free(i2); free(zb3); free(inv);
+    }
+
+    /* :235-264 m_tree */
+    const fp_t *tree_cols[8] = {p_ev, a_ev, s_ev, d1, d2, d3, b2, b3};
+    uint8_t *m_leaves = (uint8_t *)malloc(N * 256);
+    for (size_t j = 0; j < N; j++)
+        for (int c = 0; c < 8; c++) fp_to_bytes_le(m_leaves + 256 * j + 32 * c, &tree_cols[c][j]);
+    t0 = now_s();
+    orc_merkle_gen_proofs(m_leaves, 256, N, NULL, 0, out->m_root, NULL);
+    orc_stage_s[1] += now_s() - t0;
+
+    /* :274-322 */
+    fp_t k[11];
+    derive_k(k, out->m_root);
+    fp_t *l_ev = (fp_t *)malloc(N * sizeof(fp_t));
+    {
+        const fp_t gs = D.xs[S];
+        fp_t pw = FP_ONE;
+        for (size_t j = 0; j < N; j++) {
+            fp_t acc, tt, px, bx, b3x;
+            fp_mul(&acc, &k[0], &d1[j]);
+            fp_mul(&tt, &k[1], &d2[j]); fp_add(&acc, &acc, &tt);
+            fp_mul(&tt, &k[2], &d3[j]); fp_add(&acc, &acc, &tt);
+            fp_mul(&tt, &k[3], &p_ev[j]); fp_add(&acc, &acc, &tt);
+            fp_mul(&px, &k[4], &p_ev[j]); fp_mul(&tt, &px, &pw); fp_add(&acc, &acc, &tt);
+            fp_mul(&tt, &k[5], &b2[j]); fp_add(&acc, &acc, &tt);
+            fp_mul(&bx, &k[6], &b2[j]); fp_mul(&tt, &bx, &pw); fp_add(&acc, &acc, &tt);
+            fp_mul(&tt, &k[7], &b3[j]); fp_add(&acc, &acc, &tt);
+            fp_mul(&b3x, &k[8], &b3[j]); fp_mul(&tt, &b3x, &pw); fp_add(&acc, &acc, &tt);
+            fp_mul(&tt, &k[9], &a_ev[j]); fp_add(&acc, &acc, &tt);
+            fp_mul(&tt, &k[10], &s_ev[j]); fp_add(&acc, &acc, &tt);
+            l_ev[j] = acc;
+            fp_mul(&pw, &pw, &gs);
+        }
+    }
+    /* :324-348 l_tree */
+    uint8_t *l_leaves = (uint8_t *)malloc(N * 32);
+    for (size_t j = 0; j < N; j++) fp_to_bytes_le(l_leaves + 32 * j, &l_ev[j]);
+    t0 = now_s();
+    orc_merkle_gen_proofs(l_leaves, 32, N, NULL, 0, out->l_root, NULL);
+    uint32_t pos32[SPOT_CHECK_SECURITY_FACTOR];
+    orc_get_pseudorandom_indices(pos32, out->l_root, 32, (uint32_t)N, SPOT_CHECK_SECURITY_FACTOR, (uint32_t)sk);
+    size_t positions[SPOT_CHECK_SECURITY_FACTOR], aug[4 * SPOT_CHECK_SECURITY_FACTOR];
+    for (int i = 0; i < SPOT_CHECK_SECURITY_FACTOR; i++) {
+        size_t j = positions[i] = pos32[i];
+        aug[4 * i + 0] = j;
+        aug[4 * i + 1] = (j + N - sk) % N;
+        aug[4 * i + 2] = (j + o3 * sk) % N;
+        aug[4 * i + 3] = (j + o3 * 2 * sk) % N;
+    }
+    uint8_t tmp_root[32];
+    out->n_lc = SPOT_CHECK_SECURITY_FACTOR;
+    out->lc_branches = orc__gen_branches(l_leaves, 32, N, positions, SPOT_CHECK_SECURITY_FACTOR, tmp_root);
+    out->n_main = 4 * SPOT_CHECK_SECURITY_FACTOR;
+    out->main_branches = orc__gen_branches(m_leaves, 256, N, aug, 4 * SPOT_CHECK_SECURITY_FACTOR, tmp_root);
+    orc_stage_s[1] += now_s() - t0;
+
+    /* :367 */
+    t0 = now_s();
+    orc_prove_low_degree(&out->fri, l_ev, N, &D.g2, N / 4, (uint32_t)sk);
+    orc_stage_s[2] += now_s() - t0;
+
+    if (taps) {
+        memset(taps, 0, sizeof *taps);
+        taps->steps = S;
+        taps->precision = N;
+        const fp_t *ldes[9] = {k_ev, f0_ev, f1_ev, f2_ev, s_ev, p_ev, idx_ev, pidx_ev, a_ev};
+        for (int i = 0; i < 9; i++) taps->lde[i] = dup_fp(ldes[i], N);
+        for (int i = 0; i < 8; i++) taps->tree_cols[i] = dup_fp(tree_cols[i], N);
+        taps->l_evals = dup_fp(l_ev, N);
+        memcpy(taps->r, r, sizeof r);
+        memcpy(taps->k, k, sizeof k);
+        memcpy(taps->positions, pos32, sizeof pos32);
+    }
+
+    free(perm); free(coeffs); free(wit); free(comp);
+    free(k_ev); free(f0_ev); free(f1_ev); free(f2_ev); free(s_ev); free(p_ev); free(z_ev);
+    free(q1); free(q2); free(q3); free(tmpcol); free(idx_ev); free(pidx_ev); free(a_mini); free(a_ev);
+    free(inv_z); free(d1); free(d2); free(d3); free(b2); free(b3);
+    free(m_leaves); free(l_ev); free(l_leaves); free(D.xs);
+    orc_stage_s[3] = (now_s() - t_all) - orc_stage_s[0] - orc_stage_s[1] - orc_stage_s[2];
+}
+
+void orc_stark_proof_free(orc_stark_proof *p) {
+    orc__branches_free(p->main_branches, p->n_main);
+    orc__branches_free(p->lc_branches, p->n_lc);
+    orc_fri_proof_free(&p->fri);
+    memset(p, 0, sizeof *p);
+}
+
+/* utils.rs:122-130 field order; run.rs:549 compact serde_json */
+void orc_stark_proof_json(orc_buf *b, const orc_stark_proof *p) {
+    orc__buf_puts(b, "{\"m_root\":");
+    orc__buf_bytes(b, p->m_root, 32);
+    orc__buf_puts(b, ",\"l_root\":");
+    orc__buf_bytes(b, p->l_root, 32);
+    orc__buf_puts(b, ",\"a_root\":");
+    orc__buf_bytes(b, p->a_root, 32);
+    orc__buf_puts(b, ",\"main_branches\":");
+    orc__branches_json(b, p->main_branches, p->n_main);
+    orc__buf_puts(b, ",\"linear_comb_branches\":");
+    orc__branches_json(b, p->lc_branches, p->n_lc);
+    orc__buf_puts(b, ",\"fri_proof\":");
+    orc_fri_proof_json(b, &p->fri);
+    orc__buf_puts(b, "}");
+}
+
+/* verify.rs:13-258 */
+int orc_verify_r1cs_proof(const orc_stark_proof *proof, const orc_trace *t, unsigned cpus) {
+    const size_t os = t->original_steps;
+    if (os % 3 != 0 || os == 0) return 0;
+    domain_t D;
+    make_domain(&D, os);
+    const size_t S = D.steps, N = D.precision, sk = D.skips, o3 = os / 3;
+    const uint32_t lS = D.log_steps, lN = D.log_precision;
+    int ok = 1;
+
+    size_t *perm = (size_t *)malloc(S * sizeof(size_t));
+    memcpy(perm, t->permuted_indices, os * sizeof(size_t));
+    for (size_t i = os; i < S; i++) perm[i] = i;
+
+    /* :73-78 coefficient forms */
+    fp_t *k_poly = (fp_t *)calloc(S, sizeof(fp_t));
+    fp_t *f0_poly = (fp_t *)calloc(S, sizeof(fp_t)), *f1_poly = (fp_t *)calloc(S, sizeof(fp_t)), *f2_poly = (fp_t *)calloc(S, sizeof(fp_t));
+    memcpy(k_poly, t->coefficients, os * sizeof(fp_t));
+    memcpy(f0_poly, t->flag0, os * sizeof(fp_t));
+    memcpy(f1_poly, t->flag1, os * sizeof(fp_t));
+    memcpy(f2_poly, t->flag2, os * sizeof(fp_t));
+    orc_inv_best_fft(k_poly, S, &D.g1, lS, cpus);
+    orc_inv_best_fft(f0_poly, os, &D.g1, lS, cpus);
+    orc_inv_best_fft(f1_poly, os, &D.g1, lS, cpus);
+    orc_inv_best_fft(f2_poly, os, &D.g1, lS, cpus);
+
+    /* :82-85 */
+    if (!orc_verify_low_degree_proof(proof->l_root, &D.g2, &proof->fri, N / 4, (uint32_t)sk)) ok = 0;
+
+    /* :87-119 */
+    uint32_t pos32[SPOT_CHECK_SECURITY_FACTOR];
+    orc_get_pseudorandom_indices(pos32, proof->l_root, 32, (uint32_t)N, SPOT_CHECK_SECURITY_FACTOR, (uint32_t)sk);
+    size_t positions[SPOT_CHECK_SECURITY_FACTOR], aug[4 * SPOT_CHECK_SECURITY_FACTOR];
+    for (int i = 0; i < SPOT_CHECK_SECURITY_FACTOR; i++) {
+        size_t j = positions[i] = pos32[i];
+        aug[4 * i + 0] = j;
+        aug[4 * i + 1] = (j + N - sk) % N;
+        aug[4 * i + 2] = (j + o3 * sk) % N;
+        aug[4 * i + 3] = (j + 2 * o3 * sk) % N;
+    }
+    if (proof->n_main != 4 * SPOT_CHECK_SECURITY_FACTOR || proof->n_lc != SPOT_CHECK_SECURITY_FACTOR) ok = 0;
+    if (ok && !orc__verify_multi_branch(proof->m_root, aug, proof->main_branches, proof->n_main)) ok = 0;
+    if (ok && !orc__verify_multi_branch(proof->l_root, positions, proof->lc_branches, proof->n_lc)) ok = 0;
+
+    /* :121-136 */
+    fp_t *z_ev = (fp_t *)calloc(N, sizeof(fp_t));
+    fp_neg(&z_ev[0], &FP_ONE);
+    z_ev[S] = FP_ONE;
+    orc_best_fft(z_ev, S + 1, &D.g2, lN, cpus);
+    fp_t *tmpcol = (fp_t *)malloc(S * sizeof(fp_t));
+    for (size_t i = 0; i < S; i++) fp_from_u64(&tmpcol[i], (uint64_t)i);
+    fp_t *idx_ev = lde(tmpcol, S, S, N, &D.g1, &D.g2, lS, lN, cpus, NULL);
+    for (size_t i = 0; i < S; i++) fp_from_u64(&tmpcol[i], (uint64_t)perm[i]);
+    fp_t *pidx_ev = lde(tmpcol, S, S, N, &D.g1, &D.g2, lS, lN, cpus, NULL);
+
+    /* :153-175 */
+    const size_t np = t->n_pfi;
+    fp_t *xv = (fp_t *)malloc((np ? np : 1) * sizeof(fp_t)), *yv = (fp_t *)malloc((np ? np : 1) * sizeof(fp_t));
+    fp_t *interp2 = (fp_t *)malloc((np ? np : 1) * sizeof(fp_t));
+    for (size_t i = 0; i < np; i++) {
+        xv[i] = D.xs[sk * t->pfi_w[i]];
+        yv[i] = t->public_wires[t->pfi_k[i]];
+    }
+    orc_lagrange_interp(interp2, xv, yv, np);
+    const fp_t x_last = D.xs[(S - 1) * sk];
+    fp_t r[3], k[11];
+    get_random_ff_values(r, proof->a_root, (uint32_t)N, 3, 0);
+    derive_k(k, proof->m_root);
+
+    /* :177-254 */
+    for (int i = 0; ok && i < SPOT_CHECK_SECURITY_FACTOR; i++) {
+        const size_t pos = positions[i];
+        const fp_t x = D.xs[pos];
+        const orc_branch *b0 = &proof->main_branches[4 * i], *b1 = b0 + 1, *b2 = b0 + 2, *b3 = b0 + 3;
+        if (b0->leaf_bytes != 256 || b1->leaf_bytes != 256 || b2->leaf_bytes != 256 || b3->leaf_bytes != 256) { ok = 0; break; }
+        fp_t p_x, p_prev, p_w, p_2w, a_x, a_prev, s_x, d1, d2, d3, bb, bb3;
+        fp_from_bytes_le(&p_x, b0->leaf, 32);
+        fp_from_bytes_le(&p_prev, b1->leaf, 32);
+        fp_from_bytes_le(&p_w, b2->leaf, 32);
+        fp_from_bytes_le(&p_2w, b3->leaf, 32);
+        fp_from_bytes_le(&a_x, b0->leaf + 32, 32);
+        fp_from_bytes_le(&a_prev, b1->leaf + 32, 32);
+        fp_from_bytes_le(&s_x, b0->leaf + 64, 32);
+        fp_from_bytes_le(&d1, b0->leaf + 96, 32);
+        fp_from_bytes_le(&d2, b0->leaf + 128, 32);
+        fp_from_bytes_le(&d3, b0->leaf + 160, 32);
+        fp_from_bytes_le(&bb, b0->leaf + 192, 32);
+        fp_from_bytes_le(&bb3, b0->leaf + 224, 32);
+        const fp_t z = z_ev[pos];
+        fp_t kx, f0, f1, f2, lhs, rhs, u, v;
+        orc_eval_poly_at(&kx, k_poly, S, &x);
+        orc_eval_poly_at(&f0, f0_poly, S, &x);
+        orc_eval_poly_at(&f1, f1_poly, S, &x);
+        orc_eval_poly_at(&f2, f2_poly, S, &x);
+        /* Q1 */
+        fp_mul(&u, &f1, &p_prev);
+        fp_mul(&v, &kx, &s_x);
+        fp_sub(&lhs, &p_x, &u);
+        fp_sub(&lhs, &lhs, &v);
+        fp_mul(&lhs, &f0, &lhs);
+        fp_mul(&rhs, &z, &d1);
+        if (!fp_eq(&lhs, &rhs)) ok = 0;
+        /* Q2 */
+        fp_mul(&u, &p_x, &p_w);
+        fp_sub(&lhs, &p_2w, &u);
+        fp_mul(&lhs, &f2, &lhs);
+        fp_mul(&rhs, &z, &d2);
+        if (!fp_eq(&lhs, &rhs)) ok = 0;
+        /* Q3 */
+        fp_t vn, vd, t1, t2;
+        fp_mul(&t2, &r[2], &s_x);
+        fp_mul(&t1, &r[1], &idx_ev[pos]);
+        fp_add(&vn, &r[0], &t1);
+        fp_add(&vn, &vn, &t2);
+        fp_mul(&t1, &r[1], &pidx_ev[pos]);
+        fp_add(&vd, &r[0], &t1);
+        fp_add(&vd, &vd, &t2);
+        fp_mul(&u, &a_x, &vd);
+        fp_mul(&v, &a_prev, &vn);
+        fp_sub(&lhs, &u, &v);
+        fp_mul(&rhs, &z, &d3);
+        if (!fp_eq(&lhs, &rhs)) ok = 0;
+        /* B2 */
+        fp_t zb2 = FP_ONE, df, i2x;
+        for (size_t w = 0; w < np; w++) {
+            fp_sub(&df, &x, &xv[w]);
+            fp_mul(&zb2, &zb2, &df);
+        }
+        orc_eval_poly_at(&i2x, interp2, np, &x);
+        fp_sub(&lhs, &s_x, &i2x);
+        fp_mul(&rhs, &zb2, &bb);
+        if (!fp_eq(&lhs, &rhs)) ok = 0;
+        /* B3 */
+        fp_sub(&df, &x, &x_last);
+        fp_sub(&lhs, &a_x, &FP_ONE);
+        fp_mul(&rhs, &df, &bb3);
+        if (!fp_eq(&lhs, &rhs)) ok = 0;
+        /* linear combination */
+        fp_t xs_steps, l_x, acc, tt;
+        fp_pow_u64(&xs_steps, &x, (uint64_t)S);
+        if (proof->lc_branches[i].leaf_bytes != 32) { ok = 0; break; }
+        fp_from_bytes_le(&l_x, proof->lc_branches[i].leaf, 32);
+        fp_mul(&acc, &k[0], &d1);
+        fp_mul(&tt, &k[1], &d2); fp_add(&acc, &acc, &tt);
+        fp_mul(&tt, &k[2], &d3); fp_add(&acc, &acc, &tt);
+        fp_mul(&tt, &k[3], &p_x); fp_add(&acc, &acc, &tt);
+        fp_mul(&tt, &k[4], &p_x); fp_mul(&tt, &tt, &xs_steps); fp_add(&acc, &acc, &tt);
+        fp_mul(&tt, &k[5], &bb); fp_add(&acc, &acc, &tt);
+        fp_mul(&tt, &k[6], &bb); fp_mul(&tt, &tt, &xs_steps); fp_add(&acc, &acc, &tt);
+        fp_mul(&tt, &k[7], &bb3); fp_add(&acc, &acc, &tt);
+        fp_mul(&tt, &k[8], &bb3); fp_mul(&tt, &tt, &xs_steps); fp_add(&acc, &acc, &tt);
+        fp_mul(&tt, &k[9], &a_x); fp_add(&acc, &acc, &tt);
+        fp_mul(&tt, &k[10], &s_x); fp_add(&acc, &acc, &tt);
+        if (!fp_eq(&acc, &l_x)) ok = 0;
+    }
+
+    free(perm); free(k_poly); free(f0_poly); free(f1_poly); free(f2_poly);
+    free(z_ev); free(tmpcol); free(idx_ev); free(pidx_ev); free(xv); free(yv); free(interp2); free(D.xs);
+    return ok;
+}
+
+/* ---- files in, proof.json out (run.rs:528-625 without the hard-coded wtns.json side effect) -- */
+static uint8_t *slurp(const char *path, size_t *len) {
+    FILE *f = fopen(path, "rb");
+    if (!f) return NULL;
+    fseek(f, 0, SEEK_END);
+    long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    uint8_t *buf = (uint8_t *)malloc(sz > 0 ? (size_t)sz : 1);
+    if (sz > 0 && fread(buf, 1, (size_t)sz, f) != (size_t)sz) { fclose(f); free(buf); return NULL; }
+    fclose(f);
+    *len = (size_t)sz;
+    return buf;
+}
+
+int orc_prove_files(const char *r1cs_path, const char *wtns_path, const char *proof_path,
+                    unsigned cpus, int verify, double *t_prove_s) {
+    size_t rl = 0, wl = 0;
+    uint8_t *rb = slurp(r1cs_path, &rl), *wb = slurp(wtns_path, &wl);
+    if (!rb || !wb) { free(rb); free(wb); return -1; }
+    orc_r1cs r1cs;
+    int rc = orc_read_r1cs(&r1cs, rb, rl);
+    if (rc) { free(rb); free(wb); return -2; }
+    static const uint8_t BN254[32] = {1, 0, 0, 240, 147, 245, 225, 67, 145, 112, 185, 121, 72, 232, 51, 40, 93, 88,
+                                      129, 129, 182, 69, 80, 184, 41, 160, 49, 225, 114, 78, 100, 48};
+    if (memcmp(r1cs.prime, BN254, 32)) { orc_r1cs_free(&r1cs); free(rb); free(wb); return -3; } /* run.rs:344-350 */
+    size_t n_wires = 0;
+    fp_t *wit = orc_read_witness(wb, wl, &n_wires);
+    if (!wit || n_wires < r1cs.n_wires || !fp_eq(&wit[0], &FP_ONE)) { /* run.rs:358 */
+        free(wit); orc_r1cs_free(&r1cs); free(rb); free(wb);
+        return -4;
+    }
+    orc_trace tr;
+    orc_build_trace(&tr, &r1cs, wit, 1);
+    orc_stark_proof proof;
+    double t0 = now_s();
+    orc_mk_r1cs_proof(&proof, &tr, cpus, NULL);
+    if (t_prove_s) *t_prove_s = now_s() - t0;
+    orc_buf b = {0, 0, 0};
+    orc_stark_proof_json(&b, &proof);
+    int ret = 0;
+    if (proof_path) {
+        FILE *f = fopen(proof_path, "wb");
+        if (!f) ret = -5;
+        else {
+            fwrite(b.p, 1, b.len, f);
+            fclose(f);
+        }
+    }
+    if (ret == 0 && verify && !orc_verify_r1cs_proof(&proof, &tr, cpus)) ret = 1;
+    orc_buf_free(&b);
+    orc_stark_proof_free(&proof);
+    orc_trace_free(&tr);
+    free(wit);
+    orc_r1cs_free(&r1cs);
+    free(rb);
+    free(wb);
+    return ret;
+}
