@@ -1,0 +1,152 @@
+/*
+ * stark_b200.h -- C ABI of the B200 (sm_100a) backend for the stark-pure-rust hot path:
+ * NTT / low-degree extension, Blake2s Merkle commitment, FRI low-degree proof.
+ *
+ * This is the boundary a Rust FFI shim crate would bind so that the reference's own entry points
+ * keep their signatures (packages/r1cs-stark/src/prove.rs:2-10 imports exactly these):
+ *
+ *   fri::fft::best_fft / inv_best_fft          packages/fri/src/fft.rs:327-331, :359-363
+ *   fri::fft::expand_root_of_unity             packages/fri/src/fft.rs:5-14
+ *   fri::poly_utils::multi_inv                 packages/fri/src/poly_utils.rs:38-70
+ *   commitment::MerkleProofInPlace             packages/commitment/src/merkle_proof_in_place.rs:16-50
+ *     (trait MerkleTree: width/get_root/update/gen_proofs, merkle_tree.rs:60-73)
+ *   fri::fri::prove_low_degree                 packages/fri/src/fri.rs:46-62
+ *   the inv_best_fft -> best_fft pairs         packages/r1cs-stark/src/prove.rs:100-124,160-167,183-184
+ *
+ * Conventions
+ *   - Field element = the reference's in-memory `Fp([u64; 4])` (ff_utils/src/fp.rs:8-12): BN254 Fr,
+ *     Montgomery form with R = 2^256, four little-endian u64 limbs, canonical (< p).  A Rust
+ *     `Vec<Fp>` is passed as `uint64_t*` by pointer cast, no conversion.
+ *   - Digest = 32 bytes, Blake2s-256 unkeyed (commitment/src/blake.rs:28-32).
+ *   - Every function returns SB_OK (0) or a negative error; sb_last_error() gives the text.  The
+ *     reference panics on these conditions (assert!/unwrap); a Rust shim turns non-zero into panic!.
+ *   - There is NO CPU fallback: without a CUDA device of compute capability 10.x sb_init fails with
+ *     SB_ERR_NO_DEVICE and nothing else can be called.
+ *   - Pointers named `d_*` are device pointers obtained from sb_dev_alloc; all others are host
+ *     pointers (pageable or pinned).  Calls are synchronous with respect to the host unless the name
+ *     ends in `_async`; work is issued on the context's stream.
+ *   - One context per GPU per thread; a context is not re-entrant.
+ */
+#ifndef STARK_B200_H
+#define STARK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB_OK 0
+#define SB_ERR_NO_DEVICE (-1)   /* no sm_100 device / CUDA runtime failure at init            */
+#define SB_ERR_CUDA (-2)        /* a CUDA call or kernel failed                                */
+#define SB_ERR_ARG (-3)         /* size / alignment / range violation (reference: assert!)     */
+#define SB_ERR_ROOT (-4)        /* root_of_unity is not a primitive 2^log_n-th root of unity   */
+#define SB_ERR_OOM (-5)         /* device allocation failed                                    */
+
+typedef struct sb_ctx sb_ctx;
+typedef struct sb_tree sb_tree;
+typedef struct sb_fri_proof sb_fri_proof;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int sb_init(int device, sb_ctx **out);
+void sb_destroy(sb_ctx *ctx);
+const char *sb_last_error(const sb_ctx *ctx);
+/* Use an external CUDA stream (cudaStream_t passed as void*, e.g. torch's current stream). */
+int sb_set_stream(sb_ctx *ctx, void *cuda_stream);
+int sb_sync(sb_ctx *ctx);
+/* CUDA-event stopwatch on the context's stream (bench harness). */
+int sb_timer_start(sb_ctx *ctx);
+int sb_timer_stop(sb_ctx *ctx, float *ms);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t sb_launch_count(const sb_ctx *ctx);
+
+/* ---- device memory (pipelines that keep vectors resident in HBM) --------------------------- */
+int sb_dev_alloc(sb_ctx *ctx, size_t bytes, void **d_ptr);
+int sb_dev_free(sb_ctx *ctx, void *d_ptr);
+int sb_h2d(sb_ctx *ctx, void *d_dst, const void *src, size_t bytes);
+int sb_d2h(sb_ctx *ctx, void *dst, const void *d_src, size_t bytes);
+int sb_host_alloc_pinned(sb_ctx *ctx, size_t bytes, void **ptr);
+int sb_host_free_pinned(sb_ctx *ctx, void *ptr);
+
+/* ---- NTT (fri/src/fft.rs) -------------------------------------------------------------------- */
+/* best_fft (inverse = 0) / inv_best_fft (inverse = 1): `vals` has room for 2^log_n elements, the
+ * first len_in are the caller's vector, the rest is zero padding supplied here (fft.rs:335-338).
+ * In place, natural order in and out: out[k] = sum_j v[j] root^(jk) (inverse: root^-1, then / n).
+ * len_in > 2^log_n -> SB_ERR_ARG (reference: assert at fft.rs:162). */
+int sb_ntt(sb_ctx *ctx, uint64_t *vals, size_t len_in, const uint64_t root[4], uint32_t log_n, int inverse);
+/* Same on device-resident data, batched: n_polys vectors, src element stride src_stride, dst stride
+ * dst_stride (elements), d_dst must not alias d_src. */
+int sb_ntt_dev(sb_ctx *ctx, const uint64_t *d_src, size_t len_in, size_t src_stride, uint64_t *d_dst,
+               size_t dst_stride, size_t n_polys, const uint64_t root[4], uint32_t log_n, int inverse);
+/* Low-degree extension of n_cols columns: best_fft(inv_best_fft(col, root_big^(2^log_ext), log_s),
+ * root_big, log_s + log_ext) for every column (prove.rs:100-124).  cols: n_cols x col_len elements
+ * (col_len <= 2^log_s, zero padded like inv_best_fft does); out: n_cols x 2^(log_s+log_ext). */
+int sb_lde_batch(sb_ctx *ctx, const uint64_t *cols, size_t n_cols, size_t col_len, const uint64_t root_big[4],
+                 uint32_t log_s, uint32_t log_ext, uint64_t *out);
+int sb_lde_batch_dev(sb_ctx *ctx, const uint64_t *d_cols, size_t n_cols, size_t col_len, size_t col_stride,
+                     const uint64_t root_big[4], uint32_t log_s, uint32_t log_ext, uint64_t *d_out);
+/* expand_root_of_unity (fft.rs:5-14): out[i] = root^i for i < n (the reference stops when the power
+ * wraps to 1, i.e. n = order of root). */
+int sb_powers(sb_ctx *ctx, const uint64_t root[4], size_t n, uint64_t *out);
+int sb_powers_dev(sb_ctx *ctx, const uint64_t root[4], size_t n, uint64_t *d_out);
+/* multi_inv (poly_utils.rs:38-70): element-wise inverse in place, 0 -> 0. */
+int sb_batch_inverse(sb_ctx *ctx, uint64_t *vals, size_t n);
+int sb_batch_inverse_dev(sb_ctx *ctx, uint64_t *d_vals, size_t n);
+
+/* ---- Merkle (commitment/src/merkle_proof_in_place.rs, merkle_tree.rs) ------------------------- */
+/* update(leaves) + gen_proofs(&[]) + get_root(): n leaves (power of two) of leaf_bytes each, flattened.
+ * All levels stay resident in HBM inside *tree. */
+int sb_merkle_commit(sb_ctx *ctx, const void *leaves, size_t leaf_bytes, size_t n, uint8_t root[32], sb_tree **tree);
+/* Leaves taken from device-resident field columns: leaf i = to_bytes_le(col_0[i]) || ... (prove.rs:235-258,
+ * :324-327; fri.rs:120-123).  The columns must outlive the tree (openings re-read them). */
+int sb_merkle_commit_cols_dev(sb_ctx *ctx, const uint64_t *const *d_cols, size_t n_cols, size_t n, uint8_t root[32],
+                              sb_tree **tree);
+/* gen_proofs(idx): caller order, duplicates allowed (merkle_proof_in_place.rs:199-205).
+ * leaves_out: n_idx x leaf_bytes; nodes_out: n_idx x log2(n) x 32, sibling at the leaf level first, root
+ * excluded (merkle_tree.rs:25-43).  Either output may be NULL. */
+int sb_merkle_open(sb_ctx *ctx, const sb_tree *tree, const size_t *idx, size_t n_idx, uint8_t *leaves_out,
+                   uint8_t *nodes_out);
+size_t sb_tree_width(const sb_tree *tree);      /* MerkleTree::width */
+size_t sb_tree_leaf_bytes(const sb_tree *tree);
+int sb_tree_root(const sb_tree *tree, uint8_t root[32]);
+void sb_tree_free(sb_ctx *ctx, sb_tree *tree);
+
+/* ---- FRI (fri/src/fri.rs:46-224) --------------------------------------------------------------- */
+/* prove_low_degree(values, root_of_unity, max_deg_plus_1, exclude_multiples_of). n = number of values =
+ * order of root (power of two). */
+int sb_fri_prove(sb_ctx *ctx, const uint64_t *vals, size_t n, const uint64_t root[4], size_t max_deg_plus_1,
+                 uint32_t exclude_multiples_of, sb_fri_proof **out);
+/* device-resident values; `values_tree` may be the already committed tree of d_vals (the prover's l_tree,
+ * prove.rs:324-332) or NULL. */
+int sb_fri_prove_dev(sb_ctx *ctx, const uint64_t *d_vals, size_t n, const uint64_t root[4], size_t max_deg_plus_1,
+                     uint32_t exclude_multiples_of, const sb_tree *values_tree, sb_fri_proof **out);
+/* Proof accessors.  Layers 0..n_layers-2 are FriProof::Middle, the last one is FriProof::Last (fri.rs:16-26). */
+size_t sb_fri_n_layers(const sb_fri_proof *p);
+int sb_fri_layer_is_last(const sb_fri_proof *p, size_t layer);
+/* Middle: root2 (32 B); column_branches: 40 openings of the column tree (leaf 32 B, depth_col siblings);
+ * poly_branches: 160 openings of the values tree (leaf 32 B, depth_poly siblings). */
+int sb_fri_middle(const sb_fri_proof *p, size_t layer, const uint8_t **root2, size_t *n_column, size_t *depth_column,
+                  const uint8_t **column_leaves, const uint8_t **column_nodes, size_t *n_poly, size_t *depth_poly,
+                  const uint8_t **poly_leaves, const uint8_t **poly_nodes);
+/* Last: n_last elements, 32 bytes each (to_bytes_le). */
+int sb_fri_last(const sb_fri_proof *p, size_t layer, const uint8_t **values, size_t *n_last);
+/* Roots of the per-layer value trees (layer 0 = commitment of the input values): test / bench taps. */
+int sb_fri_layer_root(const sb_fri_proof *p, size_t layer, uint8_t root[32]);
+/* serde_json::to_string(&Vec<FriProof>) (compact; fri.rs:16-26 + merkle_tree.rs:14-18): returns a malloc'd
+ * NUL-terminated string the caller frees with sb_free_string. */
+char *sb_fri_proof_json(const sb_fri_proof *p);
+void sb_free_string(char *s);
+void sb_fri_proof_free(sb_fri_proof *p);
+
+/* ---- Fiat-Shamir helpers that sit between the kernels (host side, exact) ------------------------- */
+/* get_pseudorandom_indices (fri/src/utils.rs:82-109) */
+int sb_pseudorandom_indices(const uint8_t *seed, size_t seed_len, uint32_t modulus, size_t count,
+                            uint32_t exclude_multiples_of, uint32_t *out);
+/* blake (fri/src/utils.rs:5-10) */
+void sb_blake2s(const uint8_t *msg, size_t len, uint8_t out[32]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

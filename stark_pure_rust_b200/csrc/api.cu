@@ -1,0 +1,846 @@
+// api.cu -- host side of libstark_b200.so: the C ABI of include/stark_b200.h on top of the sm_100a
+// kernels (ntt.cuh, merkle.cuh, fri.cuh).  No CPU fallback anywhere: every entry point that does
+// vector work needs a live context, and sb_init fails without a compute-capability-10 device.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/stark_b200.h"
+#include "blake2s.cuh"
+#include "hostfp.h"
+#include "kernels.h"
+#include "params.h"
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct TwTable {
+    hfp::el root;
+    uint32_t log_n;
+    uint4 *d;
+};
+
+struct sb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint64_t launches = 0;
+    std::vector<TwTable> tables;
+    char err[512] = {0};
+};
+
+static int fail(sb_ctx *ctx, int code, const char *fmt, ...) {
+    if (ctx) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(ctx->err, sizeof ctx->err, fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define CU(call)                                                                                    \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? SB_ERR_OOM : SB_ERR_CUDA, "%s: %s (%s:%d)", #call, \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                                \
+    } while (0)
+#define TRY(expr)                \
+    do {                         \
+        int rc_ = (expr);        \
+        if (rc_ != SB_OK) return rc_; \
+    } while (0)
+#define LAUNCHED(ctx) ((ctx)->launches++)
+
+struct DevBuf {   // stream-ordered scratch
+    sb_ctx *ctx;
+    void *p = nullptr;
+    explicit DevBuf(sb_ctx *c) : ctx(c) {}
+    int alloc(size_t bytes) {
+        cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 16, ctx->stream);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return fail(ctx, e == cudaErrorMemoryAllocation ? SB_ERR_OOM : SB_ERR_CUDA, "cudaMallocAsync(%zu): %s", bytes,
+                        cudaGetErrorString(e));
+        }
+        return SB_OK;
+    }
+    ~DevBuf() {
+        if (p) cudaFreeAsync(p, ctx->stream);
+    }
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+};
+
+extern "C" int sb_init(int device, sb_ctx **out) {
+    if (!out) return SB_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) return SB_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SB_ERR_NO_DEVICE;
+    if (prop.major != 10) return SB_ERR_NO_DEVICE;   // kernels are built for sm_100a only
+    if (cudaSetDevice(device) != cudaSuccess) return SB_ERR_NO_DEVICE;
+    sb_ctx *ctx = new sb_ctx();
+    ctx->device = device;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return SB_ERR_NO_DEVICE;
+    }
+    ctx->own_stream = true;
+    cudaEventCreate(&ctx->ev0);
+    cudaEventCreate(&ctx->ev1);
+    // keep freed scratch cached in the stream-ordered pool
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    cudaError_t e = ntt_set_attrs();
+    if (e != cudaSuccess) {
+        fprintf(stderr, "stark_b200: kernel image not loadable on this device: %s\n", cudaGetErrorString(e));
+        sb_destroy(ctx);
+        return SB_ERR_NO_DEVICE;
+    }
+    *out = ctx;
+    return SB_OK;
+}
+
+extern "C" void sb_destroy(sb_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &t : ctx->tables) cudaFree(t.d);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char *sb_last_error(const sb_ctx *ctx) { return ctx ? ctx->err : "no context"; }
+
+extern "C" int sb_set_stream(sb_ctx *ctx, void *s) {
+    if (!ctx) return SB_ERR_ARG;
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)s;
+    ctx->own_stream = false;
+    return SB_OK;
+}
+extern "C" int sb_sync(sb_ctx *ctx) {
+    if (!ctx) return SB_ERR_ARG;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+extern "C" int sb_timer_start(sb_ctx *ctx) {
+    if (!ctx) return SB_ERR_ARG;
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    return SB_OK;
+}
+extern "C" int sb_timer_stop(sb_ctx *ctx, float *ms) {
+    if (!ctx || !ms) return SB_ERR_ARG;
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    CU(cudaEventSynchronize(ctx->ev1));
+    CU(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return SB_OK;
+}
+extern "C" uint64_t sb_launch_count(const sb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int sb_dev_alloc(sb_ctx *ctx, size_t bytes, void **p) {
+    if (!ctx || !p) return SB_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMalloc(p, bytes ? bytes : 16));
+    return SB_OK;
+}
+extern "C" int sb_dev_free(sb_ctx *ctx, void *p) {
+    if (!ctx) return SB_ERR_ARG;
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaFree(p));
+    return SB_OK;
+}
+extern "C" int sb_h2d(sb_ctx *ctx, void *d, const void *s, size_t bytes) {
+    if (!ctx) return SB_ERR_ARG;
+    CU(cudaMemcpyAsync(d, s, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+extern "C" int sb_d2h(sb_ctx *ctx, void *d, const void *s, size_t bytes) {
+    if (!ctx) return SB_ERR_ARG;
+    CU(cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+extern "C" int sb_host_alloc_pinned(sb_ctx *ctx, size_t bytes, void **p) {
+    if (!ctx || !p) return SB_ERR_ARG;
+    CU(cudaMallocHost(p, bytes ? bytes : 16));
+    return SB_OK;
+}
+extern "C" int sb_host_free_pinned(sb_ctx *ctx, void *p) {
+    if (!ctx) return SB_ERR_ARG;
+    CU(cudaFreeHost(p));
+    return SB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// twiddle tables
+// ------------------------------------------------------------------------------------------------
+static fp to_dev_fp(const hfp::el &a) {
+    fp r;
+    memcpy(r.l, a.l, 32);
+    return r;
+}
+
+static int powers_into(sb_ctx *ctx, const hfp::el &root, size_t n, uint4 *d_out) {
+    if (n == 0) return SB_OK;
+    size_t seed = n < 1024 ? n : 1024;
+    ctx->launches += powers_launch_seed(ctx->stream, d_out, seed, to_dev_fp(root));
+    hfp::el wc = hfp::pow_u64(root, 1024);
+    for (size_t cur = 1024; cur < n; cur <<= 1) {
+        ctx->launches += powers_launch_double(ctx->stream, d_out, cur, n, to_dev_fp(wc));
+        wc = hfp::sqr(wc);
+    }
+    CU(cudaGetLastError());
+    return SB_OK;
+}
+
+// w must be a primitive 2^log_n-th root of unity (log_n = 0: w = 1)
+static int check_root(sb_ctx *ctx, const hfp::el &w, uint32_t log_n) {
+    if (log_n > 28) return fail(ctx, SB_ERR_ARG, "log_n %u exceeds the field's two-adicity 28", log_n);
+    if (log_n == 0) return hfp::eq(w, hfp::ONE) ? SB_OK : fail(ctx, SB_ERR_ROOT, "root of order 1 must be 1");
+    hfp::el t = w;
+    for (uint32_t i = 0; i + 1 < log_n; i++) t = hfp::sqr(t);
+    if (!hfp::eq(t, hfp::neg(hfp::ONE))) return fail(ctx, SB_ERR_ROOT, "root_of_unity^(2^%u) != -1: not a primitive 2^%u-th root", log_n - 1, log_n);
+    return SB_OK;
+}
+
+// finds or builds a table T with w = T-root^(2^log_stride)
+static int get_table(sb_ctx *ctx, const hfp::el &w, uint32_t log_n, const uint4 **tw, uint32_t *tw_log_n, uint32_t *log_stride) {
+    TRY(check_root(ctx, w, log_n));
+    for (auto &t : ctx->tables) {
+        if (t.log_n < log_n) continue;
+        hfp::el r = t.root;
+        for (uint32_t i = 0; i < t.log_n - log_n; i++) r = hfp::sqr(r);
+        if (hfp::eq(r, w)) {
+            *tw = t.d;
+            *tw_log_n = t.log_n;
+            *log_stride = t.log_n - log_n;
+            return SB_OK;
+        }
+    }
+    TwTable t;
+    t.root = w;
+    t.log_n = log_n;
+    CU(cudaMalloc(&t.d, ((size_t)32) << log_n));
+    int rc = powers_into(ctx, w, (size_t)1 << log_n, t.d);
+    if (rc != SB_OK) {
+        cudaFree(t.d);
+        return rc;
+    }
+    ctx->tables.push_back(t);
+    *tw = t.d;
+    *tw_log_n = log_n;
+    *log_stride = 0;
+    return SB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// NTT
+// ------------------------------------------------------------------------------------------------
+static int plan_bits(uint32_t log_n, uint32_t *bits) {
+    if (log_n == 0) {
+        bits[0] = 0;
+        return 1;
+    }
+    const uint32_t maxb = NTT_LOG_TILE - 3;     // keep >= 8 contiguous columns per tile row
+    int m = (int)((log_n + maxb - 1) / maxb);
+    uint32_t base = log_n / m, rem = log_n % m;
+    for (int i = 0; i < m; i++) bits[i] = base + ((uint32_t)i < rem ? 1 : 0);
+    return m;
+}
+
+static int ntt_dev(sb_ctx *ctx, const uint4 *d_src, size_t len_in, size_t src_stride, uint4 *d_dst, size_t dst_stride,
+                   size_t n_polys, const hfp::el &root, uint32_t log_n, int inverse) {
+    const size_t n = (size_t)1 << log_n;
+    if (len_in > n) return fail(ctx, SB_ERR_ARG, "vector of %zu elements does not fit a 2^%u transform", len_in, log_n);
+    if (n_polys == 0) return SB_OK;
+    const uint4 *tw;
+    uint32_t tw_log_n, log_stride;
+    TRY(get_table(ctx, root, log_n, &tw, &tw_log_n, &log_stride));
+    uint32_t bits[NTT_MAX_PASSES];
+    const int m = plan_bits(log_n, bits);
+    DevBuf work(ctx);
+    if (m > 1) TRY(work.alloc(n_polys * n * 32));
+    hfp::el ninv = hfp::inv(hfp::from_u64((uint64_t)n));
+    uint32_t log_outer = 0;
+    for (int p = 0; p < m; p++) {
+        NttPassParams P;
+        memset(&P, 0, sizeof P);
+        const bool first = p == 0, last = p == m - 1;
+        P.src = first ? d_src : (const uint4 *)work.p;
+        P.dst = last ? d_dst : (uint4 *)work.p;
+        P.src_stride = first ? src_stride : n;
+        P.dst_stride = last ? dst_stride : n;
+        P.tw = tw;
+        P.len_in = len_in;
+        P.n_cols_total = (unsigned long long)n_polys << (log_n - bits[p]);
+        P.log_n = log_n;
+        P.log_outer = log_outer;
+        P.log_inner = log_n - log_outer - bits[p];
+        P.first = first;
+        P.last = last;
+        P.inverse = inverse ? 1 : 0;
+        P.tw_log_n = tw_log_n;
+        P.tw_log_stride = log_stride;
+        P.n_prev = (uint32_t)p;
+        for (int i = 0; i < p; i++) P.prev_bits[i] = bits[i];
+        memcpy(P.n_inv, ninv.l, 32);
+        if (ntt_launch_pass(ctx->stream, bits[p], P) < 0) return fail(ctx, SB_ERR_ARG, "internal: pass width %u", bits[p]);
+        ctx->launches++;
+        log_outer += bits[p];
+    }
+    CU(cudaGetLastError());
+    return SB_OK;
+}
+
+extern "C" int sb_ntt_dev(sb_ctx *ctx, const uint64_t *d_src, size_t len_in, size_t src_stride, uint64_t *d_dst,
+                          size_t dst_stride, size_t n_polys, const uint64_t root[4], uint32_t log_n, int inverse) {
+    if (!ctx || !d_src || !d_dst || !root) return SB_ERR_ARG;
+    if (d_src == d_dst) return fail(ctx, SB_ERR_ARG, "sb_ntt_dev is out of place");
+    return ntt_dev(ctx, (const uint4 *)d_src, len_in, src_stride, (uint4 *)d_dst, dst_stride, n_polys, hfp::from_limbs(root),
+                   log_n, inverse);
+}
+
+extern "C" int sb_ntt(sb_ctx *ctx, uint64_t *vals, size_t len_in, const uint64_t root[4], uint32_t log_n, int inverse) {
+    if (!ctx || !vals || !root) return SB_ERR_ARG;
+    if (log_n > 28) return fail(ctx, SB_ERR_ARG, "log_n %u exceeds the field's two-adicity 28", log_n);
+    const size_t n = (size_t)1 << log_n;
+    if (len_in > n) return fail(ctx, SB_ERR_ARG, "vector of %zu elements does not fit a 2^%u transform", len_in, log_n);
+    DevBuf a(ctx), b(ctx);
+    TRY(a.alloc((len_in ? len_in : 1) * 32));
+    TRY(b.alloc(n * 32));
+    CU(cudaMemcpyAsync(a.p, vals, len_in * 32, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(ntt_dev(ctx, (const uint4 *)a.p, len_in, n, (uint4 *)b.p, n, 1, hfp::from_limbs(root), log_n, inverse));
+    CU(cudaMemcpyAsync(vals, b.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+
+static int lde_dev(sb_ctx *ctx, const uint4 *d_cols, size_t n_cols, size_t col_len, size_t col_stride,
+                   const hfp::el &root_big, uint32_t log_s, uint32_t log_ext, uint4 *d_out) {
+    if (log_s + log_ext > 28) return fail(ctx, SB_ERR_ARG, "extended domain 2^%u exceeds two-adicity 28", log_s + log_ext);
+    const size_t S = (size_t)1 << log_s, N = S << log_ext;
+    if (col_len > S) return fail(ctx, SB_ERR_ARG, "column of %zu elements does not fit 2^%u", col_len, log_s);
+    // make sure the big table exists first so that the small transform reuses it with a stride
+    const uint4 *tw;
+    uint32_t a, b;
+    TRY(get_table(ctx, root_big, log_s + log_ext, &tw, &a, &b));
+    hfp::el root_small = root_big;
+    for (uint32_t i = 0; i < log_ext; i++) root_small = hfp::sqr(root_small);
+    DevBuf coef(ctx);
+    TRY(coef.alloc(n_cols * S * 32));
+    TRY(ntt_dev(ctx, d_cols, col_len, col_stride, (uint4 *)coef.p, S, n_cols, root_small, log_s, 1));
+    TRY(ntt_dev(ctx, (const uint4 *)coef.p, S, S, d_out, N, n_cols, root_big, log_s + log_ext, 0));
+    return SB_OK;
+}
+
+extern "C" int sb_lde_batch_dev(sb_ctx *ctx, const uint64_t *d_cols, size_t n_cols, size_t col_len, size_t col_stride,
+                                const uint64_t root_big[4], uint32_t log_s, uint32_t log_ext, uint64_t *d_out) {
+    if (!ctx || !d_cols || !d_out || !root_big) return SB_ERR_ARG;
+    return lde_dev(ctx, (const uint4 *)d_cols, n_cols, col_len, col_stride, hfp::from_limbs(root_big), log_s, log_ext,
+                   (uint4 *)d_out);
+}
+
+extern "C" int sb_lde_batch(sb_ctx *ctx, const uint64_t *cols, size_t n_cols, size_t col_len, const uint64_t root_big[4],
+                            uint32_t log_s, uint32_t log_ext, uint64_t *out) {
+    if (!ctx || !cols || !out || !root_big) return SB_ERR_ARG;
+    if (log_s + log_ext > 28) return fail(ctx, SB_ERR_ARG, "extended domain 2^%u exceeds two-adicity 28", log_s + log_ext);
+    const size_t N = (size_t)1 << (log_s + log_ext);
+    DevBuf in(ctx), o(ctx);
+    TRY(in.alloc(n_cols * col_len * 32));
+    TRY(o.alloc(n_cols * N * 32));
+    CU(cudaMemcpyAsync(in.p, cols, n_cols * col_len * 32, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(lde_dev(ctx, (const uint4 *)in.p, n_cols, col_len, col_len, hfp::from_limbs(root_big), log_s, log_ext, (uint4 *)o.p));
+    CU(cudaMemcpyAsync(out, o.p, n_cols * N * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+
+extern "C" int sb_powers_dev(sb_ctx *ctx, const uint64_t root[4], size_t n, uint64_t *d_out) {
+    if (!ctx || !root || !d_out) return SB_ERR_ARG;
+    return powers_into(ctx, hfp::from_limbs(root), n, (uint4 *)d_out);
+}
+extern "C" int sb_powers(sb_ctx *ctx, const uint64_t root[4], size_t n, uint64_t *out) {
+    if (!ctx || !root || !out) return SB_ERR_ARG;
+    DevBuf b(ctx);
+    TRY(b.alloc(n * 32));
+    TRY(powers_into(ctx, hfp::from_limbs(root), n, (uint4 *)b.p));
+    CU(cudaMemcpyAsync(out, b.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+
+extern "C" int sb_batch_inverse_dev(sb_ctx *ctx, uint64_t *d_vals, size_t n) {
+    if (!ctx || !d_vals) return SB_ERR_ARG;
+    if (n == 0) return SB_OK;
+    DevBuf scratch(ctx);
+    TRY(scratch.alloc(n * 32));
+    ctx->launches += batch_inverse_launch(ctx->stream, (uint4 *)d_vals, (uint4 *)scratch.p, n);
+    CU(cudaGetLastError());
+    return SB_OK;
+}
+extern "C" int sb_batch_inverse(sb_ctx *ctx, uint64_t *vals, size_t n) {
+    if (!ctx || !vals) return SB_ERR_ARG;
+    DevBuf b(ctx);
+    TRY(b.alloc(n * 32));
+    CU(cudaMemcpyAsync(b.p, vals, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(sb_batch_inverse_dev(ctx, (uint64_t *)b.p, n));
+    CU(cudaMemcpyAsync(vals, b.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Merkle
+// ------------------------------------------------------------------------------------------------
+struct sb_tree {
+    size_t n = 0;
+    uint32_t depth = 0;
+    size_t leaf_bytes = 0;
+    uint4 *d_nodes = nullptr;      // 2n - 1 digests, level l at merkle_level_off(n, l)
+    uint8_t *d_leaves = nullptr;   // owned copy of byte leaves (NULL for column-backed trees)
+    int n_cols = 0;
+    const uint4 *cols[8] = {0};
+    uint8_t root[32] = {0};
+};
+
+static bool is_pow2(size_t n) { return n && !(n & (n - 1)); }
+static uint32_t ilog2(size_t n) {
+    uint32_t l = 0;
+    while (((size_t)1 << l) < n) l++;
+    return l;
+}
+
+static void free_tree(sb_tree *t) {
+    if (!t) return;
+    if (t->d_nodes) cudaFree(t->d_nodes);
+    if (t->d_leaves) cudaFree(t->d_leaves);
+    delete t;
+}
+
+static void launch_leaves(sb_ctx *ctx, sb_tree *t, uint32_t lv) {
+    if (t->n_cols) {
+        MerkleColsParams P;
+        for (int k = 0; k < 8; k++) P.cols[k] = t->cols[k];
+        P.nodes = t->d_nodes;
+        P.n = t->n;
+        P.nc = (uint32_t)t->n_cols;
+        ctx->launches += merkle_launch_leaves_cols(ctx->stream, lv, P);
+    } else {
+        MerkleBytesParams P;
+        P.leaves = t->d_leaves;
+        P.nodes = t->d_nodes;
+        P.n = t->n;
+        P.leaf_bytes = (uint32_t)t->leaf_bytes;
+        ctx->launches += merkle_launch_leaves_bytes(ctx->stream, lv, P);
+    }
+}
+
+// hashes the leaves and every level; leaves the root in t->root (one 32-byte D2H + sync)
+static int merkle_build(sb_ctx *ctx, sb_tree *t) {
+    uint32_t level = t->depth < 3 ? t->depth : 3;
+    launch_leaves(ctx, t, level);
+    while (level < t->depth) {
+        const uint32_t lv = t->depth - level < 3 ? t->depth - level : 3;
+        ctx->launches += merkle_launch_nodes(ctx->stream, lv, t->d_nodes, t->n, level);
+        level += lv;
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(t->root, (const uint8_t *)t->d_nodes + (2 * t->n - 2) * 32, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+
+static int tree_new(sb_ctx *ctx, size_t n, size_t leaf_bytes, sb_tree **out) {
+    if (!is_pow2(n)) return fail(ctx, SB_ERR_ARG, "leaf count %zu is not a power of two", n);   // merkle_proof_in_place.rs:113
+    if (n > ((size_t)1 << 30)) return fail(ctx, SB_ERR_ARG, "tree too large");
+    sb_tree *t = new sb_tree();
+    t->n = n;
+    t->depth = ilog2(n);
+    t->leaf_bytes = leaf_bytes;
+    cudaError_t e = cudaMalloc(&t->d_nodes, (2 * n - 1) * 32);
+    if (e != cudaSuccess) {
+        delete t;
+        return fail(ctx, SB_ERR_OOM, "cudaMalloc(tree levels): %s", cudaGetErrorString(e));
+    }
+    *out = t;
+    return SB_OK;
+}
+
+extern "C" int sb_merkle_commit(sb_ctx *ctx, const void *leaves, size_t leaf_bytes, size_t n, uint8_t root[32], sb_tree **tree) {
+    if (!ctx || !leaves || !tree) return SB_ERR_ARG;
+    if (leaf_bytes >= ((size_t)1 << 31)) return fail(ctx, SB_ERR_ARG, "leaf too long");
+    sb_tree *t = nullptr;
+    TRY(tree_new(ctx, n, leaf_bytes, &t));
+    cudaError_t e = cudaMalloc(&t->d_leaves, n * leaf_bytes ? n * leaf_bytes : 16);
+    if (e != cudaSuccess) {
+        free_tree(t);
+        return fail(ctx, SB_ERR_OOM, "cudaMalloc(leaves): %s", cudaGetErrorString(e));
+    }
+    e = cudaMemcpyAsync(t->d_leaves, leaves, n * leaf_bytes, cudaMemcpyHostToDevice, ctx->stream);
+    int rc = e == cudaSuccess ? merkle_build(ctx, t) : fail(ctx, SB_ERR_CUDA, "H2D leaves: %s", cudaGetErrorString(e));
+    if (rc != SB_OK) {
+        free_tree(t);
+        return rc;
+    }
+    if (root) memcpy(root, t->root, 32);
+    *tree = t;
+    return SB_OK;
+}
+
+static int commit_cols(sb_ctx *ctx, const uint4 *const *d_cols, size_t n_cols, size_t n, sb_tree **tree) {
+    if (n_cols < 1 || n_cols > 8) return fail(ctx, SB_ERR_ARG, "1..8 columns per leaf supported, got %zu", n_cols);
+    sb_tree *t = nullptr;
+    TRY(tree_new(ctx, n, 32 * n_cols, &t));
+    t->n_cols = (int)n_cols;
+    for (size_t k = 0; k < n_cols; k++) t->cols[k] = d_cols[k];
+    int rc = merkle_build(ctx, t);
+    if (rc != SB_OK) {
+        free_tree(t);
+        return rc;
+    }
+    *tree = t;
+    return SB_OK;
+}
+
+extern "C" int sb_merkle_commit_cols_dev(sb_ctx *ctx, const uint64_t *const *d_cols, size_t n_cols, size_t n, uint8_t root[32],
+                                         sb_tree **tree) {
+    if (!ctx || !d_cols || !tree) return SB_ERR_ARG;
+    TRY(commit_cols(ctx, (const uint4 *const *)d_cols, n_cols, n, tree));
+    if (root) memcpy(root, (*tree)->root, 32);
+    return SB_OK;
+}
+
+extern "C" int sb_merkle_open(sb_ctx *ctx, const sb_tree *t, const size_t *idx, size_t n_idx, uint8_t *leaves_out, uint8_t *nodes_out) {
+    if (!ctx || !t || (!idx && n_idx)) return SB_ERR_ARG;
+    if (n_idx == 0) return SB_OK;
+    if (n_idx > ((size_t)1 << 24)) return fail(ctx, SB_ERR_ARG, "too many openings");
+    std::vector<unsigned long long> h(n_idx);
+    for (size_t i = 0; i < n_idx; i++) {
+        if (idx[i] >= t->n) return fail(ctx, SB_ERR_ARG, "leaf index %zu out of range (width %zu)", idx[i], t->n);
+        h[i] = idx[i];
+    }
+    DevBuf d_idx(ctx), d_nodes(ctx), d_leaves(ctx);
+    TRY(d_idx.alloc(n_idx * 8));
+    CU(cudaMemcpyAsync(d_idx.p, h.data(), n_idx * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (nodes_out && t->depth) {
+        TRY(d_nodes.alloc(n_idx * t->depth * 32));
+        const size_t tot = n_idx * t->depth;
+        ctx->launches += merkle_launch_open(ctx->stream, t->d_nodes, t->n, t->depth, (const unsigned long long *)d_idx.p,
+                                            (uint32_t)n_idx, (uint4 *)d_nodes.p);
+        CU(cudaMemcpyAsync(nodes_out, d_nodes.p, tot * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (leaves_out && t->leaf_bytes) {
+        TRY(d_leaves.alloc(n_idx * t->leaf_bytes));
+        if (t->n_cols) {
+            MerkleColsParams P;
+            for (int k = 0; k < 8; k++) P.cols[k] = t->cols[k];
+            P.nodes = nullptr;
+            P.n = t->n;
+            P.nc = (uint32_t)t->n_cols;
+            ctx->launches += merkle_launch_open_leaves_cols(ctx->stream, P, (const unsigned long long *)d_idx.p, (uint32_t)n_idx,
+                                                            (uint4 *)d_leaves.p);
+        } else {
+            ctx->launches += merkle_launch_gather_bytes(ctx->stream, t->d_leaves, t->leaf_bytes, (const unsigned long long *)d_idx.p,
+                                                        (uint32_t)n_idx, (uint8_t *)d_leaves.p);
+        }
+        CU(cudaMemcpyAsync(leaves_out, d_leaves.p, n_idx * t->leaf_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+
+extern "C" size_t sb_tree_width(const sb_tree *t) { return t ? t->n : 0; }
+extern "C" size_t sb_tree_leaf_bytes(const sb_tree *t) { return t ? t->leaf_bytes : 0; }
+extern "C" int sb_tree_root(const sb_tree *t, uint8_t root[32]) {
+    if (!t || !root) return SB_ERR_ARG;
+    memcpy(root, t->root, 32);
+    return SB_OK;
+}
+extern "C" void sb_tree_free(sb_ctx *ctx, sb_tree *t) {
+    if (ctx) cudaStreamSynchronize(ctx->stream);
+    free_tree(t);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fiat-Shamir helpers (host)
+// ------------------------------------------------------------------------------------------------
+extern "C" void sb_blake2s(const uint8_t *msg, size_t len, uint8_t out[32]) { b2s::hash_bytes(out, msg, len); }
+
+// fri/src/utils.rs:82-109
+extern "C" int sb_pseudorandom_indices(const uint8_t *seed, size_t seed_len, uint32_t modulus, size_t count, uint32_t excl,
+                                       uint32_t *out) {
+    if (!seed || !out) return SB_ERR_ARG;
+    if (modulus >= (1u << 24) || modulus == 0) return SB_ERR_ARG;   // utils.rs:88 assert
+    std::vector<uint8_t> data(seed, seed + seed_len);
+    while (data.size() < 4 * count) {
+        uint8_t d[32];
+        if (data.size() < 32) return SB_ERR_ARG;     // reference: slice underflow panic (utils.rs:92)
+        b2s::hash_bytes(d, data.data() + data.size() - 32, 32);
+        data.insert(data.end(), d, d + 32);
+    }
+    if (excl == 1 || (excl > 1 && modulus * (excl - 1) / excl == 0)) return SB_ERR_ARG;   // reference: division by zero
+    for (size_t i = 0; i < count; i++) {
+        uint32_t v = ((uint32_t)data[4 * i] << 24) | ((uint32_t)data[4 * i + 1] << 16) | ((uint32_t)data[4 * i + 2] << 8) | data[4 * i + 3];
+        if (excl == 0) {
+            out[i] = v % modulus;
+        } else {
+            uint32_t real = modulus * (excl - 1) / excl;
+            uint32_t t = v % real;
+            out[i] = t + 1 + t / (excl - 1);
+        }
+    }
+    return SB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FRI
+// ------------------------------------------------------------------------------------------------
+struct FriLayer {
+    bool is_last = false;
+    uint8_t values_root[32] = {0};      // root of the tree over this layer's values (tap)
+    uint8_t root2[32] = {0};
+    size_t n_column = 0, depth_column = 0, n_poly = 0, depth_poly = 0;
+    std::vector<uint8_t> column_leaves, column_nodes, poly_leaves, poly_nodes;
+    std::vector<uint8_t> last;           // n_last * 32
+};
+struct sb_fri_proof {
+    std::vector<FriLayer> layers;
+};
+
+static const size_t FRI_MIN_DEG_DIRECT = 16;   // fri.rs:14
+static const size_t FRI_QUERIES = 40;          // fri.rs:184
+
+static int fri_prove_dev(sb_ctx *ctx, const uint4 *d_vals, size_t n, const hfp::el &root, size_t max_deg_plus_1, uint32_t excl,
+                         const sb_tree *values_tree, sb_fri_proof **out) {
+    if (!is_pow2(n)) return fail(ctx, SB_ERR_ARG, "FRI needs a power-of-two number of values, got %zu", n);
+    const uint32_t log_n0 = ilog2(n);
+    const uint4 *tw;
+    uint32_t tw_log_n, log_stride;
+    TRY(get_table(ctx, root, log_n0, &tw, &tw_log_n, &log_stride));
+
+    sb_fri_proof *proof = new sb_fri_proof();
+    std::vector<sb_tree *> owned_trees;
+    std::vector<void *> owned_cols;
+    auto cleanup = [&]() {
+        cudaStreamSynchronize(ctx->stream);
+        for (auto t : owned_trees) free_tree(t);
+        for (auto p : owned_cols) cudaFree(p);
+    };
+    int rc = SB_OK;
+    const uint4 *cur = d_vals;
+    const sb_tree *cur_tree = values_tree;
+    size_t cur_n = n, bound = max_deg_plus_1;
+    uint32_t cur_stride = log_stride;
+
+    while (true) {
+        FriLayer L;
+        if (bound <= FRI_MIN_DEG_DIRECT) {
+            // fri.rs:88-112: the remaining values go into the proof verbatim (to_bytes_le each)
+            L.is_last = true;
+            L.last.resize(cur_n * 32);
+            DevBuf tmp(ctx);
+            if ((rc = tmp.alloc(cur_n * 32)) != SB_OK) break;
+            ctx->launches += fp_launch_to_bytes(ctx->stream, cur, (uint4 *)tmp.p, cur_n);
+            cudaError_t e = cudaMemcpyAsync(L.last.data(), tmp.p, cur_n * 32, cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) { rc = fail(ctx, SB_ERR_CUDA, "FRI last layer: %s", cudaGetErrorString(e)); break; }
+            proof->layers.push_back(std::move(L));
+            break;
+        }
+        if (cur_n < 4 || cur_n / 4 >= (1u << 24)) { rc = fail(ctx, SB_ERR_ARG, "FRI layer of %zu values unsupported", cur_n); break; }
+        // fri.rs:120-131: tree over the values (reused when the caller / previous layer built it)
+        if (!cur_tree) {
+            sb_tree *t = nullptr;
+            const uint4 *cols[1] = {cur};
+            if ((rc = commit_cols(ctx, cols, 1, cur_n, &t)) != SB_OK) break;
+            owned_trees.push_back(t);
+            cur_tree = t;
+        }
+        memcpy(L.values_root, cur_tree->root, 32);
+        // fri.rs:135
+        hfp::el special_x = hfp::from_bytes_le32(cur_tree->root);
+        // fri.rs:141-164
+        const size_t q = cur_n / 4;
+        void *d_col = nullptr;
+        cudaError_t e = cudaMalloc(&d_col, q * 32);
+        if (e != cudaSuccess) { rc = fail(ctx, SB_ERR_OOM, "cudaMalloc(column): %s", cudaGetErrorString(e)); break; }
+        owned_cols.push_back(d_col);
+        FriFoldParams P;
+        P.vals = cur;
+        P.col = (uint4 *)d_col;
+        P.tw = tw;
+        P.n = cur_n;
+        P.tw_log_n = tw_log_n;
+        P.tw_log_stride = cur_stride;
+        memcpy(P.special_x, special_x.l, 32);
+        ctx->launches += fri_launch_fold(ctx->stream, P);
+        // fri.rs:165-172
+        sb_tree *t2 = nullptr;
+        const uint4 *cols2[1] = {(const uint4 *)d_col};
+        if ((rc = commit_cols(ctx, cols2, 1, q, &t2)) != SB_OK) break;
+        owned_trees.push_back(t2);
+        memcpy(L.root2, t2->root, 32);
+        // fri.rs:181-190
+        uint32_t ys[FRI_QUERIES];
+        if (sb_pseudorandom_indices(t2->root, 32, (uint32_t)q, FRI_QUERIES, excl, ys) != SB_OK) {
+            rc = fail(ctx, SB_ERR_ARG, "sampler: column length %zu out of range", q);
+            break;
+        }
+        std::vector<size_t> yi(FRI_QUERIES), pp(4 * FRI_QUERIES);
+        for (size_t i = 0; i < FRI_QUERIES; i++) {
+            yi[i] = ys[i];
+            for (size_t j = 0; j < 4; j++) pp[4 * i + j] = ys[i] + q * j;     // fri.rs:193-204
+        }
+        L.n_column = FRI_QUERIES;
+        L.depth_column = t2->depth;
+        L.column_leaves.resize(FRI_QUERIES * 32);
+        L.column_nodes.resize(FRI_QUERIES * t2->depth * 32);
+        if ((rc = sb_merkle_open(ctx, t2, yi.data(), FRI_QUERIES, L.column_leaves.data(), L.column_nodes.data())) != SB_OK) break;
+        L.n_poly = 4 * FRI_QUERIES;
+        L.depth_poly = cur_tree->depth;
+        L.poly_leaves.resize(L.n_poly * 32);
+        L.poly_nodes.resize(L.n_poly * cur_tree->depth * 32);
+        if ((rc = sb_merkle_open(ctx, cur_tree, pp.data(), L.n_poly, L.poly_leaves.data(), L.poly_nodes.data())) != SB_OK) break;
+        proof->layers.push_back(std::move(L));
+        // fri.rs:215-223
+        cur = (const uint4 *)d_col;
+        cur_tree = t2;
+        cur_n = q;
+        bound /= 4;
+        cur_stride += 2;
+    }
+    cleanup();
+    if (rc != SB_OK) {
+        delete proof;
+        return rc;
+    }
+    *out = proof;
+    return SB_OK;
+}
+
+extern "C" int sb_fri_prove_dev(sb_ctx *ctx, const uint64_t *d_vals, size_t n, const uint64_t root[4], size_t max_deg_plus_1,
+                                uint32_t excl, const sb_tree *values_tree, sb_fri_proof **out) {
+    if (!ctx || !d_vals || !root || !out) return SB_ERR_ARG;
+    if (values_tree && (values_tree->n != n || values_tree->leaf_bytes != 32)) return fail(ctx, SB_ERR_ARG, "values_tree does not match the values");
+    return fri_prove_dev(ctx, (const uint4 *)d_vals, n, hfp::from_limbs(root), max_deg_plus_1, excl, values_tree, out);
+}
+
+extern "C" int sb_fri_prove(sb_ctx *ctx, const uint64_t *vals, size_t n, const uint64_t root[4], size_t max_deg_plus_1, uint32_t excl,
+                            sb_fri_proof **out) {
+    if (!ctx || !vals || !root || !out) return SB_ERR_ARG;
+    void *d = nullptr;
+    CU(cudaMalloc(&d, n * 32 ? n * 32 : 16));
+    cudaError_t e = cudaMemcpyAsync(d, vals, n * 32, cudaMemcpyHostToDevice, ctx->stream);
+    int rc = e == cudaSuccess ? fri_prove_dev(ctx, (const uint4 *)d, n, hfp::from_limbs(root), max_deg_plus_1, excl, nullptr, out)
+                              : fail(ctx, SB_ERR_CUDA, "H2D values: %s", cudaGetErrorString(e));
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    return rc;
+}
+
+extern "C" size_t sb_fri_n_layers(const sb_fri_proof *p) { return p ? p->layers.size() : 0; }
+extern "C" int sb_fri_layer_is_last(const sb_fri_proof *p, size_t i) { return (p && i < p->layers.size()) ? p->layers[i].is_last : -1; }
+extern "C" int sb_fri_middle(const sb_fri_proof *p, size_t i, const uint8_t **root2, size_t *n_column, size_t *depth_column,
+                             const uint8_t **column_leaves, const uint8_t **column_nodes, size_t *n_poly, size_t *depth_poly,
+                             const uint8_t **poly_leaves, const uint8_t **poly_nodes) {
+    if (!p || i >= p->layers.size() || p->layers[i].is_last) return SB_ERR_ARG;
+    const FriLayer &L = p->layers[i];
+    if (root2) *root2 = L.root2;
+    if (n_column) *n_column = L.n_column;
+    if (depth_column) *depth_column = L.depth_column;
+    if (column_leaves) *column_leaves = L.column_leaves.data();
+    if (column_nodes) *column_nodes = L.column_nodes.data();
+    if (n_poly) *n_poly = L.n_poly;
+    if (depth_poly) *depth_poly = L.depth_poly;
+    if (poly_leaves) *poly_leaves = L.poly_leaves.data();
+    if (poly_nodes) *poly_nodes = L.poly_nodes.data();
+    return SB_OK;
+}
+extern "C" int sb_fri_last(const sb_fri_proof *p, size_t i, const uint8_t **values, size_t *n_last) {
+    if (!p || i >= p->layers.size() || !p->layers[i].is_last) return SB_ERR_ARG;
+    if (values) *values = p->layers[i].last.data();
+    if (n_last) *n_last = p->layers[i].last.size() / 32;
+    return SB_OK;
+}
+extern "C" int sb_fri_layer_root(const sb_fri_proof *p, size_t i, uint8_t root[32]) {
+    if (!p || i >= p->layers.size() || !root || p->layers[i].is_last) return SB_ERR_ARG;
+    memcpy(root, p->layers[i].values_root, 32);
+    return SB_OK;
+}
+
+static void json_bytes(std::string &s, const uint8_t *b, size_t n) {
+    char tmp[8];
+    s.push_back('[');
+    for (size_t i = 0; i < n; i++) {
+        if (i) s.push_back(',');
+        int l = snprintf(tmp, sizeof tmp, "%u", b[i]);
+        s.append(tmp, l);
+    }
+    s.push_back(']');
+}
+// Proof{leaf,nodes} (merkle_tree.rs:14-18)
+static void json_branches(std::string &s, const uint8_t *leaves, size_t leaf_bytes, const uint8_t *nodes, size_t depth, size_t count) {
+    s.push_back('[');
+    for (size_t q = 0; q < count; q++) {
+        if (q) s.push_back(',');
+        s += "{\"leaf\":";
+        json_bytes(s, leaves + q * leaf_bytes, leaf_bytes);
+        s += ",\"nodes\":[";
+        for (size_t l = 0; l < depth; l++) {
+            if (l) s.push_back(',');
+            json_bytes(s, nodes + (q * depth + l) * 32, 32);
+        }
+        s += "]}";
+    }
+    s.push_back(']');
+}
+extern "C" char *sb_fri_proof_json(const sb_fri_proof *p) {
+    if (!p) return nullptr;
+    std::string s;
+    s.push_back('[');
+    for (size_t i = 0; i < p->layers.size(); i++) {
+        const FriLayer &L = p->layers[i];
+        if (i) s.push_back(',');
+        if (L.is_last) {
+            s += "{\"Last\":{\"last\":[";
+            for (size_t k = 0; k < L.last.size() / 32; k++) {
+                if (k) s.push_back(',');
+                json_bytes(s, L.last.data() + 32 * k, 32);
+            }
+            s += "]}}";
+        } else {
+            s += "{\"Middle\":{\"root2\":";
+            json_bytes(s, L.root2, 32);
+            s += ",\"column_branches\":";
+            json_branches(s, L.column_leaves.data(), 32, L.column_nodes.data(), L.depth_column, L.n_column);
+            s += ",\"poly_branches\":";
+            json_branches(s, L.poly_leaves.data(), 32, L.poly_nodes.data(), L.depth_poly, L.n_poly);
+            s += "}}";
+        }
+    }
+    s.push_back(']');
+    char *r = (char *)malloc(s.size() + 1);
+    if (!r) return nullptr;
+    memcpy(r, s.c_str(), s.size() + 1);
+    return r;
+}
+extern "C" void sb_free_string(char *s) { free(s); }
+extern "C" void sb_fri_proof_free(sb_fri_proof *p) { delete p; }

@@ -1,0 +1,133 @@
+// fri.cuh -- FRI 4-to-1 fold and small vector helpers.
+//
+// Replaces the per-layer arithmetic of fri/src/fri.rs:141-164: for every row i < q = n/4 the
+// reference Lagrange-interpolates the cubic through (x*iota^j, values[i + q*j]), j = 0..3
+// (poly_utils.rs:449-511 multi_interp_4, one batch inverse over n denominators) and evaluates it
+// at special_x (poly_utils.rs:442-446 eval_quartic).  The interpolant is unique, so the closed
+// form below yields the same field element: with x = w^i, iota = w^q (primitive 4th root),
+//     s_k = sum_j y_j iota^(-jk)            (inverse DFT-4 without the 1/4)
+//     column[i] = 1/4 * sum_k s_k z^k ,     z = special_x * x^-1 ,   x^-1 = w^(n-i) from the table.
+// 5 modmuls per row (z, iota^-1, three Horner steps); the 1/4 is two exact halvings.
+#pragma once
+#include "fp.cuh"
+#include "params.h"
+
+
+__device__ __forceinline__ fp fri_fold_row(const FriFoldParams &P, size_t i, const fp &sx, const fp &iota_inv) {
+    const size_t q = P.n >> 2;
+    const unsigned long long nT = 1ull << P.tw_log_n;
+    fp y0 = fp_ldg(P.vals, i), y1 = fp_ldg(P.vals, i + q), y2 = fp_ldg(P.vals, i + 2 * q), y3 = fp_ldg(P.vals, i + 3 * q);
+    fp xinv = fp_ldg_ro(P.tw, (nT - ((unsigned long long)i << P.tw_log_stride)) & (nT - 1));
+    fp z = fp_mul(sx, xinv);
+    fp a = fp_add(y0, y2), b = fp_sub(y0, y2), c = fp_add(y1, y3);
+    fp d = fp_mul(fp_sub_lazy(y1, y3), iota_inv);
+    fp s0 = fp_add(a, c), s2 = fp_sub(a, c), s1 = fp_add(b, d), s3 = fp_sub(b, d);
+    fp r = fp_add(fp_mul(s3, z), s2);
+    r = fp_add(fp_mul(r, z), s1);
+    r = fp_add(fp_mul(r, z), s0);
+    r = fp_canon(r);
+    r = fp_half(r);                 // [0,1.5p)
+    r = fp_half(r);                 // [0,1.25p)
+    return fp_canon(r);
+}
+
+__global__ void __launch_bounds__(128) fri_fold_kernel(const __grid_constant__ FriFoldParams P) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t q = P.n >> 2;
+    if (i >= q) return;
+    fp sx;
+#pragma unroll
+    for (int k = 0; k < 8; k++) sx.l[k] = P.special_x[k];
+    const unsigned long long nT = 1ull << P.tw_log_n;
+    // iota^-1 = w^(-q) = w^(3q)
+    fp iota_inv = fp_ldg_ro(P.tw, (nT - ((unsigned long long)q << P.tw_log_stride)) & (nT - 1));
+    fp r = fri_fold_row(P, i, sx, iota_inv);
+    fp_stg(P.col, i, r);
+}
+
+// ---- table of powers T[i] = w^i by doubling: T[cur + j] = T[j] * w^cur ------------------------
+__global__ void powers_double_kernel(uint4 *T, unsigned long long cur, unsigned long long n_total,
+                                     const __grid_constant__ fp wcur) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= cur || cur + j >= n_total) return;
+    fp v = fp_ldg(T, j);
+    fp_stg(T, cur + j, fp_canon(fp_mul(v, wcur)));
+}
+
+// first `count` (<= 1024) powers in one CTA: log-step doubling in shared memory
+__global__ void powers_seed_kernel(uint4 *T, unsigned long long count, const __grid_constant__ fp w) {
+    __shared__ uint4 s[2048];
+    const int t = threadIdx.x;
+    if (t == 0) {
+        fp one = fp_one();
+        s[0] = fp_lo(one); s[1] = fp_hi(one);
+    }
+    __syncthreads();
+    fp wc = w;                      // w^cur
+    for (unsigned cur = 1; cur < count; cur <<= 1) {
+        if ((unsigned)t < cur && cur + t < count) {
+            fp v = fp_from_u4(s[2 * t], s[2 * t + 1]);
+            fp r = fp_canon(fp_mul(v, wc));
+            s[2 * (cur + t)] = fp_lo(r);
+            s[2 * (cur + t) + 1] = fp_hi(r);
+        }
+        wc = fp_canon(fp_mul(wc, wc));
+        __syncthreads();
+    }
+    for (unsigned i = t; i < count; i += blockDim.x) {
+        T[2 * i] = s[2 * i];
+        T[2 * i + 1] = s[2 * i + 1];
+    }
+}
+
+// Montgomery -> canonical little-endian bytes (to_bytes_le, fp.rs:39-43) for n elements
+__global__ void fp_to_bytes_kernel(const uint4 *in, uint4 *out, unsigned long long n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fp_stg(out, i, fp_from_mont(fp_ldg(in, i)));
+}
+
+// ---- multi_inv (poly_utils.rs:38-70): element-wise inverse, 0 -> 0 ----------------------------
+// Thread t owns elements t, t+T, t+2T, ... (coalesced), runs Montgomery's trick over them with a
+// zero-skipping prefix product and one Fermat inversion per thread.
+__device__ __forceinline__ fp fp_inv_fermat(const fp &a) {
+    // a^(p-2), square-and-multiply over the fixed exponent, MSB first
+    const uint32_t e[8] = {0xeffffffFu, 0x43e1f593u, 0x79b97091u, 0x2833e848u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+    fp r = fp_one();
+    bool started = false;
+    for (int i = 7; i >= 0; i--) {
+        for (int b = 31; b >= 0; b--) {
+            if (started) r = fp_mul(r, r);
+            if ((e[i] >> b) & 1) {
+                r = started ? fp_mul(r, a) : a;
+                started = true;
+            }
+        }
+    }
+    return r;
+}
+
+__global__ void __launch_bounds__(128) batch_inverse_kernel(uint4 *vals, uint4 *scratch, unsigned long long n) {
+    const size_t T = (size_t)gridDim.x * blockDim.x;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    // forward: scratch[i] = product of the non-zero elements before i (within this thread's slice)
+    fp acc = fp_one();
+    for (size_t i = t; i < n; i += T) {
+        fp_stg(scratch, i, acc);
+        fp v = fp_canon(fp_ldg(vals, i));
+        if (!fp_is_zero_canon(v)) acc = fp_mul(acc, v);
+    }
+    fp inv = fp_inv_fermat(fp_canon(acc));
+    // backward
+    size_t cnt = (n - t + T - 1) / T;
+    for (size_t k = cnt; k-- > 0;) {
+        const size_t i = t + k * T;
+        fp v = fp_canon(fp_ldg(vals, i));
+        if (!fp_is_zero_canon(v)) {
+            fp pre = fp_ldg(scratch, i);
+            fp_stg(vals, i, fp_canon(fp_mul(inv, pre)));
+            inv = fp_mul(inv, v);
+        }
+    }
+}

@@ -1,0 +1,32 @@
+// kernels.h -- host-callable launchers of the sm_100a kernels; one translation unit per kernel family
+// (ntt_b*.cu, merkle.cu, fri.cu) so that the library builds in parallel.  Every launcher enqueues on
+// `stream` and returns the number of kernels it launched.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+struct NttPassParams;
+struct MerkleColsParams;
+struct MerkleBytesParams;
+struct FriFoldParams;
+struct fp;
+
+// ntt_b*.cu
+cudaError_t ntt_set_attrs();
+int ntt_launch_pass(cudaStream_t stream, uint32_t bits, const NttPassParams &P);
+// merkle.cu
+int merkle_launch_leaves_cols(cudaStream_t stream, uint32_t lv, const MerkleColsParams &P);
+int merkle_launch_leaves_bytes(cudaStream_t stream, uint32_t lv, const MerkleBytesParams &P);
+int merkle_launch_nodes(cudaStream_t stream, uint32_t lv, uint4 *nodes, unsigned long long n, uint32_t level);
+int merkle_launch_open(cudaStream_t stream, const uint4 *nodes, unsigned long long n, uint32_t depth,
+                       const unsigned long long *idx, uint32_t n_idx, uint4 *out);
+int merkle_launch_open_leaves_cols(cudaStream_t stream, const MerkleColsParams &P, const unsigned long long *idx,
+                                   uint32_t n_idx, uint4 *out);
+int merkle_launch_gather_bytes(cudaStream_t stream, const uint8_t *leaves, size_t leaf_bytes,
+                               const unsigned long long *idx, uint32_t n_idx, uint8_t *out);
+// fri.cu
+int fri_launch_fold(cudaStream_t stream, const FriFoldParams &P);
+int powers_launch_seed(cudaStream_t stream, uint4 *T, unsigned long long count, const fp &w);
+int powers_launch_double(cudaStream_t stream, uint4 *T, unsigned long long cur, unsigned long long n_total, const fp &wcur);
+int fp_launch_to_bytes(cudaStream_t stream, const uint4 *in, uint4 *out, unsigned long long n);
+int batch_inverse_launch(cudaStream_t stream, uint4 *vals, uint4 *scratch, unsigned long long n);

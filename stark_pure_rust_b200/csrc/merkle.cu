@@ -1,0 +1,59 @@
+// merkle.cu -- launchers of the Merkle kernels (merkle.cuh)
+#include "kernels.h"
+#include "merkle.cuh"
+
+static unsigned blocks128(size_t threads) { return (unsigned)((threads + 127) / 128); }
+
+int merkle_launch_leaves_cols(cudaStream_t s, uint32_t lv, const MerkleColsParams &P) {
+    const unsigned b = blocks128(P.n >> lv);
+    switch (lv) {
+        case 0: merkle_leaves_cols_kernel<0><<<b, 128, 0, s>>>(P); break;
+        case 1: merkle_leaves_cols_kernel<1><<<b, 128, 0, s>>>(P); break;
+        case 2: merkle_leaves_cols_kernel<2><<<b, 128, 0, s>>>(P); break;
+        default: merkle_leaves_cols_kernel<3><<<b, 128, 0, s>>>(P); break;
+    }
+    return 1;
+}
+int merkle_launch_leaves_bytes(cudaStream_t s, uint32_t lv, const MerkleBytesParams &P) {
+    const unsigned b = blocks128(P.n >> lv);
+    switch (lv) {
+        case 0: merkle_leaves_bytes_kernel<0><<<b, 128, 0, s>>>(P); break;
+        case 1: merkle_leaves_bytes_kernel<1><<<b, 128, 0, s>>>(P); break;
+        case 2: merkle_leaves_bytes_kernel<2><<<b, 128, 0, s>>>(P); break;
+        default: merkle_leaves_bytes_kernel<3><<<b, 128, 0, s>>>(P); break;
+    }
+    return 1;
+}
+int merkle_launch_nodes(cudaStream_t s, uint32_t lv, uint4 *nodes, unsigned long long n, uint32_t level) {
+    const unsigned b = blocks128((n >> level) >> lv);
+    switch (lv) {
+        case 1: merkle_nodes_kernel<1><<<b, 128, 0, s>>>(nodes, n, level); break;
+        case 2: merkle_nodes_kernel<2><<<b, 128, 0, s>>>(nodes, n, level); break;
+        default: merkle_nodes_kernel<3><<<b, 128, 0, s>>>(nodes, n, level); break;
+    }
+    return 1;
+}
+int merkle_launch_open(cudaStream_t s, const uint4 *nodes, unsigned long long n, uint32_t depth,
+                       const unsigned long long *idx, uint32_t n_idx, uint4 *out) {
+    merkle_open_kernel<<<blocks128((size_t)n_idx * depth), 128, 0, s>>>(nodes, n, depth, idx, n_idx, out);
+    return 1;
+}
+int merkle_launch_open_leaves_cols(cudaStream_t s, const MerkleColsParams &P, const unsigned long long *idx,
+                                   uint32_t n_idx, uint4 *out) {
+    merkle_open_leaves_cols_kernel<<<blocks128((size_t)n_idx * P.nc), 128, 0, s>>>(P, idx, n_idx, out);
+    return 1;
+}
+
+__global__ void gather_leaf_bytes_kernel(const uint8_t *leaves, size_t leaf_bytes, const unsigned long long *idx, uint32_t n_idx,
+                                         uint8_t *out) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)n_idx * leaf_bytes) return;
+    const size_t q = t / leaf_bytes, b = t % leaf_bytes;
+    out[t] = leaves[idx[q] * leaf_bytes + b];
+}
+int merkle_launch_gather_bytes(cudaStream_t s, const uint8_t *leaves, size_t leaf_bytes, const unsigned long long *idx,
+                               uint32_t n_idx, uint8_t *out) {
+    const size_t tot = (size_t)n_idx * leaf_bytes;
+    gather_leaf_bytes_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(leaves, leaf_bytes, idx, n_idx, out);
+    return 1;
+}

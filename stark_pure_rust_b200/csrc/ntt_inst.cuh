@@ -1,0 +1,22 @@
+// ntt_inst.cuh -- included by ntt_b*.cu: each translation unit instantiates the pass kernel for the
+// widths B in [NTT_B_LO, NTT_B_HI] (separate files only to build them in parallel).
+#include "kernels.h"
+#include "ntt.cuh"
+
+template <int B>
+static size_t ntt_smem_bytes() {
+    constexpr int R = 1 << B, CC = (1 << NTT_LOG_TILE) >> B, PITCH = CC + 1;
+    return (size_t)(2 * R * PITCH + 2 * (R / 2 > 0 ? R / 2 : 1)) * sizeof(uint4);
+}
+template <int B>
+static cudaError_t ntt_set_attr_one() {
+    return cudaFuncSetAttribute(ntt_pass_kernel<B, NTT_LOG_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)ntt_smem_bytes<B>());
+}
+template <int B>
+static int ntt_launch_one(cudaStream_t stream, const NttPassParams &P) {
+    constexpr int TILE = 1 << NTT_LOG_TILE, CC = TILE >> B;
+    unsigned long long grid = (P.n_cols_total + CC - 1) / CC;
+    ntt_pass_kernel<B, NTT_LOG_TILE><<<(unsigned)grid, TILE / 8, ntt_smem_bytes<B>(), stream>>>(P);
+    return 1;
+}

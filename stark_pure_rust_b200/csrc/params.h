@@ -1,0 +1,63 @@
+// params.h -- plain-data kernel parameter blocks shared by the host API (api.cu) and the kernel
+// translation units.  No device code here.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+// BN254 Fr element in registers / kernel parameters: 8 x u32 little-endian limbs, Montgomery form
+struct fp {
+    uint32_t l[8];
+};
+
+#ifndef NTT_LOG_TILE
+#define NTT_LOG_TILE 11            // 2048 elements = 64 KiB of shared memory per CTA
+#endif
+#define NTT_MAX_PASSES 6
+
+struct NttPassParams {
+    const uint4 *src;              // pass input  (first pass: caller's vectors, len_in each)
+    uint4 *dst;                    // pass output
+    const uint4 *tw;               // table T[e] = w_T^e, e < 2^tw_log_n
+    unsigned long long src_stride; // elements between consecutive polynomials in src / dst
+    unsigned long long dst_stride;
+    unsigned long long len_in;     // first pass: elements >= len_in read as zero
+    unsigned long long n_cols_total; // batch * (n >> B)
+    uint32_t log_n;
+    uint32_t log_outer;            // bits already transformed by earlier passes
+    uint32_t log_inner;            // log_n - log_outer - B
+    uint32_t first, last, inverse;
+    uint32_t tw_log_n;             // log2 of the table length
+    uint32_t tw_log_stride;        // w = w_T^(2^tw_log_stride)
+    uint32_t n_prev;               // last pass: widths of the earlier passes, in order
+    uint32_t prev_bits[NTT_MAX_PASSES];
+    uint32_t n_inv[8];             // Montgomery form of n^-1 (inverse transform, last pass)
+};
+
+struct MerkleColsParams {
+    const uint4 *cols[8];
+    uint4 *nodes;
+    unsigned long long n;          // leaves (power of two)
+    uint32_t nc;                   // columns per leaf, 1..8
+};
+
+struct MerkleBytesParams {
+    const uint8_t *leaves;
+    uint4 *nodes;
+    unsigned long long n;
+    uint32_t leaf_bytes;
+};
+
+// digest offset of level l (l = 0: leaf hashes) inside a tree's node array of 2n - 1 digests
+__host__ __device__ inline size_t merkle_level_off(size_t n, uint32_t level) {
+    return 2 * n - ((2 * n) >> level);
+}
+
+struct FriFoldParams {
+    const uint4 *vals;             // n values, Montgomery
+    uint4 *col;                    // n/4 outputs, Montgomery canonical
+    const uint4 *tw;               // T[e] = w_T^e
+    unsigned long long n;
+    uint32_t tw_log_n, tw_log_stride;   // layer root w = w_T^(2^tw_log_stride)
+    uint32_t special_x[8];         // Montgomery
+};

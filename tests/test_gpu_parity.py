@@ -1,0 +1,244 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the Python mirror of the reference API)
+against the CPU oracle on the same seeded inputs.  Bit-exact everywhere (integer / byte work)."""
+import ctypes as C
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import P, random_elems
+
+pytestmark = pytest.mark.gpu
+
+
+def edge_vectors(n):
+    import stark_pure_rust_b200 as sb
+    zero = np.zeros((n, 4), dtype=np.uint64)
+    d0 = zero.copy(); d0[0] = sb.field.mont_scalar(1)
+    dl = zero.copy(); dl[n - 1] = sb.field.mont_scalar(1)
+    pm1 = np.tile(sb.field.mont_scalar(P - 1), (n, 1))
+    return {"zero": zero, "delta0": d0, "delta_last": dl, "all_p_minus_1": pm1}
+
+
+def test_library_is_the_cuda_build(ctx):
+    import stark_pure_rust_b200 as sb
+    assert sb.library_path().endswith("libstark_b200.so")
+    assert ctx.launch_count() >= 0
+
+
+@pytest.mark.parametrize("log_n", [0, 1, 5, 10, 13])
+def test_expand_root_of_unity(ctx, oracle, log_n):
+    import stark_pure_rust_b200 as sb
+    w = oracle.root_of_unity(log_n)
+    got = sb.fft.expand_root_of_unity(w, order=1 << log_n, ctx=ctx)
+    want, order = oracle.expand_root_of_unity(w, 1 << log_n)
+    assert order == 1 << log_n
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("log_n", list(range(0, 15)) + [16, 17, 18, 20])
+def test_best_fft_matches_oracle(ctx, oracle, log_n):
+    import stark_pure_rust_b200 as sb
+    n = 1 << log_n
+    w = oracle.root_of_unity(log_n)
+    v = random_elems(n, 0xB200 + log_n)
+    got = sb.fft.best_fft(v, w, log_n, ctx=ctx)
+    want = oracle.best_fft(v, w, log_n)
+    assert np.array_equal(got, want), "forward NTT differs at %s" % np.argwhere((got != want).any(axis=1))[:4].ravel()
+    got_i = sb.fft.inv_best_fft(v, w, log_n, ctx=ctx)
+    want_i = oracle.best_fft(v, w, log_n, inverse=True)
+    assert np.array_equal(got_i, want_i)
+    # round trip
+    assert np.array_equal(sb.fft.inv_best_fft(got, w, log_n, ctx=ctx), v)
+
+
+@pytest.mark.parametrize("log_n,len_in", [(3, 0), (3, 5), (9, 1), (9, 300), (12, 2049), (16, 8192), (16, 6684)])
+def test_best_fft_zero_padding(ctx, oracle, log_n, len_in):
+    import stark_pure_rust_b200 as sb
+    w = oracle.root_of_unity(log_n)
+    v = random_elems(max(len_in, 1), 77 + len_in)[:len_in]
+    assert np.array_equal(sb.fft.best_fft(v, w, log_n, ctx=ctx), oracle.best_fft(v, w, log_n))
+    assert np.array_equal(sb.fft.inv_best_fft(v, w, log_n, ctx=ctx), oracle.best_fft(v, w, log_n, inverse=True))
+
+
+@pytest.mark.parametrize("log_n", [4, 9, 12])
+def test_best_fft_edge_vectors(ctx, oracle, log_n):
+    import stark_pure_rust_b200 as sb
+    w = oracle.root_of_unity(log_n)
+    for name, v in edge_vectors(1 << log_n).items():
+        assert np.array_equal(sb.fft.best_fft(v, w, log_n, ctx=ctx), oracle.best_fft(v, w, log_n)), name
+        assert np.array_equal(sb.fft.inv_best_fft(v, w, log_n, ctx=ctx), oracle.best_fft(v, w, log_n, inverse=True)), name
+
+
+def test_best_fft_other_roots(ctx, oracle):
+    """any primitive 2^k-th root works (the reference takes the root as an argument): w^3, w^-1"""
+    import stark_pure_rust_b200 as sb
+    log_n = 10
+    w = sb.field.from_mont(oracle.root_of_unity(log_n).reshape(1, 4))[0]
+    v = random_elems(1 << log_n, 5)
+    for root in (pow(w, 3, P), pow(w, -1, P), pow(w, 2**log_n - 5, P)):
+        rl = sb.field.mont_scalar(root)
+        assert np.array_equal(sb.fft.best_fft(v, rl, log_n, ctx=ctx), oracle.best_fft(v, rl, log_n))
+
+
+def test_best_fft_errors(ctx, oracle):
+    import stark_pure_rust_b200 as sb
+    w = oracle.root_of_unity(4)
+    with pytest.raises(sb.StarkB200Error) as e:        # fft.rs:162 assert
+        sb.fft.best_fft(random_elems(17, 1), w, 4, ctx=ctx)
+    assert e.value.code == -3
+    with pytest.raises(sb.StarkB200Error) as e:        # not a primitive 2^5-th root
+        sb.fft.best_fft(random_elems(8, 1), w, 5, ctx=ctx)
+    assert e.value.code == -4
+
+
+@pytest.mark.parametrize("log_s,n_cols,col_len", [(4, 1, 16), (4, 3, 15), (10, 10, 1024), (13, 6, 6684), (15, 2, 1 << 15)])
+def test_lde_batch(ctx, oracle, log_s, n_cols, col_len):
+    """prove.rs:100-124: best_fft(inv_best_fft(col, g1, log_s), g2, log_s + 3); out[8j] == col[j]"""
+    import stark_pure_rust_b200 as sb
+    g2 = oracle.root_of_unity(log_s + 3)
+    g1 = oracle.root_of_unity(log_s)
+    cols = random_elems(n_cols * col_len, 900 + log_s).reshape(n_cols, col_len, 4)
+    got = sb.fft.lde_batch(cols, g2, log_s, 3, ctx=ctx)
+    for c in range(n_cols):
+        coef = oracle.best_fft(cols[c], g1, log_s, inverse=True)
+        want = oracle.best_fft(coef, g2, log_s + 3)
+        assert np.array_equal(got[c], want), c
+        assert np.array_equal(got[c][::8][:col_len], cols[c])
+
+
+def test_multi_inv(ctx, oracle):
+    import stark_pure_rust_b200 as sb
+    for n in (1, 7, 1000, 50000):
+        v = random_elems(n, 31 + n)
+        v[::5] = 0                       # zero passthrough (poly_utils.rs:38-70)
+        assert np.array_equal(sb.poly_utils.multi_inv(v, ctx=ctx), oracle.multi_inv(v)), n
+
+
+# ---- Merkle ---------------------------------------------------------------------------------
+KAT16 = ["7fffffff", "80000000", "00000003", "00000000", "7ffffffe", "80000001", "00000004", "00000001",
+         "7ffffffd", "80000002", "00000005", "00000002", "7ffffffc", "80000003", "00000006", "00000003"]
+
+
+def test_merkle_reference_kats(ctx):
+    """commitment/src/pallarel_merkle_tree.rs:133-216"""
+    import stark_pure_rust_b200 as sb
+    t = sb.merkle.MerkleProofInPlace(ctx)
+    t.update([bytes.fromhex(x) for x in KAT16])
+    pr = t.gen_proofs([2])[0]
+    assert t.get_root().hex() == "9f04496db6a8c505e88a7db289161a540a0cb953ef81c9b86103f0d6d12e8e15"
+    assert pr.leaf == bytes.fromhex("00000003")
+    assert [x.hex() for x in pr.nodes] == [
+        "4cd90cc0d54239ee5b3fd9989b4ef4cbebbbdd08410758cbd2d291fa364c82d5",
+        "2e3d3579213e0a992d60b503f1d8fe331b8bd548e227e8dbd741ca1752077b84",
+        "9a8c87bb98f1b2e0f7036a27a343dc8fd649bedc737093c2080a34c6b9f6f375",
+        "ef459d75e20ce2f3fc4378ff20fe2d594fbcf16cccd986c2e0d3df41bd3bbe44"]
+    assert pr.validate(t.get_root(), 2)
+    t2 = sb.merkle.MerkleProofInPlace(ctx)
+    t2.update([bytes.fromhex("7fffffff")] * 4096)
+    prs = t2.gen_proofs([2, 7, 13])
+    assert t2.get_root().hex() == "a0d91c3115f9e4d9f142e7cb2f413c10f0f2f9f65d9f918b80f852f9ebc06ebc"
+    assert prs[0].nodes[0].hex() == "b72b5371ceffa4e01aa1849cdb8705406e14791db359f826bc01a392ed26b6b9"
+    assert sb.merkle.verify_multi_branch(t2.get_root(), [2, 7, 13], prs)
+
+
+@pytest.mark.parametrize("n,leaf_bytes", [(1, 32), (2, 32), (4, 40), (8, 1), (16, 4), (32, 33), (64, 64), (128, 65),
+                                          (256, 256), (1024, 40), (4096, 32), (1 << 15, 32), (1 << 13, 256), (512, 0)])
+def test_merkle_bytes_matches_oracle(ctx, oracle, n, leaf_bytes):
+    """merkle_proof_in_place.rs:106-206 incl. caller-order / duplicate indices (:199-205, test :228)"""
+    import stark_pure_rust_b200 as sb
+    rng = np.random.default_rng(n * 1000 + leaf_bytes)
+    flat = rng.integers(0, 256, size=n * leaf_bytes, dtype=np.uint8).tobytes()
+    idx = [int(x) for x in rng.integers(0, n, size=11)] + [0, n - 1, n // 2, n // 2]
+    t = sb.merkle.MerkleProofInPlace(ctx)
+    t.update([flat[i * leaf_bytes:(i + 1) * leaf_bytes] for i in range(n)])
+    prs = t.gen_proofs(idx)
+    root, nodes = oracle.merkle_gen_proofs(flat, leaf_bytes, n, idx)
+    assert t.get_root() == root
+    assert t.width() == n
+    for q, i in enumerate(idx):
+        assert prs[q].leaf == flat[i * leaf_bytes:(i + 1) * leaf_bytes]
+        assert b"".join(prs[q].nodes) == nodes[q].tobytes()
+        assert prs[q].validate(root, i)
+
+
+def test_merkle_in_place_reference_test(ctx, oracle):
+    """merkle_proof_in_place.rs:209-261: 16 leaves, indices [10,4,6,3,6,8]"""
+    import stark_pure_rust_b200 as sb
+    leaves = [bytes.fromhex(x) for x in KAT16]
+    idx = [10, 4, 6, 3, 6, 8]
+    t = sb.merkle.MerkleProofInPlace(ctx)
+    t.update(leaves)
+    prs = t.gen_proofs(idx)
+    root, nodes = oracle.merkle_gen_proofs(b"".join(leaves), 4, 16, idx)
+    assert t.get_root() == root
+    assert [b"".join(p.nodes) for p in prs] == [nodes[q].tobytes() for q in range(len(idx))]
+
+
+def test_merkle_not_power_of_two(ctx):
+    import stark_pure_rust_b200 as sb
+    t = sb.merkle.MerkleProofInPlace(ctx)
+    t.update([b"abcd"] * 12)
+    with pytest.raises(sb.StarkB200Error):            # merkle_proof_in_place.rs:113 assert
+        t.gen_proofs([0])
+
+
+@pytest.mark.parametrize("n,nc", [(8, 1), (1 << 12, 1), (1 << 10, 8), (1 << 14, 8), (64, 3), (1 << 16, 1), (256, 5), (2, 2)])
+def test_merkle_cols_dev(ctx, oracle, n, nc):
+    """column-backed leaves: to_bytes_le(col_0[i]) || ... (prove.rs:235-258, :324-327)"""
+    import stark_pure_rust_b200 as sb
+    cols = random_elems(n * nc, 4242 + n + nc).reshape(nc, n, 4)
+    dptrs = [ctx.to_device(cols[k]) for k in range(nc)]
+    arr = (C.c_void_p * nc)(*dptrs)
+    root = np.empty(32, dtype=np.uint8)
+    tree = C.c_void_p()
+    ctx.check(ctx.lib.sb_merkle_commit_cols_dev(ctx.h, arr, nc, n, root.ctypes.data_as(C.c_void_p), C.byref(tree)))
+    by = np.concatenate([oracle.fp_to_bytes_le(cols[k]).reshape(n, 1, 32) for k in range(nc)], axis=1)   # (n, nc, 32)
+    flat = by.tobytes()
+    idx = [0, n - 1, n // 3, n // 3]
+    want_root, want_nodes = oracle.merkle_gen_proofs(flat, 32 * nc, n, idx)
+    assert root.tobytes() == want_root
+    depth = (n - 1).bit_length()
+    leaves = np.empty(len(idx) * 32 * nc, dtype=np.uint8)
+    nodes = np.empty(len(idx) * depth * 32, dtype=np.uint8)
+    ia = np.asarray(idx, dtype=np.uint64)
+    ctx.check(ctx.lib.sb_merkle_open(ctx.h, tree, ia.ctypes.data_as(C.POINTER(C.c_size_t)), len(idx),
+                                     leaves.ctypes.data_as(C.c_void_p), nodes.ctypes.data_as(C.c_void_p) if depth else None))
+    assert nodes.tobytes() == want_nodes.tobytes()
+    assert leaves.tobytes() == b"".join(flat[i * 32 * nc:(i + 1) * 32 * nc] for i in idx)
+    ctx.lib.sb_tree_free(ctx.h, tree)
+    for d in dptrs:
+        ctx.free(d)
+
+
+# ---- FRI --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("log_n,deg_log", [(7, 4), (9, 6), (10, 7), (12, 9), (14, 11), (16, 13)])
+def test_prove_low_degree_matches_oracle(ctx, oracle, log_n, deg_log):
+    """fri.rs:46-224 called the way prove.rs:367 does: values = evaluations of a polynomial of degree
+    < 2^deg_log on the 2^log_n domain, bound 2^(log_n-2), exclude multiples of 8.  Compared as serde
+    JSON text (roots, 40 + 160 openings per layer, last layer) byte for byte."""
+    import stark_pure_rust_b200 as sb
+    w = oracle.root_of_unity(log_n)
+    coeffs = random_elems(1 << deg_log, 600 + log_n)
+    values = oracle.best_fft(coeffs, w, log_n)
+    want, ok = oracle.prove_low_degree_json(values, w, (1 << log_n) // 4, 8)
+    assert ok, "oracle verifier rejects its own proof"
+    got = sb.fri.prove_low_degree(values, w, (1 << log_n) // 4, 8, ctx=ctx, as_json=True)
+    assert hashlib.sha256(got.encode()).hexdigest() == hashlib.sha256(want.encode()).hexdigest()
+    assert got == want
+
+
+def test_prove_low_degree_structure(ctx, oracle):
+    import stark_pure_rust_b200 as sb
+    log_n = 10
+    w = oracle.root_of_unity(log_n)
+    values = oracle.best_fft(random_elems(64, 3), w, log_n)
+    proof = sb.fri.prove_low_degree(values, w, 256, 8, ctx=ctx)
+    # 1024 -> 256 -> 64 -> 16 (bound 256 -> 64 -> 16): two Middle layers then Last of 64 values
+    assert [list(l)[0] for l in proof] == ["Middle", "Middle", "Last"]
+    assert len(proof[0]["Middle"]["column_branches"]) == 40 and len(proof[0]["Middle"]["poly_branches"]) == 160
+    assert len(proof[-1]["Last"]["last"]) == 64
+    # column openings verify against root2, and the first layer's root2 is the next layer's values root
+    ys = sb.utils.get_pseudorandom_indices(proof[0]["Middle"]["root2"], 256, 40, 8)
+    assert all(y % 8 != 0 for y in ys)
+    assert sb.merkle.verify_multi_branch(proof[0]["Middle"]["root2"], ys, proof[0]["Middle"]["column_branches"])
