@@ -139,6 +139,12 @@ char *sb_fri_proof_json(const sb_fri_proof *p);
 void sb_free_string(char *s);
 void sb_fri_proof_free(sb_fri_proof *p);
 
+/* ---- unit-test hook for the device field library (no reference counterpart: ff_derive's arithmetic is
+ * generated code) ---- element-wise op on n raw 256-bit values, no range checks.
+ * op: 0 Montgomery product (lazy, < 2p), 1 add, 2 sub, 3 a+2p-b, 4 canonicalise, 5 halve, 6 from Montgomery,
+ *     7 to Montgomery, 8 inverse, 9 reduce [0,4p)->[0,2p), 10 canonical Montgomery product. */
+int sb_fp_vec_op(sb_ctx *ctx, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
+
 /* ---- Fiat-Shamir helpers that sit between the kernels (host side, exact) ------------------------- */
 /* get_pseudorandom_indices (fri/src/utils.rs:82-109) */
 int sb_pseudorandom_indices(const uint8_t *seed, size_t seed_len, uint32_t modulus, size_t count,

@@ -87,6 +87,7 @@ def load():
         "sb_fri_proof_free": (None, [vp]),
         "sb_pseudorandom_indices": (i32, [vp, sz, u32, sz, u32, vp]),
         "sb_blake2s": (None, [vp, sz, vp]),
+        "sb_fp_vec_op": (i32, [vp, i32, vp, vp, vp, sz]),
     }
     for name, (res, args) in proto.items():
         fn = getattr(L, name)

@@ -484,7 +484,8 @@ static int tree_new(sb_ctx *ctx, size_t n, size_t leaf_bytes, sb_tree **out) {
 }
 
 extern "C" int sb_merkle_commit(sb_ctx *ctx, const void *leaves, size_t leaf_bytes, size_t n, uint8_t root[32], sb_tree **tree) {
-    if (!ctx || !leaves || !tree) return SB_ERR_ARG;
+    if (!ctx || !tree) return SB_ERR_ARG;
+    if (!leaves && n * leaf_bytes) return fail(ctx, SB_ERR_ARG, "leaves is NULL");
     if (leaf_bytes >= ((size_t)1 << 31)) return fail(ctx, SB_ERR_ARG, "leaf too long");
     sb_tree *t = nullptr;
     TRY(tree_new(ctx, n, leaf_bytes, &t));
@@ -493,7 +494,7 @@ extern "C" int sb_merkle_commit(sb_ctx *ctx, const void *leaves, size_t leaf_byt
         free_tree(t);
         return fail(ctx, SB_ERR_OOM, "cudaMalloc(leaves): %s", cudaGetErrorString(e));
     }
-    e = cudaMemcpyAsync(t->d_leaves, leaves, n * leaf_bytes, cudaMemcpyHostToDevice, ctx->stream);
+    e = n * leaf_bytes ? cudaMemcpyAsync(t->d_leaves, leaves, n * leaf_bytes, cudaMemcpyHostToDevice, ctx->stream) : cudaSuccess;
     int rc = e == cudaSuccess ? merkle_build(ctx, t) : fail(ctx, SB_ERR_CUDA, "H2D leaves: %s", cudaGetErrorString(e));
     if (rc != SB_OK) {
         free_tree(t);
@@ -844,3 +845,19 @@ extern "C" char *sb_fri_proof_json(const sb_fri_proof *p) {
 }
 extern "C" void sb_free_string(char *s) { free(s); }
 extern "C" void sb_fri_proof_free(sb_fri_proof *p) { delete p; }
+
+// element-wise field op on raw 256-bit limbs (no range checks): unit-test hook for the device field library
+extern "C" int sb_fp_vec_op(sb_ctx *ctx, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n) {
+    if (!ctx || !a || !b || !out) return SB_ERR_ARG;
+    DevBuf da(ctx), db(ctx), dout(ctx);
+    TRY(da.alloc(n * 32));
+    TRY(db.alloc(n * 32));
+    TRY(dout.alloc(n * 32));
+    CU(cudaMemcpyAsync(da.p, a, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(db.p, b, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->launches += fp_launch_vec_op(ctx->stream, op, (const uint4 *)da.p, (const uint4 *)db.p, (uint4 *)dout.p, n);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, dout.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}

@@ -25,3 +25,7 @@ int batch_inverse_launch(cudaStream_t s, uint4 *vals, uint4 *scratch, unsigned l
     batch_inverse_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(vals, scratch, n);
     return 1;
 }
+int fp_launch_vec_op(cudaStream_t s, int op, const uint4 *a, const uint4 *b, uint4 *out, unsigned long long n) {
+    fp_vec_op_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(op, a, b, out, n);
+    return 1;
+}

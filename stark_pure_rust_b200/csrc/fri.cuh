@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(128) fri_fold_kernel(const __grid_constant__ F
 
 // ---- table of powers T[i] = w^i by doubling: T[cur + j] = T[j] * w^cur ------------------------
 __global__ void powers_double_kernel(uint4 *T, unsigned long long cur, unsigned long long n_total,
-                                     const __grid_constant__ fp wcur) {
+                                     const fp wcur) {
     const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= cur || cur + j >= n_total) return;
     fp v = fp_ldg(T, j);
@@ -55,7 +55,7 @@ __global__ void powers_double_kernel(uint4 *T, unsigned long long cur, unsigned 
 }
 
 // first `count` (<= 1024) powers in one CTA: log-step doubling in shared memory
-__global__ void powers_seed_kernel(uint4 *T, unsigned long long count, const __grid_constant__ fp w) {
+__global__ void powers_seed_kernel(uint4 *T, unsigned long long count, const fp w_in) {
     __shared__ uint4 s[2048];
     const int t = threadIdx.x;
     if (t == 0) {
@@ -63,7 +63,9 @@ __global__ void powers_seed_kernel(uint4 *T, unsigned long long count, const __g
         s[0] = fp_lo(one); s[1] = fp_hi(one);
     }
     __syncthreads();
-    fp wc = w;                      // w^cur
+    fp wc;                          // w^cur (plain copy: a __grid_constant__ source was miscompiled here)
+#pragma unroll
+    for (int k = 0; k < 8; k++) wc.l[k] = w_in.l[k];
     for (unsigned cur = 1; cur < count; cur <<= 1) {
         if ((unsigned)t < cur && cur + t < count) {
             fp v = fp_from_u4(s[2 * t], s[2 * t + 1]);
@@ -130,4 +132,33 @@ __global__ void __launch_bounds__(128) batch_inverse_kernel(uint4 *vals, uint4 *
             inv = fp_mul(inv, v);
         }
     }
+}
+
+// ---- element-wise field ops on vectors (unit tests of fp.cuh through the C ABI) -----------------
+// op: 0 mul (raw, lazy result), 1 add, 2 sub, 3 sub_lazy, 4 canon(a), 5 half(a), 6 from_mont(a),
+//     7 to_mont(a), 8 inverse(a), 9 reduce_2p(a), 10 canon(mul)
+__global__ void fp_vec_op_kernel(int op, const uint4 *a, const uint4 *b, uint4 *out, unsigned long long n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fp x = fp_ldg(a, i), y = fp_ldg(b, i), r;
+    switch (op) {
+        case 0: r = fp_mul(x, y); break;
+        case 1: r = fp_add(x, y); break;
+        case 2: r = fp_sub(x, y); break;
+        case 3: r = fp_sub_lazy(x, y); break;
+        case 4: r = fp_canon(x); break;
+        case 5: r = fp_half(x); break;
+        case 6: r = fp_from_mont(x); break;
+        case 7: r = fp_to_mont(x); break;
+        case 8: r = fp_canon(fp_inv_fermat(x)); break;
+        case 9: r = fp_reduce_2p(x); break;
+        case 10: r = fp_canon(fp_mul(x, y)); break;
+        case 11: r = fp_mul(x, x); break;
+        default: {
+            r = x;
+            for (uint32_t k = 0; k < y.l[0]; k++) r = fp_canon(fp_mul(r, r));
+            break;
+        }
+    }
+    fp_stg(out, i, r);
 }
