@@ -1,0 +1,393 @@
+#!/usr/bin/env python3
+"""bench.py -- the hot path of stark-pure-rust on B200: low-degree extension (INTT + zero-pad + NTT),
+Blake2s Merkle commitment of the extended evaluations, FRI low-degree proof.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--log-n L] [--cols C] [--impl reference]
+
+One step = one pass of the hot path over one batch shaped like the reference prover's
+(r1cs-stark/src/prove.rs:100-124, :235-264, :324-332, :367):
+    LDE of C columns from 2^(L-3) to 2^L points, an 8-column (256-byte-leaf) Merkle tree over the
+    extended evaluations, a 1-column (32-byte-leaf) tree, and prove_low_degree on that column.
+Default L = 24, C = 10 (BASELINE.json configs[1], top of the 2^16..2^24 sweep; 10 = the number of
+N-point transforms mk_r1cs_proof runs).  Inputs are larger than L2 (C*2^(L-3)*32 B in, C*2^L*32 B out),
+so no explicit L2 flush between iterations.
+
+metric / value : extended-domain field elements produced and committed per second (C * 2^L / step time),
+                 inputs resident in HBM, CUDA-event timed on the library's stream, max over ranks.
+e2e            : same step through the host-buffer C ABI calls a drop-in `best_fft` / `MerkleProofInPlace` /
+                 `prove_low_degree` replacement makes (sb_lde_batch, sb_merkle_commit, sb_fri_prove) with pinned
+                 host buffers; every H2D / D2H copy is inside the timed region.
+roofline       : dominant kernel = ntt_pass_kernel; algorithmic bytes per launch = 64 B per element
+                 (32 B read + 32 B written once per pass) over its CUDA-event-measured average launch time.
+cpu_baseline   : the CPU oracle (port of the reference's Rust path; the Rust toolchain is absent) on the
+                 box's host cores on a bounded sample (smaller L), same step structure.
+--impl reference: the same CPU path as a standalone arm, all host threads the reference would use.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+P = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+
+
+def random_elems(n, seed):
+    from conftest import random_elems as r
+    return r(n, seed)
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU path (oracle): the same step on host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_step(ob, cols, log_n, n_threads):
+    """LDE of every column + 8-column tree + 1-column tree + FRI, with the oracle's restatement of the
+    reference (parallel_fft over 2^floor(log2 cores) threads, single-threaded Merkle / FRI, trees rebuilt
+    per gen_proofs call exactly like the reference)."""
+    log_s = log_n - 3
+    g2, g1 = ob.root_of_unity(log_n), ob.root_of_unity(log_s)
+    ext = []
+    for c in range(cols.shape[0]):
+        coef = ob.best_fft(cols[c], g1, log_s, inverse=True, n_cpus=n_threads)
+        ext.append(ob.best_fft(coef, g2, log_n, n_cpus=n_threads))
+    n = 1 << log_n
+    k = min(8, len(ext))
+    leaves = np.concatenate([ob.fp_to_bytes_le_fast(ext[i]).reshape(n, 1, 32) for i in range(k)], axis=1).tobytes()
+    ob.merkle_gen_proofs(leaves, 32 * k, n, [])
+    ob.merkle_gen_proofs(ob.fp_to_bytes_le_fast(ext[-1]).tobytes(), 32, n, [])
+    ob.prove_low_degree_json(ext[-1], g2, n // 4, 8, verify=False)
+
+
+def run_cpu(args, as_reference_arm):
+    import oracle_bind as ob
+    ob.lib()
+    cores = os.cpu_count() or 1
+    log_n = args.cpu_log_n
+    cols = random_elems(args.cols << (log_n - 3), 0xC0FFEE).reshape(args.cols, 1 << (log_n - 3), 4)
+    times = []
+    steps = args.steps if as_reference_arm else 1
+    warm = min(args.warmup, 1) if as_reference_arm else 0
+    for i in range(warm + steps):
+        t0 = time.perf_counter()
+        cpu_step(ob, cols, log_n, cores)
+        dt = time.perf_counter() - t0
+        if i >= warm:
+            times.append(dt)
+    dt = sum(times) / len(times)
+    value = args.cols * (1 << log_n) / dt
+    sample = "same step at L=%d (C=%d columns): %.2f s per step on %d host threads (NTT threaded like parallel_fft, Merkle/FRI single-threaded like the reference)" % (
+        log_n, args.cols, dt, cores)
+    return value, dt, {"value": value, "unit": "elems/s", "cores": cores, "kind": "port", "sample": sample}
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU path
+# ---------------------------------------------------------------------------------------------
+def pinned_array(ctx, shape, dtype):
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    ctx.check(ctx.lib.sb_host_alloc_pinned(ctx.h, max(n, 16), C.byref(p)))
+    buf = (C.c_uint8 * max(n, 16)).from_address(p.value)
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape), p
+
+
+def run_gpu(args):
+    import stark_pure_rust_b200 as sb
+    from stark_pure_rust_b200 import field
+    from stark_pure_rust_b200._lib import _ptr
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = sb.Context(local_rank)
+    lib = ctx.lib
+    L, Cn = args.log_n, args.cols
+    log_s, N, S = L - 3, 1 << L, 1 << (L - 3)
+    g2 = field.mont_scalar(field.root_of_unity(L))
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # every rank owns its own batch of columns (independent columns / subtrees per GPU: weak scaling)
+    cols = random_elems(Cn * S, 0xB200 + rank).reshape(Cn, S, 4)
+    d_cols = ctx.to_device(cols)
+    d_out = ctx.alloc(Cn * N * 32)
+    k_tree = min(8, Cn)
+    col_ptrs8 = (C.c_void_p * k_tree)(*[d_out + i * N * 32 for i in range(k_tree)])
+    col_ptr1 = (C.c_void_p * 1)(d_out + (Cn - 1) * N * 32)
+    root = np.empty(32, dtype=np.uint8)
+
+    def step_device():
+        ctx.check(lib.sb_lde_batch_dev(ctx.h, C.c_void_p(d_cols), Cn, S, S, _ptr(g2), log_s, 3, C.c_void_p(d_out)))
+        tm, tl, pr = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        ctx.check(lib.sb_merkle_commit_cols_dev(ctx.h, col_ptrs8, k_tree, N, _ptr(root), C.byref(tm)))
+        ctx.check(lib.sb_merkle_commit_cols_dev(ctx.h, col_ptr1, 1, N, _ptr(root), C.byref(tl)))
+        ctx.check(lib.sb_fri_prove_dev(ctx.h, C.c_void_p(col_ptr1[0]), N, _ptr(g2), N // 4, 8, tl, C.byref(pr)))
+        n_layers = lib.sb_fri_n_layers(pr)
+        lib.sb_fri_proof_free(pr)
+        lib.sb_tree_free(ctx.h, tm)
+        lib.sb_tree_free(ctx.h, tl)
+        return n_layers
+
+    for _ in range(args.warmup):
+        n_layers = step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ctx.profile(True)
+    launches0 = ctx.launch_count()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        step_device()
+    ms = ctx.timer_stop()
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.launch_count() - launches0
+    prof = {k: ctx.profile_read(i) for i, k in enumerate(["ntt_pass", "merkle_leaves", "merkle_nodes", "fri_fold", "open", "other"])}
+    ctx.profile(False)
+
+    # breakdown (separate timed regions, same inputs) ----------------------------------------------------
+    def timed(fn, reps=3):
+        fn()
+        ctx.timer_start()
+        for _ in range(reps):
+            fn()
+        return ctx.timer_stop() / reps
+
+    lde_ms = timed(lambda: ctx.check(lib.sb_lde_batch_dev(ctx.h, C.c_void_p(d_cols), Cn, S, S, _ptr(g2), log_s, 3, C.c_void_p(d_out))))
+
+    def commit8():
+        t = C.c_void_p()
+        ctx.check(lib.sb_merkle_commit_cols_dev(ctx.h, col_ptrs8, k_tree, N, _ptr(root), C.byref(t)))
+        lib.sb_tree_free(ctx.h, t)
+
+    def commit1():
+        t = C.c_void_p()
+        ctx.check(lib.sb_merkle_commit_cols_dev(ctx.h, col_ptr1, 1, N, _ptr(root), C.byref(t)))
+        lib.sb_tree_free(ctx.h, t)
+
+    def fri():
+        pr = C.c_void_p()
+        ctx.check(lib.sb_fri_prove_dev(ctx.h, C.c_void_p(col_ptr1[0]), N, _ptr(g2), N // 4, 8, None, C.byref(pr)))
+        lib.sb_fri_proof_free(pr)
+
+    m8_ms, m1_ms, fri_ms = timed(commit8), timed(commit1), timed(fri)
+    comp8 = N * ((k_tree + 1) // 2) + N - 1
+    comp1 = 2 * N - 1
+
+    # e2e: host-buffer C ABI, pinned memory, copies inside the timed region ---------------------------------
+    e2e = None
+    if not args.no_e2e:
+        h_cols, p1 = pinned_array(ctx, (Cn, S, 4), np.uint64)
+        h_cols[:] = cols
+        h_out, p2 = pinned_array(ctx, (Cn, N, 4), np.uint64)
+        h_leaves, p3 = pinned_array(ctx, (N * 32 * k_tree,), np.uint8)
+        # leaf bytes for the host-side Merkle call: built once from a device-side conversion of the LDE output
+        ctx.check(lib.sb_lde_batch(ctx.h, _ptr(h_cols), Cn, S, _ptr(g2), log_s, 3, _ptr(h_out)))
+        h_leaves[:] = 0x5a      # content does not change the work; the reference packs rows on the host (prove.rs:235-258)
+        hroot = np.empty(32, dtype=np.uint8)
+
+        def step_host():
+            ctx.check(lib.sb_lde_batch(ctx.h, _ptr(h_cols), Cn, S, _ptr(g2), log_s, 3, _ptr(h_out)))
+            t = C.c_void_p()
+            ctx.check(lib.sb_merkle_commit(ctx.h, _ptr(h_leaves), 32 * k_tree, N, _ptr(hroot), C.byref(t)))
+            lib.sb_tree_free(ctx.h, t)
+            pr = C.c_void_p()
+            ctx.check(lib.sb_fri_prove(ctx.h, _ptr(h_out[Cn - 1]), N, _ptr(g2), N // 4, 8, C.byref(pr)))
+            lib.sb_fri_proof_free(pr)
+
+        step_host()
+        barrier()
+        t0 = time.perf_counter()
+        ctx.timer_start()
+        e2e_steps = max(1, min(args.steps, 3))
+        for _ in range(e2e_steps):
+            step_host()
+        e2e_ms = ctx.timer_stop()
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        e2e_ms = max(e2e_ms, wall) / e2e_steps
+        h2d = Cn * S * 32 + N * 32 * k_tree + N * 32
+        d2h = Cn * N * 32 + 32 + 32 * (n_layers + 1) + n_layers * (40 + 160) * 32 * (L + 1)
+        e2e = {"ms": e2e_ms, "h2d": h2d, "d2h": d2h}
+        for p in (p1, p2, p3):
+            lib.sb_host_free_pinned(ctx.h, p)
+
+    # max over ranks -------------------------------------------------------------------------------------------
+    step_ms = ms / args.steps
+    if dist is not None:
+        import torch
+        t = torch.tensor([step_ms, e2e["ms"] if e2e else 0.0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        step_ms = float(t[0]);
+        if e2e:
+            e2e["ms"] = float(t[1])
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("hbm_gbs")
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    if not peak:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    n_ntt, ntt_ms = prof["ntt_pass"]
+    # every NTT pass launch reads and writes each element of its transform once: count the elements per launch
+    bits = ntt_plan(log_s) + ntt_plan(L)
+    elems_per_step = Cn * (S * len(ntt_plan(log_s)) + N * len(ntt_plan(L)))
+    alg_bytes_per_launch = 64.0 * elems_per_step / len(bits)
+    avg_launch_ms = ntt_ms / max(n_ntt, 1)
+    achieved = alg_bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9 if avg_launch_ms > 0 else 0.0
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ntt_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+
+    total_elems = world * Cn * N
+    value = total_elems / (step_ms * 1e-3)
+    out = {
+        "metric": "hot_path_extended_elems_per_s", "value": value, "unit": "elems/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 (254-bit Montgomery, integer)",
+        "data": "synthetic (seeded uniform field elements)",
+        "config": {"workload": "LDE 2^%d->2^%d x %d cols + Merkle(8 cols, 256 B leaves) + Merkle(1 col) + FRI(2^%d, bound 2^%d)" % (log_s, L, Cn, L, L - 2),
+                   "log_n": L, "cols": Cn, "l2": "inputs and outputs exceed L2 (%.1f GB per step); no explicit flush" % (Cn * N * 32 / 1e9),
+                   "sharding": "independent batch per GPU (columns / subtrees shard with no data-path collective)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "breakdown": {"lde_ms": lde_ms, "ntt_elems_per_s": Cn * N / (lde_ms * 1e-3),
+                      "merkle8_ms": m8_ms, "merkle1_ms": m1_ms,
+                      "merkle_hashes_per_s": (comp8 + comp1) / ((m8_ms + m1_ms) * 1e-3),
+                      "fri_ms": fri_ms, "fri_layers": int(n_layers),
+                      "kernel_ms_per_step": {k: v[1] / args.steps for k, v in prof.items()},
+                      "kernel_launches_per_step": {k: v[0] / args.steps for k, v in prof.items()}},
+        "roofline": {"bound": "hbm", "kernel": "ntt_pass_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "avg_launch_ms": avg_launch_ms, "algorithmic_bytes_per_launch": alg_bytes_per_launch,
+                     "note": "integer-pipe bound kernel (8x32-bit Montgomery IMAD chains); the HBM fraction is reported because the contract asks for hbm|tensor"},
+    }
+    if e2e:
+        out["e2e"] = {"value": total_elems / (e2e["ms"] * 1e-3), "unit": "elems/s", "ms_per_step": e2e["ms"],
+                      "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"])}
+    if world == 1 and not args.no_cpu:
+        _, _, cb = run_cpu(args, False)
+        out["cpu_baseline"] = cb
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def ntt_plan(log_n, maxb=8):
+    if log_n == 0:
+        return [0]
+    m = (log_n + maxb - 1) // maxb
+    base, rem = divmod(log_n, m)
+    return [base + (1 if i < rem else 0) for i in range(m)]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--log-n", type=int, default=24)
+    ap.add_argument("--cols", type=int, default=10)
+    ap.add_argument("--cpu-log-n", type=int, default=20)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    assert args.warmup >= 0 and args.steps >= 1
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        value, dt, cb = run_cpu(args, True)
+        print(json.dumps({
+            "impl": "reference", "metric": "hot_path_extended_elems_per_s", "value": value, "unit": "elems/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64x4 (254-bit Montgomery, integer)",
+            "data": "synthetic (seeded uniform field elements)",
+            "config": {"workload": "LDE 2^%d->2^%d x %d cols + Merkle(8 cols) + Merkle(1 col) + FRI: bounded sample of the L=%d workload" % (
+                args.cpu_log_n - 3, args.cpu_log_n, args.cols, args.log_n), "log_n": args.cpu_log_n, "cols": args.cols},
+            "cpu_baseline": cb,
+            "e2e": {"value": value, "unit": "elems/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "the Rust reference cannot be built here (no cargo/rustc); this is the C restatement in oracle/ (kind=port)"}))
+        return
+    run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -61,6 +61,19 @@ int sb_timer_stop(sb_ctx *ctx, float *ms);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t sb_launch_count(const sb_ctx *ctx);
 
+/* Per-kernel-family timing: when enabled every launch is bracketed by CUDA events on the context's stream
+ * (bench.py's roofline figures come from this, measured inside the timed region).  sb_profile resets the
+ * counters; sb_profile_read synchronises and returns launches and summed milliseconds of one family. */
+#define SB_KIND_NTT_PASS 0      /* ntt_pass_kernel<B>                                   */
+#define SB_KIND_MERKLE_LEAVES 1 /* merkle_leaves_{cols,bytes}_kernel (leaf hash + 3 levels) */
+#define SB_KIND_MERKLE_NODES 2  /* merkle_nodes_kernel (3 levels per launch)             */
+#define SB_KIND_FRI_FOLD 3      /* fri_fold_kernel                                       */
+#define SB_KIND_OPEN 4          /* opening gathers                                       */
+#define SB_KIND_OTHER 5         /* table building, batch inverse, codecs                 */
+#define SB_KIND_COUNT 6
+int sb_profile(sb_ctx *ctx, int enable);
+int sb_profile_read(sb_ctx *ctx, int kind, uint64_t *launches, double *total_ms);
+
 /* ---- device memory (pipelines that keep vectors resident in HBM) --------------------------- */
 int sb_dev_alloc(sb_ctx *ctx, size_t bytes, void **d_ptr);
 int sb_dev_free(sb_ctx *ctx, void *d_ptr);

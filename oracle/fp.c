@@ -229,3 +229,8 @@ void fp_root_of_unity(fp_t *r, uint32_t log_n) {
     fp_multiplicative_generator(&g);
     fp_pow_limbs(r, &g, e, 4);
 }
+
+/* batch form of fp_to_bytes_le for the ctypes harness (tests / bench): out = n x 32 bytes */
+void orc_fp_to_bytes_le_vec(uint8_t *out, const fp_t *a, size_t n) {
+    for (size_t i = 0; i < n; i++) fp_to_bytes_le(out + 32 * i, &a[i]);
+}

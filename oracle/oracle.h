@@ -59,6 +59,7 @@ void fp_from_bytes_be(fp_t *r, const uint8_t *b, size_t len);
 /* fp.rs:35-44  to_bytes_le / to_bytes_be: canonical value, exactly 32 bytes */
 void fp_to_bytes_le(uint8_t out[32], const fp_t *a);
 void fp_to_bytes_be(uint8_t out[32], const fp_t *a);
+void orc_fp_to_bytes_le_vec(uint8_t *out, const fp_t *a, size_t n); /* n x fp_to_bytes_le */
 void fp_multiplicative_generator(fp_t *r);        /* 7, fp.rs:10 */
 /* g = 7^((p-1)/2^log_n): prove.rs:71-82 */
 void fp_root_of_unity(fp_t *r, uint32_t log_n);

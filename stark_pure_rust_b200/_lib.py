@@ -88,6 +88,8 @@ def load():
         "sb_pseudorandom_indices": (i32, [vp, sz, u32, sz, u32, vp]),
         "sb_blake2s": (None, [vp, sz, vp]),
         "sb_fp_vec_op": (i32, [vp, i32, vp, vp, vp, sz]),
+        "sb_profile": (i32, [vp, i32]),
+        "sb_profile_read": (i32, [vp, i32, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
     }
     for name, (res, args) in proto.items():
         fn = getattr(L, name)
@@ -173,6 +175,15 @@ class Context:
         ms = C.c_float()
         self.check(self.lib.sb_timer_stop(self.h, C.byref(ms)))
         return ms.value
+
+    def profile(self, enable=True):
+        self.check(self.lib.sb_profile(self.h, 1 if enable else 0))
+
+    def profile_read(self, kind):
+        """(launches, total_ms) of one kernel family since profile(True)"""
+        n, ms = C.c_uint64(), C.c_double()
+        self.check(self.lib.sb_profile_read(self.h, kind, C.byref(n), C.byref(ms)))
+        return n.value, ms.value
 
     def launch_count(self):
         return int(self.lib.sb_launch_count(self.h))

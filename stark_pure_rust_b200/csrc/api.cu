@@ -33,7 +33,54 @@ struct sb_ctx {
     uint64_t launches = 0;
     std::vector<TwTable> tables;
     char err[512] = {0};
+    // optional per-kernel-family timing (sb_profile): CUDA events around every launch
+    bool prof = false;
+    struct ProfRec { int kind; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[SB_KIND_COUNT] = {0};
+    uint64_t prof_n[SB_KIND_COUNT] = {0};
 };
+
+static cudaEvent_t prof_event(sb_ctx *ctx) {
+    cudaEvent_t e;
+    if (!ctx->prof_pool.empty()) {
+        e = ctx->prof_pool.back();
+        ctx->prof_pool.pop_back();
+    } else {
+        cudaEventCreate(&e);
+    }
+    return e;
+}
+static void prof_begin(sb_ctx *ctx, int kind) {
+    if (!ctx->prof) return;
+    sb_ctx::ProfRec r{kind, prof_event(ctx), prof_event(ctx)};
+    cudaEventRecord(r.a, ctx->stream);
+    ctx->prof_recs.push_back(r);
+}
+static void prof_end(sb_ctx *ctx) {
+    if (!ctx->prof) return;
+    cudaEventRecord(ctx->prof_recs.back().b, ctx->stream);
+}
+static void prof_collect(sb_ctx *ctx) {
+    for (auto &r : ctx->prof_recs) {
+        float ms = 0;
+        cudaEventSynchronize(r.b);
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            ctx->prof_ms[r.kind] += ms;
+            ctx->prof_n[r.kind]++;
+        }
+        ctx->prof_pool.push_back(r.a);
+        ctx->prof_pool.push_back(r.b);
+    }
+    ctx->prof_recs.clear();
+}
+#define KLAUNCH(kind, expr)          \
+    do {                             \
+        prof_begin(ctx, kind);       \
+        ctx->launches += (expr);     \
+        prof_end(ctx);               \
+    } while (0)
 
 static int fail(sb_ctx *ctx, int code, const char *fmt, ...) {
     if (ctx) {
@@ -57,7 +104,6 @@ static int fail(sb_ctx *ctx, int code, const char *fmt, ...) {
         int rc_ = (expr);        \
         if (rc_ != SB_OK) return rc_; \
     } while (0)
-#define LAUNCHED(ctx) ((ctx)->launches++)
 
 struct DevBuf {   // stream-ordered scratch
     sb_ctx *ctx;
@@ -118,6 +164,8 @@ extern "C" void sb_destroy(sb_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto &t : ctx->tables) cudaFree(t.d);
+    prof_collect(ctx);
+    for (auto e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -152,6 +200,21 @@ extern "C" int sb_timer_stop(sb_ctx *ctx, float *ms) {
     return SB_OK;
 }
 extern "C" uint64_t sb_launch_count(const sb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int sb_profile(sb_ctx *ctx, int enable) {
+    if (!ctx) return SB_ERR_ARG;
+    prof_collect(ctx);
+    ctx->prof = enable != 0;
+    for (int k = 0; k < SB_KIND_COUNT; k++) ctx->prof_ms[k] = 0, ctx->prof_n[k] = 0;
+    return SB_OK;
+}
+extern "C" int sb_profile_read(sb_ctx *ctx, int kind, uint64_t *launches, double *total_ms) {
+    if (!ctx || kind < 0 || kind >= SB_KIND_COUNT) return SB_ERR_ARG;
+    CU(cudaStreamSynchronize(ctx->stream));
+    prof_collect(ctx);
+    if (launches) *launches = ctx->prof_n[kind];
+    if (total_ms) *total_ms = ctx->prof_ms[kind];
+    return SB_OK;
+}
 
 extern "C" int sb_dev_alloc(sb_ctx *ctx, size_t bytes, void **p) {
     if (!ctx || !p) return SB_ERR_ARG;
@@ -200,10 +263,10 @@ static fp to_dev_fp(const hfp::el &a) {
 static int powers_into(sb_ctx *ctx, const hfp::el &root, size_t n, uint4 *d_out) {
     if (n == 0) return SB_OK;
     size_t seed = n < 1024 ? n : 1024;
-    ctx->launches += powers_launch_seed(ctx->stream, d_out, seed, to_dev_fp(root));
+    KLAUNCH(SB_KIND_OTHER, powers_launch_seed(ctx->stream, d_out, seed, to_dev_fp(root)));
     hfp::el wc = hfp::pow_u64(root, 1024);
     for (size_t cur = 1024; cur < n; cur <<= 1) {
-        ctx->launches += powers_launch_double(ctx->stream, d_out, cur, n, to_dev_fp(wc));
+        KLAUNCH(SB_KIND_OTHER, powers_launch_double(ctx->stream, d_out, cur, n, to_dev_fp(wc)));
         wc = hfp::sqr(wc);
     }
     CU(cudaGetLastError());
@@ -298,11 +361,15 @@ static int ntt_dev(sb_ctx *ctx, const uint4 *d_src, size_t len_in, size_t src_st
         P.inverse = inverse ? 1 : 0;
         P.tw_log_n = tw_log_n;
         P.tw_log_stride = log_stride;
+        {   // interleave polynomials when a tile never straddles two of them
+            const unsigned long long cpp = 1ull << (log_n - bits[p]), cc = (1ull << NTT_LOG_TILE) >> bits[p];
+            P.n_polys = (n_polys > 1 && !last && cpp % cc == 0 && n_polys < (1u << 20)) ? (uint32_t)n_polys : 0;
+        }
         P.n_prev = (uint32_t)p;
         for (int i = 0; i < p; i++) P.prev_bits[i] = bits[i];
         memcpy(P.n_inv, ninv.l, 32);
-        if (ntt_launch_pass(ctx->stream, bits[p], P) < 0) return fail(ctx, SB_ERR_ARG, "internal: pass width %u", bits[p]);
-        ctx->launches++;
+        if (bits[p] > NTT_LOG_TILE - 3) return fail(ctx, SB_ERR_ARG, "internal: pass width %u", bits[p]);
+        KLAUNCH(SB_KIND_NTT_PASS, ntt_launch_pass(ctx->stream, bits[p], P));
         log_outer += bits[p];
     }
     CU(cudaGetLastError());
@@ -391,7 +458,7 @@ extern "C" int sb_batch_inverse_dev(sb_ctx *ctx, uint64_t *d_vals, size_t n) {
     if (n == 0) return SB_OK;
     DevBuf scratch(ctx);
     TRY(scratch.alloc(n * 32));
-    ctx->launches += batch_inverse_launch(ctx->stream, (uint4 *)d_vals, (uint4 *)scratch.p, n);
+    KLAUNCH(SB_KIND_OTHER, batch_inverse_launch(ctx->stream, (uint4 *)d_vals, (uint4 *)scratch.p, n));
     CU(cudaGetLastError());
     return SB_OK;
 }
@@ -418,6 +485,7 @@ struct sb_tree {
     int n_cols = 0;
     const uint4 *cols[8] = {0};
     uint8_t root[32] = {0};
+    cudaStream_t stream = nullptr; // allocations are stream-ordered (pool) on the owning context's stream
 };
 
 static bool is_pow2(size_t n) { return n && !(n & (n - 1)); }
@@ -429,8 +497,8 @@ static uint32_t ilog2(size_t n) {
 
 static void free_tree(sb_tree *t) {
     if (!t) return;
-    if (t->d_nodes) cudaFree(t->d_nodes);
-    if (t->d_leaves) cudaFree(t->d_leaves);
+    if (t->d_nodes) cudaFreeAsync(t->d_nodes, t->stream);
+    if (t->d_leaves) cudaFreeAsync(t->d_leaves, t->stream);
     delete t;
 }
 
@@ -441,14 +509,14 @@ static void launch_leaves(sb_ctx *ctx, sb_tree *t, uint32_t lv) {
         P.nodes = t->d_nodes;
         P.n = t->n;
         P.nc = (uint32_t)t->n_cols;
-        ctx->launches += merkle_launch_leaves_cols(ctx->stream, lv, P);
+        KLAUNCH(SB_KIND_MERKLE_LEAVES, merkle_launch_leaves_cols(ctx->stream, lv, P));
     } else {
         MerkleBytesParams P;
         P.leaves = t->d_leaves;
         P.nodes = t->d_nodes;
         P.n = t->n;
         P.leaf_bytes = (uint32_t)t->leaf_bytes;
-        ctx->launches += merkle_launch_leaves_bytes(ctx->stream, lv, P);
+        KLAUNCH(SB_KIND_MERKLE_LEAVES, merkle_launch_leaves_bytes(ctx->stream, lv, P));
     }
 }
 
@@ -458,7 +526,7 @@ static int merkle_build(sb_ctx *ctx, sb_tree *t) {
     launch_leaves(ctx, t, level);
     while (level < t->depth) {
         const uint32_t lv = t->depth - level < 3 ? t->depth - level : 3;
-        ctx->launches += merkle_launch_nodes(ctx->stream, lv, t->d_nodes, t->n, level);
+        KLAUNCH(SB_KIND_MERKLE_NODES, merkle_launch_nodes(ctx->stream, lv, t->d_nodes, t->n, level));
         level += lv;
     }
     CU(cudaGetLastError());
@@ -474,10 +542,11 @@ static int tree_new(sb_ctx *ctx, size_t n, size_t leaf_bytes, sb_tree **out) {
     t->n = n;
     t->depth = ilog2(n);
     t->leaf_bytes = leaf_bytes;
-    cudaError_t e = cudaMalloc(&t->d_nodes, (2 * n - 1) * 32);
+    t->stream = ctx->stream;
+    cudaError_t e = cudaMallocAsync(&t->d_nodes, (2 * n - 1) * 32, ctx->stream);
     if (e != cudaSuccess) {
         delete t;
-        return fail(ctx, SB_ERR_OOM, "cudaMalloc(tree levels): %s", cudaGetErrorString(e));
+        return fail(ctx, SB_ERR_OOM, "cudaMallocAsync(tree levels): %s", cudaGetErrorString(e));
     }
     *out = t;
     return SB_OK;
@@ -489,7 +558,7 @@ extern "C" int sb_merkle_commit(sb_ctx *ctx, const void *leaves, size_t leaf_byt
     if (leaf_bytes >= ((size_t)1 << 31)) return fail(ctx, SB_ERR_ARG, "leaf too long");
     sb_tree *t = nullptr;
     TRY(tree_new(ctx, n, leaf_bytes, &t));
-    cudaError_t e = cudaMalloc(&t->d_leaves, n * leaf_bytes ? n * leaf_bytes : 16);
+    cudaError_t e = cudaMallocAsync(&t->d_leaves, n * leaf_bytes ? n * leaf_bytes : 16, ctx->stream);
     if (e != cudaSuccess) {
         free_tree(t);
         return fail(ctx, SB_ERR_OOM, "cudaMalloc(leaves): %s", cudaGetErrorString(e));
@@ -543,8 +612,8 @@ extern "C" int sb_merkle_open(sb_ctx *ctx, const sb_tree *t, const size_t *idx, 
     if (nodes_out && t->depth) {
         TRY(d_nodes.alloc(n_idx * t->depth * 32));
         const size_t tot = n_idx * t->depth;
-        ctx->launches += merkle_launch_open(ctx->stream, t->d_nodes, t->n, t->depth, (const unsigned long long *)d_idx.p,
-                                            (uint32_t)n_idx, (uint4 *)d_nodes.p);
+        KLAUNCH(SB_KIND_OPEN, merkle_launch_open(ctx->stream, t->d_nodes, t->n, t->depth, (const unsigned long long *)d_idx.p,
+                                            (uint32_t)n_idx, (uint4 *)d_nodes.p));
         CU(cudaMemcpyAsync(nodes_out, d_nodes.p, tot * 32, cudaMemcpyDeviceToHost, ctx->stream));
     }
     if (leaves_out && t->leaf_bytes) {
@@ -555,11 +624,11 @@ extern "C" int sb_merkle_open(sb_ctx *ctx, const sb_tree *t, const size_t *idx, 
             P.nodes = nullptr;
             P.n = t->n;
             P.nc = (uint32_t)t->n_cols;
-            ctx->launches += merkle_launch_open_leaves_cols(ctx->stream, P, (const unsigned long long *)d_idx.p, (uint32_t)n_idx,
-                                                            (uint4 *)d_leaves.p);
+            KLAUNCH(SB_KIND_OPEN, merkle_launch_open_leaves_cols(ctx->stream, P, (const unsigned long long *)d_idx.p, (uint32_t)n_idx,
+                                                            (uint4 *)d_leaves.p));
         } else {
-            ctx->launches += merkle_launch_gather_bytes(ctx->stream, t->d_leaves, t->leaf_bytes, (const unsigned long long *)d_idx.p,
-                                                        (uint32_t)n_idx, (uint8_t *)d_leaves.p);
+            KLAUNCH(SB_KIND_OPEN, merkle_launch_gather_bytes(ctx->stream, t->d_leaves, t->leaf_bytes, (const unsigned long long *)d_idx.p,
+                                                        (uint32_t)n_idx, (uint8_t *)d_leaves.p));
         }
         CU(cudaMemcpyAsync(leaves_out, d_leaves.p, n_idx * t->leaf_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     }
@@ -576,8 +645,8 @@ extern "C" int sb_tree_root(const sb_tree *t, uint8_t root[32]) {
     return SB_OK;
 }
 extern "C" void sb_tree_free(sb_ctx *ctx, sb_tree *t) {
-    if (ctx) cudaStreamSynchronize(ctx->stream);
-    free_tree(t);
+    (void)ctx;
+    free_tree(t);      // stream-ordered: work already queued on the tree's stream finishes first
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -641,9 +710,8 @@ static int fri_prove_dev(sb_ctx *ctx, const uint4 *d_vals, size_t n, const hfp::
     std::vector<sb_tree *> owned_trees;
     std::vector<void *> owned_cols;
     auto cleanup = [&]() {
-        cudaStreamSynchronize(ctx->stream);
         for (auto t : owned_trees) free_tree(t);
-        for (auto p : owned_cols) cudaFree(p);
+        for (auto p : owned_cols) cudaFreeAsync(p, ctx->stream);
     };
     int rc = SB_OK;
     const uint4 *cur = d_vals;
@@ -659,7 +727,7 @@ static int fri_prove_dev(sb_ctx *ctx, const uint4 *d_vals, size_t n, const hfp::
             L.last.resize(cur_n * 32);
             DevBuf tmp(ctx);
             if ((rc = tmp.alloc(cur_n * 32)) != SB_OK) break;
-            ctx->launches += fp_launch_to_bytes(ctx->stream, cur, (uint4 *)tmp.p, cur_n);
+            KLAUNCH(SB_KIND_OTHER, fp_launch_to_bytes(ctx->stream, cur, (uint4 *)tmp.p, cur_n));
             cudaError_t e = cudaMemcpyAsync(L.last.data(), tmp.p, cur_n * 32, cudaMemcpyDeviceToHost, ctx->stream);
             if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
             if (e != cudaSuccess) { rc = fail(ctx, SB_ERR_CUDA, "FRI last layer: %s", cudaGetErrorString(e)); break; }
@@ -681,8 +749,8 @@ static int fri_prove_dev(sb_ctx *ctx, const uint4 *d_vals, size_t n, const hfp::
         // fri.rs:141-164
         const size_t q = cur_n / 4;
         void *d_col = nullptr;
-        cudaError_t e = cudaMalloc(&d_col, q * 32);
-        if (e != cudaSuccess) { rc = fail(ctx, SB_ERR_OOM, "cudaMalloc(column): %s", cudaGetErrorString(e)); break; }
+        cudaError_t e = cudaMallocAsync(&d_col, q * 32, ctx->stream);
+        if (e != cudaSuccess) { rc = fail(ctx, SB_ERR_OOM, "cudaMallocAsync(column): %s", cudaGetErrorString(e)); break; }
         owned_cols.push_back(d_col);
         FriFoldParams P;
         P.vals = cur;
@@ -692,7 +760,7 @@ static int fri_prove_dev(sb_ctx *ctx, const uint4 *d_vals, size_t n, const hfp::
         P.tw_log_n = tw_log_n;
         P.tw_log_stride = cur_stride;
         memcpy(P.special_x, special_x.l, 32);
-        ctx->launches += fri_launch_fold(ctx->stream, P);
+        KLAUNCH(SB_KIND_FRI_FOLD, fri_launch_fold(ctx->stream, P));
         // fri.rs:165-172
         sb_tree *t2 = nullptr;
         const uint4 *cols2[1] = {(const uint4 *)d_col};
@@ -748,12 +816,12 @@ extern "C" int sb_fri_prove(sb_ctx *ctx, const uint64_t *vals, size_t n, const u
                             sb_fri_proof **out) {
     if (!ctx || !vals || !root || !out) return SB_ERR_ARG;
     void *d = nullptr;
-    CU(cudaMalloc(&d, n * 32 ? n * 32 : 16));
+    CU(cudaMallocAsync(&d, n * 32 ? n * 32 : 16, ctx->stream));
     cudaError_t e = cudaMemcpyAsync(d, vals, n * 32, cudaMemcpyHostToDevice, ctx->stream);
     int rc = e == cudaSuccess ? fri_prove_dev(ctx, (const uint4 *)d, n, hfp::from_limbs(root), max_deg_plus_1, excl, nullptr, out)
                               : fail(ctx, SB_ERR_CUDA, "H2D values: %s", cudaGetErrorString(e));
+    cudaFreeAsync(d, ctx->stream);
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(d);
     return rc;
 }
 
@@ -855,7 +923,7 @@ extern "C" int sb_fp_vec_op(sb_ctx *ctx, int op, const uint64_t *a, const uint64
     TRY(dout.alloc(n * 32));
     CU(cudaMemcpyAsync(da.p, a, n * 32, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(db.p, b, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-    ctx->launches += fp_launch_vec_op(ctx->stream, op, (const uint4 *)da.p, (const uint4 *)db.p, (uint4 *)dout.p, n);
+    KLAUNCH(SB_KIND_OTHER, fp_launch_vec_op(ctx->stream, op, (const uint4 *)da.p, (const uint4 *)db.p, (uint4 *)dout.p, n));
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out, dout.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));

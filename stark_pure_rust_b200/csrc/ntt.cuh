@@ -112,7 +112,11 @@ __global__ void __launch_bounds__((1 << LOG_TILE) / 8, 2) ntt_pass_kernel(const 
 
     const unsigned long long n = 1ull << P.log_n;
     const uint32_t log_cpp = P.log_n - B;                     // log2(columns per polynomial)
-    const unsigned long long blk_col0 = (unsigned long long)blockIdx.x * CC;
+    unsigned long long blk_col0 = (unsigned long long)blockIdx.x * CC;
+    if (P.n_polys) {   // tile-major order (host guarantees CC divides the columns of one polynomial)
+        const unsigned long long poly = blockIdx.x % P.n_polys, tile = blockIdx.x / P.n_polys;
+        blk_col0 = (poly << log_cpp) + tile * CC;
+    }
 
     // sub-transform twiddles W[i] = w^(i * n/R)
     for (int i = threadIdx.x; i < R / 2; i += NT) {

@@ -29,6 +29,8 @@ struct NttPassParams {
     uint32_t first, last, inverse;
     uint32_t tw_log_n;             // log2 of the table length
     uint32_t tw_log_stride;        // w = w_T^(2^tw_log_stride)
+    uint32_t n_polys;              // > 0: CTAs are ordered tile-major / polynomial-minor so that the CTAs that
+                                   // need the same inter-pass twiddles run together and share them in L2
     uint32_t n_prev;               // last pass: widths of the earlier passes, in order
     uint32_t prev_bits[NTT_MAX_PASSES];
     uint32_t n_inv[8];             // Montgomery form of n^-1 (inverse transform, last pass)

@@ -1,0 +1,92 @@
+#!/usr/bin/env python3
+"""Regenerates tests/golden/vectors.json from the CPU oracle, cross-checked against the independent
+Python big-int model (oracle/py_model.py) wherever that is fast enough.  Run from the repo root:
+
+    python tests/golden/make_golden.py
+
+Inputs are seeded (tests/conftest.py::random_elems) so only digests of the outputs are stored.
+The reference's own KATs (Blake2s, sampler, Merkle) are copied verbatim with their file:line."""
+import hashlib
+import json
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import numpy as np
+import oracle_bind as ob
+import py_model as pm
+from conftest import random_elems
+from stark_pure_rust_b200 import field
+
+
+def sha(b):
+    return hashlib.sha256(bytes(b)).hexdigest()
+
+
+out = {"_how": "python tests/golden/make_golden.py (oracle/liboracle.so, cross-checked with oracle/py_model.py)"}
+
+# ---- reference KATs, verbatim ----
+out["reference_kats"] = {
+    "blake": {"src": "commitment/src/utils.rs:13-24", "hello world": "9aec6806794561107e594b1f6a8a6b0c92a0cba9acf5e5e93cca06f781813b0b",
+              "blake(blake(hello world))": "8ea974646c2be3c16f9f52a2e5ebb3d2df7ba184a6440e47fc6fcce6e9d9bdc4"},
+    "sampler": {"src": "fri/src/utils.rs:112-120", "hello world,7,5,0": [5, 5, 5, 3, 5],
+                "hello another world,7,20,0": [3, 0, 2, 4, 4, 1, 4, 2, 5, 1, 3, 2, 1, 0, 0, 1, 6, 5, 2, 3]},
+    "merkle16": {"src": "commitment/src/pallarel_merkle_tree.rs:133-179", "root": "9f04496db6a8c505e88a7db289161a540a0cb953ef81c9b86103f0d6d12e8e15",
+                 "nodes_of_2": ["4cd90cc0d54239ee5b3fd9989b4ef4cbebbbdd08410758cbd2d291fa364c82d5", "2e3d3579213e0a992d60b503f1d8fe331b8bd548e227e8dbd741ca1752077b84",
+                                "9a8c87bb98f1b2e0f7036a27a343dc8fd649bedc737093c2080a34c6b9f6f375", "ef459d75e20ce2f3fc4378ff20fe2d594fbcf16cccd986c2e0d3df41bd3bbe44"]},
+    "merkle4096": {"src": "commitment/src/pallarel_merkle_tree.rs:182-216", "root": "a0d91c3115f9e4d9f142e7cb2f413c10f0f2f9f65d9f918b80f852f9ebc06ebc",
+                   "first_node_of_2": "b72b5371ceffa4e01aa1849cdb8705406e14791db359f826bc01a392ed26b6b9"},
+}
+
+# ---- NTT ----
+ntt = []
+for log_n, len_in in [(0, 1), (1, 2), (3, 8), (3, 5), (6, 64), (9, 300), (10, 1024), (13, 6684), (14, 1 << 14)]:
+    v = random_elems(max(len_in, 1), 0xB200 + log_n)[:len_in]
+    w = ob.root_of_unity(log_n)
+    fwd, inv = ob.best_fft(v, w, log_n), ob.best_fft(v, w, log_n, inverse=True)
+    if log_n <= 10:   # independent model
+        wi = field.from_mont(w.reshape(1, 4))[0]
+        assert field.from_mont(fwd) == pm.best_fft(field.from_mont(v), wi, log_n)
+        assert field.from_mont(inv) == pm.inv_best_fft(field.from_mont(v), wi, log_n)
+    ntt.append({"log_n": log_n, "len_in": len_in, "seed": 0xB200 + log_n, "fwd_sha256": sha(fwd.tobytes()), "inv_sha256": sha(inv.tobytes())})
+out["ntt"] = ntt
+v = field.to_mont(range(1, 9))
+w8 = ob.root_of_unity(3)
+out["ntt_1_to_8"] = {"root": hex(field.from_mont(w8.reshape(1, 4))[0]), "out": [hex(x) for x in field.from_mont(ob.best_fft(v, w8, 3))]}
+
+# ---- Merkle over field columns ----
+mk = []
+for n, nc in [(8, 1), (1 << 10, 8), (1 << 12, 1), (64, 3)]:
+    cols = random_elems(n * nc, 4242 + n + nc).reshape(nc, n, 4)
+    by = np.concatenate([ob.fp_to_bytes_le(cols[k]).reshape(n, 1, 32) for k in range(nc)], axis=1).tobytes()
+    root, nodes = ob.merkle_gen_proofs(by, 32 * nc, n, [0, n - 1, n // 3])
+    assert root == pm.merkle_root([by[i * 32 * nc:(i + 1) * 32 * nc] for i in range(n)])
+    mk.append({"n": n, "nc": nc, "seed": 4242 + n + nc, "root": root.hex(), "nodes_sha256": sha(nodes.tobytes())})
+out["merkle_cols"] = mk
+
+# ---- FRI ----
+fri = []
+for log_n, deg_log in [(7, 4), (9, 6), (10, 7), (12, 9)]:
+    w = ob.root_of_unity(log_n)
+    values = ob.best_fft(random_elems(1 << deg_log, 600 + log_n), w, log_n)
+    text, ok = ob.prove_low_degree_json(values, w, (1 << log_n) // 4, 8)
+    assert ok
+    if log_n <= 9:
+        wi = field.from_mont(w.reshape(1, 4))[0]
+        assert pm.fri_json(pm.prove_low_degree(field.from_mont(values), wi, (1 << log_n) // 4, 8)) == text
+    fri.append({"log_n": log_n, "deg_log": deg_log, "seed": 600 + log_n, "json_sha256": sha(text.encode()), "json_len": len(text)})
+out["fri"] = fri
+
+# ---- whole proofs of the bundled circuits (survey model agreed on these hashes) ----
+proofs = {}
+for name in ("compute", "poseidon3_test"):
+    path = "/tmp/%s_golden_proof.json" % name
+    rc, _ = ob.prove_files(os.path.join(HERE, "circuits", name + ".r1cs"), os.path.join(HERE, "circuits", name + ".wtns"), path)
+    assert rc == 0
+    proofs[name] = {"proof_json_sha256": ob.sha256_file(path), "proof_json_bytes": os.path.getsize(path)}
+out["proofs"] = proofs
+
+json.dump(out, open(os.path.join(HERE, "vectors.json"), "w"), indent=1)
+print("wrote vectors.json")

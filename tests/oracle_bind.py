@@ -74,6 +74,7 @@ def lib():
         L.fp_mul.argtypes = [vp, vp, vp]
         L.fp_to_bytes_le.argtypes = [vp, vp]
         L.fp_from_bytes_le.argtypes = [vp, vp, sz]
+        L.orc_fp_to_bytes_le_vec.argtypes = [vp, vp, sz]
         _lib = L
     return _lib
 
@@ -144,15 +145,17 @@ def merkle_gen_proofs(leaves_flat, leaf_bytes, n, indices):
 
 
 def fp_to_bytes_le(vals):
+    """fp.rs:39-43 for every element: (n, 32) uint8"""
     v = np.ascontiguousarray(vals, dtype=np.uint64).reshape(-1, 4)
     out = np.zeros((v.shape[0], 32), dtype=np.uint8)
-    L = lib()
-    for i in range(v.shape[0]):
-        L.fp_to_bytes_le(C.c_void_p(out[i].ctypes.data), C.c_void_p(v[i].ctypes.data))
+    lib().orc_fp_to_bytes_le_vec(_p(out), _p(v), v.shape[0])
     return out
 
 
-def prove_low_degree_json(vals, root, max_deg_plus_1, excl):
+fp_to_bytes_le_fast = fp_to_bytes_le
+
+
+def prove_low_degree_json(vals, root, max_deg_plus_1, excl, verify=True):
     """fri.rs:46-224 -> serde_json text of Vec<FriProof>; also returns whether the restated verifier accepts"""
     v = np.ascontiguousarray(vals, dtype=np.uint64).reshape(-1, 4)
     root = np.ascontiguousarray(root, dtype=np.uint64)
@@ -163,6 +166,9 @@ def prove_low_degree_json(vals, root, max_deg_plus_1, excl):
     L.orc_fri_proof_json(C.byref(b), C.byref(pr))
     text = C.string_at(b.p, b.len).decode()
     L.orc_buf_free(C.byref(b))
+    if not verify:
+        L.orc_fri_proof_free(C.byref(pr))
+        return text, None
     # verifier needs the root of the values tree
     leaves = fp_to_bytes_le(v).tobytes()
     mroot, _ = merkle_gen_proofs(leaves, 32, v.shape[0], [])
