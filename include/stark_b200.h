@@ -152,6 +152,29 @@ char *sb_fri_proof_json(const sb_fri_proof *p);
 void sb_free_string(char *s);
 void sb_fri_proof_free(sb_fri_proof *p);
 
+/* ---- the caller of the hot path: mk_r1cs_proof (r1cs-stark/src/prove.rs:14-378), device resident -------- */
+/* Same arguments as the reference function (prove.rs:14-26); n_constraints / n_wires only feed an assert there.
+ * All field vectors are Montgomery limbs; traces / coefficients / flags have original_steps elements. */
+typedef struct {
+    size_t original_steps;              /* coefficients.len(), a multiple of 3 (prove.rs:30-35) */
+    const uint64_t *witness_trace, *computational_trace, *coefficients, *flag0, *flag1, *flag2;
+    const size_t *permuted_indices;     /* original_steps entries */
+    size_t n_public;
+    const uint64_t *public_wires;       /* n_public elements */
+    size_t n_pfi;                       /* public_first_indices: (k, w) pairs -> (public_wires[k], xs[8 w]) */
+    const size_t *pfi_k, *pfi_w;
+} sb_trace;
+typedef struct sb_stark_proof sb_stark_proof;
+/* Returns SB_ERR_ARG where the reference panics (witness not satisfying the circuit: utils.rs:379-418, :489, :514;
+ * precision beyond the sampler's 2^24 or the field's two-adicity). */
+int sb_prove_r1cs(sb_ctx *ctx, const sb_trace *trace, sb_stark_proof **out);
+int sb_stark_proof_roots(const sb_stark_proof *p, uint8_t m_root[32], uint8_t l_root[32], uint8_t a_root[32]);
+/* CUDA-event stage times of that proof: [0] LDE/NTT, [1] m_tree commit, [2] FRI, [3] the rest, [4] total (ms). */
+int sb_stark_proof_stage_ms(const sb_stark_proof *p, double ms[5]);
+/* serde_json::to_string(&StarkProof) (utils.rs:122-130, run.rs:549): malloc'd, free with sb_free_string. */
+char *sb_stark_proof_json(const sb_stark_proof *p, size_t *len);
+void sb_stark_proof_free(sb_stark_proof *p);
+
 /* ---- unit-test hook for the device field library (no reference counterpart: ff_derive's arithmetic is
  * generated code) ---- element-wise op on n raw 256-bit values, no range checks.
  * op: 0 Montgomery product (lazy, < 2p), 1 add, 2 sub, 3 a+2p-b, 4 canonicalise, 5 halve, 6 from Montgomery,

@@ -202,6 +202,9 @@ void orc_stark_proof_json(orc_buf *b, const orc_stark_proof *p);
 int orc_prove_files(const char *r1cs_path, const char *wtns_path, const char *proof_path,
                     unsigned cpus, int verify, double *t_prove_s);
 
+/* trace arrays of a circuit for the test harness (caller frees with orc_trace_free) */
+int orc_trace_from_files(const char *r1cs_path, const char *wtns_path, orc_trace *out);
+
 /* per-stage wall-clock of the last orc_mk_r1cs_proof in this thread (seconds):
  * [0]=ntt/lde [1]=merkle [2]=fri [3]=pointwise+rest */
 extern __thread double orc_stage_s[4];

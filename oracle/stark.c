@@ -842,3 +842,22 @@ int orc_prove_files(const char *r1cs_path, const char *wtns_path, const char *pr
     free(wb);
     return ret;
 }
+
+/* test harness helpers: the trace arrays of a circuit (run.rs:109-452 up to the mk_r1cs_proof call), and
+ * verification of a serialised proof's pieces is done by comparing JSON text with orc_prove_files' output. */
+int orc_trace_from_files(const char *r1cs_path, const char *wtns_path, orc_trace *out) {
+    size_t rl = 0, wl = 0;
+    uint8_t *rb = slurp(r1cs_path, &rl), *wb = slurp(wtns_path, &wl);
+    if (!rb || !wb) { free(rb); free(wb); return -1; }
+    orc_r1cs r1cs;
+    if (orc_read_r1cs(&r1cs, rb, rl)) { free(rb); free(wb); return -2; }
+    size_t n_wires = 0;
+    fp_t *wit = orc_read_witness(wb, wl, &n_wires);
+    if (!wit || n_wires < r1cs.n_wires) { free(wit); orc_r1cs_free(&r1cs); free(rb); free(wb); return -4; }
+    orc_build_trace(out, &r1cs, wit, 1);
+    free(wit);
+    orc_r1cs_free(&r1cs);
+    free(rb);
+    free(wb);
+    return 0;
+}

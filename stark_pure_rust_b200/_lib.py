@@ -88,6 +88,11 @@ def load():
         "sb_pseudorandom_indices": (i32, [vp, sz, u32, sz, u32, vp]),
         "sb_blake2s": (None, [vp, sz, vp]),
         "sb_fp_vec_op": (i32, [vp, i32, vp, vp, vp, sz]),
+        "sb_prove_r1cs": (i32, [vp, vp, C.POINTER(vp)]),
+        "sb_stark_proof_roots": (i32, [vp, vp, vp, vp]),
+        "sb_stark_proof_stage_ms": (i32, [vp, C.POINTER(C.c_double)]),
+        "sb_stark_proof_json": (vp, [vp, szp]),
+        "sb_stark_proof_free": (None, [vp]),
         "sb_profile": (i32, [vp, i32]),
         "sb_profile_read": (i32, [vp, i32, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
     }

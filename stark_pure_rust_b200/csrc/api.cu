@@ -1,130 +1,11 @@
 // api.cu -- host side of libstark_b200.so: the C ABI of include/stark_b200.h on top of the sm_100a
 // kernels (ntt.cuh, merkle.cuh, fri.cuh).  No CPU fallback anywhere: every entry point that does
 // vector work needs a live context, and sb_init fails without a compute-capability-10 device.
-#include <cuda_runtime.h>
-#include <stdarg.h>
-#include <stdio.h>
-#include <stdlib.h>
-#include <string.h>
-
-#include <string>
-#include <vector>
-
-#include "../../include/stark_b200.h"
-#include "blake2s.cuh"
-#include "hostfp.h"
-#include "kernels.h"
-#include "params.h"
+#include "internal.h"
 
 // ------------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------------
-struct TwTable {
-    hfp::el root;
-    uint32_t log_n;
-    uint4 *d;
-};
-
-struct sb_ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    uint64_t launches = 0;
-    std::vector<TwTable> tables;
-    char err[512] = {0};
-    // optional per-kernel-family timing (sb_profile): CUDA events around every launch
-    bool prof = false;
-    struct ProfRec { int kind; cudaEvent_t a, b; };
-    std::vector<ProfRec> prof_recs;
-    std::vector<cudaEvent_t> prof_pool;
-    double prof_ms[SB_KIND_COUNT] = {0};
-    uint64_t prof_n[SB_KIND_COUNT] = {0};
-};
-
-static cudaEvent_t prof_event(sb_ctx *ctx) {
-    cudaEvent_t e;
-    if (!ctx->prof_pool.empty()) {
-        e = ctx->prof_pool.back();
-        ctx->prof_pool.pop_back();
-    } else {
-        cudaEventCreate(&e);
-    }
-    return e;
-}
-static void prof_begin(sb_ctx *ctx, int kind) {
-    if (!ctx->prof) return;
-    sb_ctx::ProfRec r{kind, prof_event(ctx), prof_event(ctx)};
-    cudaEventRecord(r.a, ctx->stream);
-    ctx->prof_recs.push_back(r);
-}
-static void prof_end(sb_ctx *ctx) {
-    if (!ctx->prof) return;
-    cudaEventRecord(ctx->prof_recs.back().b, ctx->stream);
-}
-static void prof_collect(sb_ctx *ctx) {
-    for (auto &r : ctx->prof_recs) {
-        float ms = 0;
-        cudaEventSynchronize(r.b);
-        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
-            ctx->prof_ms[r.kind] += ms;
-            ctx->prof_n[r.kind]++;
-        }
-        ctx->prof_pool.push_back(r.a);
-        ctx->prof_pool.push_back(r.b);
-    }
-    ctx->prof_recs.clear();
-}
-#define KLAUNCH(kind, expr)          \
-    do {                             \
-        prof_begin(ctx, kind);       \
-        ctx->launches += (expr);     \
-        prof_end(ctx);               \
-    } while (0)
-
-static int fail(sb_ctx *ctx, int code, const char *fmt, ...) {
-    if (ctx) {
-        va_list ap;
-        va_start(ap, fmt);
-        vsnprintf(ctx->err, sizeof ctx->err, fmt, ap);
-        va_end(ap);
-    }
-    return code;
-}
-
-#define CU(call)                                                                                    \
-    do {                                                                                            \
-        cudaError_t e_ = (call);                                                                    \
-        if (e_ != cudaSuccess)                                                                      \
-            return fail(ctx, e_ == cudaErrorMemoryAllocation ? SB_ERR_OOM : SB_ERR_CUDA, "%s: %s (%s:%d)", #call, \
-                        cudaGetErrorString(e_), __FILE__, __LINE__);                                \
-    } while (0)
-#define TRY(expr)                \
-    do {                         \
-        int rc_ = (expr);        \
-        if (rc_ != SB_OK) return rc_; \
-    } while (0)
-
-struct DevBuf {   // stream-ordered scratch
-    sb_ctx *ctx;
-    void *p = nullptr;
-    explicit DevBuf(sb_ctx *c) : ctx(c) {}
-    int alloc(size_t bytes) {
-        cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 16, ctx->stream);
-        if (e != cudaSuccess) {
-            p = nullptr;
-            return fail(ctx, e == cudaErrorMemoryAllocation ? SB_ERR_OOM : SB_ERR_CUDA, "cudaMallocAsync(%zu): %s", bytes,
-                        cudaGetErrorString(e));
-        }
-        return SB_OK;
-    }
-    ~DevBuf() {
-        if (p) cudaFreeAsync(p, ctx->stream);
-    }
-    DevBuf(const DevBuf &) = delete;
-    DevBuf &operator=(const DevBuf &) = delete;
-};
-
 extern "C" int sb_init(int device, sb_ctx **out) {
     if (!out) return SB_ERR_ARG;
     *out = nullptr;
@@ -254,12 +135,6 @@ extern "C" int sb_host_free_pinned(sb_ctx *ctx, void *p) {
 // ------------------------------------------------------------------------------------------------
 // twiddle tables
 // ------------------------------------------------------------------------------------------------
-static fp to_dev_fp(const hfp::el &a) {
-    fp r;
-    memcpy(r.l, a.l, 32);
-    return r;
-}
-
 static int powers_into(sb_ctx *ctx, const hfp::el &root, size_t n, uint4 *d_out) {
     if (n == 0) return SB_OK;
     size_t seed = n < 1024 ? n : 1024;
@@ -284,7 +159,7 @@ static int check_root(sb_ctx *ctx, const hfp::el &w, uint32_t log_n) {
 }
 
 // finds or builds a table T with w = T-root^(2^log_stride)
-static int get_table(sb_ctx *ctx, const hfp::el &w, uint32_t log_n, const uint4 **tw, uint32_t *tw_log_n, uint32_t *log_stride) {
+int get_table(sb_ctx *ctx, const hfp::el &w, uint32_t log_n, const uint4 **tw, uint32_t *tw_log_n, uint32_t *log_stride) {
     TRY(check_root(ctx, w, log_n));
     for (auto &t : ctx->tables) {
         if (t.log_n < log_n) continue;
@@ -328,7 +203,7 @@ static int plan_bits(uint32_t log_n, uint32_t *bits) {
     return m;
 }
 
-static int ntt_dev(sb_ctx *ctx, const uint4 *d_src, size_t len_in, size_t src_stride, uint4 *d_dst, size_t dst_stride,
+int ntt_dev(sb_ctx *ctx, const uint4 *d_src, size_t len_in, size_t src_stride, uint4 *d_dst, size_t dst_stride,
                    size_t n_polys, const hfp::el &root, uint32_t log_n, int inverse) {
     const size_t n = (size_t)1 << log_n;
     if (len_in > n) return fail(ctx, SB_ERR_ARG, "vector of %zu elements does not fit a 2^%u transform", len_in, log_n);
@@ -399,7 +274,7 @@ extern "C" int sb_ntt(sb_ctx *ctx, uint64_t *vals, size_t len_in, const uint64_t
     return SB_OK;
 }
 
-static int lde_dev(sb_ctx *ctx, const uint4 *d_cols, size_t n_cols, size_t col_len, size_t col_stride,
+int lde_dev(sb_ctx *ctx, const uint4 *d_cols, size_t n_cols, size_t col_len, size_t col_stride,
                    const hfp::el &root_big, uint32_t log_s, uint32_t log_ext, uint4 *d_out) {
     if (log_s + log_ext > 28) return fail(ctx, SB_ERR_ARG, "extended domain 2^%u exceeds two-adicity 28", log_s + log_ext);
     const size_t S = (size_t)1 << log_s, N = S << log_ext;
@@ -476,26 +351,7 @@ extern "C" int sb_batch_inverse(sb_ctx *ctx, uint64_t *vals, size_t n) {
 // ------------------------------------------------------------------------------------------------
 // Merkle
 // ------------------------------------------------------------------------------------------------
-struct sb_tree {
-    size_t n = 0;
-    uint32_t depth = 0;
-    size_t leaf_bytes = 0;
-    uint4 *d_nodes = nullptr;      // 2n - 1 digests, level l at merkle_level_off(n, l)
-    uint8_t *d_leaves = nullptr;   // owned copy of byte leaves (NULL for column-backed trees)
-    int n_cols = 0;
-    const uint4 *cols[8] = {0};
-    uint8_t root[32] = {0};
-    cudaStream_t stream = nullptr; // allocations are stream-ordered (pool) on the owning context's stream
-};
-
-static bool is_pow2(size_t n) { return n && !(n & (n - 1)); }
-static uint32_t ilog2(size_t n) {
-    uint32_t l = 0;
-    while (((size_t)1 << l) < n) l++;
-    return l;
-}
-
-static void free_tree(sb_tree *t) {
+void free_tree(sb_tree *t) {
     if (!t) return;
     if (t->d_nodes) cudaFreeAsync(t->d_nodes, t->stream);
     if (t->d_leaves) cudaFreeAsync(t->d_leaves, t->stream);
@@ -574,7 +430,25 @@ extern "C" int sb_merkle_commit(sb_ctx *ctx, const void *leaves, size_t leaf_byt
     return SB_OK;
 }
 
-static int commit_cols(sb_ctx *ctx, const uint4 *const *d_cols, size_t n_cols, size_t n, sb_tree **tree) {
+// byte leaves already on the device; the tree takes ownership of d_leaves (allocated with cudaMallocAsync)
+int commit_bytes_owned(sb_ctx *ctx, uint8_t *d_leaves, size_t leaf_bytes, size_t n, sb_tree **tree) {
+    sb_tree *t = nullptr;
+    int rc = tree_new(ctx, n, leaf_bytes, &t);
+    if (rc != SB_OK) {
+        cudaFreeAsync(d_leaves, ctx->stream);
+        return rc;
+    }
+    t->d_leaves = d_leaves;
+    rc = merkle_build(ctx, t);
+    if (rc != SB_OK) {
+        free_tree(t);
+        return rc;
+    }
+    *tree = t;
+    return SB_OK;
+}
+
+int commit_cols(sb_ctx *ctx, const uint4 *const *d_cols, size_t n_cols, size_t n, sb_tree **tree) {
     if (n_cols < 1 || n_cols > 8) return fail(ctx, SB_ERR_ARG, "1..8 columns per leaf supported, got %zu", n_cols);
     sb_tree *t = nullptr;
     TRY(tree_new(ctx, n, 32 * n_cols, &t));
@@ -683,22 +557,7 @@ extern "C" int sb_pseudorandom_indices(const uint8_t *seed, size_t seed_len, uin
 // ------------------------------------------------------------------------------------------------
 // FRI
 // ------------------------------------------------------------------------------------------------
-struct FriLayer {
-    bool is_last = false;
-    uint8_t values_root[32] = {0};      // root of the tree over this layer's values (tap)
-    uint8_t root2[32] = {0};
-    size_t n_column = 0, depth_column = 0, n_poly = 0, depth_poly = 0;
-    std::vector<uint8_t> column_leaves, column_nodes, poly_leaves, poly_nodes;
-    std::vector<uint8_t> last;           // n_last * 32
-};
-struct sb_fri_proof {
-    std::vector<FriLayer> layers;
-};
-
-static const size_t FRI_MIN_DEG_DIRECT = 16;   // fri.rs:14
-static const size_t FRI_QUERIES = 40;          // fri.rs:184
-
-static int fri_prove_dev(sb_ctx *ctx, const uint4 *d_vals, size_t n, const hfp::el &root, size_t max_deg_plus_1, uint32_t excl,
+int fri_prove_dev(sb_ctx *ctx, const uint4 *d_vals, size_t n, const hfp::el &root, size_t max_deg_plus_1, uint32_t excl,
                          const sb_tree *values_tree, sb_fri_proof **out) {
     if (!is_pow2(n)) return fail(ctx, SB_ERR_ARG, "FRI needs a power-of-two number of values, got %zu", n);
     const uint32_t log_n0 = ilog2(n);
@@ -855,7 +714,7 @@ extern "C" int sb_fri_layer_root(const sb_fri_proof *p, size_t i, uint8_t root[3
     return SB_OK;
 }
 
-static void json_bytes(std::string &s, const uint8_t *b, size_t n) {
+void json_bytes(std::string &s, const uint8_t *b, size_t n) {
     char tmp[8];
     s.push_back('[');
     for (size_t i = 0; i < n; i++) {
@@ -866,7 +725,7 @@ static void json_bytes(std::string &s, const uint8_t *b, size_t n) {
     s.push_back(']');
 }
 // Proof{leaf,nodes} (merkle_tree.rs:14-18)
-static void json_branches(std::string &s, const uint8_t *leaves, size_t leaf_bytes, const uint8_t *nodes, size_t depth, size_t count) {
+void json_branches(std::string &s, const uint8_t *leaves, size_t leaf_bytes, const uint8_t *nodes, size_t depth, size_t count) {
     s.push_back('[');
     for (size_t q = 0; q < count; q++) {
         if (q) s.push_back(',');
@@ -881,9 +740,7 @@ static void json_branches(std::string &s, const uint8_t *leaves, size_t leaf_byt
     }
     s.push_back(']');
 }
-extern "C" char *sb_fri_proof_json(const sb_fri_proof *p) {
-    if (!p) return nullptr;
-    std::string s;
+void fri_proof_json_into(std::string &s, const sb_fri_proof *p) {
     s.push_back('[');
     for (size_t i = 0; i < p->layers.size(); i++) {
         const FriLayer &L = p->layers[i];
@@ -906,6 +763,11 @@ extern "C" char *sb_fri_proof_json(const sb_fri_proof *p) {
         }
     }
     s.push_back(']');
+}
+extern "C" char *sb_fri_proof_json(const sb_fri_proof *p) {
+    if (!p) return nullptr;
+    std::string s;
+    fri_proof_json_into(s, p);
     char *r = (char *)malloc(s.size() + 1);
     if (!r) return nullptr;
     memcpy(r, s.c_str(), s.size() + 1);

@@ -1,0 +1,178 @@
+// internal.h -- definitions shared by the host translation units of libstark_b200.so (api.cu, prover.cu).
+// Not part of the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/stark_b200.h"
+#include "blake2s.cuh"
+#include "hostfp.h"
+#include "kernels.h"
+#include "params.h"
+
+struct TwTable {
+    hfp::el root;
+    uint32_t log_n;
+    uint4 *d;
+};
+
+struct sb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint64_t launches = 0;
+    std::vector<TwTable> tables;
+    char err[512] = {0};
+    // optional per-kernel-family timing (sb_profile): CUDA events around every launch
+    bool prof = false;
+    struct ProfRec { int kind; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[SB_KIND_COUNT] = {0};
+    uint64_t prof_n[SB_KIND_COUNT] = {0};
+};
+
+static cudaEvent_t prof_event(sb_ctx *ctx) {
+    cudaEvent_t e;
+    if (!ctx->prof_pool.empty()) {
+        e = ctx->prof_pool.back();
+        ctx->prof_pool.pop_back();
+    } else {
+        cudaEventCreate(&e);
+    }
+    return e;
+}
+static void prof_begin(sb_ctx *ctx, int kind) {
+    if (!ctx->prof) return;
+    sb_ctx::ProfRec r{kind, prof_event(ctx), prof_event(ctx)};
+    cudaEventRecord(r.a, ctx->stream);
+    ctx->prof_recs.push_back(r);
+}
+static void prof_end(sb_ctx *ctx) {
+    if (!ctx->prof) return;
+    cudaEventRecord(ctx->prof_recs.back().b, ctx->stream);
+}
+static void prof_collect(sb_ctx *ctx) {
+    for (auto &r : ctx->prof_recs) {
+        float ms = 0;
+        cudaEventSynchronize(r.b);
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            ctx->prof_ms[r.kind] += ms;
+            ctx->prof_n[r.kind]++;
+        }
+        ctx->prof_pool.push_back(r.a);
+        ctx->prof_pool.push_back(r.b);
+    }
+    ctx->prof_recs.clear();
+}
+#define KLAUNCH(kind, expr)          \
+    do {                             \
+        prof_begin(ctx, kind);       \
+        ctx->launches += (expr);     \
+        prof_end(ctx);               \
+    } while (0)
+
+static int fail(sb_ctx *ctx, int code, const char *fmt, ...) {
+    if (ctx) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(ctx->err, sizeof ctx->err, fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define CU(call)                                                                                    \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? SB_ERR_OOM : SB_ERR_CUDA, "%s: %s (%s:%d)", #call, \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                                \
+    } while (0)
+#define TRY(expr)                \
+    do {                         \
+        int rc_ = (expr);        \
+        if (rc_ != SB_OK) return rc_; \
+    } while (0)
+
+struct DevBuf {   // stream-ordered scratch
+    sb_ctx *ctx;
+    void *p = nullptr;
+    explicit DevBuf(sb_ctx *c) : ctx(c) {}
+    int alloc(size_t bytes) {
+        cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 16, ctx->stream);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return fail(ctx, e == cudaErrorMemoryAllocation ? SB_ERR_OOM : SB_ERR_CUDA, "cudaMallocAsync(%zu): %s", bytes,
+                        cudaGetErrorString(e));
+        }
+        return SB_OK;
+    }
+    ~DevBuf() {
+        if (p) cudaFreeAsync(p, ctx->stream);
+    }
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+};
+
+struct sb_tree {
+    size_t n = 0;
+    uint32_t depth = 0;
+    size_t leaf_bytes = 0;
+    uint4 *d_nodes = nullptr;      // 2n - 1 digests, level l at merkle_level_off(n, l)
+    uint8_t *d_leaves = nullptr;   // owned copy of byte leaves (NULL for column-backed trees)
+    int n_cols = 0;
+    const uint4 *cols[8] = {0};
+    uint8_t root[32] = {0};
+    cudaStream_t stream = nullptr; // allocations are stream-ordered (pool) on the owning context's stream
+};
+
+static bool is_pow2(size_t n) { return n && !(n & (n - 1)); }
+static uint32_t ilog2(size_t n) {
+    uint32_t l = 0;
+    while (((size_t)1 << l) < n) l++;
+    return l;
+}
+
+struct FriLayer {
+    bool is_last = false;
+    uint8_t values_root[32] = {0};      // root of the tree over this layer's values (tap)
+    uint8_t root2[32] = {0};
+    size_t n_column = 0, depth_column = 0, n_poly = 0, depth_poly = 0;
+    std::vector<uint8_t> column_leaves, column_nodes, poly_leaves, poly_nodes;
+    std::vector<uint8_t> last;           // n_last * 32
+};
+struct sb_fri_proof {
+    std::vector<FriLayer> layers;
+};
+
+static const size_t FRI_MIN_DEG_DIRECT = 16;   // fri.rs:14
+static const size_t FRI_QUERIES = 40;          // fri.rs:184
+
+static fp to_dev_fp(const hfp::el &a) {
+    fp r;
+    memcpy(r.l, a.l, 32);
+    return r;
+}
+
+// ---- functions defined in api.cu ---------------------------------------------------------------
+int get_table(sb_ctx *ctx, const hfp::el &w, uint32_t log_n, const uint4 **tw, uint32_t *tw_log_n, uint32_t *log_stride);
+int ntt_dev(sb_ctx *ctx, const uint4 *d_src, size_t len_in, size_t src_stride, uint4 *d_dst, size_t dst_stride, size_t n_polys,
+            const hfp::el &root, uint32_t log_n, int inverse);
+int lde_dev(sb_ctx *ctx, const uint4 *d_cols, size_t n_cols, size_t col_len, size_t col_stride, const hfp::el &root_big,
+            uint32_t log_s, uint32_t log_ext, uint4 *d_out);
+void free_tree(sb_tree *t);
+int commit_bytes_owned(sb_ctx *ctx, uint8_t *d_leaves, size_t leaf_bytes, size_t n, sb_tree **tree);
+int commit_cols(sb_ctx *ctx, const uint4 *const *d_cols, size_t n_cols, size_t n, sb_tree **tree);
+int fri_prove_dev(sb_ctx *ctx, const uint4 *d_vals, size_t n, const hfp::el &root, size_t max_deg_plus_1, uint32_t excl,
+                  const sb_tree *values_tree, sb_fri_proof **out);
+void json_bytes(std::string &s, const uint8_t *b, size_t n);
+void json_branches(std::string &s, const uint8_t *leaves, size_t leaf_bytes, const uint8_t *nodes, size_t depth, size_t count);
+void fri_proof_json_into(std::string &s, const sb_fri_proof *p);

@@ -1,0 +1,226 @@
+// pointwise.cuh -- the element-wise stage of mk_r1cs_proof (r1cs-stark/src/prove.rs:133-232, :287-322)
+// between the NTT and Merkle kernels: constraint quotients, accumulator prefix products, boundary
+// quotients and the 11-term linear combination, all on device-resident columns (Montgomery in memory).
+// Formulas: SURVEY.md A.9; indices are mod N, sk = 8 (EXTENSION_FACTOR, utils.rs:134).
+//
+// inv_z (prove.rs:203, utils.rs:173-178): z[j] = g2^(jS) - 1 takes 8 values because g2^S is a primitive
+// 8th root of unity, so multi_inv(z) is a table of 8 inverses with entry 0 equal to 0 (0 -> 0 rule,
+// poly_utils.rs:38-70); likewise X = (g2^S)^j in the linear combination (prove.rs:287-322).
+#pragma once
+#include "fp.cuh"
+#include "params.h"
+
+struct PwConsts {
+    uint32_t inv_z8[8][8];     // multi_inv(z)[j] for j mod 8
+    uint32_t pw8[8][8];        // (g2^S)^(j mod 8)
+    uint32_t r[3][8];          // accumulator challenges (utils.rs:272-290)
+    uint32_t k[11][8];         // linear-combination challenges (prove.rs:274-283)
+    uint32_t one[8];
+    uint32_t x_last[8];        // xs[N - sk] (utils.rs:459)
+};
+
+__device__ __forceinline__ fp pw_const(const uint32_t (&c)[8]) {
+    fp r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = c[i];
+    return r;
+}
+__device__ __forceinline__ bool pw_is_zero(const fp &a) { return fp_is_zero_canon(fp_canon(a)); }
+
+// out[i] = Fp::from(v[i]) (v == NULL: v[i] = i): the index columns of prove.rs:160-167
+__global__ void pw_u64_to_fp_kernel(const unsigned long long *v, uint4 *out, unsigned long long n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long x = v ? v[i] : (unsigned long long)i;
+    fp a = fp_zero();
+    a.l[0] = (uint32_t)x;
+    a.l[1] = (uint32_t)(x >> 32);
+    fp_stg(out, i, fp_to_mont(a));
+}
+
+// accumulator-tree leaves (utils.rs:250-270): u64_LE(permuted_index[j]) || to_bytes_le(witness_trace[j]), 40 B
+__global__ void pw_a_leaves_kernel(const unsigned long long *perm, const uint4 *wit, uint32_t *leaves, unsigned long long n) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    fp w = fp_from_mont(fp_ldg(wit, j));
+    uint32_t *o = leaves + 10 * j;
+    o[0] = (uint32_t)perm[j];
+    o[1] = (uint32_t)(perm[j] >> 32);
+#pragma unroll
+    for (int i = 0; i < 8; i++) o[2 + i] = w.l[i];
+}
+
+// d1 = q1 * inv_z, d2 = q2 * inv_z  (utils.rs:181-248, :379-418)
+//   q1[j] = f0[j] * (p[j] - f1[j] p[j - sk] - k[j] s[j]);  q2[j] = f2[j] * (p[j + 2 o3 sk] - p[j] p[j + o3 sk])
+struct PwQ12Params {
+    const uint4 *k, *f0, *f1, *f2, *s, *p;
+    uint4 *d1, *d2;
+    unsigned long long n, o3sk;      // o3sk = (original_steps / 3) * sk
+    int *err;                        // set when q != 0 where inv_z == 0 (reference: assert, utils.rs:379-418)
+};
+__global__ void __launch_bounds__(128) pw_q12_kernel(const __grid_constant__ PwQ12Params P, const __grid_constant__ PwConsts Cst) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.n) return;
+    const size_t N = P.n;
+    fp pj = fp_ldg(P.p, j);
+    fp t1 = fp_mul(fp_ldg(P.f1, j), fp_ldg(P.p, (j + N - 8) % N));
+    fp t2 = fp_mul(fp_ldg(P.k, j), fp_ldg(P.s, j));
+    fp q1 = fp_mul(fp_sub(fp_sub(pj, t1), t2), fp_ldg(P.f0, j));
+    fp t3 = fp_mul(pj, fp_ldg(P.p, (j + P.o3sk) % N));
+    fp q2 = fp_mul(fp_sub(fp_ldg(P.p, (j + 2 * P.o3sk) % N), t3), fp_ldg(P.f2, j));
+    fp iz = pw_const(Cst.inv_z8[j & 7]);
+    if ((j & 7) == 0 && !(pw_is_zero(q1) && pw_is_zero(q2))) atomicExch(P.err, 1);
+    fp_stg(P.d1, j, fp_canon(fp_mul(q1, iz)));
+    fp_stg(P.d2, j, fp_canon(fp_mul(q2, iz)));
+}
+
+// accumulator factors (utils.rs:293-339): nmr_j = r0 + r1*j + r2*w_j, dnm_j = r0 + r1*perm[j] + r2*w_j
+// (the reference reads j and perm[j] back from the index LDEs at j*sk, where they equal the inputs)
+__global__ void __launch_bounds__(128) pw_acc_terms_kernel(const unsigned long long *perm, const uint4 *wit, uint4 *nmr, uint4 *dnm,
+                                                          unsigned long long n, const __grid_constant__ PwConsts Cst) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    fp r0 = pw_const(Cst.r[0]), r1 = pw_const(Cst.r[1]), r2 = pw_const(Cst.r[2]);
+    fp a = fp_zero(), b = fp_zero();
+    a.l[0] = (uint32_t)j; a.l[1] = (uint32_t)((unsigned long long)j >> 32);
+    b.l[0] = (uint32_t)perm[j]; b.l[1] = (uint32_t)(perm[j] >> 32);
+    fp t2 = fp_mul(r2, fp_ldg(wit, j));
+    fp vn = fp_add(fp_add(r0, fp_mul(r1, fp_to_mont(a))), t2);
+    fp vd = fp_add(fp_add(r0, fp_mul(r1, fp_to_mont(b))), t2);
+    fp_stg(nmr, j, fp_canon(vn));
+    fp_stg(dnm, j, fp_canon(vd));
+}
+
+// ---- inclusive prefix product over n elements in three launches ------------------------------------
+// chunk c = elements [c*len, (c+1)*len): (1) per-chunk products, (2) exclusive scan of the chunk products
+// in one CTA, (3) per-chunk rescan seeded with the chunk's prefix.
+__global__ void __launch_bounds__(128) scan_chunk_reduce_kernel(const uint4 *in, uint4 *partial, unsigned long long n, unsigned long long len) {
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t lo = c * len;
+    if (lo >= n) return;
+    const size_t hi = lo + len < n ? lo + len : n;
+    fp acc = fp_ldg(in, lo);
+    for (size_t i = lo + 1; i < hi; i++) acc = fp_mul(acc, fp_ldg(in, i));
+    fp_stg(partial, c, fp_canon(acc));
+}
+// in place: partial[c] <- product of partial[0..c) (exclusive), n_chunks <= 1024 * per
+__global__ void __launch_bounds__(1024) scan_partials_kernel(uint4 *partial, unsigned long long n_chunks) {
+    __shared__ uint4 s[2048];
+    const unsigned t = threadIdx.x;
+    const size_t per = (n_chunks + 1023) / 1024;
+    const size_t lo = t * per, hi = lo + per < n_chunks ? lo + per : n_chunks;
+    fp acc = fp_one();
+    for (size_t i = lo; i < hi; i++) acc = fp_mul(acc, fp_ldg(partial, i));
+    acc = fp_canon(acc);
+    s[2 * t] = fp_lo(acc); s[2 * t + 1] = fp_hi(acc);
+    __syncthreads();
+    for (unsigned d = 1; d < 1024; d <<= 1) {        // Hillis-Steele inclusive scan of the 1024 thread totals
+        fp v = fp_from_u4(s[2 * t], s[2 * t + 1]);
+        fp u = v;
+        if (t >= d) u = fp_canon(fp_mul(fp_from_u4(s[2 * (t - d)], s[2 * (t - d) + 1]), v));
+        __syncthreads();
+        s[2 * t] = fp_lo(u); s[2 * t + 1] = fp_hi(u);
+        __syncthreads();
+    }
+    fp pre = t ? fp_from_u4(s[2 * (t - 1)], s[2 * (t - 1) + 1]) : fp_one();
+    for (size_t i = lo; i < hi; i++) {
+        fp v = fp_ldg(partial, i);
+        fp_stg(partial, i, fp_canon(pre));
+        pre = fp_mul(pre, v);
+    }
+}
+__global__ void __launch_bounds__(128) scan_chunk_apply_kernel(const uint4 *in, const uint4 *partial_excl, uint4 *out, unsigned long long n,
+                                                              unsigned long long len) {
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t lo = c * len;
+    if (lo >= n) return;
+    const size_t hi = lo + len < n ? lo + len : n;
+    fp acc = fp_ldg(partial_excl, c);
+    for (size_t i = lo; i < hi; i++) {
+        acc = fp_mul(acc, fp_ldg(in, i));
+        fp_stg(out, i, fp_canon(acc));
+    }
+}
+
+// out[i] = a[i] * b[i]
+__global__ void __launch_bounds__(128) pw_mul_kernel(const uint4 *a, const uint4 *b, uint4 *out, unsigned long long n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fp_stg(out, i, fp_canon(fp_mul(fp_ldg(a, i), fp_ldg(b, i))));
+}
+
+// d3 = q3 * inv_z (utils.rs:344-376): q3[j] = a[j] (r0 + r1 pidx[j] + r2 s[j]) - a[j - sk] (r0 + r1 idx[j] + r2 s[j])
+struct PwQ3Params {
+    const uint4 *a, *s, *idx, *pidx;
+    uint4 *d3;
+    unsigned long long n;
+    int *err;
+};
+__global__ void __launch_bounds__(128) pw_q3_kernel(const __grid_constant__ PwQ3Params P, const __grid_constant__ PwConsts Cst) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.n) return;
+    const size_t N = P.n;
+    fp r0 = pw_const(Cst.r[0]), r1 = pw_const(Cst.r[1]), r2 = pw_const(Cst.r[2]);
+    fp t2 = fp_mul(r2, fp_ldg(P.s, j));
+    fp vn = fp_add(fp_add(r0, fp_mul(r1, fp_ldg(P.idx, j))), t2);
+    fp vd = fp_add(fp_add(r0, fp_mul(r1, fp_ldg(P.pidx, j))), t2);
+    fp u = fp_mul(fp_ldg(P.a, j), vd);
+    fp v = fp_mul(fp_ldg(P.a, (j + N - 8) % N), vn);
+    fp q3 = fp_sub(u, v);
+    if ((j & 7) == 0 && !pw_is_zero(q3)) atomicExch(P.err, 1);
+    fp_stg(P.d3, j, fp_canon(fp_mul(q3, pw_const(Cst.inv_z8[j & 7]))));
+}
+
+// zb3[j] = xs[j] - xs[N - sk] (utils.rs:458-474), written behind zb2 so that one batch inverse serves both
+__global__ void __launch_bounds__(128) pw_zb3_kernel(const uint4 *xs, uint4 *zb3, unsigned long long n, const __grid_constant__ PwConsts Cst) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    fp_stg(zb3, j, fp_canon(fp_sub(fp_ldg(xs, j), pw_const(Cst.x_last))));
+}
+
+// b2 = (s - i2) * inv(zb2), b3 = (a - 1) * inv(zb3)  (utils.rs:477-524); in place over the inverse arrays
+struct PwB23Params {
+    const uint4 *s, *a, *i2;     // i2 == NULL: the interpolant is the zero polynomial (no public wire in use)
+    uint4 *inv_zb2, *inv_zb3;    // in: inverses, out: b2, b3
+    unsigned long long n;
+    int *err;
+};
+__global__ void __launch_bounds__(128) pw_b23_kernel(const __grid_constant__ PwB23Params P, const __grid_constant__ PwConsts Cst) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.n) return;
+    fp i2 = P.i2 ? fp_ldg(P.i2, j) : fp_zero();
+    fp df2 = fp_sub(fp_ldg(P.s, j), i2);
+    fp inv2 = fp_ldg(P.inv_zb2, j);
+    if (pw_is_zero(inv2) && !pw_is_zero(df2)) atomicExch(P.err, 2);     // utils.rs:489
+    fp_stg(P.inv_zb2, j, fp_canon(fp_mul(df2, inv2)));
+    fp df3 = fp_sub(fp_ldg(P.a, j), pw_const(Cst.one));
+    fp inv3 = fp_ldg(P.inv_zb3, j);
+    if (pw_is_zero(inv3) && !pw_is_zero(df3)) atomicExch(P.err, 3);     // utils.rs:514
+    fp_stg(P.inv_zb3, j, fp_canon(fp_mul(df3, inv3)));
+}
+
+// l[j] = k0 d1 + k1 d2 + k2 d3 + k3 p + k4 p X + k5 b2 + k6 b2 X + k7 b3 + k8 b3 X + k9 a + k10 s,  X = (g2^S)^j
+// (prove.rs:287-322)
+struct PwLParams {
+    const uint4 *d1, *d2, *d3, *p, *b2, *b3, *a, *s;
+    uint4 *l;
+    unsigned long long n;
+};
+__global__ void __launch_bounds__(128) pw_l_kernel(const __grid_constant__ PwLParams P, const __grid_constant__ PwConsts Cst) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.n) return;
+    fp X = pw_const(Cst.pw8[j & 7]);
+    fp pj = fp_ldg(P.p, j), b2 = fp_ldg(P.b2, j), b3 = fp_ldg(P.b3, j);
+    fp acc = fp_mul(fp_ldg(P.d1, j), pw_const(Cst.k[0]));
+    acc = fp_add(acc, fp_mul(fp_ldg(P.d2, j), pw_const(Cst.k[1])));
+    acc = fp_add(acc, fp_mul(fp_ldg(P.d3, j), pw_const(Cst.k[2])));
+    acc = fp_add(acc, fp_mul(pj, pw_const(Cst.k[3])));
+    acc = fp_add(acc, fp_mul(fp_mul(pj, pw_const(Cst.k[4])), X));
+    acc = fp_add(acc, fp_mul(b2, pw_const(Cst.k[5])));
+    acc = fp_add(acc, fp_mul(fp_mul(b2, pw_const(Cst.k[6])), X));
+    acc = fp_add(acc, fp_mul(b3, pw_const(Cst.k[7])));
+    acc = fp_add(acc, fp_mul(fp_mul(b3, pw_const(Cst.k[8])), X));
+    acc = fp_add(acc, fp_mul(fp_ldg(P.a, j), pw_const(Cst.k[9])));
+    acc = fp_add(acc, fp_mul(fp_ldg(P.s, j), pw_const(Cst.k[10])));
+    fp_stg(P.l, j, fp_canon(acc));
+}

@@ -1,0 +1,442 @@
+// prover.cu -- device-resident mk_r1cs_proof (r1cs-stark/src/prove.rs:14-378): the caller of the hot path,
+// so that only the traces go in and only roots / openings / the FRI proof come out.
+// Stage order and every formula follow the reference; citations are to r1cs-stark/src/prove.rs unless noted.
+#include "internal.h"
+#include "pointwise.cuh"
+
+static const uint32_t EXTENSION_FACTOR = 8, LOG_EXTENSION_FACTOR = 3;    // utils.rs:134-135
+static const size_t SPOT_CHECK_SECURITY_FACTOR = 80;                     // utils.rs:136
+
+struct sb_stark_proof {
+    uint8_t m_root[32], l_root[32], a_root[32];
+    size_t depth = 0;                                       // log2(precision)
+    std::vector<uint8_t> main_leaves, main_nodes;           // 320 openings of the m_tree (256-byte leaves)
+    std::vector<uint8_t> lc_leaves, lc_nodes;               // 80 openings of the l_tree (32-byte leaves)
+    sb_fri_proof *fri = nullptr;
+    double stage_ms[5] = {0, 0, 0, 0, 0};                   // lde, merkle, fri, pointwise, total (CUDA events / host clock)
+    ~sb_stark_proof() { delete fri; }
+};
+
+static unsigned nblk(size_t n, unsigned t = 128) { return (unsigned)((n + t - 1) / t); }
+
+// utils.rs:14-23: named log2_ceil, really floor(log2 v) + 1
+static uint32_t log2_ceil_quirk(size_t v) {
+    uint32_t l = 1;
+    while (v > 1) {
+        v /= 2;
+        l++;
+    }
+    return l;
+}
+
+// inclusive prefix product of n elements, in place allowed (out may equal in)
+static int prefix_product(sb_ctx *ctx, const uint4 *in, uint4 *out, size_t n) {
+    size_t len = 64;
+    while ((n + len - 1) / len > 1024 * 64) len *= 2;
+    const size_t chunks = (n + len - 1) / len;
+    DevBuf part(ctx);
+    TRY(part.alloc(chunks * 32));
+    prof_begin(ctx, SB_KIND_OTHER);
+    scan_chunk_reduce_kernel<<<nblk(chunks), 128, 0, ctx->stream>>>(in, (uint4 *)part.p, n, len);
+    scan_partials_kernel<<<1, 1024, 0, ctx->stream>>>((uint4 *)part.p, chunks);
+    scan_chunk_apply_kernel<<<nblk(chunks), 128, 0, ctx->stream>>>(in, (const uint4 *)part.p, out, n, len);
+    prof_end(ctx);
+    ctx->launches += 3;
+    CU(cudaGetLastError());
+    return SB_OK;
+}
+
+// host: coefficients of the interpolant through (xs[i], ys[i]) (poly_utils.rs:409-439) and of
+// prod (X - xs[i]) (poly_utils.rs:362-373).  O(n^2) scalar work, n = number of public wires in use.
+static void host_zpoly(std::vector<hfp::el> &root, const std::vector<hfp::el> &xs) {
+    root.assign(1, hfp::ONE);
+    for (const auto &x : xs) {
+        root.insert(root.begin(), hfp::ZERO);                       // multiply by X
+        for (size_t j = 0; j + 1 < root.size(); j++) root[j] = hfp::add(root[j], hfp::neg(hfp::mul(root[j + 1], x)));
+    }
+}
+static void host_lagrange(std::vector<hfp::el> &out, const std::vector<hfp::el> &xs, const std::vector<hfp::el> &ys) {
+    const size_t n = xs.size();
+    out.assign(n, hfp::ZERO);
+    if (!n) return;
+    std::vector<hfp::el> root;
+    host_zpoly(root, xs);                                          // degree n, root[n] = 1
+    std::vector<hfp::el> num(n);
+    for (size_t i = 0; i < n; i++) {
+        // num = root / (X - xs[i]) by synthetic division, denom = num(xs[i])
+        num[n - 1] = root[n];
+        for (size_t j = n - 1; j-- > 0;) num[j] = hfp::add(root[j + 1], hfp::mul(num[j + 1], xs[i]));
+        hfp::el denom = hfp::ZERO;
+        for (size_t j = n; j-- > 0;) denom = hfp::add(hfp::mul(denom, xs[i]), num[j]);
+        hfp::el scale = hfp::mul(ys[i], hfp::inv(denom));
+        for (size_t j = 0; j < n; j++) out[j] = hfp::add(out[j], hfp::mul(num[j], scale));
+    }
+}
+
+static void put_const(uint32_t (&dst)[8], const hfp::el &v) { memcpy(dst, v.l, 32); }
+
+extern "C" int sb_prove_r1cs(sb_ctx *ctx, const sb_trace *t, sb_stark_proof **out) {
+    if (!ctx || !t || !out) return SB_ERR_ARG;
+    const size_t os = t->original_steps;
+    if (os == 0 || os % 3 != 0) return fail(ctx, SB_ERR_ARG, "original_steps %zu must be a positive multiple of 3", os);   // :33
+    if (!t->witness_trace || !t->computational_trace || !t->coefficients || !t->flag0 || !t->flag1 || !t->flag2 || !t->permuted_indices)
+        return fail(ctx, SB_ERR_ARG, "missing trace array");
+    // :37-53 sizes
+    const uint32_t log_steps = log2_ceil_quirk(os - 1);
+    size_t S = (size_t)1 << log_steps;
+    if (S < 8) return fail(ctx, SB_ERR_ARG, "traces shorter than 8 steps hit the reference's unpatched log_steps (prove.rs:39-41)");
+    const uint32_t log_prec = log_steps + LOG_EXTENSION_FACTOR;
+    if (log_prec > 28) return fail(ctx, SB_ERR_ARG, "precision 2^%u exceeds the field's two-adicity (prove.rs:51-53)", log_prec);
+    const size_t N = S * EXTENSION_FACTOR, sk = EXTENSION_FACTOR, o3 = os / 3;
+    if (N >= ((size_t)1 << 24)) return fail(ctx, SB_ERR_ARG, "precision 2^%u: the sampler asserts modulus < 2^24 (fri/src/utils.rs:88)", log_prec);
+    if (os > S) return fail(ctx, SB_ERR_ARG, "internal: steps < original_steps");
+
+    cudaEvent_t ev[8];
+    for (auto &e : ev) cudaEventCreate(&e);
+    auto mark = [&](int i) { cudaEventRecord(ev[i], ctx->stream); };
+    sb_stark_proof *proof = new sb_stark_proof();
+    proof->depth = log_prec;
+    std::vector<sb_tree *> trees;
+    int rc = SB_OK;
+    struct Cleanup {
+        std::vector<sb_tree *> &trees;
+        cudaEvent_t *ev;
+        ~Cleanup() {
+            for (auto x : trees) free_tree(x);
+            for (int i = 0; i < 8; i++) cudaEventDestroy(ev[i]);
+        }
+    } cleanup{trees, ev};
+#define PTRY(expr)                 \
+    do {                           \
+        rc = (expr);               \
+        if (rc != SB_OK) {         \
+            delete proof;          \
+            return rc;             \
+        }                          \
+    } while (0)
+#define PCU(call)                                                                                              \
+    do {                                                                                                       \
+        cudaError_t e_ = (call);                                                                               \
+        if (e_ != cudaSuccess) {                                                                               \
+            delete proof;                                                                                      \
+            return fail(ctx, SB_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+        }                                                                                                      \
+    } while (0)
+
+    // :71-94 roots of unity: g2 = 7^((p-1)/N); the N-entry power table doubles as `xs`
+    hfp::el g2;
+    {
+        uint64_t e[4] = {hfp::PMOD[0] - 1, hfp::PMOD[1], hfp::PMOD[2], hfp::PMOD[3]};   // (p - 1) >> log_prec
+        for (uint32_t i = 0; i < log_prec; i++) {
+            for (int k = 0; k < 3; k++) e[k] = (e[k] >> 1) | (e[k + 1] << 63);
+            e[3] >>= 1;
+        }
+        g2 = hfp::pow_limbs(hfp::from_u64(7), e, 4);
+    }
+    const uint4 *xs;
+    uint32_t tw_log_n, tw_stride;
+    PTRY(get_table(ctx, g2, log_prec, &xs, &tw_log_n, &tw_stride));
+    if (tw_stride != 0) {
+        delete proof;
+        return fail(ctx, SB_ERR_ARG, "internal: power table of g2 must have stride 1");
+    }
+    auto host_xs = [&](size_t i, hfp::el *v) -> cudaError_t {   // xs[i] fetched from the device table (a few scalars only)
+        cudaError_t e = cudaMemcpyAsync(v, (const uint8_t *)xs + 32 * i, 32, cudaMemcpyDeviceToHost, ctx->stream);
+        return e == cudaSuccess ? cudaStreamSynchronize(ctx->stream) : e;
+    };
+
+    // ---- device buffers ------------------------------------------------------------------------------
+    // in8: the eight S-point input columns K F0 F1 F2 S P idx pidx (zero padded, :55-68, :105-113)
+    // ev : nine N-point LDE columns, same order + A;  q : d1 d2 d3 b2 b3 l
+    DevBuf in8(ctx), evb(ctx), qb(ctx), perm_d(ctx), amini(ctx), err_d(ctx);
+    PTRY(in8.alloc(8 * S * 32));
+    PTRY(evb.alloc(9 * N * 32));
+    PTRY(qb.alloc(6 * N * 32));
+    PTRY(perm_d.alloc(S * 8));
+    PTRY(amini.alloc(3 * S * 32));
+    PTRY(err_d.alloc(sizeof(int)));
+    auto in_col = [&](int c) { return (uint4 *)in8.p + 2 * (size_t)c * S; };
+    auto ev_col = [&](int c) { return (uint4 *)evb.p + 2 * (size_t)c * N; };
+    auto q_col = [&](int c) { return (uint4 *)qb.p + 2 * (size_t)c * N; };
+    enum { K_ = 0, F0_, F1_, F2_, S_, P_, IDX_, PIDX_, A_ };
+    enum { D1_ = 0, D2_, D3_, B2_, B3_, L_ };
+
+    mark(0);
+    PCU(cudaMemsetAsync(in8.p, 0, 8 * S * 32, ctx->stream));
+    PCU(cudaMemsetAsync(err_d.p, 0, sizeof(int), ctx->stream));
+    const uint64_t *srcs[6] = {t->coefficients, t->flag0, t->flag1, t->flag2, t->witness_trace, t->computational_trace};
+    for (int c = 0; c < 6; c++) PCU(cudaMemcpyAsync(in_col(c), srcs[c], os * 32, cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<unsigned long long> perm(S);
+    for (size_t i = 0; i < os; i++) {
+        if (t->permuted_indices[i] >= S) {
+            delete proof;
+            return fail(ctx, SB_ERR_ARG, "permuted index out of range");
+        }
+        perm[i] = t->permuted_indices[i];
+    }
+    for (size_t i = os; i < S; i++) perm[i] = i;                                                    // :55-56
+    PCU(cudaMemcpyAsync(perm_d.p, perm.data(), S * 8, cudaMemcpyHostToDevice, ctx->stream));
+    pw_u64_to_fp_kernel<<<nblk(S), 128, 0, ctx->stream>>>(nullptr, in_col(IDX_), S);                 // :160-163
+    pw_u64_to_fp_kernel<<<nblk(S), 128, 0, ctx->stream>>>((const unsigned long long *)perm_d.p, in_col(PIDX_), S);
+    ctx->launches += 2;
+
+    // :100-124, :160-167 the eight LDEs in one batch
+    PTRY(lde_dev(ctx, in_col(0), 8, S, S, g2, log_steps, LOG_EXTENSION_FACTOR, ev_col(0)));
+    mark(1);
+
+    // ---- constants of the pointwise stage ---------------------------------------------------------------
+    PwConsts Cst;
+    memset(&Cst, 0, sizeof Cst);
+    hfp::el gs, x_last;
+    PCU(host_xs(S, &gs));                   // g2^S: primitive 8th root of unity (:287-290)
+    PCU(host_xs(N - sk, &x_last));          // utils.rs:459
+    {
+        hfp::el pw = hfp::ONE;
+        for (int i = 0; i < 8; i++) {
+            put_const(Cst.pw8[i], pw);
+            hfp::el z = hfp::add(pw, hfp::neg(hfp::ONE));                   // z[j] = g2^(jS) - 1 (utils.rs:173-178)
+            put_const(Cst.inv_z8[i], hfp::is_zero(z) ? hfp::ZERO : hfp::inv(z));   // multi_inv: 0 -> 0
+            pw = hfp::mul(pw, gs);
+        }
+        put_const(Cst.one, hfp::ONE);
+        put_const(Cst.x_last, x_last);
+    }
+
+    // :133-151 + :203-214 (d1, d2)
+    {
+        PwQ12Params P;
+        P.k = ev_col(K_); P.f0 = ev_col(F0_); P.f1 = ev_col(F1_); P.f2 = ev_col(F2_); P.s = ev_col(S_); P.p = ev_col(P_);
+        P.d1 = q_col(D1_); P.d2 = q_col(D2_);
+        P.n = N; P.o3sk = o3 * sk; P.err = (int *)err_d.p;
+        pw_q12_kernel<<<nblk(N), 128, 0, ctx->stream>>>(P, Cst);
+        ctx->launches++;
+    }
+
+    // :171 a_root (utils.rs:250-270): S leaves of 40 bytes
+    sb_tree *a_tree = nullptr;
+    {
+        uint8_t *d_leaves = nullptr;
+        PCU(cudaMallocAsync(&d_leaves, S * 40, ctx->stream));
+        pw_a_leaves_kernel<<<nblk(S), 128, 0, ctx->stream>>>((const unsigned long long *)perm_d.p, in_col(S_), (uint32_t *)d_leaves, S);
+        ctx->launches++;
+        rc = commit_bytes_owned(ctx, d_leaves, 40, S, &a_tree);
+        if (rc != SB_OK) {
+            delete proof;
+            return rc;
+        }
+        trees.push_back(a_tree);
+        memcpy(proof->a_root, a_tree->root, 32);
+    }
+    // :172 r = get_random_ff_values(a_root, precision, 3, 0) (utils.rs:272-290)
+    {
+        uint32_t idx[24];
+        if (sb_pseudorandom_indices(proof->a_root, 32, (uint32_t)N, 24, 0, idx) != SB_OK) {
+            delete proof;
+            return fail(ctx, SB_ERR_ARG, "sampler rejected precision %zu", N);
+        }
+        for (int i = 0; i < 3; i++) {
+            uint8_t b[32];
+            for (int j = 0; j < 8; j++) {     // utils.rs:29-38: each u32 big-endian, the 32 bytes then read little-endian
+                uint32_t v = idx[8 * i + j];
+                b[4 * j] = (uint8_t)(v >> 24); b[4 * j + 1] = (uint8_t)(v >> 16); b[4 * j + 2] = (uint8_t)(v >> 8); b[4 * j + 3] = (uint8_t)v;
+            }
+            put_const(Cst.r[i], hfp::from_bytes_le32(b));
+        }
+    }
+    // :175-184 accumulator (utils.rs:293-339) and its LDE
+    {
+        uint4 *nmr = (uint4 *)amini.p, *dnm = nmr + 2 * S, *am = dnm + 2 * S;
+        pw_acc_terms_kernel<<<nblk(S), 128, 0, ctx->stream>>>((const unsigned long long *)perm_d.p, in_col(S_), nmr, dnm, S, Cst);
+        ctx->launches++;
+        PTRY(prefix_product(ctx, nmr, nmr, S));
+        PTRY(prefix_product(ctx, dnm, dnm, S));
+        PTRY(sb_batch_inverse_dev(ctx, (uint64_t *)dnm, S));
+        pw_mul_kernel<<<nblk(S), 128, 0, ctx->stream>>>(nmr, dnm, am, S);
+        ctx->launches++;
+        mark(2);
+        PTRY(lde_dev(ctx, am, 1, S, S, g2, log_steps, LOG_EXTENSION_FACTOR, ev_col(A_)));
+        mark(3);
+    }
+    // :192-214 d3
+    {
+        PwQ3Params P;
+        P.a = ev_col(A_); P.s = ev_col(S_); P.idx = ev_col(IDX_); P.pidx = ev_col(PIDX_);
+        P.d3 = q_col(D3_); P.n = N; P.err = (int *)err_d.p;
+        pw_q3_kernel<<<nblk(N), 128, 0, ctx->stream>>>(P, Cst);
+        ctx->launches++;
+    }
+    // :216-232 boundary quotients.  i2 and zb2 are polynomials of degree < n_pub evaluated on the whole domain:
+    // the reference does that with eval_poly_at / a product per point (O(N n_pub)); an N-point NTT of the same
+    // coefficients gives the same field elements.
+    {
+        const size_t np = t->n_pfi;
+        if (np + 1 > N) {
+            delete proof;
+            return fail(ctx, SB_ERR_ARG, "more public wires than domain points");
+        }
+        std::vector<hfp::el> xv(np), yv(np), interp, zroot;
+        for (size_t i = 0; i < np; i++) {       // utils.rs:421-435
+            if (t->pfi_w[i] >= S || t->pfi_k[i] >= t->n_public) {
+                delete proof;
+                return fail(ctx, SB_ERR_ARG, "public_first_indices out of range");
+            }
+            yv[i] = hfp::from_limbs(t->public_wires + 4 * t->pfi_k[i]);
+        }
+        if (np) {
+            std::vector<unsigned long long> pos(np);
+            for (size_t i = 0; i < np; i++) pos[i] = sk * t->pfi_w[i];
+            DevBuf dpos(ctx), dx(ctx);
+            PTRY(dpos.alloc(np * 8));
+            PTRY(dx.alloc(np * 32));
+            PCU(cudaMemcpyAsync(dpos.p, pos.data(), np * 8, cudaMemcpyHostToDevice, ctx->stream));
+            ctx->launches += merkle_launch_gather_bytes(ctx->stream, (const uint8_t *)xs, 32, (const unsigned long long *)dpos.p, (uint32_t)np,
+                                                        (uint8_t *)dx.p);
+            PCU(cudaMemcpyAsync(xv.data(), dx.p, np * 32, cudaMemcpyDeviceToHost, ctx->stream));
+            PCU(cudaStreamSynchronize(ctx->stream));
+        }
+        host_lagrange(interp, xv, yv);
+        host_zpoly(zroot, xv);
+        DevBuf coef(ctx), i2b(ctx);
+        PTRY(coef.alloc((2 * np + 1) * 32));
+        uint4 *zb2 = q_col(B2_), *zb3 = q_col(B3_);          // B2_ and B3_ are adjacent: one 2N batch inverse
+        if (np) PCU(cudaMemcpyAsync(coef.p, interp.data(), np * 32, cudaMemcpyHostToDevice, ctx->stream));
+        PCU(cudaMemcpyAsync((uint8_t *)coef.p + np * 32, zroot.data(), (np + 1) * 32, cudaMemcpyHostToDevice, ctx->stream));
+        if (np) {
+            PTRY(i2b.alloc(N * 32));
+            PTRY(ntt_dev(ctx, (const uint4 *)coef.p, np, np, (uint4 *)i2b.p, N, 1, g2, log_prec, 0));
+        }
+        PTRY(ntt_dev(ctx, (const uint4 *)coef.p + 2 * np, np + 1, np + 1, zb2, N, 1, g2, log_prec, 0));
+        pw_zb3_kernel<<<nblk(N), 128, 0, ctx->stream>>>(xs, zb3, N, Cst);
+        ctx->launches++;
+        PTRY(sb_batch_inverse_dev(ctx, (uint64_t *)zb2, 2 * N));
+        PwB23Params P;
+        P.s = ev_col(S_); P.a = ev_col(A_); P.i2 = np ? (const uint4 *)i2b.p : nullptr;
+        P.inv_zb2 = zb2; P.inv_zb3 = zb3; P.n = N; P.err = (int *)err_d.p;
+        pw_b23_kernel<<<nblk(N), 128, 0, ctx->stream>>>(P, Cst);
+        ctx->launches++;
+    }
+    // the reference's asserts (utils.rs:379-418, :489, :514) -> error code
+    {
+        int err = 0;
+        PCU(cudaMemcpyAsync(&err, err_d.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        PCU(cudaStreamSynchronize(ctx->stream));
+        PCU(cudaGetLastError());
+        if (err) {
+            delete proof;
+            return fail(ctx, SB_ERR_ARG, err == 1 ? "invalid D1/D2/D3: the witness does not satisfy the constraints (utils.rs:379-418)"
+                                                  : (err == 2 ? "invalid B2: public wires do not match the trace (utils.rs:489)" : "invalid B3 (utils.rs:514)"));
+        }
+    }
+    mark(4);
+    // :235-264 m_tree over p a s d1 d2 d3 b2 b3
+    sb_tree *m_tree = nullptr;
+    {
+        const uint4 *cols[8] = {ev_col(P_), ev_col(A_), ev_col(S_), q_col(D1_), q_col(D2_), q_col(D3_), q_col(B2_), q_col(B3_)};
+        PTRY(commit_cols(ctx, cols, 8, N, &m_tree));
+        trees.push_back(m_tree);
+        memcpy(proof->m_root, m_tree->root, 32);
+    }
+    mark(5);
+    // :274-283 k[i] = int_BE(blake(m_root || i)) mod p
+    put_const(Cst.k[0], hfp::ONE);
+    for (int i = 1; i < 11; i++) {
+        uint8_t msg[33], h[32], le[32];
+        memcpy(msg, proof->m_root, 32);
+        msg[32] = (uint8_t)i;
+        b2s::hash_bytes(h, msg, 33);
+        for (int b = 0; b < 32; b++) le[b] = h[31 - b];
+        put_const(Cst.k[i], hfp::from_bytes_le32(le));
+    }
+    // :287-322 l
+    {
+        PwLParams P;
+        P.d1 = q_col(D1_); P.d2 = q_col(D2_); P.d3 = q_col(D3_); P.p = ev_col(P_); P.b2 = q_col(B2_); P.b3 = q_col(B3_);
+        P.a = ev_col(A_); P.s = ev_col(S_); P.l = q_col(L_); P.n = N;
+        pw_l_kernel<<<nblk(N), 128, 0, ctx->stream>>>(P, Cst);
+        ctx->launches++;
+    }
+    // :324-332 l_tree
+    sb_tree *l_tree = nullptr;
+    {
+        const uint4 *cols[1] = {q_col(L_)};
+        PTRY(commit_cols(ctx, cols, 1, N, &l_tree));
+        trees.push_back(l_tree);
+        memcpy(proof->l_root, l_tree->root, 32);
+    }
+    // :337-362 spot-check positions and openings
+    {
+        uint32_t pos32[SPOT_CHECK_SECURITY_FACTOR];
+        if (sb_pseudorandom_indices(proof->l_root, 32, (uint32_t)N, SPOT_CHECK_SECURITY_FACTOR, (uint32_t)sk, pos32) != SB_OK) {
+            delete proof;
+            return fail(ctx, SB_ERR_ARG, "sampler rejected precision %zu", N);
+        }
+        std::vector<size_t> positions(SPOT_CHECK_SECURITY_FACTOR), aug(4 * SPOT_CHECK_SECURITY_FACTOR);
+        for (size_t i = 0; i < SPOT_CHECK_SECURITY_FACTOR; i++) {
+            const size_t j = positions[i] = pos32[i];
+            aug[4 * i + 0] = j;
+            aug[4 * i + 1] = (j + N - sk) % N;
+            aug[4 * i + 2] = (j + o3 * sk) % N;
+            aug[4 * i + 3] = (j + o3 * 2 * sk) % N;
+        }
+        proof->lc_leaves.resize(positions.size() * 32);
+        proof->lc_nodes.resize(positions.size() * log_prec * 32);
+        PTRY(sb_merkle_open(ctx, l_tree, positions.data(), positions.size(), proof->lc_leaves.data(), proof->lc_nodes.data()));
+        proof->main_leaves.resize(aug.size() * 256);
+        proof->main_nodes.resize(aug.size() * log_prec * 32);
+        PTRY(sb_merkle_open(ctx, m_tree, aug.data(), aug.size(), proof->main_leaves.data(), proof->main_nodes.data()));
+    }
+    mark(6);
+    // :367 FRI on l with the committed l_tree
+    PTRY(fri_prove_dev(ctx, q_col(L_), N, g2, N / 4, (uint32_t)sk, l_tree, &proof->fri));
+    mark(7);
+    PCU(cudaStreamSynchronize(ctx->stream));
+    float ms;
+    auto span = [&](int a, int b) { return cudaEventElapsedTime(&ms, ev[a], ev[b]) == cudaSuccess ? (double)ms : 0.0; };
+    proof->stage_ms[0] = span(0, 1) + span(2, 3);
+    proof->stage_ms[1] = span(4, 5);
+    proof->stage_ms[2] = span(6, 7);
+    proof->stage_ms[4] = span(0, 7);
+    proof->stage_ms[3] = proof->stage_ms[4] - proof->stage_ms[0] - proof->stage_ms[1] - proof->stage_ms[2];
+    *out = proof;
+    return SB_OK;
+#undef PTRY
+#undef PCU
+}
+
+extern "C" int sb_stark_proof_roots(const sb_stark_proof *p, uint8_t m_root[32], uint8_t l_root[32], uint8_t a_root[32]) {
+    if (!p) return SB_ERR_ARG;
+    if (m_root) memcpy(m_root, p->m_root, 32);
+    if (l_root) memcpy(l_root, p->l_root, 32);
+    if (a_root) memcpy(a_root, p->a_root, 32);
+    return SB_OK;
+}
+extern "C" int sb_stark_proof_stage_ms(const sb_stark_proof *p, double ms[5]) {
+    if (!p || !ms) return SB_ERR_ARG;
+    memcpy(ms, p->stage_ms, sizeof p->stage_ms);
+    return SB_OK;
+}
+// serde_json::to_string(&StarkProof) (utils.rs:122-130 field order; run.rs:549 compact)
+extern "C" char *sb_stark_proof_json(const sb_stark_proof *p, size_t *len) {
+    if (!p) return nullptr;
+    std::string s;
+    s.reserve((size_t)3 << 20);
+    s += "{\"m_root\":";
+    json_bytes(s, p->m_root, 32);
+    s += ",\"l_root\":";
+    json_bytes(s, p->l_root, 32);
+    s += ",\"a_root\":";
+    json_bytes(s, p->a_root, 32);
+    s += ",\"main_branches\":";
+    json_branches(s, p->main_leaves.data(), 256, p->main_nodes.data(), p->depth, p->main_leaves.size() / 256);
+    s += ",\"linear_comb_branches\":";
+    json_branches(s, p->lc_leaves.data(), 32, p->lc_nodes.data(), p->depth, p->lc_leaves.size() / 32);
+    s += ",\"fri_proof\":";
+    fri_proof_json_into(s, p->fri);
+    s += "}";
+    char *r = (char *)malloc(s.size() + 1);
+    if (!r) return nullptr;
+    memcpy(r, s.c_str(), s.size() + 1);
+    if (len) *len = s.size();
+    return r;
+}
+extern "C" void sb_stark_proof_free(sb_stark_proof *p) { delete p; }

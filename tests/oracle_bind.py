@@ -35,6 +35,17 @@ class FriProof(C.Structure):
     _fields_ = [("layers", C.POINTER(FriLayer)), ("n_layers", C.c_size_t)]
 
 
+class Trace(C.Structure):
+    """orc_trace (oracle.h): run.rs:109-308, 390-419"""
+    _fields_ = [("original_steps", C.c_size_t),
+                ("witness_trace", C.c_void_p), ("computational_trace", C.c_void_p), ("coefficients", C.c_void_p),
+                ("flag0", C.c_void_p), ("flag1", C.c_void_p), ("flag2", C.c_void_p),
+                ("permuted_indices", C.c_void_p),
+                ("n_public", C.c_size_t), ("public_wires", C.c_void_p),
+                ("n_pfi", C.c_size_t), ("pfi_k", C.c_void_p), ("pfi_w", C.c_void_p),
+                ("n_constraints", C.c_size_t), ("n_wires", C.c_size_t)]
+
+
 _lib = None
 
 
@@ -70,6 +81,9 @@ def lib():
         L.orc_buf_free.argtypes = [C.POINTER(Buf)]
         L.orc_prove_files.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint, C.c_int, C.POINTER(C.c_double)]
         L.orc_prove_files.restype = C.c_int
+        L.orc_trace_from_files.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(Trace)]
+        L.orc_trace_from_files.restype = C.c_int
+        L.orc_trace_free.argtypes = [C.POINTER(Trace)]
         L.fp_root_of_unity.argtypes = [vp, u32]
         L.fp_mul.argtypes = [vp, vp, vp]
         L.fp_to_bytes_le.argtypes = [vp, vp]
@@ -186,3 +200,26 @@ def prove_files(r1cs, wtns, out_path, n_cpus=None, verify=True):
 
 def sha256_file(path):
     return hashlib.sha256(open(path, "rb").read()).hexdigest()
+
+
+def trace_from_files(r1cs, wtns):
+    """the arguments of mk_r1cs_proof for a circuit, as numpy copies (dict)"""
+    t = Trace()
+    rc = lib().orc_trace_from_files(r1cs.encode(), wtns.encode(), C.byref(t))
+    assert rc == 0, rc
+    os_ = t.original_steps
+
+    def fp_arr(p, n):
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint64)), shape=(n, 4)).copy() if n else np.zeros((0, 4), dtype=np.uint64)
+
+    def sz_arr(p, n):
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_size_t)), shape=(n,)).copy() if n else np.zeros(0, dtype=np.uint64)
+
+    out = {"original_steps": os_,
+           "witness_trace": fp_arr(t.witness_trace, os_), "computational_trace": fp_arr(t.computational_trace, os_),
+           "coefficients": fp_arr(t.coefficients, os_), "flag0": fp_arr(t.flag0, os_), "flag1": fp_arr(t.flag1, os_),
+           "flag2": fp_arr(t.flag2, os_), "permuted_indices": sz_arr(t.permuted_indices, os_),
+           "public_wires": fp_arr(t.public_wires, t.n_public),
+           "pfi_k": sz_arr(t.pfi_k, t.n_pfi), "pfi_w": sz_arr(t.pfi_w, t.n_pfi)}
+    lib().orc_trace_free(C.byref(t))
+    return out

@@ -242,3 +242,45 @@ def test_prove_low_degree_structure(ctx, oracle):
     ys = sb.utils.get_pseudorandom_indices(proof[0]["Middle"]["root2"], 256, 40, 8)
     assert all(y % 8 != 0 for y in ys)
     assert sb.merkle.verify_multi_branch(proof[0]["Middle"]["root2"], ys, proof[0]["Middle"]["column_branches"])
+
+
+# ---- whole prover ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["compute", "poseidon3_test"])
+def test_mk_r1cs_proof_bit_identical(ctx, oracle, name, tmp_path):
+    """prove.rs:14-378 device resident: proof.json byte-identical to the oracle's (and to the committed golden
+    hash, which the survey's independent model also reproduced)"""
+    import json
+    import os
+    import stark_pure_rust_b200 as sb
+    from conftest import ROOT
+    d = os.path.join(ROOT, "tests", "golden", "circuits")
+    tr = oracle.trace_from_files(os.path.join(d, name + ".r1cs"), os.path.join(d, name + ".wtns"))
+    text = sb.prove.mk_r1cs_proof(tr["witness_trace"], tr["computational_trace"], tr["public_wires"],
+                                  list(zip(tr["pfi_k"].tolist(), tr["pfi_w"].tolist())), tr["permuted_indices"], tr["coefficients"],
+                                  tr["flag0"], tr["flag1"], tr["flag2"], ctx=ctx)
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "vectors.json")))["proofs"][name]
+    out = str(tmp_path / "p.json")
+    rc, _ = oracle.prove_files(os.path.join(d, name + ".r1cs"), os.path.join(d, name + ".wtns"), out)
+    assert rc == 0
+    want = open(out).read()
+    if text != want:
+        a, b = json.loads(text), json.loads(want)
+        for key in ("a_root", "m_root", "l_root"):
+            assert a[key] == b[key], key
+    assert text == want
+    assert len(text) == gold["proof_json_bytes"] and hashlib.sha256(text.encode()).hexdigest() == gold["proof_json_sha256"]
+
+
+def test_mk_r1cs_proof_rejects_bad_witness(ctx, oracle):
+    """the reference panics in calc_d1 when the trace does not satisfy the constraints (utils.rs:379-384)"""
+    import os
+    import stark_pure_rust_b200 as sb
+    from conftest import ROOT
+    d = os.path.join(ROOT, "tests", "golden", "circuits")
+    tr = oracle.trace_from_files(os.path.join(d, "compute.r1cs"), os.path.join(d, "compute.wtns"))
+    bad = tr["computational_trace"].copy()
+    bad[3] = sb.field.mont_scalar(12345)
+    with pytest.raises(sb.StarkB200Error) as e:
+        sb.prove.mk_r1cs_proof(tr["witness_trace"], bad, tr["public_wires"], list(zip(tr["pfi_k"].tolist(), tr["pfi_w"].tolist())),
+                               tr["permuted_indices"], tr["coefficients"], tr["flag0"], tr["flag1"], tr["flag2"], ctx=ctx)
+    assert e.value.code == -3
