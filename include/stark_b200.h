@@ -175,6 +175,12 @@ int sb_stark_proof_stage_ms(const sb_stark_proof *p, double ms[5]);
 char *sb_stark_proof_json(const sb_stark_proof *p, size_t *len);
 void sb_stark_proof_free(sb_stark_proof *p);
 
+/* prove_with_file_path (r1cs-stark/src/run.rs:528-554): parse <r1cs> (circom2bellman_core/src/reader.rs:4-89) and
+ * <wtns> (r1cs-stark/src/reader.rs:7-42), arrange the traces (run.rs:109-308, :390-419), prove on the device and
+ * write the proof as compact JSON.  proof_path may be NULL.  stage_ms (may be NULL): [0] LDE [1] m_tree [2] FRI
+ * [3] rest of the GPU pipeline [4] sb_prove_r1cs wall clock [5] host front end [6] JSON + file write. */
+int sb_prove_files(sb_ctx *ctx, const char *r1cs_path, const char *wtns_path, const char *proof_path, double stage_ms[7]);
+
 /* ---- unit-test hook for the device field library (no reference counterpart: ff_derive's arithmetic is
  * generated code) ---- element-wise op on n raw 256-bit values, no range checks.
  * op: 0 Montgomery product (lazy, < 2p), 1 add, 2 sub, 3 a+2p-b, 4 canonicalise, 5 halve, 6 from Montgomery,

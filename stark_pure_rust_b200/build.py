@@ -13,7 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libstark_b200.so")
-SOURCES = ["api.cu", "ntt.cu", "ntt_b05.cu", "ntt_b6.cu", "ntt_b7.cu", "ntt_b8.cu", "merkle.cu", "fri.cu", "prover.cu"]
+CLI = os.path.join(HERE, "r1cs-stark")
+SOURCES = ["api.cu", "ntt.cu", "ntt_b05.cu", "ntt_b6.cu", "ntt_b7.cu", "ntt_b8.cu", "merkle.cu", "fri.cu", "prover.cu", "frontend.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ARCH + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-O3,-Wall", "-c"]
@@ -52,6 +53,13 @@ def build(force=False, verbose=False):
         r = subprocess.run([NVCC] + LFLAGS + ["-o", LIB] + objs, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    # the command-line front end (r1cs-stark/src/main.rs): plain C++ against the C ABI
+    main_src = os.path.join(CSRC, "main.cpp")
+    if force or not os.path.exists(CLI) or os.path.getmtime(CLI) < max(os.path.getmtime(main_src), os.path.getmtime(LIB)):
+        r = subprocess.run(["g++", "-O2", "-std=c++17", "-o", CLI, main_src, "-L" + HERE, "-lstark_b200", "-Wl,-rpath,$ORIGIN"],
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("building r1cs-stark failed:\n" + r.stdout + r.stderr)
     return LIB
 
 

@@ -715,12 +715,18 @@ extern "C" int sb_fri_layer_root(const sb_fri_proof *p, size_t i, uint8_t root[3
 }
 
 void json_bytes(std::string &s, const uint8_t *b, size_t n) {
-    char tmp[8];
+    // serde_json prints a Vec<u8> / BlakeDigest(Vec<u8>) as an array of decimal integers
+    static char tab[256][4];
+    static uint8_t len[256];
+    static bool init = false;
+    if (!init) {
+        for (int v = 0; v < 256; v++) len[v] = (uint8_t)snprintf(tab[v], 4, "%d", v);
+        init = true;
+    }
     s.push_back('[');
     for (size_t i = 0; i < n; i++) {
         if (i) s.push_back(',');
-        int l = snprintf(tmp, sizeof tmp, "%u", b[i]);
-        s.append(tmp, l);
+        s.append(tab[b[i]], len[b[i]]);
     }
     s.push_back(']');
 }

@@ -1,0 +1,269 @@
+// frontend.cu -- host front end of the prover: iden3 .r1cs / .wtns parsing and the R1CS -> trace arrangement
+// the reference does before calling mk_r1cs_proof.  O(nnz) scalar work, stays on the CPU by design
+// (SURVEY.md §8f next-2); the vectors it produces go straight into sb_prove_r1cs.
+//
+//   read_r1cs      circom2bellman_core/src/reader.rs:4-89
+//   read_witness   r1cs-stark/src/reader.rs:7-42
+//   build_trace    r1cs-stark/src/run.rs:109-308 (calc_coefficients_and_witness, calc_flags),
+//                  :390-419 (permuted_indices, public_first_indices), :344-361 (prime / witness[0] checks)
+//   sb_prove_files r1cs-stark/src/run.rs:528-554 (prove_with_file_path)
+#include "internal.h"
+
+namespace {
+
+struct Reader {
+    const uint8_t *p;
+    size_t left;
+    bool ok = true;
+    bool need(size_t n) {
+        if (left < n) ok = false;
+        return ok;
+    }
+    uint32_t u32() {
+        if (!need(4)) return 0;
+        uint32_t v = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+        p += 4;
+        left -= 4;
+        return v;
+    }
+    uint64_t u64() {
+        uint64_t lo = u32(), hi = u32();
+        return lo | (hi << 32);
+    }
+    void bytes(uint8_t *out, size_t n) {
+        if (!need(n)) {
+            memset(out, 0, n);
+            return;
+        }
+        memcpy(out, p, n);
+        p += n;
+        left -= n;
+    }
+};
+
+struct Term {
+    uint32_t wire;
+    hfp::el coef;
+};
+struct R1cs {
+    uint32_t field_size = 0, n_wires = 0, n_pub_out = 0, n_pub_in = 0, n_priv = 0, n_constraints = 0;
+    uint64_t n_labels = 0;
+    uint8_t prime[32];
+    std::vector<std::vector<Term>> factors;     // 3 per constraint: A, B, C
+};
+
+const uint8_t BN254_FR_LE[32] = {1, 0, 0, 240, 147, 245, 225, 67, 145, 112, 185, 121, 72, 232, 51, 40,
+                                 93, 88, 129, 129, 182, 69, 80, 184, 41, 160, 49, 225, 114, 78, 100, 48};   // run.rs:344-350
+
+bool slurp(const char *path, std::vector<uint8_t> &out) {
+    FILE *f = fopen(path, "rb");
+    if (!f) return false;
+    fseek(f, 0, SEEK_END);
+    long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    out.resize(sz > 0 ? (size_t)sz : 0);
+    bool ok = sz <= 0 || fread(out.data(), 1, (size_t)sz, f) == (size_t)sz;
+    fclose(f);
+    return ok;
+}
+
+// reader.rs:4-89: magic, version 1, 3 sections, header section first, then the constraint section; labels ignored
+const char *read_r1cs(const std::vector<uint8_t> &buf, R1cs &r) {
+    Reader p{buf.data(), buf.size()};
+    if (p.u32() != 0x73633172u) return "not an r1cs file (magic)";
+    if (p.u32() != 1) return "r1cs version must be 1";
+    if (p.u32() != 3) return "r1cs must have 3 sections";
+    if (p.u32() != 1) return "first r1cs section must be the header";
+    p.u64();
+    r.field_size = p.u32();
+    p.bytes(r.prime, 32);
+    r.n_wires = p.u32();
+    r.n_pub_out = p.u32();
+    r.n_pub_in = p.u32();
+    r.n_priv = p.u32();
+    r.n_labels = p.u64();
+    r.n_constraints = p.u32();
+    if (p.u32() != 2) return "second r1cs section must be the constraints";
+    p.u64();
+    if (!p.ok) return "truncated r1cs header";
+    r.factors.resize((size_t)3 * r.n_constraints);
+    for (size_t c = 0; c < (size_t)3 * r.n_constraints; c++) {
+        uint32_t n = p.u32();
+        if (!p.ok || (size_t)n * 36 > p.left) return "truncated r1cs constraints";
+        r.factors[c].resize(n);
+        for (uint32_t i = 0; i < n; i++) {
+            uint8_t v[32];
+            r.factors[c][i].wire = p.u32();
+            p.bytes(v, 32);
+            r.factors[c][i].coef = hfp::from_bytes_le32(v);      // T::from_bytes_le(value), run.rs:156
+        }
+    }
+    return p.ok ? nullptr : "truncated r1cs constraints";
+}
+
+// reader.rs:7-42: "wtns", 5 skipped words, field size, modulus, n_wires, 3 skipped words, the values
+const char *read_witness(const std::vector<uint8_t> &buf, std::vector<hfp::el> &w) {
+    Reader p{buf.data(), buf.size()};
+    if (p.u32() != 1936618615u) return "not a wtns file (magic)";
+    for (int i = 0; i < 5; i++) p.u32();
+    uint32_t field_size = p.u32();
+    if (field_size != 32) return "witness field size must be 32 bytes";
+    uint8_t tmp[32];
+    p.bytes(tmp, 32);
+    uint32_t n = p.u32();
+    p.u32();
+    p.u32();
+    p.u32();
+    if (!p.ok || (size_t)n * 32 > p.left) return "truncated wtns file";
+    w.resize(n);
+    for (uint32_t i = 0; i < n; i++) {
+        p.bytes(tmp, 32);
+        w[i] = hfp::from_bytes_le32(tmp);                          // run.rs:353-357
+    }
+    return nullptr;
+}
+
+struct Trace {
+    std::vector<hfp::el> wit, comp, coef, f0, f1, f2, pub;
+    std::vector<size_t> perm, pfi_k, pfi_w;
+};
+
+// run.rs:109-281, :283-308, :390-419
+const char *build_trace(const R1cs &r, const std::vector<hfp::el> &witness, Trace &t) {
+    const size_t n_wires = r.n_wires;
+    if (witness.size() < n_wires || n_wires == 0) return "witness shorter than the circuit's wire count";
+    std::vector<hfp::el> wit[3], comp[3], coef[3];
+    std::vector<std::vector<std::pair<uint8_t, size_t>>> uses(n_wires);
+    std::vector<size_t> last;
+    size_t acc = 0;
+    for (size_t c = 0; c < r.n_constraints; c++) {
+        size_t n = 0;
+        for (int k = 0; k < 3; k++) n = std::max(n, r.factors[3 * c + k].size());
+        for (int k = 0; k < 3; k++) {
+            const auto &f = r.factors[3 * c + k];
+            hfp::el run = hfp::ZERO;
+            for (size_t i = 0; i < n; i++) {
+                size_t w;
+                hfp::el cf;
+                if (i < f.size()) {
+                    w = f[i].wire;
+                    if (w >= n_wires) return "wire id out of range";
+                    cf = f[i].coef;
+                    run = hfp::add(run, hfp::mul(cf, witness[w]));
+                } else {                                           // padding row: LAST wire, coefficient 0 (run.rs:165-176)
+                    w = n_wires - 1;
+                    cf = hfp::ZERO;
+                }
+                uses[w].push_back({(uint8_t)k, coef[k].size()});
+                wit[k].push_back(witness[w]);
+                coef[k].push_back(cf);
+                comp[k].push_back(run);
+            }
+        }
+        acc += n;
+        last.push_back(acc - 1);
+    }
+    const size_t a = acc, os = 3 * a;
+    if (a == 0) return "circuit has no constraint rows";
+    for (int k = 0; k < 3; k++) {
+        t.wit.insert(t.wit.end(), wit[k].begin(), wit[k].end());
+        t.comp.insert(t.comp.end(), comp[k].begin(), comp[k].end());
+        t.coef.insert(t.coef.end(), coef[k].begin(), coef[k].end());
+    }
+    // calc_flags, run.rs:283-308
+    t.f0.assign(os, hfp::ONE);
+    t.f1.assign(os, hfp::ONE);
+    t.f2.assign(os, hfp::ZERO);
+    for (size_t l : last) {
+        size_t k = (l + 1) % a;
+        t.f1[k] = t.f1[k + a] = t.f1[k + 2 * a] = hfp::ZERO;
+        t.f2[l] = hfp::ONE;
+    }
+    // copy permutation, run.rs:390-401
+    t.perm.assign(os, 0);
+    for (const auto &vs : uses) {
+        if (vs.empty()) continue;
+        size_t old_w = a * vs.back().first + vs.back().second;
+        for (const auto &kv : vs) {
+            size_t w = a * kv.first + kv.second;
+            t.perm[w] = old_w;
+            old_w = w;
+        }
+    }
+    // public wires and their first uses, run.rs:359-361, :413-419
+    const size_t n_pub = 1 + (size_t)r.n_pub_in + r.n_pub_out;
+    if (n_pub > witness.size() || n_pub > n_wires) return "more public wires than wires";
+    t.pub.assign(witness.begin(), witness.begin() + n_pub);
+    for (size_t w = 0; w < n_pub; w++) {
+        if (!uses[w].empty()) {
+            t.pfi_k.push_back(w);
+            t.pfi_w.push_back(a * uses[w].front().first + uses[w].front().second);
+        }
+    }
+    return nullptr;
+}
+
+}  // namespace
+
+// prove_with_file_path (run.rs:528-554): files in, proof.json out (no trailing newline, run.rs:551).
+// proof_path may be NULL (timing only).  stage_ms (may be NULL): [0] LDE [1] m_tree [2] FRI [3] rest [4] GPU total,
+// [5] host front end (parse + trace arrangement), [6] JSON serialisation + write.
+extern "C" int sb_prove_files(sb_ctx *ctx, const char *r1cs_path, const char *wtns_path, const char *proof_path, double stage_ms[7]) {
+    if (!ctx || !r1cs_path || !wtns_path) return SB_ERR_ARG;
+    auto now = []() {
+        struct timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    };
+    const double t0 = now();
+    std::vector<uint8_t> rb, wb;
+    if (!slurp(r1cs_path, rb)) return fail(ctx, SB_ERR_ARG, "cannot read %s", r1cs_path);
+    if (!slurp(wtns_path, wb)) return fail(ctx, SB_ERR_ARG, "cannot read %s", wtns_path);
+    R1cs r;
+    std::vector<hfp::el> witness;
+    const char *e = read_r1cs(rb, r);
+    if (e) return fail(ctx, SB_ERR_ARG, "%s: %s", r1cs_path, e);
+    if (memcmp(r.prime, BN254_FR_LE, 32) != 0) return fail(ctx, SB_ERR_ARG, "%s: field is not BN254 Fr (run.rs:344-350)", r1cs_path);
+    e = read_witness(wb, witness);
+    if (e) return fail(ctx, SB_ERR_ARG, "%s: %s", wtns_path, e);
+    if (witness.empty() || !hfp::eq(witness[0], hfp::ONE)) return fail(ctx, SB_ERR_ARG, "witness[0] must be 1 (run.rs:358)");
+    Trace t;
+    e = build_trace(r, witness, t);
+    if (e) return fail(ctx, SB_ERR_ARG, "%s", e);
+    sb_trace st;
+    st.original_steps = t.coef.size();
+    st.witness_trace = (const uint64_t *)t.wit.data();
+    st.computational_trace = (const uint64_t *)t.comp.data();
+    st.coefficients = (const uint64_t *)t.coef.data();
+    st.flag0 = (const uint64_t *)t.f0.data();
+    st.flag1 = (const uint64_t *)t.f1.data();
+    st.flag2 = (const uint64_t *)t.f2.data();
+    st.permuted_indices = t.perm.data();
+    st.n_public = t.pub.size();
+    st.public_wires = (const uint64_t *)t.pub.data();
+    st.n_pfi = t.pfi_k.size();
+    st.pfi_k = t.pfi_k.data();
+    st.pfi_w = t.pfi_w.data();
+    const double t1 = now();
+    sb_stark_proof *proof = nullptr;
+    TRY(sb_prove_r1cs(ctx, &st, &proof));
+    const double t2 = now();
+    int rc = SB_OK;
+    if (proof_path) {
+        size_t len = 0;
+        char *s = sb_stark_proof_json(proof, &len);
+        FILE *f = s ? fopen(proof_path, "wb") : nullptr;
+        if (!f || fwrite(s, 1, len, f) != len) rc = fail(ctx, SB_ERR_ARG, "cannot write %s", proof_path);
+        if (f) fclose(f);
+        free(s);
+    }
+    const double t3 = now();
+    if (stage_ms) {
+        sb_stark_proof_stage_ms(proof, stage_ms);
+        stage_ms[4] = t2 - t1;          // wall clock of sb_prove_r1cs (includes host scalar work between kernels)
+        stage_ms[5] = t1 - t0;
+        stage_ms[6] = t3 - t2;
+    }
+    sb_stark_proof_free(proof);
+    return rc;
+}

@@ -1,0 +1,32 @@
+// r1cs-stark <r1cs> <wtns> <proof.json> -- the reference binary's command line (r1cs-stark/src/main.rs:4-11) on the
+// B200 backend: prove and write proof.json (compact serde_json layout, run.rs:549-551).  The reference then also
+// re-verifies the proof on the CPU (run.rs:618-622); verification is outside the accelerated path and is left to
+// the reference's verifier (or the oracle's restatement of it).
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "../../include/stark_b200.h"
+
+int main(int argc, char **argv) {
+    if (argc < 4) {
+        fprintf(stderr, "usage: %s <r1cs> <wtns> <proof.json> [device]\n", argv[0]);
+        return 2;
+    }
+    sb_ctx *ctx = nullptr;
+    int rc = sb_init(argc > 4 ? atoi(argv[4]) : 0, &ctx);
+    if (rc != SB_OK) {
+        fprintf(stderr, "r1cs-stark: no B200 (sm_100) device available; there is no CPU fallback (error %d)\n", rc);
+        return 1;
+    }
+    double ms[7] = {0};
+    rc = sb_prove_files(ctx, argv[1], argv[2], argv[3], ms);
+    if (rc != SB_OK) {
+        fprintf(stderr, "r1cs-stark: %s (error %d)\n", sb_last_error(ctx), rc);
+        sb_destroy(ctx);
+        return 1;
+    }
+    printf("Produced STARK proof: front end %.3f ms, GPU prove %.3f ms (LDE %.3f, m_tree %.3f, FRI %.3f, rest %.3f), JSON %.3f ms\n",
+           ms[5], ms[4], ms[0], ms[1], ms[2], ms[3], ms[6]);
+    sb_destroy(ctx);
+    return 0;
+}

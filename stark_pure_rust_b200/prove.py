@@ -56,3 +56,12 @@ def mk_r1cs_proof(witness_trace, computational_trace, public_wires, public_first
         return text
     finally:
         ctx.lib.sb_stark_proof_free(h)
+
+
+def prove_with_file_path(r1cs_path, wtns_path, proof_path, ctx=None):
+    """run.rs:528-554.  Returns the stage times in ms: [LDE, m_tree, FRI, rest, prove wall, front end, JSON]."""
+    ctx = ctx or default_context()
+    ms = (C.c_double * 7)()
+    ctx.check(ctx.lib.sb_prove_files(ctx.h, str(r1cs_path).encode(), str(wtns_path).encode(),
+                                     str(proof_path).encode() if proof_path else None, ms))
+    return list(ms)

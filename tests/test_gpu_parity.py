@@ -284,3 +284,61 @@ def test_mk_r1cs_proof_rejects_bad_witness(ctx, oracle):
         sb.prove.mk_r1cs_proof(tr["witness_trace"], bad, tr["public_wires"], list(zip(tr["pfi_k"].tolist(), tr["pfi_w"].tolist())),
                                tr["permuted_indices"], tr["coefficients"], tr["flag0"], tr["flag1"], tr["flag2"], ctx=ctx)
     assert e.value.code == -3
+
+
+@pytest.mark.parametrize("name", ["compute", "poseidon3_test"])
+def test_prove_with_file_path_and_cli(ctx, oracle, name, tmp_path):
+    """run.rs:528-554 + main.rs:4-11: product-side parsers / trace arrangement / JSON writer, no oracle on the path"""
+    import json
+    import os
+    import subprocess
+    import stark_pure_rust_b200 as sb
+    from conftest import ROOT
+    d = os.path.join(ROOT, "tests", "golden", "circuits")
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "vectors.json")))["proofs"][name]
+    out = str(tmp_path / "proof.json")
+    ms = sb.prove.prove_with_file_path(os.path.join(d, name + ".r1cs"), os.path.join(d, name + ".wtns"), out, ctx=ctx)
+    assert oracle.sha256_file(out) == gold["proof_json_sha256"] and os.path.getsize(out) == gold["proof_json_bytes"]
+    assert ms[4] > 0
+    out2 = str(tmp_path / "proof_cli.json")
+    r = subprocess.run([os.path.join(ROOT, "stark_pure_rust_b200", "r1cs-stark"), os.path.join(d, name + ".r1cs"),
+                        os.path.join(d, name + ".wtns"), out2], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert oracle.sha256_file(out2) == gold["proof_json_sha256"]
+
+
+def test_prove_with_file_path_errors(ctx, tmp_path):
+    import os
+    import stark_pure_rust_b200 as sb
+    from conftest import ROOT
+    d = os.path.join(ROOT, "tests", "golden", "circuits")
+    with pytest.raises(sb.StarkB200Error):
+        sb.prove.prove_with_file_path(os.path.join(d, "missing.r1cs"), os.path.join(d, "compute.wtns"), None, ctx=ctx)
+    bad = tmp_path / "bad.r1cs"
+    bad.write_bytes(b"nope" + bytes(100))
+    with pytest.raises(sb.StarkB200Error):
+        sb.prove.prove_with_file_path(bad, os.path.join(d, "compute.wtns"), None, ctx=ctx)
+    # witness of another circuit: the constraint check of the reference fires (utils.rs:379-418)
+    with pytest.raises(sb.StarkB200Error):
+        sb.prove.prove_with_file_path(os.path.join(d, "poseidon3_test.r1cs"), os.path.join(d, "compute.wtns"), None, ctx=ctx)
+
+
+@pytest.mark.parametrize("n_constraints,avg_terms,seed", [(40, 2.0, 3), (300, 3.0, 1), (1200, 4.0, 7)])
+def test_prove_synthetic_circuits(ctx, oracle, n_constraints, avg_terms, seed, tmp_path):
+    """seeded synthetic circuits (tools/gen_r1cs.py: linear and multi-term-C constraints, padding rows, public
+    inputs): proof.json of the CUDA pipeline == the oracle's, and the oracle's restated verifier accepts it"""
+    import os
+    import sys
+    import stark_pure_rust_b200 as sb
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_r1cs
+    prefix = str(tmp_path / "syn")
+    wit, cons = gen_r1cs.generate(n_constraints, avg_terms, 2, seed)
+    gen_r1cs.write_files(prefix, wit, cons, 2)
+    want = str(tmp_path / "want.json")
+    rc, _ = oracle.prove_files(prefix + ".r1cs", prefix + ".wtns", want)
+    assert rc == 0                      # 0 = proved and verified by the oracle
+    got = str(tmp_path / "got.json")
+    sb.prove.prove_with_file_path(prefix + ".r1cs", prefix + ".wtns", got, ctx=ctx)
+    assert oracle.sha256_file(got) == oracle.sha256_file(want)
