@@ -159,10 +159,11 @@ static int check_root(sb_ctx *ctx, const hfp::el &w, uint32_t log_n) {
 }
 
 // finds or builds a table T with w = T-root^(2^log_stride)
-int get_table(sb_ctx *ctx, const hfp::el &w, uint32_t log_n, const uint4 **tw, uint32_t *tw_log_n, uint32_t *log_stride) {
+int get_table(sb_ctx *ctx, const hfp::el &w, uint32_t log_n, const uint4 **tw, uint32_t *tw_log_n, uint32_t *log_stride,
+              bool dense) {
     TRY(check_root(ctx, w, log_n));
     for (auto &t : ctx->tables) {
-        if (t.log_n < log_n) continue;
+        if (t.log_n < log_n || (dense && t.log_n != log_n)) continue;
         hfp::el r = t.root;
         for (uint32_t i = 0; i < t.log_n - log_n; i++) r = hfp::sqr(r);
         if (hfp::eq(r, w)) {

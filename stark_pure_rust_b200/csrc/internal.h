@@ -163,7 +163,9 @@ static fp to_dev_fp(const hfp::el &a) {
 }
 
 // ---- functions defined in api.cu ---------------------------------------------------------------
-int get_table(sb_ctx *ctx, const hfp::el &w, uint32_t log_n, const uint4 **tw, uint32_t *tw_log_n, uint32_t *log_stride);
+// dense: the caller indexes the table directly (the prover's `xs`), so a strided view of a larger cached table will not do
+int get_table(sb_ctx *ctx, const hfp::el &w, uint32_t log_n, const uint4 **tw, uint32_t *tw_log_n, uint32_t *log_stride,
+              bool dense = false);
 int ntt_dev(sb_ctx *ctx, const uint4 *d_src, size_t len_in, size_t src_stride, uint4 *d_dst, size_t dst_stride, size_t n_polys,
             const hfp::el &root, uint32_t log_n, int inverse);
 int lde_dev(sb_ctx *ctx, const uint4 *d_cols, size_t n_cols, size_t col_len, size_t col_stride, const hfp::el &root_big,

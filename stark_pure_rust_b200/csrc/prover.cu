@@ -135,7 +135,7 @@ extern "C" int sb_prove_r1cs(sb_ctx *ctx, const sb_trace *t, sb_stark_proof **ou
     }
     const uint4 *xs;
     uint32_t tw_log_n, tw_stride;
-    PTRY(get_table(ctx, g2, log_prec, &xs, &tw_log_n, &tw_stride));
+    PTRY(get_table(ctx, g2, log_prec, &xs, &tw_log_n, &tw_stride, true));
     if (tw_stride != 0) {
         delete proof;
         return fail(ctx, SB_ERR_ARG, "internal: power table of g2 must have stride 1");
