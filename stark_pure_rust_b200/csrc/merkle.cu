@@ -2,6 +2,7 @@
 #include "kernels.h"
 #include "merkle.cuh"
 
+static_assert(MERKLE_THREADS == 128, "launchers assume 128-thread CTAs");
 static unsigned blocks128(size_t threads) { return (unsigned)((threads + 127) / 128); }
 
 int merkle_launch_leaves_cols(cudaStream_t s, uint32_t lv, const MerkleColsParams &P) {

@@ -30,23 +30,35 @@ __device__ __forceinline__ void digest_load(uint32_t (&d)[8], const uint4 *nodes
 }
 
 
-// reduce 2^LV digests held by this thread LV levels up, storing every intermediate level.
-// d[i] is node (first + i) of level `level`; n = number of leaves of the tree.
-template <int LV>
-__device__ __forceinline__ void merkle_reduce_regs(uint32_t (&d)[1 << LV][8], uint4 *nodes, size_t n,
-                                                   uint32_t level, size_t first) {
+// Per-thread digest scratch in shared memory: digest i, word w of thread t lives at sd[(i * 8 + w) * 128 + t]
+// (word-interleaved by thread: every lane stays in its own bank).  Keeping the 2^LV digests there instead of
+// in a register array lets the loops below stay rolled, so the kernel holds ONE copy of the leaf compression
+// and ONE of the node compression (~40 KB of SASS) instead of 2^LV + 2^LV - 1 inlined copies (290 KB, which
+// missed the instruction cache on every iteration: ncu showed 3.3 "no instruction" stall cycles per issue).
+#define MERKLE_THREADS 128
+__device__ __forceinline__ void sd_put(uint32_t *sd, int i, const uint32_t (&d)[8]) {
 #pragma unroll
+    for (int k = 0; k < 8; k++) sd[(i * 8 + k) * MERKLE_THREADS] = d[k];
+}
+
+// reduce the 2^LV digests of this thread LV levels up, storing every intermediate level.
+// digest i is node (first + i) of level `level`; n = number of leaves of the tree.
+template <int LV>
+__device__ __forceinline__ void merkle_reduce_smem(uint32_t *sd, uint4 *nodes, size_t n, uint32_t level, size_t first) {
+#pragma unroll 1
     for (int s = 0; s < LV; s++) {
         const int cnt = 1 << (LV - 1 - s);      // nodes produced at this step
         const size_t off = merkle_level_off(n, level + s + 1), base = first >> (s + 1);
-#pragma unroll
+#pragma unroll 1
         for (int i = 0; i < cnt; i++) {
             uint32_t m[16], o[8];
 #pragma unroll
-            for (int k = 0; k < 8; k++) { m[k] = d[2 * i][k]; m[k + 8] = d[2 * i + 1][k]; }
+            for (int k = 0; k < 8; k++) {
+                m[k] = sd[((2 * i) * 8 + k) * MERKLE_THREADS];
+                m[k + 8] = sd[((2 * i + 1) * 8 + k) * MERKLE_THREADS];
+            }
             b2s::hash64(o, m);
-#pragma unroll
-            for (int k = 0; k < 8; k++) d[i][k] = o[k];
+            sd_put(sd, i, o);                   // i <= 2i: never overwrites an unread child
             digest_store(nodes, off + base + i, o);
         }
     }
@@ -79,17 +91,20 @@ __device__ __forceinline__ void merkle_leaf_from_cols(uint32_t (&out)[8], const 
 }
 
 template <int LV>
-__global__ void __launch_bounds__(128) merkle_leaves_cols_kernel(const __grid_constant__ MerkleColsParams P) {
+__global__ void __launch_bounds__(MERKLE_THREADS, 4) merkle_leaves_cols_kernel(const __grid_constant__ MerkleColsParams P) {
+    __shared__ uint32_t sd_all[(1 << LV) * 8 * MERKLE_THREADS];
+    uint32_t *sd = sd_all + threadIdx.x;
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t first = t << LV;
     if (first >= P.n) return;
-    uint32_t d[1 << LV][8];
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < (1 << LV); i++) {
-        merkle_leaf_from_cols(d[i], P, first + i);
-        digest_store(P.nodes, first + i, d[i]);
+        uint32_t h[8];
+        merkle_leaf_from_cols(h, P, first + i);
+        digest_store(P.nodes, first + i, h);
+        sd_put(sd, i, h);
     }
-    merkle_reduce_regs<LV>(d, P.nodes, P.n, 0, first);
+    merkle_reduce_smem<LV>(sd, P.nodes, P.n, 0, first);
 }
 
 // ---- leaves = n byte strings of leaf_bytes each (caller's Vec<Vec<u8>>, flattened) ----------
@@ -123,31 +138,39 @@ __device__ __forceinline__ void merkle_leaf_from_bytes(uint32_t (&out)[8], const
 }
 
 template <int LV>
-__global__ void __launch_bounds__(128) merkle_leaves_bytes_kernel(const __grid_constant__ MerkleBytesParams P) {
+__global__ void __launch_bounds__(MERKLE_THREADS, 4) merkle_leaves_bytes_kernel(const __grid_constant__ MerkleBytesParams P) {
+    __shared__ uint32_t sd_all[(1 << LV) * 8 * MERKLE_THREADS];
+    uint32_t *sd = sd_all + threadIdx.x;
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t first = t << LV;
     if (first >= P.n) return;
-    uint32_t d[1 << LV][8];
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < (1 << LV); i++) {
-        merkle_leaf_from_bytes(d[i], P.leaves + (first + i) * (size_t)P.leaf_bytes, P.leaf_bytes);
-        digest_store(P.nodes, first + i, d[i]);
+        uint32_t h[8];
+        merkle_leaf_from_bytes(h, P.leaves + (first + i) * (size_t)P.leaf_bytes, P.leaf_bytes);
+        digest_store(P.nodes, first + i, h);
+        sd_put(sd, i, h);
     }
-    merkle_reduce_regs<LV>(d, P.nodes, P.n, 0, first);
+    merkle_reduce_smem<LV>(sd, P.nodes, P.n, 0, first);
 }
 
 // ---- inner levels: each thread lifts 2^LV nodes of level `level` LV levels up -----------------
 template <int LV>
-__global__ void __launch_bounds__(128) merkle_nodes_kernel(uint4 *nodes, unsigned long long n, uint32_t level) {
+__global__ void __launch_bounds__(MERKLE_THREADS, 4) merkle_nodes_kernel(uint4 *nodes, unsigned long long n, uint32_t level) {
+    __shared__ uint32_t sd_all[(1 << LV) * 8 * MERKLE_THREADS];
+    uint32_t *sd = sd_all + threadIdx.x;
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t first = t << LV;
     const size_t width = n >> level;
     if (first >= width) return;
     const size_t off = merkle_level_off(n, level);
-    uint32_t d[1 << LV][8];
 #pragma unroll
-    for (int i = 0; i < (1 << LV); i++) digest_load(d[i], nodes, off + first + i);
-    merkle_reduce_regs<LV>(d, nodes, n, level, first);
+    for (int i = 0; i < (1 << LV); i++) {
+        uint32_t d[8];
+        digest_load(d, nodes, off + first + i);
+        sd_put(sd, i, d);
+    }
+    merkle_reduce_smem<LV>(sd, nodes, n, level, first);
 }
 
 // ---- openings: sibling digests leaf level first, root excluded (merkle_tree.rs:25-43) --------
