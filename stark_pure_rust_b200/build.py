@@ -18,7 +18,7 @@ SOURCES = ["api.cu", "ntt.cu", "ntt_b05.cu", "ntt_b6.cu", "ntt_b7.cu", "ntt_b8.c
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ARCH + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-O3,-Wall", "-c"]
-LFLAGS = ARCH + ["-shared", "--cudart", "static"]
+LFLAGS = ARCH + ["-shared", "--cudart", "static", "-lpthread"]
 
 
 def _headers():

@@ -45,12 +45,28 @@ extern "C" void sb_destroy(sb_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto &t : ctx->tables) cudaFree(t.d);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
     prof_collect(ctx);
     for (auto e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+void *pinned_arena(sb_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->pinned_bytes) return ctx->pinned;
+    cudaStreamSynchronize(ctx->stream);            // an upload from the old arena may still be in flight
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    ctx->pinned = nullptr;
+    ctx->pinned_bytes = 0;
+    const size_t want = bytes + bytes / 8;
+    if (cudaMallocHost(&ctx->pinned, want) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    ctx->pinned_bytes = want;
+    return ctx->pinned;
 }
 
 extern "C" const char *sb_last_error(const sb_ctx *ctx) { return ctx ? ctx->err : "no context"; }

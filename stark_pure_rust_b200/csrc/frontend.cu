@@ -9,6 +9,10 @@
 //   sb_prove_files r1cs-stark/src/run.rs:528-554 (prove_with_file_path)
 #include "internal.h"
 
+#include <algorithm>
+#include <atomic>
+#include <thread>
+
 namespace {
 
 struct Reader {
@@ -41,15 +45,17 @@ struct Reader {
     }
 };
 
-struct Term {
-    uint32_t wire;
-    hfp::el coef;
+// One A / B / C factor of a constraint, left in place in the file image: n terms of (u32 wire, 32-byte LE coefficient)
+struct FactorRef {
+    const uint8_t *terms;
+    uint32_t n;
 };
 struct R1cs {
     uint32_t field_size = 0, n_wires = 0, n_pub_out = 0, n_pub_in = 0, n_priv = 0, n_constraints = 0;
     uint64_t n_labels = 0;
     uint8_t prime[32];
-    std::vector<std::vector<Term>> factors;     // 3 per constraint: A, B, C
+    std::vector<FactorRef> factors;             // 3 per constraint: A, B, C
+    std::vector<size_t> row_off;                // row_off[c] = rows of the constraints before c (run.rs:128-135: max of the three lengths)
 };
 
 const uint8_t BN254_FR_LE[32] = {1, 0, 0, 240, 147, 245, 225, 67, 145, 112, 185, 121, 72, 232, 51, 40,
@@ -67,7 +73,22 @@ bool slurp(const char *path, std::vector<uint8_t> &out) {
     return ok;
 }
 
-// reader.rs:4-89: magic, version 1, 3 sections, header section first, then the constraint section; labels ignored
+// body(lo, hi) over [0, n) on up to 16 host threads (the O(nnz) scalar work below: ~2 Montgomery products per term)
+template <class F>
+void parallel_for(size_t n, size_t min_grain, F body) {
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t T = std::min<size_t>(std::min<unsigned>(hw ? hw : 1, 16), n / (min_grain ? min_grain : 1));
+    if (T <= 1) {
+        body((size_t)0, n);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (size_t i = 0; i < T; i++) th.emplace_back([=]() { body(n * i / T, n * (i + 1) / T); });
+    for (auto &t : th) t.join();
+}
+
+// reader.rs:4-89: magic, version 1, 3 sections, header section first, then the constraint section; labels ignored.
+// Only the structure is decoded here (one u32 per factor); coefficients are converted where they are used.
 const char *read_r1cs(const std::vector<uint8_t> &buf, R1cs &r) {
     Reader p{buf.data(), buf.size()};
     if (p.u32() != 0x73633172u) return "not an r1cs file (magic)";
@@ -86,17 +107,20 @@ const char *read_r1cs(const std::vector<uint8_t> &buf, R1cs &r) {
     if (p.u32() != 2) return "second r1cs section must be the constraints";
     p.u64();
     if (!p.ok) return "truncated r1cs header";
+    if ((size_t)r.n_constraints * 12 > p.left) return "truncated r1cs constraints";
     r.factors.resize((size_t)3 * r.n_constraints);
-    for (size_t c = 0; c < (size_t)3 * r.n_constraints; c++) {
-        uint32_t n = p.u32();
-        if (!p.ok || (size_t)n * 36 > p.left) return "truncated r1cs constraints";
-        r.factors[c].resize(n);
-        for (uint32_t i = 0; i < n; i++) {
-            uint8_t v[32];
-            r.factors[c][i].wire = p.u32();
-            p.bytes(v, 32);
-            r.factors[c][i].coef = hfp::from_bytes_le32(v);      // T::from_bytes_le(value), run.rs:156
+    r.row_off.assign((size_t)r.n_constraints + 1, 0);
+    for (size_t c = 0; c < r.n_constraints; c++) {
+        size_t rows = 0;
+        for (int k = 0; k < 3; k++) {
+            uint32_t n = p.u32();
+            if (!p.ok || (size_t)n * 36 > p.left) return "truncated r1cs constraints";
+            r.factors[3 * c + k] = FactorRef{p.p, n};
+            p.p += (size_t)n * 36;
+            p.left -= (size_t)n * 36;
+            rows = std::max<size_t>(rows, n);
         }
+        r.row_off[c + 1] = r.row_off[c] + rows;
     }
     return p.ok ? nullptr : "truncated r1cs constraints";
 }
@@ -116,88 +140,106 @@ const char *read_witness(const std::vector<uint8_t> &buf, std::vector<hfp::el> &
     p.u32();
     if (!p.ok || (size_t)n * 32 > p.left) return "truncated wtns file";
     w.resize(n);
-    for (uint32_t i = 0; i < n; i++) {
-        p.bytes(tmp, 32);
-        w[i] = hfp::from_bytes_le32(tmp);                          // run.rs:353-357
-    }
+    const uint8_t *vals = p.p;
+    parallel_for(n, 4096, [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; i++) w[i] = hfp::from_bytes_le32(vals + 32 * i);     // run.rs:353-357
+    });
     return nullptr;
 }
 
+// the six original_steps-long vectors mk_r1cs_proof takes, carved out of the context's pinned staging arena so that
+// their upload runs at PCIe speed; perm / public data are small and stay in ordinary vectors
 struct Trace {
-    std::vector<hfp::el> wit, comp, coef, f0, f1, f2, pub;
+    size_t os = 0;
+    hfp::el *wit = nullptr, *comp = nullptr, *coef = nullptr, *f0 = nullptr, *f1 = nullptr, *f2 = nullptr;
+    std::vector<hfp::el> pub;
     std::vector<size_t> perm, pfi_k, pfi_w;
 };
 
 // run.rs:109-281, :283-308, :390-419
-const char *build_trace(const R1cs &r, const std::vector<hfp::el> &witness, Trace &t) {
-    const size_t n_wires = r.n_wires;
+const char *build_trace(sb_ctx *ctx, const R1cs &r, const std::vector<hfp::el> &witness, Trace &t) {
+    const size_t n_wires = r.n_wires, nc = r.n_constraints;
     if (witness.size() < n_wires || n_wires == 0) return "witness shorter than the circuit's wire count";
-    std::vector<hfp::el> wit[3], comp[3], coef[3];
-    std::vector<std::vector<std::pair<uint8_t, size_t>>> uses(n_wires);
-    std::vector<size_t> last;
-    size_t acc = 0;
-    for (size_t c = 0; c < r.n_constraints; c++) {
-        size_t n = 0;
-        for (int k = 0; k < 3; k++) n = std::max(n, r.factors[3 * c + k].size());
-        for (int k = 0; k < 3; k++) {
-            const auto &f = r.factors[3 * c + k];
-            hfp::el run = hfp::ZERO;
-            for (size_t i = 0; i < n; i++) {
-                size_t w;
-                hfp::el cf;
-                if (i < f.size()) {
-                    w = f[i].wire;
-                    if (w >= n_wires) return "wire id out of range";
-                    cf = f[i].coef;
-                    run = hfp::add(run, hfp::mul(cf, witness[w]));
-                } else {                                           // padding row: LAST wire, coefficient 0 (run.rs:165-176)
-                    w = n_wires - 1;
-                    cf = hfp::ZERO;
+    const size_t a = r.row_off[nc], os = 3 * a;
+    if (a == 0) return "circuit has no constraint rows";
+    hfp::el *arena = (hfp::el *)pinned_arena(ctx, 6 * os * sizeof(hfp::el));
+    if (!arena) return "cannot allocate the pinned staging arena";
+    t.os = os;
+    t.coef = arena; t.f0 = arena + os; t.f1 = arena + 2 * os; t.f2 = arena + 3 * os; t.wit = arena + 4 * os; t.comp = arena + 5 * os;
+    std::vector<uint32_t> wire_at(os);
+    std::atomic<int> bad(0);
+    // rows of constraint c sit at row_off[c] .. in each third k (A, B, C); threads take ranges of constraints
+    parallel_for(nc, 64, [&](size_t c0, size_t c1) {
+        for (size_t c = c0; c < c1; c++) {
+            const size_t off = r.row_off[c], n = r.row_off[c + 1] - off;
+            for (int k = 0; k < 3; k++) {
+                const FactorRef &f = r.factors[3 * c + k];
+                hfp::el run = hfp::ZERO;
+                for (size_t i = 0; i < n; i++) {
+                    const size_t pos = (size_t)k * a + off + i;
+                    uint32_t w;
+                    if (i < f.n) {
+                        const uint8_t *term = f.terms + 36 * i;
+                        memcpy(&w, term, 4);
+                        if (w >= n_wires) {
+                            bad.store(1);
+                            w = 0;
+                        }
+                        const hfp::el cf = hfp::from_bytes_le32(term + 4);     // T::from_bytes_le(value), run.rs:156
+                        run = hfp::add(run, hfp::mul(cf, witness[w]));
+                        t.coef[pos] = cf;
+                    } else {                                           // padding row: LAST wire, coefficient 0 (run.rs:165-176)
+                        w = (uint32_t)(n_wires - 1);
+                        t.coef[pos] = hfp::ZERO;
+                    }
+                    wire_at[pos] = w;
+                    t.wit[pos] = witness[w];
+                    t.comp[pos] = run;
                 }
-                uses[w].push_back({(uint8_t)k, coef[k].size()});
-                wit[k].push_back(witness[w]);
-                coef[k].push_back(cf);
-                comp[k].push_back(run);
             }
         }
-        acc += n;
-        last.push_back(acc - 1);
-    }
-    const size_t a = acc, os = 3 * a;
-    if (a == 0) return "circuit has no constraint rows";
-    for (int k = 0; k < 3; k++) {
-        t.wit.insert(t.wit.end(), wit[k].begin(), wit[k].end());
-        t.comp.insert(t.comp.end(), comp[k].begin(), comp[k].end());
-        t.coef.insert(t.coef.end(), coef[k].begin(), coef[k].end());
-    }
+    });
+    if (bad.load()) return "wire id out of range";
     // calc_flags, run.rs:283-308
-    t.f0.assign(os, hfp::ONE);
-    t.f1.assign(os, hfp::ONE);
-    t.f2.assign(os, hfp::ZERO);
-    for (size_t l : last) {
-        size_t k = (l + 1) % a;
+    parallel_for(os, 1 << 16, [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; i++) {
+            t.f0[i] = hfp::ONE;
+            t.f1[i] = hfp::ONE;
+            t.f2[i] = hfp::ZERO;
+        }
+    });
+    for (size_t c = 0; c < nc; c++) {
+        if (r.row_off[c + 1] == r.row_off[c]) continue;     // cannot happen for well-formed circuits (every constraint has a term)
+        const size_t l = r.row_off[c + 1] - 1, k = (l + 1) % a;
         t.f1[k] = t.f1[k + a] = t.f1[k + 2 * a] = hfp::ZERO;
         t.f2[l] = hfp::ONE;
     }
-    // copy permutation, run.rs:390-401
+    // copy permutation, run.rs:390-401: the uses of a wire in (constraint, factor, row) order form a cycle,
+    // perm[first use] = last use, perm[use j] = use j-1
+    const size_t NONE = (size_t)-1;
+    std::vector<size_t> first(n_wires, NONE), prev(n_wires, NONE);
     t.perm.assign(os, 0);
-    for (const auto &vs : uses) {
-        if (vs.empty()) continue;
-        size_t old_w = a * vs.back().first + vs.back().second;
-        for (const auto &kv : vs) {
-            size_t w = a * kv.first + kv.second;
-            t.perm[w] = old_w;
-            old_w = w;
+    for (size_t c = 0; c < nc; c++) {
+        const size_t off = r.row_off[c], n = r.row_off[c + 1] - off;
+        for (int k = 0; k < 3; k++) {
+            for (size_t i = 0; i < n; i++) {
+                const size_t pos = (size_t)k * a + off + i;
+                const uint32_t w = wire_at[pos];
+                if (first[w] == NONE) first[w] = pos; else t.perm[pos] = prev[w];
+                prev[w] = pos;
+            }
         }
     }
+    for (size_t w = 0; w < n_wires; w++)
+        if (first[w] != NONE) t.perm[first[w]] = prev[w];
     // public wires and their first uses, run.rs:359-361, :413-419
     const size_t n_pub = 1 + (size_t)r.n_pub_in + r.n_pub_out;
     if (n_pub > witness.size() || n_pub > n_wires) return "more public wires than wires";
     t.pub.assign(witness.begin(), witness.begin() + n_pub);
     for (size_t w = 0; w < n_pub; w++) {
-        if (!uses[w].empty()) {
+        if (first[w] != NONE) {
             t.pfi_k.push_back(w);
-            t.pfi_w.push_back(a * uses[w].front().first + uses[w].front().second);
+            t.pfi_w.push_back(first[w]);
         }
     }
     return nullptr;
@@ -228,16 +270,16 @@ extern "C" int sb_prove_files(sb_ctx *ctx, const char *r1cs_path, const char *wt
     if (e) return fail(ctx, SB_ERR_ARG, "%s: %s", wtns_path, e);
     if (witness.empty() || !hfp::eq(witness[0], hfp::ONE)) return fail(ctx, SB_ERR_ARG, "witness[0] must be 1 (run.rs:358)");
     Trace t;
-    e = build_trace(r, witness, t);
+    e = build_trace(ctx, r, witness, t);
     if (e) return fail(ctx, SB_ERR_ARG, "%s", e);
     sb_trace st;
-    st.original_steps = t.coef.size();
-    st.witness_trace = (const uint64_t *)t.wit.data();
-    st.computational_trace = (const uint64_t *)t.comp.data();
-    st.coefficients = (const uint64_t *)t.coef.data();
-    st.flag0 = (const uint64_t *)t.f0.data();
-    st.flag1 = (const uint64_t *)t.f1.data();
-    st.flag2 = (const uint64_t *)t.f2.data();
+    st.original_steps = t.os;
+    st.witness_trace = (const uint64_t *)t.wit;
+    st.computational_trace = (const uint64_t *)t.comp;
+    st.coefficients = (const uint64_t *)t.coef;
+    st.flag0 = (const uint64_t *)t.f0;
+    st.flag1 = (const uint64_t *)t.f1;
+    st.flag2 = (const uint64_t *)t.f2;
     st.permuted_indices = t.perm.data();
     st.n_public = t.pub.size();
     st.public_wires = (const uint64_t *)t.pub.data();

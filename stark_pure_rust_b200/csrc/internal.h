@@ -30,6 +30,9 @@ struct sb_ctx {
     uint64_t launches = 0;
     std::vector<TwTable> tables;
     char err[512] = {0};
+    // pinned host staging arena (front end -> sb_prove_r1cs uploads); grows on demand, freed in sb_destroy
+    void *pinned = nullptr;
+    size_t pinned_bytes = 0;
     // optional per-kernel-family timing (sb_profile): CUDA events around every launch
     bool prof = false;
     struct ProfRec { int kind; cudaEvent_t a, b; };
@@ -163,6 +166,8 @@ static fp to_dev_fp(const hfp::el &a) {
 }
 
 // ---- functions defined in api.cu ---------------------------------------------------------------
+// returns a pinned host buffer of at least `bytes` owned by the context (contents are scratch), NULL on failure
+void *pinned_arena(sb_ctx *ctx, size_t bytes);
 // dense: the caller indexes the table directly (the prover's `xs`), so a strided view of a larger cached table will not do
 int get_table(sb_ctx *ctx, const hfp::el &w, uint32_t log_n, const uint4 **tw, uint32_t *tw_log_n, uint32_t *log_stride,
               bool dense = false);

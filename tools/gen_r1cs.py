@@ -50,12 +50,14 @@ def generate(n_constraints, avg_terms, n_pub, seed):
 
 def write_files(prefix, wit, cons, n_pub):
     n_wires = len(wit)
-    body = b""
+    parts = []                      # joined once: repeated bytes += is quadratic (20 MB at 30k constraints)
     for a, b, c in cons:
         for f in (a, b, c):
-            body += struct.pack("<I", len(f))
+            parts.append(struct.pack("<I", len(f)))
             for w, cf in f:
-                body += struct.pack("<I", w) + int(cf % P).to_bytes(32, "little")
+                parts.append(struct.pack("<I", w))
+                parts.append(int(cf % P).to_bytes(32, "little"))
+    body = b"".join(parts)
     header = struct.pack("<I", 32) + P.to_bytes(32, "little") + struct.pack("<IIIIQI", n_wires, 0, n_pub, n_wires - 1 - n_pub, n_wires, len(cons))
     labels = b"".join(struct.pack("<Q", i) for i in range(n_wires))
     with open(prefix + ".r1cs", "wb") as f:
@@ -68,8 +70,7 @@ def write_files(prefix, wit, cons, n_pub):
         f.write(struct.pack("<IQ", 1, 40))                           # section 1 header: id + u64 size  (3 words)
         f.write(struct.pack("<I", 32) + P.to_bytes(32, "little") + struct.pack("<I", n_wires))
         f.write(struct.pack("<IQ", 2, 32 * n_wires))                 # section 2 header (3 words)
-        for v in wit:
-            f.write(int(v).to_bytes(32, "little"))
+        f.write(b"".join(int(v).to_bytes(32, "little") for v in wit))
     rows = sum(max(len(a), len(b), len(c)) for a, b, c in cons)
     return {"n_wires": n_wires, "n_constraints": len(cons), "a_trace_len": rows, "original_steps": 3 * rows}
 

@@ -1,0 +1,60 @@
+#!/usr/bin/env python3
+"""Prove a seeded synthetic circuit of sha256_2_test's scale (BASELINE.json configs[3]; the real .r1cs is missing
+from the reference mount) on the B200 pipeline, print the stage times, optionally time the CPU oracle too.
+
+    python tools/prove_large.py [--constraints 30000] [--avg-terms 8] [--cpu] [--reps 3]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import gen_r1cs
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--constraints", type=int, default=30000)
+    ap.add_argument("--avg-terms", type=float, default=8.0)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--cpu", action="store_true")
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--dir", default="/tmp")
+    a = ap.parse_args()
+    prefix = os.path.join(a.dir, "syn_%d_%g_%d" % (a.constraints, a.avg_terms, a.seed))
+    t0 = time.perf_counter()
+    wit, cons = gen_r1cs.generate(a.constraints, a.avg_terms, 2, a.seed)
+    info = gen_r1cs.write_files(prefix, wit, cons, 2)
+    print("generated", info, "in %.1f s" % (time.perf_counter() - t0), flush=True)
+    import stark_pure_rust_b200 as sb
+    ctx = sb.default_context()
+    out = prefix + ".proof.json"
+    res = {"circuit": info}
+    for r in range(a.reps):
+        t0 = time.perf_counter()
+        ms = sb.prove.prove_with_file_path(prefix + ".r1cs", prefix + ".wtns", out, ctx=ctx)
+        wall = (time.perf_counter() - t0) * 1e3
+        import hashlib
+        print("sha256", hashlib.sha256(open(out, "rb").read()).hexdigest())
+        print("gpu rep %d: wall %.1f ms | LDE %.2f m_tree %.2f FRI %.2f rest %.2f | prove %.2f | front end %.2f | json+write %.2f | proof %d bytes" % (
+            r, wall, ms[0], ms[1], ms[2], ms[3], ms[4], ms[5], ms[6], os.path.getsize(out)), flush=True)
+        res["gpu"] = {"wall_ms": wall, "stage_ms": ms}
+    if a.cpu:
+        import oracle_bind as ob
+        want = prefix + ".oracle.json"
+        t0 = time.perf_counter()
+        rc, _ = ob.prove_files(prefix + ".r1cs", prefix + ".wtns", want, verify=False)
+        cpu_s = time.perf_counter() - t0
+        same = ob.sha256_file(want) == ob.sha256_file(out)
+        print("cpu oracle: rc %d, %.2f s on %d threads; proof.json identical: %s" % (rc, cpu_s, os.cpu_count(), same), flush=True)
+        res["cpu"] = {"s": cpu_s, "identical": same}
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()
