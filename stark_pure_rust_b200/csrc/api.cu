@@ -349,7 +349,7 @@ extern "C" int sb_batch_inverse_dev(sb_ctx *ctx, uint64_t *d_vals, size_t n) {
     if (!ctx || !d_vals) return SB_ERR_ARG;
     if (n == 0) return SB_OK;
     DevBuf scratch(ctx);
-    TRY(scratch.alloc(n * 32));
+    TRY(scratch.alloc(batch_inverse_scratch_elems(n) * 32));
     KLAUNCH(SB_KIND_OTHER, batch_inverse_launch(ctx->stream, (uint4 *)d_vals, (uint4 *)scratch.p, n));
     CU(cudaGetLastError());
     return SB_OK;

@@ -2,6 +2,10 @@
 #include "kernels.h"
 #include "fri.cuh"
 
+// slices of the two-level batch inverse: 148 SMs x 16 CTAs x 128 threads
+static const unsigned BINV_THREADS = 148 * 16 * 128;
+static const unsigned long long BINV_TWO_LEVEL_MIN = (unsigned long long)BINV_THREADS * 8;
+
 int fri_launch_fold(cudaStream_t s, const FriFoldParams &P) {
     const size_t q = P.n >> 2;
     fri_fold_kernel<<<(unsigned)((q + 127) / 128), 128, 0, s>>>(P);
@@ -20,10 +24,21 @@ int fp_launch_to_bytes(cudaStream_t s, const uint4 *in, uint4 *out, unsigned lon
     fp_to_bytes_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(in, out, n);
     return 1;
 }
+// scratch must hold batch_inverse_scratch_elems(n) elements
+unsigned long long batch_inverse_scratch_elems(unsigned long long n) {
+    return n + (n > BINV_TWO_LEVEL_MIN ? 2 * (unsigned long long)BINV_THREADS : 0);
+}
 int batch_inverse_launch(cudaStream_t s, uint4 *vals, uint4 *scratch, unsigned long long n) {
-    size_t threads = n < (size_t)148 * 16 * 128 ? n : (size_t)148 * 16 * 128;
-    batch_inverse_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(vals, scratch, n);
-    return 1;
+    if (n <= BINV_TWO_LEVEL_MIN) {
+        size_t threads = n < (size_t)BINV_THREADS ? n : (size_t)BINV_THREADS;
+        batch_inverse_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(vals, scratch, n);
+        return 1;
+    }
+    uint4 *tot = scratch + 2 * n, *tot_scratch = tot + 2 * (size_t)BINV_THREADS;
+    batch_inverse_fwd_kernel<<<BINV_THREADS / 128, 128, 0, s>>>(vals, scratch, tot, n);
+    batch_inverse_kernel<<<(BINV_THREADS / 64 + 127) / 128, 128, 0, s>>>(tot, tot_scratch, BINV_THREADS);
+    batch_inverse_bwd_kernel<<<BINV_THREADS / 128, 128, 0, s>>>(vals, scratch, tot, n);
+    return 3;
 }
 int fp_launch_vec_op(cudaStream_t s, int op, const uint4 *a, const uint4 *b, uint4 *out, unsigned long long n) {
     fp_vec_op_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(op, a, b, out, n);

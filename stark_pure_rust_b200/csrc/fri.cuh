@@ -134,6 +134,39 @@ __global__ void __launch_bounds__(128) batch_inverse_kernel(uint4 *vals, uint4 *
     }
 }
 
+// Two-level variant for large n: the per-thread Fermat inversion (~380 products) would dominate once a thread owns
+// only a few dozen elements, so the slice products are themselves batch-inverted (recursively, by the kernel above)
+// and the cost per element drops to the 3 products of Montgomery's trick.
+//   fwd : scratch[i] = product of the non-zero elements before i in the slice; tot[t] = product of the whole slice
+//   bwd : tot[t] holds the inverse of the slice product on entry
+__global__ void __launch_bounds__(128) batch_inverse_fwd_kernel(const uint4 *vals, uint4 *scratch, uint4 *tot, unsigned long long n) {
+    const size_t T = (size_t)gridDim.x * blockDim.x;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    fp acc = fp_one();
+    for (size_t i = t; i < n; i += T) {
+        fp_stg(scratch, i, acc);
+        fp v = fp_canon(fp_ldg(vals, i));
+        if (!fp_is_zero_canon(v)) acc = fp_mul(acc, v);
+    }
+    fp_stg(tot, t, fp_canon(acc));      // never zero
+}
+__global__ void __launch_bounds__(128) batch_inverse_bwd_kernel(uint4 *vals, const uint4 *scratch, const uint4 *tot, unsigned long long n) {
+    const size_t T = (size_t)gridDim.x * blockDim.x;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    fp inv = fp_ldg(tot, t);
+    size_t cnt = (n - t + T - 1) / T;
+    for (size_t k = cnt; k-- > 0;) {
+        const size_t i = t + k * T;
+        fp v = fp_canon(fp_ldg(vals, i));
+        if (!fp_is_zero_canon(v)) {
+            fp pre = fp_ldg(scratch, i);
+            fp_stg(vals, i, fp_canon(fp_mul(inv, pre)));
+            inv = fp_mul(inv, v);
+        }
+    }
+}
+
 // ---- element-wise field ops on vectors (unit tests of fp.cuh through the C ABI) -----------------
 // op: 0 mul (raw, lazy result), 1 add, 2 sub, 3 sub_lazy, 4 canon(a), 5 half(a), 6 from_mont(a),
 //     7 to_mont(a), 8 inverse(a), 9 reduce_2p(a), 10 canon(mul)

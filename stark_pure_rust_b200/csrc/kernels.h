@@ -29,5 +29,6 @@ int fri_launch_fold(cudaStream_t stream, const FriFoldParams &P);
 int powers_launch_seed(cudaStream_t stream, uint4 *T, unsigned long long count, const fp &w);
 int powers_launch_double(cudaStream_t stream, uint4 *T, unsigned long long cur, unsigned long long n_total, const fp &wcur);
 int fp_launch_to_bytes(cudaStream_t stream, const uint4 *in, uint4 *out, unsigned long long n);
+unsigned long long batch_inverse_scratch_elems(unsigned long long n);
 int batch_inverse_launch(cudaStream_t stream, uint4 *vals, uint4 *scratch, unsigned long long n);
 int fp_launch_vec_op(cudaStream_t stream, int op, const uint4 *a, const uint4 *b, uint4 *out, unsigned long long n);

@@ -115,6 +115,18 @@ def test_multi_inv(ctx, oracle):
         assert np.array_equal(sb.poly_utils.multi_inv(v, ctx=ctx), oracle.multi_inv(v)), n
 
 
+def test_multi_inv_two_level(ctx, oracle):
+    """n above 148*16*128*8 takes the two-level path (slice products inverted by a nested batch inverse);
+    a run of zeros covers a whole slice whose product stays 1"""
+    import stark_pure_rust_b200 as sb
+    n = 148 * 16 * 128 * 8 + 12345
+    v = random_elems(n, 977)
+    v[::7] = 0
+    v[5::148 * 16 * 128] = 0             # every element of slice 5
+    got = sb.poly_utils.multi_inv(v, ctx=ctx)
+    assert np.array_equal(got, oracle.multi_inv(v))
+
+
 # ---- Merkle ---------------------------------------------------------------------------------
 KAT16 = ["7fffffff", "80000000", "00000003", "00000000", "7ffffffe", "80000001", "00000004", "00000001",
          "7ffffffd", "80000002", "00000005", "00000002", "7ffffffc", "80000003", "00000006", "00000003"]
