@@ -350,6 +350,145 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------
+# one commitment sharded over the GPUs (BASELINE.json configs[4])
+# ---------------------------------------------------------------------------------------------
+def run_gpu_sharded(args):
+    """ONE job over all ranks: column c is extended on rank c % world, one grouped NCCL send/recv turns the
+    column-sharded evaluations into row-range shards, every rank hashes the subtree over its rows (8-column tree and
+    1-column tree), the 32-byte subtree roots are all-gathered and the top levels finished on every rank; FRI runs on the
+    rank that extended the last column (replica from layer 0 on).  value = C * 2^L / step time: strong scaling."""
+    import torch
+    import torch.distributed as dist
+    import stark_pure_rust_b200 as sb
+    from stark_pure_rust_b200 import field, sharded
+    from stark_pure_rust_b200._lib import _ptr
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = sb.Context(local_rank)
+    lib = ctx.lib
+    be = sharded.CudaBackend(ctx, dev)
+    L, Cn = args.log_n, args.cols
+    log_s, N, S = L - 3, 1 << L, 1 << (L - 3)
+    if L > 25:
+        ctx.check(lib.sb_set_extended_domain(ctx.h, 1))
+    g2 = field.mont_scalar(field.root_of_unity(L))
+    mine = sharded.owned_columns(Cn, world, rank)
+    k_tree = min(8, Cn)
+    fri_owner = (Cn - 1) % world
+    # pinned host inputs of the columns this rank extends (the e2e leg uploads them inside the timed region)
+    h_cols = torch.from_numpy(random_elems(max(len(mine), 1) * S, 0xB200 + rank).view(np.int64).reshape(max(len(mine), 1), S, 4)).pin_memory()
+    d_cols = h_cols[:len(mine)].to(dev)
+    sc = sharded.ShardedCommitter(be, dist if world > 1 else None)
+    roots = {}
+
+    def step(upload=False):
+        cols = h_cols[:len(mine)].to(dev, non_blocking=True) if upload else d_cols
+        ext = be.lde(cols, g2, log_s, 3)
+        rows = sc.exchange({c: ext[k] for k, c in enumerate(mine)}, Cn, N)
+        tm = sc.commit_rows(rows, list(range(k_tree)), N)
+        tl = sc.commit_rows(rows, [Cn - 1], N)
+        n_layers = 0
+        if rank == fri_owner:
+            pr = C.c_void_p()
+            ctx.check(lib.sb_fri_prove_dev(ctx.h, C.c_void_p(ext[mine.index(Cn - 1)].data_ptr()), N, _ptr(g2), N // 4, 8, None, C.byref(pr)))
+            n_layers = lib.sb_fri_n_layers(pr)
+            lib.sb_fri_proof_free(pr)
+        roots["m"], roots["l"] = tm.get_root(), tl.get_root()
+        tm.free(); tl.free()
+        return n_layers
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ctx.profile(True)
+    launches0 = ctx.launch_count()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        step()
+    ms = ctx.timer_stop()
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.launch_count() - launches0
+    prof = {k: ctx.profile_read(i) for i, k in enumerate(["ntt_pass", "merkle_leaves", "merkle_nodes", "fri_fold", "open", "other"])}
+    ctx.profile(False)
+    # exchange alone
+    ext = be.lde(d_cols, g2, log_s, 3)
+    barrier()
+    ctx.timer_start()
+    for _ in range(3):
+        sc.exchange({c: ext[k] for k, c in enumerate(mine)}, Cn, N)
+    xch_ms = ctx.timer_stop() / 3
+    del ext
+    # e2e: inputs start in pinned host memory, roots come back to the host
+    step(upload=True)
+    barrier()
+    t0 = time.perf_counter()
+    ctx.timer_start()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        step(upload=True)
+    e2e_ms = ctx.timer_stop()
+    barrier()
+    e2e_ms = max(e2e_ms, (time.perf_counter() - t0) * 1e3) / e2e_steps
+    step_ms = ms / args.steps
+    t = torch.tensor([step_ms, e2e_ms, xch_ms, float(launches)], device=dev, dtype=torch.float64)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        step_ms, e2e_ms, xch_ms, launches = float(tmax[0]), float(tmax[1]), float(tmax[2]), int(tsum[3])
+    if rank == 0:
+        n_ntt, ntt_ms = prof["ntt_pass"]
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = peaks.get("hbm_gbs") or 6650.0
+        elems_rank0 = len(mine) * (S * len(ntt_plan(log_s)) + N * len(ntt_plan(L)))
+        n_pass = len(ntt_plan(log_s)) + len(ntt_plan(L))
+        alg = 64.0 * elems_rank0 / n_pass
+        avg = ntt_ms / max(n_ntt, 1)
+        ach = alg / (avg * 1e-3) / 1e9 if avg > 0 else 0.0
+        total = Cn * N
+        xbytes = len(mine) * (N - N // world) * 32
+        print(json.dumps({
+            "metric": "hot_path_extended_elems_per_s", "value": total / (step_ms * 1e-3), "unit": "elems/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u32x8 (254-bit Montgomery, integer)", "data": "synthetic (seeded uniform field elements)",
+            "config": {"workload": "ONE job sharded over %d GPU(s): LDE 2^%d->2^%d x %d cols (column c on rank c %% world) -> NCCL send/recv to row shards -> "
+                                   "subtree Merkle(8 cols) + Merkle(1 col), all_gather of subtree roots -> FRI(2^%d) on rank %d" % (world, log_s, L, Cn, L, fri_owner),
+                       "log_n": L, "cols": Cn, "mode": "sharded", "l2": "inputs and outputs exceed L2; no explicit flush"},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "breakdown": {"exchange_ms": xch_ms, "exchange_bytes_sent_rank0": xbytes,
+                          "exchange_gbs_rank0": xbytes / (xch_ms * 1e-3) / 1e9 if xch_ms > 0 else None,
+                          "kernel_ms_per_step_rank0": {k: v[1] / args.steps for k, v in prof.items()},
+                          "m_root": roots["m"].hex(), "l_root": roots["l"].hex()},
+            "roofline": {"bound": "hbm", "kernel": "ntt_pass_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": None, "avg_launch_ms": avg, "algorithmic_bytes_per_launch": alg,
+                         "note": "rank 0's launches; the kernel is bound by the IMAD.WIDE issue rate, see DESIGN.md 4.2"},
+            "e2e": {"value": total / (e2e_ms * 1e-3), "unit": "elems/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": Cn * S * 32, "d2h_bytes_per_step": 64 * world + 2 * 32 * world * world}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def ntt_plan(log_n, maxb=8):
     if log_n == 0:
         return [0]
@@ -369,6 +508,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--mode", default="replicas", choices=["replicas", "sharded"],
+                    help="replicas: every GPU runs its own batch (weak scaling, default); sharded: ONE job over all GPUs (strong scaling)")
     args = ap.parse_args()
     assert args.warmup >= 0 and args.steps >= 1
     if args.impl == "reference":
@@ -386,7 +527,10 @@ def main():
             "e2e": {"value": value, "unit": "elems/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "the Rust reference cannot be built here (no cargo/rustc); this is the C restatement in oracle/ (kind=port)"}))
         return
-    run_gpu(args)
+    if args.mode == "sharded":
+        run_gpu_sharded(args)
+    else:
+        run_gpu(args)
 
 
 if __name__ == "__main__":

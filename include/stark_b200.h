@@ -58,6 +58,11 @@ int sb_sync(sb_ctx *ctx);
 /* CUDA-event stopwatch on the context's stream (bench harness). */
 int sb_timer_start(sb_ctx *ctx);
 int sb_timer_stop(sb_ctx *ctx, float *ms);
+/* Domains beyond the reference's limits (BASELINE.json configs[4], N = 2^26): the reference sampler asserts
+ * modulus < 2^24 (fri/src/utils.rs:88), so prove_low_degree cannot take more than 2^26 values with columns of 2^24.
+ * enable = 1 applies the same rule to larger moduli (exact in u32 while modulus * 7 < 2^32); default 0 = the
+ * reference's behaviour (SB_ERR_ARG where it would panic).  No parity target exists in this range. */
+int sb_set_extended_domain(sb_ctx *ctx, int enable);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t sb_launch_count(const sb_ctx *ctx);
 

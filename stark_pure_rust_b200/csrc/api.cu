@@ -545,11 +545,15 @@ extern "C" void sb_tree_free(sb_ctx *ctx, sb_tree *t) {
 // ------------------------------------------------------------------------------------------------
 extern "C" void sb_blake2s(const uint8_t *msg, size_t len, uint8_t out[32]) { b2s::hash_bytes(out, msg, len); }
 
-// fri/src/utils.rs:82-109
-extern "C" int sb_pseudorandom_indices(const uint8_t *seed, size_t seed_len, uint32_t modulus, size_t count, uint32_t excl,
-                                       uint32_t *out) {
+// fri/src/utils.rs:82-109.  `extended`: lift the reference's `modulus < 2^24` assert (utils.rs:88) for domains the
+// reference cannot handle (BASELINE config 5, N = 2^26); the rule itself is unchanged and the u32 arithmetic stays
+// exact as long as modulus * (excl - 1) < 2^32.
+int pseudorandom_indices(const uint8_t *seed, size_t seed_len, uint32_t modulus, size_t count, uint32_t excl, uint32_t *out,
+                         bool extended) {
     if (!seed || !out) return SB_ERR_ARG;
-    if (modulus >= (1u << 24) || modulus == 0) return SB_ERR_ARG;   // utils.rs:88 assert
+    if (modulus == 0) return SB_ERR_ARG;
+    if (!extended && modulus >= (1u << 24)) return SB_ERR_ARG;   // utils.rs:88 assert
+    if (excl > 1 && (uint64_t)modulus * (excl - 1) >= ((uint64_t)1 << 32)) return SB_ERR_ARG;
     std::vector<uint8_t> data(seed, seed + seed_len);
     while (data.size() < 4 * count) {
         uint8_t d[32];
@@ -568,6 +572,15 @@ extern "C" int sb_pseudorandom_indices(const uint8_t *seed, size_t seed_len, uin
             out[i] = t + 1 + t / (excl - 1);
         }
     }
+    return SB_OK;
+}
+extern "C" int sb_pseudorandom_indices(const uint8_t *seed, size_t seed_len, uint32_t modulus, size_t count, uint32_t excl,
+                                       uint32_t *out) {
+    return pseudorandom_indices(seed, seed_len, modulus, count, excl, out, false);
+}
+extern "C" int sb_set_extended_domain(sb_ctx *ctx, int enable) {
+    if (!ctx) return SB_ERR_ARG;
+    ctx->extended_domain = enable != 0;
     return SB_OK;
 }
 
@@ -610,7 +623,7 @@ int fri_prove_dev(sb_ctx *ctx, const uint4 *d_vals, size_t n, const hfp::el &roo
             proof->layers.push_back(std::move(L));
             break;
         }
-        if (cur_n < 4 || cur_n / 4 >= (1u << 24)) { rc = fail(ctx, SB_ERR_ARG, "FRI layer of %zu values unsupported", cur_n); break; }
+        if (cur_n < 4 || (cur_n / 4 >= (1u << 24) && !(ctx->extended_domain && cur_n / 4 <= (1u << 28)))) { rc = fail(ctx, SB_ERR_ARG, "FRI layer of %zu values unsupported", cur_n); break; }
         // fri.rs:120-131: tree over the values (reused when the caller / previous layer built it)
         if (!cur_tree) {
             sb_tree *t = nullptr;
@@ -645,7 +658,7 @@ int fri_prove_dev(sb_ctx *ctx, const uint4 *d_vals, size_t n, const hfp::el &roo
         memcpy(L.root2, t2->root, 32);
         // fri.rs:181-190
         uint32_t ys[FRI_QUERIES];
-        if (sb_pseudorandom_indices(t2->root, 32, (uint32_t)q, FRI_QUERIES, excl, ys) != SB_OK) {
+        if (pseudorandom_indices(t2->root, 32, (uint32_t)q, FRI_QUERIES, excl, ys, ctx->extended_domain) != SB_OK) {
             rc = fail(ctx, SB_ERR_ARG, "sampler: column length %zu out of range", q);
             break;
         }

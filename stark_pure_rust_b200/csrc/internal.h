@@ -30,6 +30,7 @@ struct sb_ctx {
     uint64_t launches = 0;
     std::vector<TwTable> tables;
     char err[512] = {0};
+    bool extended_domain = false;      // sb_set_extended_domain: FRI layers beyond the reference sampler's 2^24 limit
     // pinned host staging arena (front end -> sb_prove_r1cs uploads); grows on demand, freed in sb_destroy
     void *pinned = nullptr;
     size_t pinned_bytes = 0;
@@ -166,6 +167,8 @@ static fp to_dev_fp(const hfp::el &a) {
 }
 
 // ---- functions defined in api.cu ---------------------------------------------------------------
+int pseudorandom_indices(const uint8_t *seed, size_t seed_len, uint32_t modulus, size_t count, uint32_t excl, uint32_t *out,
+                         bool extended);
 // returns a pinned host buffer of at least `bytes` owned by the context (contents are scratch), NULL on failure
 void *pinned_arena(sb_ctx *ctx, size_t bytes);
 // dense: the caller indexes the table directly (the prover's `xs`), so a strided view of a larger cached table will not do

@@ -354,3 +354,34 @@ def test_prove_synthetic_circuits(ctx, oracle, n_constraints, avg_terms, seed, t
     got = str(tmp_path / "got.json")
     sb.prove.prove_with_file_path(prefix + ".r1cs", prefix + ".wtns", got, ctx=ctx)
     assert oracle.sha256_file(got) == oracle.sha256_file(want)
+
+
+# ---- sharded commitment -------------------------------------------------------------------
+def _run_sharded_check(world, log_n, n_cols):
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    script = os.path.join(ROOT, "tools", "sharded_check.py")
+    if world == 1:
+        cmd = [sys.executable, script, str(log_n), str(n_cols)]
+    else:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+               "--master-port", str(29600 + world), script, str(log_n), str(n_cols)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "SHARDED_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_sharded_commit_world1():
+    """the sharded code path with one rank (no collective): same root and openings as the plain column tree"""
+    _run_sharded_check(1, 14, 5)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_commit_multi_gpu(world):
+    """column-sharded LDE -> NCCL send/recv to row shards -> subtree commit -> all_gather of roots, against one
+    single-GPU tree over all columns.  Needs `world` GPUs on the box (gpurun --gpus N); skipped otherwise."""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    _run_sharded_check(world, 16, 9)
