@@ -316,8 +316,26 @@ def run_gpu(args):
     except Exception:
         pass
 
+    # integer roofline of the same kernel: algorithmic Montgomery products ((n/2) log2 n per transform,
+    # + n for the inverse's scaling) over the kernel's measured time, against the measured issue-rate ceiling of a
+    # register-only chain of Montgomery products on this GPU (sb_pipe_peak)
+    alg_modmuls = Cn * ((S // 2) * log_s + S + (N // 2) * L)
+    peak_mm, peak_imad = C.c_double(), C.c_double()
+    ctx.check(lib.sb_pipe_peak(ctx.h, 0, C.byref(peak_mm)))
+    ctx.check(lib.sb_pipe_peak(ctx.h, 1, C.byref(peak_imad)))
+    mm_rate = alg_modmuls / (ntt_ms / args.steps * 1e-3) if ntt_ms > 0 else 0.0
+    int_pipe = {"kernel": "ntt_pass_kernel", "unit": "Montgomery products/s", "achieved": mm_rate, "peak": peak_mm.value,
+                "frac": mm_rate / peak_mm.value if peak_mm.value else None,
+                "algorithmic_modmuls_per_step": alg_modmuls,
+                "imad_wide_per_s_peak_measured": peak_imad.value,
+                "imad_wide_per_s_needed": mm_rate * 128,
+                "note": "peak = register-only chains of fp_mul timed live on this GPU; one product = 128 IMAD.WIDE.U32 (quarter-rate fmaheavy pipe)"}
+
     total_elems = world * Cn * N
     value = total_elems / (step_ms * 1e-3)
+    prove = None
+    if world == 1 and not args.no_prove:
+        prove = run_prove_extras(ctx, args)
     out = {
         "metric": "hot_path_extended_elems_per_s", "value": value, "unit": "elems/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
@@ -337,8 +355,11 @@ def run_gpu(args):
         "roofline": {"bound": "hbm", "kernel": "ntt_pass_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "avg_launch_ms": avg_launch_ms, "algorithmic_bytes_per_launch": alg_bytes_per_launch,
-                     "note": "integer-pipe bound kernel (8x32-bit Montgomery IMAD chains); the HBM fraction is reported because the contract asks for hbm|tensor"},
+                     "note": "integer-pipe bound kernel (8x32-bit Montgomery IMAD chains); the HBM fraction is reported because the contract asks for hbm|tensor; see int_pipe"},
+        "int_pipe": int_pipe,
     }
+    if prove:
+        out["prove"] = prove
     if e2e:
         out["e2e"] = {"value": total_elems / (e2e["ms"] * 1e-3), "unit": "elems/s", "ms_per_step": e2e["ms"],
                       "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"])}
@@ -348,6 +369,59 @@ def run_gpu(args):
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def run_prove_extras(ctx, args):
+    """BASELINE.json's first metric, "prove sec per circuit": the whole r1cs-stark pipeline (sb_prove_files: parse, trace
+    arrangement, device-resident mk_r1cs_proof, proof.json written) on the bundled poseidon3_test (configs[2]) and on a
+    seeded synthetic circuit of sha256_2_test's scale (configs[3]; the real .r1cs is missing from the reference mount),
+    next to the CPU oracle's prover on the box's host cores for the first one (the second takes ~70 s on 16 cores)."""
+    import tempfile
+    import stark_pure_rust_b200 as sb
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    out = {}
+    tmp = tempfile.mkdtemp(prefix="sb_bench_")
+
+    def gpu_prove(r1cs, wtns, reps=3):
+        best = None
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            ms = sb.prove.prove_with_file_path(r1cs, wtns, os.path.join(tmp, "proof.json"), ctx=ctx)
+            wall = time.perf_counter() - t0
+            if best is None or wall < best[0]:
+                best = (wall, ms)
+        return {"gpu_s": best[0], "gpu_stage_ms": {"lde": best[1][0], "m_tree": best[1][1], "fri": best[1][2], "pointwise_and_rest": best[1][3],
+                                                   "device_total": best[1][4], "host_front_end": best[1][5], "json_write": best[1][6]},
+                "proof_bytes": os.path.getsize(os.path.join(tmp, "proof.json"))}
+
+    d = os.path.join(ROOT, "tests", "golden", "circuits")
+    r = gpu_prove(os.path.join(d, "poseidon3_test.r1cs"), os.path.join(d, "poseidon3_test.wtns"))
+    if not args.no_cpu:
+        import oracle_bind as ob
+        t0 = time.perf_counter()
+        rc, _ = ob.prove_files(os.path.join(d, "poseidon3_test.r1cs"), os.path.join(d, "poseidon3_test.wtns"), os.path.join(tmp, "oracle.json"), verify=False)
+        r["cpu_s"] = time.perf_counter() - t0
+        r["cpu_cores"] = os.cpu_count()
+        r["identical_proof_json"] = ob.sha256_file(os.path.join(tmp, "oracle.json")) == ob.sha256_file(os.path.join(tmp, "proof.json"))
+    r["precision"] = 1 << 16
+    out["poseidon3_test"] = r
+    import gen_r1cs
+    wit, cons = gen_r1cs.generate(30000, 8.0, 2, 1)
+    info = gen_r1cs.write_files(os.path.join(tmp, "syn"), wit, cons, 2)
+    r = gpu_prove(os.path.join(tmp, "syn.r1cs"), os.path.join(tmp, "syn.wtns"))
+    r.update(info)
+    r["precision"] = 1 << 23
+    if args.prove_cpu_large and not args.no_cpu:
+        import oracle_bind as ob
+        t0 = time.perf_counter()
+        ob.prove_files(os.path.join(tmp, "syn.r1cs"), os.path.join(tmp, "syn.wtns"), os.path.join(tmp, "oracle.json"), verify=False)
+        r["cpu_s"] = time.perf_counter() - t0
+        r["cpu_cores"] = os.cpu_count()
+        r["identical_proof_json"] = ob.sha256_file(os.path.join(tmp, "oracle.json")) == ob.sha256_file(os.path.join(tmp, "proof.json"))
+    out["synthetic_30000_constraints (sha256_2_test scale)"] = r
+    import shutil
+    shutil.rmtree(tmp, ignore_errors=True)
+    return out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -508,6 +582,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-prove", action="store_true", help="skip the prove-sec-per-circuit extras")
+    ap.add_argument("--prove-cpu-large", action="store_true", help="also time the CPU oracle on the 2^23 synthetic circuit (~70 s)")
     ap.add_argument("--mode", default="replicas", choices=["replicas", "sharded"],
                     help="replicas: every GPU runs its own batch (weak scaling, default); sharded: ONE job over all GPUs (strong scaling)")
     args = ap.parse_args()

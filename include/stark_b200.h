@@ -79,6 +79,10 @@ uint64_t sb_launch_count(const sb_ctx *ctx);
 int sb_profile(sb_ctx *ctx, int enable);
 int sb_profile_read(sb_ctx *ctx, int kind, uint64_t *launches, double *total_ms);
 
+/* Measured issue-rate ceiling of the integer pipe the field arithmetic runs on (bench.py's integer roofline): a
+ * register-only probe kernel timed with CUDA events.  which = 0: Montgomery products / s, 1: IMAD.WIDE.U32 / s. */
+int sb_pipe_peak(sb_ctx *ctx, int which, double *ops_per_s);
+
 /* ---- device memory (pipelines that keep vectors resident in HBM) --------------------------- */
 int sb_dev_alloc(sb_ctx *ctx, size_t bytes, void **d_ptr);
 int sb_dev_free(sb_ctx *ctx, void *d_ptr);

@@ -95,6 +95,7 @@ def load():
         "sb_stark_proof_free": (None, [vp]),
         "sb_prove_files": (i32, [vp, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_double)]),
         "sb_set_extended_domain": (i32, [vp, i32]),
+        "sb_pipe_peak": (i32, [vp, i32, C.POINTER(C.c_double)]),
         "sb_profile": (i32, [vp, i32]),
         "sb_profile_read": (i32, [vp, i32, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
     }

@@ -827,3 +827,37 @@ extern "C" int sb_fp_vec_op(sb_ctx *ctx, int op, const uint64_t *a, const uint64
     CU(cudaStreamSynchronize(ctx->stream));
     return SB_OK;
 }
+
+// Measured issue-rate ceilings for bench.py's integer roofline: a register-only kernel of independent chains, timed with
+// CUDA events on the context's stream (best of 5).  which = 0: Montgomery products per second, 1: IMAD.WIDE.U32 per second.
+extern "C" int sb_pipe_peak(sb_ctx *ctx, int which, double *ops_per_s) {
+    if (!ctx || !ops_per_s || which < 0 || which > 1) return SB_ERR_ARG;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, ctx->device));
+    const unsigned blocks = (unsigned)prop.multiProcessorCount * 2;        // 16 warps per SM, like ntt_pass_kernel
+    DevBuf out(ctx);
+    TRY(out.alloc((size_t)blocks * 256 * 32));
+    hfp::el g = hfp::from_u64(7);
+    fp seed;
+    memcpy(seed.l, g.l, 32);
+    const uint32_t iters = which == 0 ? 512 : 4096;
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a));
+    CU(cudaEventCreate(&b));
+    double best = 0;
+    for (int rep = 0; rep < 6; rep++) {
+        cudaEventRecord(a, ctx->stream);
+        const double ops = pipe_probe_launch(ctx->stream, which, (uint4 *)out.p, blocks, iters, seed);
+        cudaEventRecord(b, ctx->stream);
+        ctx->launches++;
+        cudaEventSynchronize(b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        if (rep > 0 && ms > 0 && ops / (ms * 1e-3) > best) best = ops / (ms * 1e-3);
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    CU(cudaGetLastError());
+    *ops_per_s = best;
+    return SB_OK;
+}

@@ -44,3 +44,13 @@ int fp_launch_vec_op(cudaStream_t s, int op, const uint4 *a, const uint4 *b, uin
     fp_vec_op_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(op, a, b, out, n);
     return 1;
 }
+
+// returns the number of probe operations (Montgomery products / IMAD.WIDE) the launch performs in total
+double pipe_probe_launch(cudaStream_t s, int mode, uint4 *out, unsigned blocks, uint32_t iters, const fp &seed) {
+    if (mode == 0) {
+        pipe_probe_kernel<0><<<blocks, 256, 0, s>>>(out, iters, seed);
+        return 2.0 * iters * blocks * 256.0;
+    }
+    pipe_probe_kernel<1><<<blocks, 256, 0, s>>>(out, iters, seed);
+    return 32.0 * iters * blocks * 256.0;
+}

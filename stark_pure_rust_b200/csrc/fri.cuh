@@ -195,3 +195,46 @@ __global__ void fp_vec_op_kernel(int op, const uint4 *a, const uint4 *b, uint4 *
     }
     fp_stg(out, i, r);
 }
+
+// ---- issue-rate probes (bench.py's integer roofline): no memory traffic inside the loop ----------------------
+// mode 0: independent chains of Montgomery products (what every arithmetic kernel here is made of)
+// mode 1: independent chains of IMAD.WIDE.U32 (the instruction a Montgomery product is made of: 128 per product)
+template <int MODE>
+__global__ void __launch_bounds__(256) pipe_probe_kernel(uint4 *out, uint32_t iters, const fp seed) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (MODE == 0) {
+        fp x[2], m;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            m.l[k] = seed.l[k];
+            x[0].l[k] = seed.l[k] ^ (t * 2654435761u);
+            x[1].l[k] = seed.l[(k + 3) & 7] + t;
+        }
+        x[0].l[7] &= 0x0fffffffu; x[1].l[7] &= 0x0fffffffu;
+#pragma unroll 1
+        for (uint32_t i = 0; i < iters; i++) {
+            x[0] = fp_mul(x[0], m);
+            x[1] = fp_mul(x[1], m);
+        }
+        fp r = fp_add(x[0], x[1]);
+        fp_stg(out, t, r);
+    } else {
+        unsigned long long w[8];
+        const uint32_t m = seed.l[0] | 1u;
+#pragma unroll
+        for (int k = 0; k < 8; k++) w[k] = ((unsigned long long)(t + k) << 32) | seed.l[k];
+#pragma unroll 1
+        for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    asm volatile("{.reg .u32 lo, hi; mov.b64 {lo, hi}, %0; xor.b32 lo, lo, hi; mul.wide.u32 %0, lo, %1;}" : "+l"(w[k]) : "r"(m));
+            }
+        }
+        unsigned long long acc = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc += w[k];
+        out[t] = make_uint4((uint32_t)acc, (uint32_t)(acc >> 32), 0, 0);
+    }
+}

@@ -32,3 +32,4 @@ int fp_launch_to_bytes(cudaStream_t stream, const uint4 *in, uint4 *out, unsigne
 unsigned long long batch_inverse_scratch_elems(unsigned long long n);
 int batch_inverse_launch(cudaStream_t stream, uint4 *vals, uint4 *scratch, unsigned long long n);
 int fp_launch_vec_op(cudaStream_t stream, int op, const uint4 *a, const uint4 *b, uint4 *out, unsigned long long n);
+double pipe_probe_launch(cudaStream_t stream, int mode, uint4 *out, unsigned blocks, uint32_t iters, const fp &seed);
