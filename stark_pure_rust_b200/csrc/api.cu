@@ -745,20 +745,30 @@ extern "C" int sb_fri_layer_root(const sb_fri_proof *p, size_t i, uint8_t root[3
 }
 
 void json_bytes(std::string &s, const uint8_t *b, size_t n) {
-    // serde_json prints a Vec<u8> / BlakeDigest(Vec<u8>) as an array of decimal integers
+    // serde_json prints a Vec<u8> / BlakeDigest(Vec<u8>) as an array of decimal integers.  Written straight into the
+    // string's buffer (at most 4 characters per byte): the proof is megabytes of these.
     static char tab[256][4];
     static uint8_t len[256];
     static bool init = false;
     if (!init) {
-        for (int v = 0; v < 256; v++) len[v] = (uint8_t)snprintf(tab[v], 4, "%d", v);
+        for (int v = 0; v < 256; v++) {
+            char t[8];
+            len[v] = (uint8_t)snprintf(t, sizeof t, "%d,", v);
+            memcpy(tab[v], t, 4);
+        }
         init = true;
     }
-    s.push_back('[');
+    const size_t at = s.size();
+    s.resize(at + 4 * n + 2);
+    char *w = &s[at];
+    *w++ = '[';
     for (size_t i = 0; i < n; i++) {
-        if (i) s.push_back(',');
-        s.append(tab[b[i]], len[b[i]]);
+        memcpy(w, tab[b[i]], 4);
+        w += len[b[i]];
     }
-    s.push_back(']');
+    if (n) w--;                   // the last element's comma
+    *w++ = ']';
+    s.resize((size_t)(w - &s[0]));
 }
 // Proof{leaf,nodes} (merkle_tree.rs:14-18)
 void json_branches(std::string &s, const uint8_t *leaves, size_t leaf_bytes, const uint8_t *nodes, size_t depth, size_t count) {

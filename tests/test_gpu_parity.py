@@ -385,3 +385,122 @@ def test_sharded_commit_multi_gpu(world):
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     _run_sharded_check(world, 16, 9)
+
+
+# ---- BASELINE.json full sizes: size-independent properties (the oracle takes minutes at these sizes) ------------
+def _fri_verify_python(proof, values_root, root_int, n, max_deg_plus_1, excl):
+    """fri.rs:244-404 restated with Python big ints on the GPU proof: every opening validates against its root, the
+    sampled column values equal the degree-<4 interpolant of the four row values at special_x, and the last layer is a
+    polynomial of degree < its bound."""
+    import stark_pure_rust_b200 as sb
+    from stark_pure_rust_b200 import field
+    Pm = field.P
+    w, bound, root = root_int, max_deg_plus_1, values_root
+    for layer in proof[:-1]:
+        m = layer["Middle"]
+        q = n // 4
+        special_x = int.from_bytes(root, "little") % Pm                       # fri.rs:275
+        ys = sb.utils.get_pseudorandom_indices(m["root2"], q, 40, excl)
+        assert sb.merkle.verify_multi_branch(m["root2"], ys, m["column_branches"])
+        pos = [y + q * j for y in ys for j in range(4)]
+        assert sb.merkle.verify_multi_branch(root, pos, m["poly_branches"])
+        iota = pow(w, q, Pm)
+        for k, y in enumerate(ys):
+            x = pow(w, y, Pm)
+            xs = [x * pow(iota, j, Pm) % Pm for j in range(4)]
+            vs = [int.from_bytes(m["poly_branches"][4 * k + j].leaf, "little") for j in range(4)]
+            acc = 0                                                          # Lagrange through the four points
+            for i in range(4):
+                num, den = 1, 1
+                for j in range(4):
+                    if i != j:
+                        num = num * (special_x - xs[j]) % Pm
+                        den = den * (xs[i] - xs[j]) % Pm
+                acc = (acc + vs[i] * num * pow(den, -1, Pm)) % Pm
+            assert acc == int.from_bytes(m["column_branches"][k].leaf, "little")
+        root, w, n, bound = m["root2"], pow(w, 4, Pm), q, bound // 4
+    last = [int.from_bytes(b, "little") for b in proof[-1]["Last"]["last"]]
+    assert len(last) == n
+    # degree check of the last layer by evaluating the interpolant of the first `bound` points at the others is O(n^2)
+    # with n <= 64: Lagrange at a few extra points
+    xs = [pow(w, i, Pm) for i in range(n)]
+    for probe in range(bound, min(n, bound + 3)):
+        acc = 0
+        for i in range(bound):
+            num, den = 1, 1
+            for j in range(bound):
+                if i != j:
+                    num = num * (xs[probe] - xs[j]) % Pm
+                    den = den * (xs[i] - xs[j]) % Pm
+            acc = (acc + last[i] * num * pow(den, -1, Pm)) % Pm
+        assert acc == last[probe]
+    return True
+
+
+def test_full_size_2_24_properties(ctx):
+    """BASELINE.json configs[1] top of the sweep (one 2^24 column): LDE restricted to the original domain returns the
+    input, INTT(NTT) round trip with the zero upper 7/8, Merkle checksum-of-checksums and openings, FRI self-consistency."""
+    import stark_pure_rust_b200 as sb
+    from stark_pure_rust_b200 import field
+    from stark_pure_rust_b200._lib import _ptr
+    L, log_s = 24, 21
+    N, S = 1 << L, 1 << log_s
+    g2i = field.root_of_unity(L)
+    col = random_elems(S, 2424)
+    ext = sb.fft.lde_batch(col.reshape(1, S, 4), g2i, log_s, 3, ctx=ctx)[0]
+    assert np.array_equal(ext[::8], col)                                        # the subgroup LDE keeps the trace values
+    coef = sb.fft.inv_best_fft(ext, g2i, L, ctx=ctx)
+    assert not coef[S:].any()                                                   # degree < S
+    assert np.array_equal(sb.fft.best_fft(coef[:S], pow(g2i, 8, field.P), log_s, ctx=ctx), col)
+    # Merkle: the root of the whole tree is H(root(first half) || root(second half)); openings validate on the host
+    leaves = np.ascontiguousarray(ext).view(np.uint8).reshape(N, 32)            # any 32-byte leaves will do
+    def commit(buf, n):
+        root, t = np.empty(32, dtype=np.uint8), C.c_void_p()
+        ctx.check(ctx.lib.sb_merkle_commit(ctx.h, _ptr(buf), 32, n, _ptr(root), C.byref(t)))
+        return root.tobytes(), t
+    root, tree = commit(leaves, N)
+    r0, t0 = commit(leaves[: N // 2], N // 2)
+    r1, t1 = commit(leaves[N // 2:], N // 2)
+    assert sb.utils.blake(r0 + r1) == root
+    idx = np.array([0, N - 1, N // 2, 12345678, 12345678], dtype=np.uint64)
+    lv, nd = np.empty(idx.size * 32, dtype=np.uint8), np.empty(idx.size * L * 32, dtype=np.uint8)
+    ctx.check(ctx.lib.sb_merkle_open(ctx.h, tree, idx.ctypes.data_as(C.POINTER(C.c_size_t)), idx.size, _ptr(lv), _ptr(nd)))
+    for q, i in enumerate(idx):
+        pr = sb.merkle.Proof(lv[32 * q:32 * q + 32].tobytes(), [nd[(q * L + l) * 32:(q * L + l + 1) * 32].tobytes() for l in range(L)])
+        assert pr.leaf == leaves[int(i)].tobytes() and pr.validate(root, int(i))
+    for t in (tree, t0, t1):
+        ctx.lib.sb_tree_free(ctx.h, t)
+    # FRI on the extended column (degree < S <= N/4)
+    proof = sb.fri.prove_low_degree(ext, g2i, N // 4, 8, ctx=ctx)
+    assert [list(l)[0] for l in proof] == ["Middle"] * 9 + ["Last"]
+    # root of the values tree: leaves are to_bytes_le of the values
+    vals_tree = sb.merkle.MerkleProofInPlace(ctx)
+    h, rootv, tv = C.c_void_p(), np.empty(32, dtype=np.uint8), C.c_void_p()
+    d = ctx.to_device(ext)
+    ptrs = (C.c_void_p * 1)(d)
+    ctx.check(ctx.lib.sb_merkle_commit_cols_dev(ctx.h, ptrs, 1, N, _ptr(rootv), C.byref(tv)))
+    ctx.lib.sb_tree_free(ctx.h, tv)
+    ctx.free(d)
+    assert _fri_verify_python(proof, rootv.tobytes(), g2i, N, N // 4, 8)
+
+
+def test_synthetic_sha256_scale_prove_matches_golden(ctx, tmp_path):
+    """BASELINE.json configs[3] stand-in (tools/gen_r1cs.py 30000 constraints, avg 8 terms, seed 1: 955086 steps, precision
+    2^23): proof.json hash equals the CPU oracle's, recorded in tests/golden/vectors.json (the oracle needs ~70 s on 16
+    cores / 3 min on 8 for this circuit, so it is not re-run here)."""
+    import json
+    import os
+    import sys
+    import stark_pure_rust_b200 as sb
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_r1cs
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "vectors.json")))["proofs"]["synthetic_30000_8_2_1"]
+    prefix = str(tmp_path / "syn")
+    wit, cons = gen_r1cs.generate(30000, 8.0, 2, 1)
+    info = gen_r1cs.write_files(prefix, wit, cons, 2)
+    assert info["original_steps"] == gold["original_steps"]
+    out = str(tmp_path / "proof.json")
+    sb.prove.prove_with_file_path(prefix + ".r1cs", prefix + ".wtns", out, ctx=ctx)
+    assert hashlib.sha256(open(out, "rb").read()).hexdigest() == gold["proof_json_sha256"]
+    assert os.path.getsize(out) == gold["proof_json_bytes"]
