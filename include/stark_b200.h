@@ -143,6 +143,11 @@ int sb_fri_prove(sb_ctx *ctx, const uint64_t *vals, size_t n, const uint64_t roo
  * prove.rs:324-332) or NULL. */
 int sb_fri_prove_dev(sb_ctx *ctx, const uint64_t *d_vals, size_t n, const uint64_t root[4], size_t max_deg_plus_1,
                      uint32_t exclude_multiples_of, const sb_tree *values_tree, sb_fri_proof **out);
+/* One fold step (fri.rs:135-164): d_col[i] (n/4 elements) = the degree-<4 interpolant through
+ * (x * iota^j, d_vals[i + j n/4]), j < 4, evaluated at special_x = int_LE(values_root) mod p.  Used by the sharded
+ * prover, whose first values tree is spread over several GPUs (stark_pure_rust_b200/sharded.py). */
+int sb_fri_fold_dev(sb_ctx *ctx, const uint64_t *d_vals, size_t n, const uint64_t root[4], const uint8_t values_root[32],
+                    uint64_t *d_col);
 /* Proof accessors.  Layers 0..n_layers-2 are FriProof::Middle, the last one is FriProof::Last (fri.rs:16-26). */
 size_t sb_fri_n_layers(const sb_fri_proof *p);
 int sb_fri_layer_is_last(const sb_fri_proof *p, size_t layer);
@@ -200,6 +205,9 @@ int sb_fp_vec_op(sb_ctx *ctx, int op, const uint64_t *a, const uint64_t *b, uint
 /* get_pseudorandom_indices (fri/src/utils.rs:82-109) */
 int sb_pseudorandom_indices(const uint8_t *seed, size_t seed_len, uint32_t modulus, size_t count,
                             uint32_t exclude_multiples_of, uint32_t *out);
+/* same, honouring the context's sb_set_extended_domain setting (moduli >= 2^24) */
+int sb_pseudorandom_indices_ctx(const sb_ctx *ctx, const uint8_t *seed, size_t seed_len, uint32_t modulus, size_t count,
+                                uint32_t exclude_multiples_of, uint32_t *out);
 /* blake (fri/src/utils.rs:5-10) */
 void sb_blake2s(const uint8_t *msg, size_t len, uint8_t out[32]);
 

@@ -77,6 +77,7 @@ def load():
         "sb_tree_free": (None, [vp, vp]),
         "sb_fri_prove": (i32, [vp, vp, sz, vp, sz, u32, C.POINTER(vp)]),
         "sb_fri_prove_dev": (i32, [vp, vp, sz, vp, sz, u32, vp, C.POINTER(vp)]),
+        "sb_fri_fold_dev": (i32, [vp, vp, sz, vp, vp, vp]),
         "sb_fri_n_layers": (sz, [vp]),
         "sb_fri_layer_is_last": (i32, [vp, sz]),
         "sb_fri_middle": (i32, [vp, sz, C.POINTER(vp), szp, szp, C.POINTER(vp), C.POINTER(vp), szp, szp, C.POINTER(vp), C.POINTER(vp)]),
@@ -86,6 +87,7 @@ def load():
         "sb_free_string": (None, [vp]),
         "sb_fri_proof_free": (None, [vp]),
         "sb_pseudorandom_indices": (i32, [vp, sz, u32, sz, u32, vp]),
+        "sb_pseudorandom_indices_ctx": (i32, [vp, vp, sz, u32, sz, u32, vp]),
         "sb_blake2s": (None, [vp, sz, vp]),
         "sb_fp_vec_op": (i32, [vp, i32, vp, vp, vp, sz]),
         "sb_prove_r1cs": (i32, [vp, vp, C.POINTER(vp)]),

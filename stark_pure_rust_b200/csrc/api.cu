@@ -578,6 +578,10 @@ extern "C" int sb_pseudorandom_indices(const uint8_t *seed, size_t seed_len, uin
                                        uint32_t *out) {
     return pseudorandom_indices(seed, seed_len, modulus, count, excl, out, false);
 }
+extern "C" int sb_pseudorandom_indices_ctx(const sb_ctx *ctx, const uint8_t *seed, size_t seed_len, uint32_t modulus, size_t count,
+                                           uint32_t excl, uint32_t *out) {
+    return pseudorandom_indices(seed, seed_len, modulus, count, excl, out, ctx && ctx->extended_domain);
+}
 extern "C" int sb_set_extended_domain(sb_ctx *ctx, int enable) {
     if (!ctx) return SB_ERR_ARG;
     ctx->extended_domain = enable != 0;
@@ -691,6 +695,29 @@ int fri_prove_dev(sb_ctx *ctx, const uint4 *d_vals, size_t n, const hfp::el &roo
         return rc;
     }
     *out = proof;
+    return SB_OK;
+}
+
+// one fold (fri.rs:135-164) on device-resident values: the sharded prover runs layer 0 against a values tree whose
+// subtrees live on several GPUs and only needs the column from this GPU
+extern "C" int sb_fri_fold_dev(sb_ctx *ctx, const uint64_t *d_vals, size_t n, const uint64_t root[4], const uint8_t values_root[32],
+                               uint64_t *d_col) {
+    if (!ctx || !d_vals || !root || !values_root || !d_col) return SB_ERR_ARG;
+    if (!is_pow2(n) || n < 4) return fail(ctx, SB_ERR_ARG, "FRI fold needs a power-of-two number of values >= 4, got %zu", n);
+    const uint4 *tw;
+    uint32_t tw_log_n, log_stride;
+    TRY(get_table(ctx, hfp::from_limbs(root), ilog2(n), &tw, &tw_log_n, &log_stride));
+    hfp::el special_x = hfp::from_bytes_le32(values_root);      // fri.rs:135
+    FriFoldParams P;
+    P.vals = (const uint4 *)d_vals;
+    P.col = (uint4 *)d_col;
+    P.tw = tw;
+    P.n = n;
+    P.tw_log_n = tw_log_n;
+    P.tw_log_stride = log_stride;
+    memcpy(P.special_x, special_x.l, 32);
+    KLAUNCH(SB_KIND_FRI_FOLD, fri_launch_fold(ctx->stream, P));
+    CU(cudaGetLastError());
     return SB_OK;
 }
 

@@ -110,8 +110,36 @@ class CudaBackend:
     def free(self, tree):
         self.ctx.lib.sb_tree_free(self.ctx.h, tree[0])
 
+    def fri_fold(self, vals, root_limbs, values_root):
+        """fri.rs:135-164: (n, 4) values -> (n/4, 4) column at special_x = int_LE(values_root) mod p"""
+        n = vals.shape[0]
+        col = self.empty(n // 4, 4)
+        root = np.ascontiguousarray(root_limbs, dtype=np.uint64)
+        vr = np.frombuffer(bytes(values_root), dtype=np.uint8).copy()
+        self.ctx.check(self.ctx.lib.sb_fri_fold_dev(self.ctx.h, C.c_void_p(vals.data_ptr()), n, C.c_void_p(root.ctypes.data),
+                                                    C.c_void_p(vr.ctypes.data), C.c_void_p(col.data_ptr())))
+        return col
+
+    def fri_rest(self, col, root_limbs, max_deg_plus_1, excl, tree):
+        """prove_low_degree on the folded column with its already committed tree -> list of layers (fri.py layout)"""
+        from . import fri
+        root = np.ascontiguousarray(root_limbs, dtype=np.uint64)
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.sb_fri_prove_dev(self.ctx.h, C.c_void_p(col.data_ptr()), col.shape[0], C.c_void_p(root.ctypes.data),
+                                                     max_deg_plus_1, excl, tree[0], C.byref(h)))
+        try:
+            return fri.unpack_proof(self.ctx, h)
+        finally:
+            self.ctx.lib.sb_fri_proof_free(h)
+
     def root_tensor(self, root):
         return self.torch.frombuffer(bytearray(root), dtype=self.torch.uint8).to(self.device)
+
+    def bytes_tensor(self, a):
+        return self.torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint8)).to(self.device)
+
+    def leaf_bytes(self, tree):
+        return tree[2]
 
 
 # ---- the sharded commitment ----------------------------------------------------------------------------
@@ -144,17 +172,27 @@ class ShardedTree:
 
     def gen_proofs(self, indices, dist=None, group=None):
         """every rank calls this with the same indices (they come out of the Fiat-Shamir sampler, which every rank
-        runs on the same root) and gets all openings, in caller order, duplicates allowed"""
+        runs on the same root) and gets all openings, in caller order, duplicates allowed.  Each opening is owned by
+        exactly one rank, so the exchange is one all_reduce(SUM) of a byte matrix that is zero outside the caller's rows
+        (a few hundred KB; no pickling on the path)."""
         local = self.gen_proofs_local(indices)
         if self.world == 1 or dist is None:
-            parts = [local]
-        else:
-            parts = [None] * self.world
-            dist.all_gather_object(parts, local, group=group)
-        merged = {}
-        for p in parts:
-            merged.update(p)
-        return [merged[p] for p in range(len(indices))]
+            return [local[p] for p in range(len(indices))]
+        lb = self.backend.leaf_bytes(self.local_tree)
+        depth = self.n.bit_length() - 1
+        row = lb + 32 * depth
+        buf = np.zeros((len(indices), row), dtype=np.uint8)
+        for p, (leaf, nodes) in local.items():
+            buf[p, :lb] = np.frombuffer(leaf, dtype=np.uint8)
+            buf[p, lb:] = np.frombuffer(b"".join(nodes), dtype=np.uint8)
+        t = self.backend.bytes_tensor(buf)
+        dist.all_reduce(t, group=group)
+        raw = t.cpu().numpy().tobytes()
+        out = []
+        for p in range(len(indices)):
+            r = raw[p * row:(p + 1) * row]
+            out.append((r[:lb], [r[lb + 32 * l:lb + 32 * (l + 1)] for l in range(depth)]))
+        return out
 
     def free(self):
         if self.local_tree is not None:
@@ -210,3 +248,49 @@ class ShardedCommitter:
             b = allr.cpu().numpy().tobytes()
             roots = [b[32 * i:32 * (i + 1)] for i in range(self.world)]
         return ShardedTree(self.backend, tree, n, self.world, self.rank, roots)
+
+
+def prove_low_degree_sharded(backend, values_tree, vals, owner, root_int, n, max_deg_plus_1, excl, dist=None, group=None,
+                             replicate=False):
+    """fri.rs:46-224 when the values tree of layer 0 is a ShardedTree (the prover's l_tree, prove.rs:324-332, built
+    over row shards) and the values themselves sit whole on rank `owner` (the rank that extended / combined that
+    column).  Layer 0: the owner folds and commits the column, broadcasts the 32-byte root2, every rank derives the
+    same query positions (fri.rs:181-204) and contributes the openings of the rows it owns; layers >= 1 hold <= n/4
+    values and run on the owner alone.  Returns the proof (fri.py layout) on the owner and None
+    elsewhere; replicate=True broadcasts it (pickled) to every rank."""
+    from . import field, merkle as mk
+    world, rank = values_tree.world, values_tree.rank
+    if max_deg_plus_1 <= 16:
+        raise ValueError("a direct (Last-only) proof has no layer to shard")      # fri.rs:88 MIN_DEG_DIRECT_CHECKING
+    q = n // 4
+    w_limbs = field.mont_scalar(root_int)
+    w4_limbs = field.mont_scalar(pow(root_int, 4, field.P))
+    rest, col_tree, column_branches = None, None, None
+    if rank == owner:
+        col = backend.fri_fold(vals, w_limbs, values_tree.get_root())
+        root2, col_tree = backend.commit_cols([col])
+    else:
+        root2 = bytes(32)
+    if world > 1:
+        t = backend.root_tensor(root2)
+        dist.broadcast(t, owner if group is None else dist.get_global_rank(group, owner), group=group)
+        root2 = t.cpu().numpy().tobytes()
+    ys = utils.get_pseudorandom_indices(root2, q, 40, excl, ctx=getattr(backend, "ctx", None))                      # fri.rs:181-190
+    positions = [y + q * j for y in ys for j in range(4)]                        # fri.rs:193-204
+    poly = values_tree.gen_proofs(positions, dist if world > 1 else None, group)
+    layer0 = None
+    if rank == owner:
+        cb = backend.open(col_tree, ys)
+        layer0 = {"Middle": {"root2": root2,
+                             "column_branches": [mk.Proof(leaf, nodes) for leaf, nodes in cb],
+                             "poly_branches": [mk.Proof(leaf, nodes) for leaf, nodes in poly]}}
+        rest = backend.fri_rest(col, w4_limbs, max_deg_plus_1 // 4, excl, col_tree)
+        backend.free(col_tree)
+        proof = [layer0] + rest
+    else:
+        proof = None
+    if replicate and world > 1 and dist is not None:
+        box = [proof]
+        dist.broadcast_object_list(box, owner if group is None else dist.get_global_rank(group, owner), group=group)
+        proof = box[0]
+    return proof

@@ -16,12 +16,16 @@ def blake(message):
     return out.tobytes()
 
 
-def get_pseudorandom_indices(seed, modulus, count, exclude_multiples_of=0):
-    """utils.rs:82-109"""
+def get_pseudorandom_indices(seed, modulus, count, exclude_multiples_of=0, ctx=None):
+    """utils.rs:82-109.  With a context whose extended domain is enabled (sb_set_extended_domain) moduli >= 2^24
+    are accepted; the reference asserts modulus < 2^24 (utils.rs:88)."""
     lib = load()
     s = np.frombuffer(bytes(seed), dtype=np.uint8)
     out = np.empty(count, dtype=np.uint32)
-    rc = lib.sb_pseudorandom_indices(_ptr(s) if s.size else None, s.size, modulus, count, exclude_multiples_of, _ptr(out))
+    if ctx is not None:
+        rc = lib.sb_pseudorandom_indices_ctx(ctx.h, _ptr(s) if s.size else None, s.size, modulus, count, exclude_multiples_of, _ptr(out))
+    else:
+        rc = lib.sb_pseudorandom_indices(_ptr(s) if s.size else None, s.size, modulus, count, exclude_multiples_of, _ptr(out))
     if rc != 0:
         raise StarkB200Error(rc, "get_pseudorandom_indices: the reference panics on these arguments")
     return [int(x) for x in out]

@@ -61,6 +61,12 @@ class OracleBackend:
     def root_tensor(self, root):
         return self.torch.frombuffer(bytearray(root), dtype=self.torch.uint8).clone()
 
+    def bytes_tensor(self, a):
+        return self.torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint8).copy())
+
+    def leaf_bytes(self, tree):
+        return tree[2]
+
 
 def _worker(rank, world, port, n_cols, log_s, ret):
     import torch.distributed as dist

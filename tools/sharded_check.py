@@ -54,6 +54,21 @@ def main():
         ok = ok and all(merkle.Proof(leaf, nodes).validate(root1, i) for (leaf, nodes), i in zip(proofs, idx))
         be.free(t1)
         print(("SHARDED_OK" if ok else "SHARDED_MISMATCH"), "world", world, "L", L, "cols", Cn, "root", tree.get_root().hex(), flush=True)
+    # FRI with the row-sharded values tree of the last column (the prover's l_tree) against the single-GPU prover
+    lc = Cn - 1
+    owner = lc % world
+    ltree = sc.commit_rows(rows, [lc], N)
+    vals = ext[mine.index(lc)] if rank == owner else None
+    g2i = field.root_of_unity(L)
+    proof = sharded.prove_low_degree_sharded(be, ltree, vals, owner, g2i, N, N // 4, 8, dist if world > 1 else None, replicate=True)
+    if rank == 0:
+        want = sb.fri.prove_low_degree(full[lc].cpu().numpy().view(np.uint64), g2i, N // 4, 8, ctx=ctx)
+        same = len(proof) == len(want)
+        for a, b in zip(proof, want):
+            same = same and a == b
+        print(("SHARDED_FRI_OK" if same else "SHARDED_FRI_MISMATCH"), "layers", len(proof), flush=True)
+        ok = ok and same
+    ltree.free()
     tree.free()
     if world > 1:
         dist.barrier()
