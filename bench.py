@@ -333,9 +333,11 @@ def run_gpu(args):
 
     total_elems = world * Cn * N
     value = total_elems / (step_ms * 1e-3)
-    prove = None
+    prove = sweep = None
     if world == 1 and not args.no_prove:
         prove = run_prove_extras(ctx, args)
+    if world == 1 and not args.no_sweep:
+        sweep = run_sweep(ctx, args)
     out = {
         "metric": "hot_path_extended_elems_per_s", "value": value, "unit": "elems/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
@@ -360,6 +362,8 @@ def run_gpu(args):
     }
     if prove:
         out["prove"] = prove
+    if sweep:
+        out["sweep"] = sweep
     if e2e:
         out["e2e"] = {"value": total_elems / (e2e["ms"] * 1e-3), "unit": "elems/s", "ms_per_step": e2e["ms"],
                       "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"])}
@@ -369,6 +373,44 @@ def run_gpu(args):
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def run_sweep(ctx, args):
+    """BASELINE.json configs[1]: batched fft / inv_fft / LDE sweep over domains 2^16..2^24 on one GPU, device resident,
+    CUDA-event timed (best of 3 after a warm-up).  elems/s = columns * 2^k / t.  The reference's LDE is the subgroup LDE
+    (inv_best_fft at 2^(k-3), zero pad, best_fft at 2^k: prove.rs:100-124); that is the parity-checked variant."""
+    from stark_pure_rust_b200 import field
+    from stark_pure_rust_b200._lib import _ptr
+    lib = ctx.lib
+    rows = []
+    kmax = min(24, args.log_n)
+    cmax = 10
+    src = ctx.to_device(random_elems(cmax << kmax, 0x5EED).reshape(-1, 4))
+    dst = ctx.alloc((cmax << kmax) * 32)
+
+    def best(fn):
+        fn()
+        t = []
+        for _ in range(3):
+            ctx.timer_start()
+            fn()
+            t.append(ctx.timer_stop())
+        return min(t)
+
+    for k in range(16, kmax + 1, 2):
+        n, s = 1 << k, 1 << (k - 3)
+        w = field.mont_scalar(field.root_of_unity(k))
+        row = {"log_n": k}
+        for cols in (1, 10):
+            f = best(lambda: ctx.check(lib.sb_ntt_dev(ctx.h, C.c_void_p(src), n, n, C.c_void_p(dst), n, cols, _ptr(w), k, 0)))
+            i = best(lambda: ctx.check(lib.sb_ntt_dev(ctx.h, C.c_void_p(src), n, n, C.c_void_p(dst), n, cols, _ptr(w), k, 1)))
+            l = best(lambda: ctx.check(lib.sb_lde_batch_dev(ctx.h, C.c_void_p(src), cols, s, s, _ptr(w), k - 3, 3, C.c_void_p(dst))))
+            row["cols%d" % cols] = {"fft_elems_per_s": cols * n / (f * 1e-3), "inv_fft_elems_per_s": cols * n / (i * 1e-3),
+                                    "lde_elems_per_s": cols * n / (l * 1e-3), "fft_ms": f, "inv_fft_ms": i, "lde_ms": l}
+        rows.append(row)
+    ctx.free(src)
+    ctx.free(dst)
+    return rows
 
 
 def run_prove_extras(ctx, args):
@@ -581,6 +623,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the 2^16..2^24 fft / inv_fft / LDE sweep")
     ap.add_argument("--no-prove", action="store_true", help="skip the prove-sec-per-circuit extras")
     ap.add_argument("--prove-cpu-large", action="store_true", help="also time the CPU oracle on the 2^23 synthetic circuit (~70 s)")
     ap.add_argument("--mode", default="replicas", choices=["replicas", "sharded"],

@@ -220,18 +220,20 @@ static int plan_bits(uint32_t log_n, uint32_t *bits) {
     return m;
 }
 
-int ntt_dev(sb_ctx *ctx, const uint4 *d_src, size_t len_in, size_t src_stride, uint4 *d_dst, size_t dst_stride,
-                   size_t n_polys, const hfp::el &root, uint32_t log_n, int inverse) {
+// coset_log > 0: the coset transforms of a low-degree extension (see NttPassParams); `root` is then the root of the
+// 2^log_n-point transform (W^(2^coset_log)) and the table must be the extended domain's (tw of W).
+static int ntt_dev_tw(sb_ctx *ctx, const uint4 *d_src, size_t len_in, size_t src_stride, uint4 *d_dst, size_t dst_stride,
+                      size_t n_polys, uint32_t log_n, int inverse, const uint4 *tw, uint32_t tw_log_n, uint32_t log_stride,
+                      uint32_t coset_log) {
     const size_t n = (size_t)1 << log_n;
     if (len_in > n) return fail(ctx, SB_ERR_ARG, "vector of %zu elements does not fit a 2^%u transform", len_in, log_n);
     if (n_polys == 0) return SB_OK;
-    const uint4 *tw;
-    uint32_t tw_log_n, log_stride;
-    TRY(get_table(ctx, root, log_n, &tw, &tw_log_n, &log_stride));
+    const uint32_t coset_m1 = coset_log ? (1u << coset_log) - 1 : 0;
+    const size_t n_batch = coset_m1 ? n_polys * coset_m1 : n_polys;       // transforms in flight
     uint32_t bits[NTT_MAX_PASSES];
     const int m = plan_bits(log_n, bits);
     DevBuf work(ctx);
-    if (m > 1) TRY(work.alloc(n_polys * n * 32));
+    if (m > 1) TRY(work.alloc(n_batch * n * 32));
     hfp::el ninv = hfp::inv(hfp::from_u64((uint64_t)n));
     uint32_t log_outer = 0;
     for (int p = 0; p < m; p++) {
@@ -244,7 +246,7 @@ int ntt_dev(sb_ctx *ctx, const uint4 *d_src, size_t len_in, size_t src_stride, u
         P.dst_stride = last ? dst_stride : n;
         P.tw = tw;
         P.len_in = len_in;
-        P.n_cols_total = (unsigned long long)n_polys << (log_n - bits[p]);
+        P.n_cols_total = (unsigned long long)n_batch << (log_n - bits[p]);
         P.log_n = log_n;
         P.log_outer = log_outer;
         P.log_inner = log_n - log_outer - bits[p];
@@ -253,9 +255,12 @@ int ntt_dev(sb_ctx *ctx, const uint4 *d_src, size_t len_in, size_t src_stride, u
         P.inverse = inverse ? 1 : 0;
         P.tw_log_n = tw_log_n;
         P.tw_log_stride = log_stride;
-        {   // interleave polynomials when a tile never straddles two of them
+        P.coset_m1 = coset_m1;
+        P.coset_log = coset_log;
+        {   // interleave polynomials when a tile never straddles two of them (the coset transforms also in the last
+            // pass: the CTAs that fill the same output lines then run together)
             const unsigned long long cpp = 1ull << (log_n - bits[p]), cc = (1ull << NTT_LOG_TILE) >> bits[p];
-            P.n_polys = (n_polys > 1 && !last && cpp % cc == 0 && n_polys < (1u << 20)) ? (uint32_t)n_polys : 0;
+            P.n_polys = (n_batch > 1 && (!last || coset_m1) && cpp % cc == 0 && n_batch < (1u << 20)) ? (uint32_t)n_batch : 0;
         }
         P.n_prev = (uint32_t)p;
         for (int i = 0; i < p; i++) P.prev_bits[i] = bits[i];
@@ -266,6 +271,17 @@ int ntt_dev(sb_ctx *ctx, const uint4 *d_src, size_t len_in, size_t src_stride, u
     }
     CU(cudaGetLastError());
     return SB_OK;
+}
+
+int ntt_dev(sb_ctx *ctx, const uint4 *d_src, size_t len_in, size_t src_stride, uint4 *d_dst, size_t dst_stride,
+                   size_t n_polys, const hfp::el &root, uint32_t log_n, int inverse) {
+    const size_t n = (size_t)1 << log_n;
+    if (len_in > n) return fail(ctx, SB_ERR_ARG, "vector of %zu elements does not fit a 2^%u transform", len_in, log_n);
+    if (n_polys == 0) return SB_OK;
+    const uint4 *tw;
+    uint32_t tw_log_n, log_stride;
+    TRY(get_table(ctx, root, log_n, &tw, &tw_log_n, &log_stride));
+    return ntt_dev_tw(ctx, d_src, len_in, src_stride, d_dst, dst_stride, n_polys, log_n, inverse, tw, tw_log_n, log_stride, 0);
 }
 
 extern "C" int sb_ntt_dev(sb_ctx *ctx, const uint64_t *d_src, size_t len_in, size_t src_stride, uint64_t *d_dst,
@@ -291,21 +307,33 @@ extern "C" int sb_ntt(sb_ctx *ctx, uint64_t *vals, size_t len_in, const uint64_t
     return SB_OK;
 }
 
+// Low-degree extension (prove.rs:100-124: best_fft(inv_best_fft(col, W^E, log_s), W, log_s + log_ext), E = 2^log_ext).
+// The zero-padded forward transform is computed coset by coset: out[E k + r] = sum_j (c_j W^(j r)) (W^E)^(j k), i.e. E - 1
+// transforms of S points on pre-scaled coefficients; coset r = 0 is the input column itself (same field elements, the
+// arithmetic is exact), so it is copied.  This skips the three degenerate butterfly stages and one eighth of the rest.
 int lde_dev(sb_ctx *ctx, const uint4 *d_cols, size_t n_cols, size_t col_len, size_t col_stride,
                    const hfp::el &root_big, uint32_t log_s, uint32_t log_ext, uint4 *d_out) {
     if (log_s + log_ext > 28) return fail(ctx, SB_ERR_ARG, "extended domain 2^%u exceeds two-adicity 28", log_s + log_ext);
     const size_t S = (size_t)1 << log_s, N = S << log_ext;
     if (col_len > S) return fail(ctx, SB_ERR_ARG, "column of %zu elements does not fit 2^%u", col_len, log_s);
-    // make sure the big table exists first so that the small transform reuses it with a stride
+    if (n_cols == 0) return SB_OK;
+    // the extended domain's table serves both transforms: W^E with stride E, and the coset scaling W^(j r)
     const uint4 *tw;
-    uint32_t a, b;
-    TRY(get_table(ctx, root_big, log_s + log_ext, &tw, &a, &b));
-    hfp::el root_small = root_big;
-    for (uint32_t i = 0; i < log_ext; i++) root_small = hfp::sqr(root_small);
+    uint32_t tw_log_n, log_stride;
+    TRY(get_table(ctx, root_big, log_s + log_ext, &tw, &tw_log_n, &log_stride));
+    if (log_ext == 0 || log_ext > 8) {
+        hfp::el root_small = root_big;
+        for (uint32_t i = 0; i < log_ext; i++) root_small = hfp::sqr(root_small);
+        DevBuf coef(ctx);
+        TRY(coef.alloc(n_cols * S * 32));
+        TRY(ntt_dev(ctx, d_cols, col_len, col_stride, (uint4 *)coef.p, S, n_cols, root_small, log_s, 1));
+        return ntt_dev(ctx, (const uint4 *)coef.p, S, S, d_out, N, n_cols, root_big, log_s + log_ext, 0);
+    }
     DevBuf coef(ctx);
     TRY(coef.alloc(n_cols * S * 32));
-    TRY(ntt_dev(ctx, d_cols, col_len, col_stride, (uint4 *)coef.p, S, n_cols, root_small, log_s, 1));
-    TRY(ntt_dev(ctx, (const uint4 *)coef.p, S, S, d_out, N, n_cols, root_big, log_s + log_ext, 0));
+    TRY(ntt_dev_tw(ctx, d_cols, col_len, col_stride, (uint4 *)coef.p, S, n_cols, log_s, 1, tw, tw_log_n, log_stride + log_ext, 0));
+    KLAUNCH(SB_KIND_OTHER, lde_launch_coset0(ctx->stream, d_cols, col_len, col_stride, d_out, N, S, log_ext, n_cols));
+    TRY(ntt_dev_tw(ctx, (const uint4 *)coef.p, S, S, d_out, N, n_cols, log_s, 0, tw, tw_log_n, log_stride + log_ext, log_ext));
     return SB_OK;
 }
 

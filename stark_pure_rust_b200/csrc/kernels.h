@@ -14,6 +14,8 @@ struct fp;
 // ntt_b*.cu
 cudaError_t ntt_set_attrs();
 int ntt_launch_pass(cudaStream_t stream, uint32_t bits, const NttPassParams &P);
+int lde_launch_coset0(cudaStream_t stream, const uint4 *in, unsigned long long col_len, unsigned long long in_stride, uint4 *out,
+                      unsigned long long out_stride, unsigned long long s_len, uint32_t log_ext, unsigned long long n_cols);
 // merkle.cu
 int merkle_launch_leaves_cols(cudaStream_t stream, uint32_t lv, const MerkleColsParams &P);
 int merkle_launch_leaves_bytes(cudaStream_t stream, uint32_t lv, const MerkleBytesParams &P);

@@ -142,9 +142,21 @@ __global__ void __launch_bounds__((1 << LOG_TILE) / 8, 2) ntt_pass_kernel(const 
                 e = (ntt_digitrev_inv(P, gl) << B) + r;
             }
             if (!P.first || e < P.len_in) {
-                const uint4 *s = P.src + 2 * (poly * P.src_stride + e);
-                lo = s[0];
-                hi = s[1];
+                if (P.first && P.coset_m1) {
+                    // coefficient e of column poly / coset_m1, scaled onto coset r: c_e * W^(e r)
+                    const unsigned long long col = poly / P.coset_m1, rr = poly % P.coset_m1 + 1;
+                    const uint4 *s = P.src + 2 * (col * P.src_stride + e);
+                    fp v = fp_from_u4(s[0], s[1]);
+                    const unsigned long long nT = 1ull << P.tw_log_n;
+                    const unsigned long long ti = ((e * rr) << (P.tw_log_stride - P.coset_log)) & (nT - 1);
+                    v = fp_mul(v, fp_ldg_ro(P.tw, ti));
+                    lo = fp_lo(v);
+                    hi = fp_hi(v);
+                } else {
+                    const uint4 *s = P.src + 2 * (poly * P.src_stride + e);
+                    lo = s[0];
+                    hi = s[1];
+                }
             }
         }
         slo[r * PITCH + j] = lo;
@@ -181,6 +193,12 @@ __global__ void __launch_bounds__((1 << LOG_TILE) / 8, 2) ntt_pass_kernel(const 
             v = fp_canon(v);
         }
         (void)n;
-        fp_stg(P.dst, poly * P.dst_stride + e, v);
+        if (P.last && P.coset_m1) {
+            const unsigned long long col = poly / P.coset_m1, rr = poly % P.coset_m1 + 1;
+            fp_stg(P.dst, col * P.dst_stride + (e << P.coset_log) + rr, v);
+        } else {
+            fp_stg(P.dst, poly * P.dst_stride + e, v);
+        }
     }
 }
+

@@ -34,6 +34,11 @@ struct NttPassParams {
     uint32_t n_prev;               // last pass: widths of the earlier passes, in order
     uint32_t prev_bits[NTT_MAX_PASSES];
     uint32_t n_inv[8];             // Montgomery form of n^-1 (inverse transform, last pass)
+    // coset mode (low-degree extension by 2^coset_log, lde_dev): the batch holds (column, r) pairs, r = 1 .. 2^coset_log - 1
+    // (polynomial id = column * coset_m1 + r - 1).  The first pass reads coefficient j of `column` and scales it by
+    // W^(j r) (W = the extended domain's root, w = W^(2^coset_log)); the last pass writes output k to element
+    // k * 2^coset_log + r of `column`.  coset_m1 == 0: plain transform.
+    uint32_t coset_m1, coset_log;
 };
 
 struct MerkleColsParams {

@@ -3,7 +3,7 @@
 # kernel (ntt_pass_kernel: the six passes of one LDE) and of the 8-column Merkle leaf kernel.  Outputs in gpurun_out/.
 set -u
 TAG=${1:-r01}
-CMD="python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu --no-prove"
+CMD="python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu --no-prove --no-sweep"
 $CMD > gpurun_out/plain_${TAG}.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_${TAG}.csv $CMD > gpurun_out/ncu_list_${TAG}.log 2>&1
 echo "launch list rc=$?"

@@ -4,7 +4,7 @@
 NS=${1:-"1 2"}; L=${2:-26}; C=${3:-8}; TAG=${4:-r01}
 for N in $NS; do
   if [ "$N" = "1" ]; then LAUNCH="python"; else LAUNCH="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29700+N))"; fi
-  $LAUNCH bench.py --gpus $N --steps 5 --warmup 3 --no-cpu --no-prove > gpurun_out/scale_replicas_${TAG}_n$N.json 2> gpurun_out/scale_replicas_${TAG}_n$N.err
+  $LAUNCH bench.py --gpus $N --steps 5 --warmup 3 --no-cpu --no-prove --no-sweep > gpurun_out/scale_replicas_${TAG}_n$N.json 2> gpurun_out/scale_replicas_${TAG}_n$N.err
   echo "replicas N=$N rc=$?"; tail -c 400 gpurun_out/scale_replicas_${TAG}_n$N.json | head -c 10 >/dev/null
   $LAUNCH bench.py --gpus $N --mode sharded --log-n $L --cols $C --steps 3 --warmup 2 > gpurun_out/scale_sharded_${TAG}_L${L}_n$N.json 2> gpurun_out/scale_sharded_${TAG}_L${L}_n$N.err
   echo "sharded N=$N rc=$?"
