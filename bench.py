@@ -604,6 +604,81 @@ def run_gpu_sharded(args):
         dist.destroy_process_group()
 
 
+def run_gpu_sharded_ntt(args):
+    """ONE 2^L-point transform over all ranks: natural-order slabs in and out, four-step with three NCCL
+    all_to_all exchanges (stark_pure_rust_b200/sharded.py::distributed_ntt).  value = 2^L / step time: strong scaling."""
+    import torch
+    import torch.distributed as dist
+    import stark_pure_rust_b200 as sb
+    from stark_pure_rust_b200 import field, sharded
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = sb.Context(local_rank)
+    be = sharded.CudaBackend(ctx, dev)
+    L = args.log_n
+    n = 1 << L
+    w = field.root_of_unity(L)
+    h_x = torch.from_numpy(random_elems(n // world, 0xA11 + rank).view(np.int64)).pin_memory()
+    x = h_x.to(dev)
+    d = dist if world > 1 else None
+
+    def step(upload=False):
+        xin = h_x.to(dev, non_blocking=True) if upload else x
+        y = sharded.distributed_ntt(be, xin, w, L, False, d)
+        if upload:
+            return y.to("cpu", non_blocking=True)
+        return y
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ctx.launch_count()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        step()
+    ms = ctx.timer_stop() / args.steps
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.launch_count() - launches0
+    step(upload=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        step(upload=True)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / 3
+    t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ms, e2e_ms = float(t[0]), float(t[1])
+        print(json.dumps({
+            "metric": "ntt_elems_per_s", "value": n / (ms * 1e-3), "unit": "elems/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u32x8 (254-bit Montgomery, integer)", "data": "synthetic (seeded uniform field elements)",
+            "config": {"workload": "ONE best_fft of 2^%d points over %d GPU(s), natural-order slabs in and out, four-step with 3 all_to_all" % (L, world),
+                       "log_n": L, "mode": "sharded-ntt", "l2": "vector exceeds L2; no explicit flush"},
+            "gpu_launches": int(launches) * world, "clocks": clocks,
+            "breakdown": {"exchange_bytes_per_rank_per_all_to_all": (n // world) * 32 * (world - 1) // world},
+            "e2e": {"value": n / (e2e_ms * 1e-3), "unit": "elems/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": n * 32}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def ntt_plan(log_n, maxb=8):
     if log_n == 0:
         return [0]
@@ -626,7 +701,7 @@ def main():
     ap.add_argument("--no-sweep", action="store_true", help="skip the 2^16..2^24 fft / inv_fft / LDE sweep")
     ap.add_argument("--no-prove", action="store_true", help="skip the prove-sec-per-circuit extras")
     ap.add_argument("--prove-cpu-large", action="store_true", help="also time the CPU oracle on the 2^23 synthetic circuit (~70 s)")
-    ap.add_argument("--mode", default="replicas", choices=["replicas", "sharded"],
+    ap.add_argument("--mode", default="replicas", choices=["replicas", "sharded", "sharded-ntt"],
                     help="replicas: every GPU runs its own batch (weak scaling, default); sharded: ONE job over all GPUs (strong scaling)")
     args = ap.parse_args()
     assert args.warmup >= 0 and args.steps >= 1
@@ -645,7 +720,9 @@ def main():
             "e2e": {"value": value, "unit": "elems/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "the Rust reference cannot be built here (no cargo/rustc); this is the C restatement in oracle/ (kind=port)"}))
         return
-    if args.mode == "sharded":
+    if args.mode == "sharded-ntt":
+        run_gpu_sharded_ntt(args)
+    elif args.mode == "sharded":
         run_gpu_sharded(args)
     else:
         run_gpu(args)

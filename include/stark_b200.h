@@ -101,6 +101,10 @@ int sb_ntt(sb_ctx *ctx, uint64_t *vals, size_t len_in, const uint64_t root[4], u
  * dst_stride (elements), d_dst must not alias d_src. */
 int sb_ntt_dev(sb_ctx *ctx, const uint64_t *d_src, size_t len_in, size_t src_stride, uint64_t *d_dst,
                size_t dst_stride, size_t n_polys, const uint64_t root[4], uint32_t log_n, int inverse);
+/* Twiddle step of a 2^log_n-point transform split four-step style over several GPUs (stark_pure_rust_b200/sharded.py,
+ * SURVEY.md 8e(5)): d_vals[r * cols + c] *= root^((row0 + r) * c) (inverse: root^-1), canonical result. */
+int sb_twiddle_mul_dev(sb_ctx *ctx, uint64_t *d_vals, size_t rows, size_t cols, size_t row0, const uint64_t root[4],
+                       uint32_t log_n, int inverse);
 /* Low-degree extension of n_cols columns: best_fft(inv_best_fft(col, root_big^(2^log_ext), log_s),
  * root_big, log_s + log_ext) for every column (prove.rs:100-124).  cols: n_cols x col_len elements
  * (col_len <= 2^log_s, zero padded like inv_best_fft does); out: n_cols x 2^(log_s+log_ext). */

@@ -77,6 +77,7 @@ def load():
         "sb_tree_free": (None, [vp, vp]),
         "sb_fri_prove": (i32, [vp, vp, sz, vp, sz, u32, C.POINTER(vp)]),
         "sb_fri_prove_dev": (i32, [vp, vp, sz, vp, sz, u32, vp, C.POINTER(vp)]),
+        "sb_twiddle_mul_dev": (i32, [vp, vp, sz, sz, sz, vp, u32, i32]),
         "sb_fri_fold_dev": (i32, [vp, vp, sz, vp, vp, vp]),
         "sb_fri_n_layers": (sz, [vp]),
         "sb_fri_layer_is_last": (i32, [vp, sz]),

@@ -292,6 +292,19 @@ extern "C" int sb_ntt_dev(sb_ctx *ctx, const uint64_t *d_src, size_t len_in, siz
                    log_n, inverse);
 }
 
+// four-step twiddle step of a transform split over several GPUs (sharded.py::distributed_ntt)
+extern "C" int sb_twiddle_mul_dev(sb_ctx *ctx, uint64_t *d_vals, size_t rows, size_t cols, size_t row0, const uint64_t root[4],
+                                  uint32_t log_n, int inverse) {
+    if (!ctx || !d_vals || !root) return SB_ERR_ARG;
+    if (log_n > 28) return fail(ctx, SB_ERR_ARG, "log_n %u exceeds the field's two-adicity 28", log_n);
+    const uint4 *tw;
+    uint32_t tw_log_n, log_stride;
+    TRY(get_table(ctx, hfp::from_limbs(root), log_n, &tw, &tw_log_n, &log_stride));
+    KLAUNCH(SB_KIND_OTHER, twiddle_mul_launch(ctx->stream, (uint4 *)d_vals, rows, cols, row0, tw, tw_log_n, log_stride, log_n, inverse ? 1 : 0));
+    CU(cudaGetLastError());
+    return SB_OK;
+}
+
 extern "C" int sb_ntt(sb_ctx *ctx, uint64_t *vals, size_t len_in, const uint64_t root[4], uint32_t log_n, int inverse) {
     if (!ctx || !vals || !root) return SB_ERR_ARG;
     if (log_n > 28) return fail(ctx, SB_ERR_ARG, "log_n %u exceeds the field's two-adicity 28", log_n);

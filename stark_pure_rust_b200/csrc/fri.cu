@@ -54,3 +54,11 @@ double pipe_probe_launch(cudaStream_t s, int mode, uint4 *out, unsigned blocks, 
     pipe_probe_kernel<1><<<blocks, 256, 0, s>>>(out, iters, seed);
     return 32.0 * iters * blocks * 256.0;
 }
+
+int twiddle_mul_launch(cudaStream_t s, uint4 *vals, unsigned long long rows, unsigned long long cols, unsigned long long row0,
+                       const uint4 *tw, uint32_t tw_log_n, uint32_t tw_log_stride, uint32_t log_n, int inverse) {
+    const unsigned long long total = rows * cols;
+    if (total == 0) return 0;
+    twiddle_mul_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(vals, rows, cols, row0, tw, tw_log_n, tw_log_stride, log_n, inverse);
+    return 1;
+}

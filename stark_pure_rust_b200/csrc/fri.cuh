@@ -196,6 +196,20 @@ __global__ void fp_vec_op_kernel(int op, const uint4 *a, const uint4 *b, uint4 *
     fp_stg(out, i, r);
 }
 
+// ---- four-step twiddles (distributed transform, sharded.py): vals[r][c] *= w^((row0 + r) * c), w = T[1 << stride] ----
+__global__ void twiddle_mul_kernel(uint4 *vals, unsigned long long rows, unsigned long long cols, unsigned long long row0,
+                                   const uint4 *tw, uint32_t tw_log_n, uint32_t tw_log_stride, uint32_t log_n, int inverse) {
+    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= rows * cols) return;
+    const unsigned long long r = t / cols, c = t % cols;
+    const unsigned long long n_mask = (1ull << log_n) - 1, nT = 1ull << tw_log_n;
+    const unsigned long long e = ((row0 + r) * c) & n_mask;
+    unsigned long long ti = e << tw_log_stride;
+    if (inverse) ti = (nT - ti) & (nT - 1);
+    fp v = fp_ldg(vals, t);
+    fp_stg(vals, t, fp_canon(fp_mul(v, fp_ldg_ro(tw, ti))));
+}
+
 // ---- issue-rate probes (bench.py's integer roofline): no memory traffic inside the loop ----------------------
 // mode 0: independent chains of Montgomery products (what every arithmetic kernel here is made of)
 // mode 1: independent chains of IMAD.WIDE.U32 (the instruction a Montgomery product is made of: 128 per product)

@@ -35,3 +35,5 @@ unsigned long long batch_inverse_scratch_elems(unsigned long long n);
 int batch_inverse_launch(cudaStream_t stream, uint4 *vals, uint4 *scratch, unsigned long long n);
 int fp_launch_vec_op(cudaStream_t stream, int op, const uint4 *a, const uint4 *b, uint4 *out, unsigned long long n);
 double pipe_probe_launch(cudaStream_t stream, int mode, uint4 *out, unsigned blocks, uint32_t iters, const fp &seed);
+int twiddle_mul_launch(cudaStream_t stream, uint4 *vals, unsigned long long rows, unsigned long long cols, unsigned long long row0,
+                       const uint4 *tw, uint32_t tw_log_n, uint32_t tw_log_stride, uint32_t log_n, int inverse);

@@ -132,6 +132,23 @@ class CudaBackend:
         finally:
             self.ctx.lib.sb_fri_proof_free(h)
 
+    def ntt_batch(self, x, root_int, log_n, inverse=False):
+        """(polys, 2^log_n, 4) contiguous -> same shape: best_fft / inv_best_fft of every row (fft.rs:327-379)"""
+        from . import field
+        polys, n = x.shape[0], 1 << log_n
+        out = self.empty(polys, n, 4)
+        root = field.mont_scalar(root_int)
+        self.ctx.check(self.ctx.lib.sb_ntt_dev(self.ctx.h, C.c_void_p(x.data_ptr()), n, n, C.c_void_p(out.data_ptr()), n, polys,
+                                               C.c_void_p(root.ctypes.data), log_n, 1 if inverse else 0))
+        return out
+
+    def twiddle_mul(self, x, row0, root_int, log_n, inverse=False):
+        """x[r][c] *= root^((row0 + r) c) in place (inverse: root^-1)"""
+        from . import field
+        root = field.mont_scalar(root_int)
+        self.ctx.check(self.ctx.lib.sb_twiddle_mul_dev(self.ctx.h, C.c_void_p(x.data_ptr()), x.shape[0], x.shape[1], row0,
+                                                       C.c_void_p(root.ctypes.data), log_n, 1 if inverse else 0))
+
     def root_tensor(self, root):
         return self.torch.frombuffer(bytearray(root), dtype=self.torch.uint8).to(self.device)
 
@@ -294,3 +311,47 @@ def prove_low_degree_sharded(backend, values_tree, vals, owner, root_int, n, max
         dist.broadcast_object_list(box, owner if group is None else dist.get_global_rank(group, owner), group=group)
         proof = box[0]
     return proof
+
+
+# ---- one transform over several GPUs ---------------------------------------------------
+def distributed_ntt(backend, x_local, root_int, log_n, inverse=False, dist=None, group=None):
+    """best_fft / inv_best_fft (fft.rs:327-379) of ONE 2^log_n-point vector spread over the ranks in natural order:
+    rank r holds elements [r n/g, (r+1) n/g) on entry and the same range of the result on return.  Four-step
+    decomposition n = n1 n2 (j = j1 n2 + j2, k = k1 + n1 k2):
+        all_to_all (row slabs -> column slabs), n1-point transforms along j1, twiddle w^(j2 k1),
+        all_to_all (-> k1 slabs), n2-point transforms along j2, all_to_all (-> natural order).
+    The local transforms are the batched single-GPU kernels; the transposes in between are torch copies; the three
+    exchanges are NCCL all_to_all_single calls of n/g elements each.  The inverse works the same way with w^-1 (the two
+    local inverses contribute 1/n1 and 1/n2)."""
+    from . import field
+    g = dist.get_world_size(group) if dist is not None else 1
+    rank = dist.get_rank(group) if dist is not None else 0
+    n = 1 << log_n
+    if g == 1:
+        return backend.ntt_batch(x_local.reshape(1, n, 4), root_int, log_n, inverse).reshape(n, 4)
+    log_n1 = (log_n + 1) // 2
+    log_n2 = log_n - log_n1
+    n1, n2 = 1 << log_n1, 1 << log_n2
+    if g & (g - 1) or n1 % g or n2 % g:
+        raise ValueError("world size %d must be a power of two dividing both factors of 2^%d" % (g, log_n))
+    if x_local.shape[0] != n // g:
+        raise ValueError("rank slab must hold n / world = %d elements" % (n // g))
+    a, b = n1 // g, n2 // g
+
+    def exchange(t):
+        out = backend.empty(*t.shape)
+        dist.all_to_all_single(out, t, group=group)
+        return out
+
+    # rows j1 in [rank a, (rank+1) a) -> columns j2 in [rank b, (rank+1) b), all j1
+    m1 = exchange(x_local.reshape(a, g, b, 4).permute(1, 0, 2, 3).contiguous())          # [rho][j1'][j2'] = [j1][j2']
+    col = m1.reshape(n1, b, 4).transpose(0, 1).contiguous()                              # [j2'][j1]
+    col = backend.ntt_batch(col, pow(root_int, n2, field.P), log_n1, inverse)            # [j2'][k1]
+    backend.twiddle_mul(col, rank * b, root_int, log_n, inverse)                         # * w^(j2 k1)
+    # columns -> k1 slabs, all j2
+    m2 = exchange(col.reshape(b, g, a, 4).permute(1, 0, 2, 3).contiguous())              # [sigma][j2'][k1'] = [j2][k1']
+    row = m2.reshape(n2, a, 4).transpose(0, 1).contiguous()                              # [k1'][j2]
+    row = backend.ntt_batch(row, pow(root_int, n1, field.P), log_n2, inverse)            # [k1'][k2] = X[k1 + n1 k2]
+    # k1 slabs -> natural order: rank u owns k2 in [u b, (u+1) b)
+    m3 = exchange(row.reshape(a, g, b, 4).permute(1, 0, 2, 3).contiguous())              # [tau][k1'][k2'] = [k1][k2']
+    return m3.reshape(n1, b, 4).transpose(0, 1).contiguous().reshape(n // g, 4)          # [k2'][k1]

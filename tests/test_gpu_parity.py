@@ -369,7 +369,7 @@ def _run_sharded_check(world, log_n, n_cols):
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
                "--master-port", str(29600 + world), script, str(log_n), str(n_cols)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and "SHARDED_OK" in r.stdout and "SHARDED_FRI_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.returncode == 0 and "SHARDED_OK" in r.stdout and "SHARDED_FRI_OK" in r.stdout and "SHARDED_NTT_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 def test_sharded_commit_world1():

@@ -58,6 +58,22 @@ class OracleBackend:
     def free(self, tree):
         pass
 
+    def ntt_batch(self, x, root_int, log_n, inverse=False):
+        from stark_pure_rust_b200 import field
+        root = field.mont_scalar(root_int)
+        out = self.empty(*x.shape)
+        for k in range(x.shape[0]):
+            out[k] = self.from_numpy(self.ob.best_fft(self._np(x[k]), root, log_n, inverse=inverse))
+        return out
+
+    def twiddle_mul(self, x, row0, root_int, log_n, inverse=False):
+        from stark_pure_rust_b200 import field
+        w = pow(root_int, -1, field.P) if inverse else root_int
+        rows, cols = x.shape[0], x.shape[1]
+        vals = field.from_mont(self._np(x).reshape(-1, 4))
+        out = [v * pow(w, ((row0 + i // cols) * (i % cols)) % (1 << log_n), field.P) % field.P for i, v in enumerate(vals)]
+        x.copy_(self.from_numpy(field.to_mont(out)).reshape(rows, cols, 4))
+
     def root_tensor(self, root):
         return self.torch.frombuffer(bytearray(root), dtype=self.torch.uint8).clone()
 
@@ -102,6 +118,50 @@ def _worker(rank, world, port, n_cols, log_s, ret):
         dist.barrier()
     finally:
         dist.destroy_process_group()
+
+
+def _ntt_worker(rank, world, port, log_n, ret):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from conftest import random_elems
+        import oracle_bind as ob
+        from stark_pure_rust_b200 import field, sharded
+        be = OracleBackend()
+        n = 1 << log_n
+        x = random_elems(n, 99 + log_n)
+        w = field.root_of_unity(log_n)
+        lo, hi = sharded.row_range(n, world, rank)
+        ok = True
+        for inverse in (False, True):
+            got = sharded.distributed_ntt(be, be.from_numpy(x[lo:hi]), w, log_n, inverse, dist)
+            want = ob.best_fft(x, field.mont_scalar(w), log_n, inverse=inverse)
+            ok = ok and np.array_equal(be._np(got), want[lo:hi])
+        flags = [None] * world
+        dist.all_gather_object(flags, bool(ok))
+        if rank == 0:
+            ret.put(all(flags))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,log_n", [(2, 6), (2, 9), (4, 8)])
+def test_distributed_ntt_matches_single_process(world, log_n):
+    """four-step transform over `world` ranks (three all_to_all exchanges): every rank's slab of the result equals the
+    oracle's best_fft / inv_best_fft of the whole vector"""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000) + world * 11 + log_n
+    procs = [ctx.Process(target=_ntt_worker, args=(r, world, port, log_n, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    assert ret.get(timeout=5) is True
 
 
 @pytest.mark.parametrize("world,n_cols", [(2, 3), (2, 8), (4, 5)])

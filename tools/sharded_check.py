@@ -68,6 +68,21 @@ def main():
             same = same and a == b
         print(("SHARDED_FRI_OK" if same else "SHARDED_FRI_MISMATCH"), "layers", len(proof), flush=True)
         ok = ok and same
+    # one transform over all ranks (four-step, three all_to_all exchanges) against the single-GPU transform
+    x = random_elems(N, 31337)
+    lo, hi = sharded.row_range(N, world, rank)
+    ntt_ok = True
+    for inverse in (False, True):
+        got = sharded.distributed_ntt(be, be.from_numpy(x[lo:hi]), g2i, L, inverse, dist if world > 1 else None)
+        want = sb.fft.best_fft(x, g2i, L, ctx=ctx, inverse=inverse)
+        ntt_ok = ntt_ok and np.array_equal(got.cpu().numpy().view(np.uint64), want[lo:hi])
+    if world > 1:
+        flag = torch.tensor([1 if ntt_ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ntt_ok = bool(flag.item())
+    if rank == 0:
+        print(("SHARDED_NTT_OK" if ntt_ok else "SHARDED_NTT_MISMATCH"), flush=True)
+    ok = ok and ntt_ok
     ltree.free()
     tree.free()
     if world > 1:
