@@ -22,6 +22,10 @@ extern "C" int sb_init(int device, sb_ctx **out) {
         return SB_ERR_NO_DEVICE;
     }
     ctx->own_stream = true;
+    if (const char *e = getenv("SB_TABLE_CACHE_BYTES")) {
+        const unsigned long long v = strtoull(e, nullptr, 10);
+        if (v) ctx->table_cache_bytes = (size_t)v;
+    }
     cudaEventCreate(&ctx->ev0);
     cudaEventCreate(&ctx->ev1);
     // keep freed scratch cached in the stream-ordered pool
@@ -183,15 +187,35 @@ int get_table(sb_ctx *ctx, const hfp::el &w, uint32_t log_n, const uint4 **tw, u
         hfp::el r = t.root;
         for (uint32_t i = 0; i < t.log_n - log_n; i++) r = hfp::sqr(r);
         if (hfp::eq(r, w)) {
+            t.last_use = ++ctx->table_clock;
             *tw = t.d;
             *tw_log_n = t.log_n;
             *log_stride = t.log_n - log_n;
             return SB_OK;
         }
     }
+    // soft cap: drop least-recently-used tables, but never one of the four most recently used (a single API call
+    // works with at most three: the extended domain's, a strided view of it, and the prover's dense copy)
+    {
+        size_t total = (size_t)32 << log_n;
+        for (auto &t : ctx->tables) total += (size_t)32 << t.log_n;
+        while (total > ctx->table_cache_bytes && ctx->tables.size() > 4) {
+            size_t lru = 0;
+            for (size_t i = 1; i < ctx->tables.size(); i++)
+                if (ctx->tables[i].last_use < ctx->tables[lru].last_use) lru = i;
+            size_t newer = 0;
+            for (auto &t : ctx->tables) newer += t.last_use > ctx->tables[lru].last_use;
+            if (newer < 4) break;
+            cudaStreamSynchronize(ctx->stream);
+            cudaFree(ctx->tables[lru].d);
+            total -= (size_t)32 << ctx->tables[lru].log_n;
+            ctx->tables.erase(ctx->tables.begin() + lru);
+        }
+    }
     TwTable t;
     t.root = w;
     t.log_n = log_n;
+    t.last_use = ++ctx->table_clock;
     CU(cudaMalloc(&t.d, ((size_t)32) << log_n));
     int rc = powers_into(ctx, w, (size_t)1 << log_n, t.d);
     if (rc != SB_OK) {

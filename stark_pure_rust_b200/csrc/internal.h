@@ -20,6 +20,7 @@ struct TwTable {
     hfp::el root;
     uint32_t log_n;
     uint4 *d;
+    uint64_t last_use;
 };
 
 struct sb_ctx {
@@ -29,6 +30,8 @@ struct sb_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint64_t launches = 0;
     std::vector<TwTable> tables;
+    uint64_t table_clock = 0;
+    size_t table_cache_bytes = (size_t)8 << 30;   // soft cap of the twiddle-table cache (SB_TABLE_CACHE_BYTES)
     char err[512] = {0};
     bool extended_domain = false;      // sb_set_extended_domain: FRI layers beyond the reference sampler's 2^24 limit
     // pinned host staging arena (front end -> sb_prove_r1cs uploads); grows on demand, freed in sb_destroy
