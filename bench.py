@@ -289,6 +289,17 @@ def run_gpu(args):
         step_ms = float(t[0]);
         if e2e:
             e2e["ms"] = float(t[1])
+    prove_multi = None
+    if world > 1 and not args.no_prove:
+        # BASELINE.json configs[3] at N > 1: one proof per GPU (replicas); aggregate = N proofs / slowest rank
+        import torch
+        p = run_prove_extras(ctx, args, large_only=True, sync=barrier)
+        key = [k for k in p if k.startswith("synthetic")][0]
+        barrier()
+        t = torch.tensor([p[key]["gpu_s"]], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        prove_multi = {key: dict(p[key], gpu_s_max_over_ranks=float(t[0]), proofs_per_s_all_gpus=world / float(t[0]),
+                                 note="one proof per GPU, concurrently; every process runs its own host front end")}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -351,6 +362,8 @@ def run_gpu(args):
     prove = sweep = None
     if world == 1 and not args.no_prove:
         prove = run_prove_extras(ctx, args)
+    elif prove_multi:
+        prove = prove_multi
     if world == 1 and not args.no_sweep:
         sweep = run_sweep(ctx, args)
     out = {
@@ -428,7 +441,7 @@ def run_sweep(ctx, args):
     return rows
 
 
-def run_prove_extras(ctx, args):
+def run_prove_extras(ctx, args, large_only=False, sync=None):
     """BASELINE.json's first metric, "prove sec per circuit": the whole r1cs-stark pipeline (sb_prove_files: parse, trace
     arrangement, device-resident mk_r1cs_proof, proof.json written) on the bundled poseidon3_test (configs[2]) and on a
     seeded synthetic circuit of sha256_2_test's scale (configs[3]; the real .r1cs is missing from the reference mount),
@@ -453,7 +466,7 @@ def run_prove_extras(ctx, args):
 
     d = os.path.join(ROOT, "tests", "golden", "circuits")
     r = gpu_prove(os.path.join(d, "poseidon3_test.r1cs"), os.path.join(d, "poseidon3_test.wtns"))
-    if not args.no_cpu:
+    if not args.no_cpu and not large_only:
         import oracle_bind as ob
         t0 = time.perf_counter()
         rc, _ = ob.prove_files(os.path.join(d, "poseidon3_test.r1cs"), os.path.join(d, "poseidon3_test.wtns"), os.path.join(tmp, "oracle.json"), verify=False)
@@ -465,6 +478,8 @@ def run_prove_extras(ctx, args):
     import gen_r1cs
     wit, cons = gen_r1cs.generate(30000, 8.0, 2, 1)
     info = gen_r1cs.write_files(os.path.join(tmp, "syn"), wit, cons, 2)
+    if sync:
+        sync()              # N > 1: all ranks prove at the same time
     r = gpu_prove(os.path.join(tmp, "syn.r1cs"), os.path.join(tmp, "syn.wtns"))
     r.update(info)
     r["precision"] = 1 << 23

@@ -178,6 +178,19 @@ __global__ void __launch_bounds__(128) pw_zb3_kernel(const uint4 *xs, uint4 *zb3
     fp_stg(zb3, j, fp_canon(fp_sub(fp_ldg(xs, j), pw_const(Cst.x_last))));
 }
 
+// out[j] = sum_k coef[k] xs[j]^k (Horner): the boundary polynomials i2 / zb2 when only a few public wires are in use
+// (prove.rs:216-224 evaluates them point by point as well; for many public wires an N-point NTT of the same
+// coefficients is used instead -- identical field elements either way)
+__global__ void __launch_bounds__(128) pw_poly_eval_kernel(const uint4 *xs, const uint4 *coef, uint32_t n_coef, uint4 *out,
+                                                           unsigned long long n) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const fp x = fp_ldg(xs, j);
+    fp acc = fp_ldg_ro(coef, n_coef - 1);
+    for (uint32_t k = n_coef - 1; k-- > 0;) acc = fp_add(fp_mul(acc, x), fp_ldg_ro(coef, k));
+    fp_stg(out, j, fp_canon(acc));
+}
+
 // b2 = (s - i2) * inv(zb2), b3 = (a - 1) * inv(zb3)  (utils.rs:477-524); in place over the inverse arrays
 struct PwB23Params {
     const uint4 *s, *a, *i2;     // i2 == NULL: the interpolant is the zero polynomial (no public wire in use)

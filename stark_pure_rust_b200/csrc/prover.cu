@@ -301,11 +301,22 @@ extern "C" int sb_prove_r1cs(sb_ctx *ctx, const sb_trace *t, sb_stark_proof **ou
         uint4 *zb2 = q_col(B2_), *zb3 = q_col(B3_);          // B2_ and B3_ are adjacent: one 2N batch inverse
         if (np) PCU(cudaMemcpyAsync(coef.p, interp.data(), np * 32, cudaMemcpyHostToDevice, ctx->stream));
         PCU(cudaMemcpyAsync((uint8_t *)coef.p + np * 32, zroot.data(), (np + 1) * 32, cudaMemcpyHostToDevice, ctx->stream));
+        const bool horner = np + 1 <= 24;      // ~np products per point against the ~log2(N)/2 + 2 of a transform
         if (np) {
             PTRY(i2b.alloc(N * 32));
-            PTRY(ntt_dev(ctx, (const uint4 *)coef.p, np, np, (uint4 *)i2b.p, N, 1, g2, log_prec, 0));
+            if (horner) {
+                pw_poly_eval_kernel<<<nblk(N), 128, 0, ctx->stream>>>(xs, (const uint4 *)coef.p, (uint32_t)np, (uint4 *)i2b.p, N);
+                ctx->launches++;
+            } else {
+                PTRY(ntt_dev(ctx, (const uint4 *)coef.p, np, np, (uint4 *)i2b.p, N, 1, g2, log_prec, 0));
+            }
         }
-        PTRY(ntt_dev(ctx, (const uint4 *)coef.p + 2 * np, np + 1, np + 1, zb2, N, 1, g2, log_prec, 0));
+        if (horner) {
+            pw_poly_eval_kernel<<<nblk(N), 128, 0, ctx->stream>>>(xs, (const uint4 *)coef.p + 2 * np, (uint32_t)np + 1, zb2, N);
+            ctx->launches++;
+        } else {
+            PTRY(ntt_dev(ctx, (const uint4 *)coef.p + 2 * np, np + 1, np + 1, zb2, N, 1, g2, log_prec, 0));
+        }
         pw_zb3_kernel<<<nblk(N), 128, 0, ctx->stream>>>(xs, zb3, N, Cst);
         ctx->launches++;
         PTRY(sb_batch_inverse_dev(ctx, (uint64_t *)zb2, 2 * N));

@@ -335,10 +335,11 @@ def test_prove_with_file_path_errors(ctx, tmp_path):
         sb.prove.prove_with_file_path(os.path.join(d, "poseidon3_test.r1cs"), os.path.join(d, "compute.wtns"), None, ctx=ctx)
 
 
-@pytest.mark.parametrize("n_constraints,avg_terms,seed", [(40, 2.0, 3), (300, 3.0, 1), (1200, 4.0, 7)])
-def test_prove_synthetic_circuits(ctx, oracle, n_constraints, avg_terms, seed, tmp_path):
+@pytest.mark.parametrize("n_constraints,avg_terms,seed,n_pub", [(40, 2.0, 3, 2), (300, 3.0, 1, 2), (1200, 4.0, 7, 2), (400, 3.0, 11, 60)])
+def test_prove_synthetic_circuits(ctx, oracle, n_constraints, avg_terms, seed, n_pub, tmp_path):
     """seeded synthetic circuits (tools/gen_r1cs.py: linear and multi-term-C constraints, padding rows, public
-    inputs): proof.json of the CUDA pipeline == the oracle's, and the oracle's restated verifier accepts it"""
+    inputs): proof.json of the CUDA pipeline == the oracle's, and the oracle's restated verifier accepts it.
+    n_pub = 2 takes the Horner evaluation of the boundary polynomials, n_pub = 60 the NTT of their coefficients."""
     import os
     import sys
     import stark_pure_rust_b200 as sb
@@ -346,8 +347,8 @@ def test_prove_synthetic_circuits(ctx, oracle, n_constraints, avg_terms, seed, t
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import gen_r1cs
     prefix = str(tmp_path / "syn")
-    wit, cons = gen_r1cs.generate(n_constraints, avg_terms, 2, seed)
-    gen_r1cs.write_files(prefix, wit, cons, 2)
+    wit, cons = gen_r1cs.generate(n_constraints, avg_terms, n_pub, seed)
+    gen_r1cs.write_files(prefix, wit, cons, n_pub)
     want = str(tmp_path / "want.json")
     rc, _ = oracle.prove_files(prefix + ".r1cs", prefix + ".wtns", want)
     assert rc == 0                      # 0 = proved and verified by the oracle
