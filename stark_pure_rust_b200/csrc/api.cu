@@ -458,10 +458,15 @@ static void launch_leaves(sb_ctx *ctx, sb_tree *t, uint32_t lv) {
     }
 }
 
-// hashes the leaves and every level; leaves the root in t->root (one 32-byte D2H + sync)
-static int merkle_build(sb_ctx *ctx, sb_tree *t) {
+// hashes the leaves and every level; leaves the root in t->root (one 32-byte D2H + sync).
+// fold != NULL: the leaves are produced by the FRI fold of *fold (fused kernel), which also writes the column t->cols[0].
+static int merkle_build(sb_ctx *ctx, sb_tree *t, const FriFoldParams *fold = nullptr) {
     uint32_t level = t->depth < 3 ? t->depth : 3;
-    launch_leaves(ctx, t, level);
+    if (fold) {
+        KLAUNCH(SB_KIND_FRI_FOLD, merkle_launch_leaves_fold(ctx->stream, level, *fold, t->d_nodes));
+    } else {
+        launch_leaves(ctx, t, level);
+    }
     while (level < t->depth) {
         const uint32_t lv = t->depth - level < 3 ? t->depth - level : 3;
         KLAUNCH(SB_KIND_MERKLE_NODES, merkle_launch_nodes(ctx->stream, lv, t->d_nodes, t->n, level));
@@ -537,6 +542,22 @@ int commit_cols(sb_ctx *ctx, const uint4 *const *d_cols, size_t n_cols, size_t n
     t->n_cols = (int)n_cols;
     for (size_t k = 0; k < n_cols; k++) t->cols[k] = d_cols[k];
     int rc = merkle_build(ctx, t);
+    if (rc != SB_OK) {
+        free_tree(t);
+        return rc;
+    }
+    *tree = t;
+    return SB_OK;
+}
+
+// FRI: column = fold(values) and the tree over the column in one pass over the data (fri.rs:141-172)
+static int commit_fold(sb_ctx *ctx, const FriFoldParams &F, sb_tree **tree) {
+    const size_t q = F.n >> 2;
+    sb_tree *t = nullptr;
+    TRY(tree_new(ctx, q, 32, &t));
+    t->n_cols = 1;
+    t->cols[0] = F.col;
+    int rc = merkle_build(ctx, t, &F);
     if (rc != SB_OK) {
         free_tree(t);
         return rc;
@@ -718,11 +739,9 @@ int fri_prove_dev(sb_ctx *ctx, const uint4 *d_vals, size_t n, const hfp::el &roo
         P.tw_log_n = tw_log_n;
         P.tw_log_stride = cur_stride;
         memcpy(P.special_x, special_x.l, 32);
-        KLAUNCH(SB_KIND_FRI_FOLD, fri_launch_fold(ctx->stream, P));
-        // fri.rs:165-172
+        // fri.rs:141-172: fold and commit the column in one kernel
         sb_tree *t2 = nullptr;
-        const uint4 *cols2[1] = {(const uint4 *)d_col};
-        if ((rc = commit_cols(ctx, cols2, 1, q, &t2)) != SB_OK) break;
+        if ((rc = commit_fold(ctx, P, &t2)) != SB_OK) break;
         owned_trees.push_back(t2);
         memcpy(L.root2, t2->root, 32);
         // fri.rs:181-190

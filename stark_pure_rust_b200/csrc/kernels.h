@@ -18,6 +18,7 @@ int lde_launch_coset0(cudaStream_t stream, const uint4 *in, unsigned long long c
                       unsigned long long out_stride, unsigned long long s_len, uint32_t log_ext, unsigned long long n_cols);
 // merkle.cu
 int merkle_launch_leaves_cols(cudaStream_t stream, uint32_t lv, const MerkleColsParams &P);
+int merkle_launch_leaves_fold(cudaStream_t stream, uint32_t lv, const FriFoldParams &F, uint4 *nodes);
 int merkle_launch_leaves_bytes(cudaStream_t stream, uint32_t lv, const MerkleBytesParams &P);
 int merkle_launch_nodes(cudaStream_t stream, uint32_t lv, uint4 *nodes, unsigned long long n, uint32_t level);
 int merkle_launch_open(cudaStream_t stream, const uint4 *nodes, unsigned long long n, uint32_t depth,

@@ -15,6 +15,16 @@ int merkle_launch_leaves_cols(cudaStream_t s, uint32_t lv, const MerkleColsParam
     }
     return 1;
 }
+int merkle_launch_leaves_fold(cudaStream_t s, uint32_t lv, const FriFoldParams &F, uint4 *nodes) {
+    const unsigned b = blocks128((F.n >> 2) >> lv);
+    switch (lv) {
+        case 0: merkle_leaves_fold_kernel<0><<<b, 128, 0, s>>>(F, nodes); break;
+        case 1: merkle_leaves_fold_kernel<1><<<b, 128, 0, s>>>(F, nodes); break;
+        case 2: merkle_leaves_fold_kernel<2><<<b, 128, 0, s>>>(F, nodes); break;
+        default: merkle_leaves_fold_kernel<3><<<b, 128, 0, s>>>(F, nodes); break;
+    }
+    return 1;
+}
 int merkle_launch_leaves_bytes(cudaStream_t s, uint32_t lv, const MerkleBytesParams &P) {
     const unsigned b = blocks128(P.n >> lv);
     switch (lv) {

@@ -13,6 +13,7 @@
 #pragma once
 #include "blake2s.cuh"
 #include "fp.cuh"
+#include "fri_fold.cuh"
 #include "params.h"
 
 struct digest_t {
@@ -105,6 +106,35 @@ __global__ void __launch_bounds__(MERKLE_THREADS, 4) merkle_leaves_cols_kernel(c
         sd_put(sd, i, h);
     }
     merkle_reduce_smem<LV>(sd, P.nodes, P.n, 0, first);
+}
+
+// ---- FRI: fold fused with the next layer's leaf hashing (fri.rs:141-172) ----------------------------------------
+// leaf i of the column tree = to_bytes_le(column[i]) where column[i] is folded from four values of the current layer;
+// the column is also written out (it is the next layer's input and the opened leaves are re-read from it).
+template <int LV>
+__global__ void __launch_bounds__(MERKLE_THREADS, 4) merkle_leaves_fold_kernel(const __grid_constant__ FriFoldParams F, uint4 *nodes) {
+    __shared__ uint32_t sd_all[(1 << LV) * 8 * MERKLE_THREADS];
+    uint32_t *sd = sd_all + threadIdx.x;
+    const size_t q = F.n >> 2;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t first = t << LV;
+    if (first >= q) return;
+    fp sx;
+#pragma unroll
+    for (int k = 0; k < 8; k++) sx.l[k] = F.special_x[k];
+    const unsigned long long nT = 1ull << F.tw_log_n;
+    const fp iota_inv = fp_ldg_ro(F.tw, (nT - ((unsigned long long)q << F.tw_log_stride)) & (nT - 1));
+#pragma unroll 1
+    for (int i = 0; i < (1 << LV); i++) {
+        fp r = fri_fold_row(F, first + i, sx, iota_inv);
+        fp_stg(F.col, first + i, r);
+        fp c = fp_from_mont(r);
+        uint32_t h[8];
+        b2s::hash32(h, c.l);
+        digest_store(nodes, first + i, h);
+        sd_put(sd, i, h);
+    }
+    merkle_reduce_smem<LV>(sd, nodes, q, 0, first);
 }
 
 // ---- leaves = n byte strings of leaf_bytes each (caller's Vec<Vec<u8>>, flattened) ----------
