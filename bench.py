@@ -94,6 +94,25 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """pin this process (and therefore its pinned host buffers, first touch) to the CPUs NVML reports as local to the GPU:
+    with one process per GPU the e2e leg otherwise drags half of its PCIe traffic across the socket interconnect"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        n = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n)
+        cpus = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (w >> b) & 1}
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return len(allowed)
+    except Exception:
+        pass
+    return None
+
+
 # ---------------------------------------------------------------------------------------------
 # CPU path (oracle): the same step on host cores
 # ---------------------------------------------------------------------------------------------
@@ -157,6 +176,7 @@ def run_gpu(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
+    numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         import torch
         import torch.distributed as dist
@@ -373,7 +393,8 @@ def run_gpu(args):
         "data": "synthetic (seeded uniform field elements)",
         "config": {"workload": "LDE 2^%d->2^%d x %d cols + Merkle(8 cols, 256 B leaves) + Merkle(1 col) + FRI(2^%d, bound 2^%d)" % (log_s, L, Cn, L, L - 2),
                    "log_n": L, "cols": Cn, "l2": "inputs and outputs exceed L2 (%.1f GB per step); no explicit flush" % (Cn * N * 32 / 1e9),
-                   "sharding": "independent batch per GPU (columns / subtrees shard with no data-path collective)"},
+                   "sharding": "independent batch per GPU (columns / subtrees shard with no data-path collective)",
+                   "cpu_affinity": ("GPU-local NUMA node, %d CPUs" % numa_cpus) if numa_cpus else "unchanged"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "breakdown": {"lde_ms": lde_ms, "ntt_elems_per_s": Cn * N / (lde_ms * 1e-3),

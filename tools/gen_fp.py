@@ -106,6 +106,9 @@ def emulate(stmts, env):
                 else:
                     # a dropped carry must be provably zero in our usage
                     assert tot >> 32 == 0, f"{op}: carry dropped but non-zero"
+            elif kind in ("shl", "shr"):
+                assert srcs[1][0] == "i" and 0 < v[1] < 32 and not sets_c
+                wr(dst, (v[0] << v[1]) if kind == "shl" else (v[0] >> v[1]))
             elif kind in ("add", "addc"):
                 tot = v[0] + v[1] + cin
                 wr(dst, tot)
@@ -175,9 +178,21 @@ def chain(st, first_op, rest_op, last_op, dsts, a_list, b_list, c_list):
         st.add(op, dsts[i], a_list[i], b_list[i], *([c_list[i]] if c_list else []))
 
 
+assert PL[0] == 0xF0000001 and NINV32 == (-(2**28 + 1)) % 2**32
+
+
+def mont_m(st, m, x0):
+    """m = x0 * (-p^-1) mod 2^32.  (-p^-1 = -(2^28 + 1), so shifts would do, but m heads the dependency chain of the whole
+    row and one IMAD has a shorter latency than shift + add + negate: measured slower on B200.)"""
+    st.add("mul.lo.u32", m, x0, imm(NINV32))
+
+
 def mp_rows(st, X, Y, m):
     """T += m * p with T = X (even-aligned words 0..7) + Y (odd-aligned: Y[j] is word j+1).
-    Odd chain first, then even chain, whose carry out of word 7 lands in word 8 = Y[7]."""
+    Odd chain first, then even chain, whose carry out of word 7 lands in word 8 = Y[7].
+    (p0 = 2^32 - 2^28 + 1 would allow replacing the product m * p0 by shifts: word 0 becomes 0 by construction and word 1
+    receives m - (m >> 4) + borrow(m << 28, m).  Tried on B200: the extra ALU instructions cost more than the IMAD.WIDE they
+    save -- the LDE went from 34.2 to 34.8 ms -- so the plain product stays.)"""
     # odd limbs p1,p3,p5,p7 -> Y0..Y7
     for k, j in enumerate((1, 3, 5, 7)):
         lo = "mad.lo.cc.u32" if k == 0 else "madc.lo.cc.u32"
@@ -199,7 +214,7 @@ def gen_mul():
     # ---- row 0 reduction (E = a_even * b0, O = a_odd * b0 already set by the caller) ----
     st = Stmt()
     m = st.temp("m")
-    st.add("mul.lo.u32", m, reg("E", 0), imm(NINV32))
+    mont_m(st, m, reg("E", 0))
     mp_rows(st, "E", "O", m)
     stmts.append(st)
     # ---- rows 1..7 ----
@@ -220,7 +235,7 @@ def gen_mul():
             st.add(lo, reg(X, 2 * k), reg("a", j), bi, reg(X, 2 * k))
             st.add("madc.hi.cc.u32", reg(X, 2 * k + 1), reg("a", j), bi, reg(X, 2 * k + 1))
         st.add("addc.u32", reg(Y, 7), reg(Y, 7), imm(0))
-        st.add("mul.lo.u32", m, reg(X, 0), imm(NINV32))
+        mont_m(st, m, reg(X, 0))
         mp_rows(st, X, Y, m)
         stmts.append(st)
     # ---- final shift: r = (X >> 32) + Y with X = O, Y = E after row 7 ----
@@ -369,9 +384,10 @@ def generate():
     s += "// r = a*b/2^256 mod p (lazy: r < a*b/R + p; < 2p when a*b < p*R).  Requires a < 2^256 - p.\n"
     s += "__device__ __forceinline__ void mont_mul(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {\n"
     s += "    uint32_t E[8], O[8];\n"
-    s += "#pragma unroll\n    for (int k = 0; k < 4; k++) {\n"
-    s += "        E[2 * k] = a[2 * k] * b[0];          E[2 * k + 1] = __umulhi(a[2 * k], b[0]);\n"
-    s += "        O[2 * k] = a[2 * k + 1] * b[0];      O[2 * k + 1] = __umulhi(a[2 * k + 1], b[0]);\n"
+    s += "#pragma unroll\n    for (int k = 0; k < 4; k++) {      // 64-bit products: one IMAD.WIDE each\n"
+    s += "        const unsigned long long e = (unsigned long long)a[2 * k] * b[0], o = (unsigned long long)a[2 * k + 1] * b[0];\n"
+    s += "        E[2 * k] = (uint32_t)e;      E[2 * k + 1] = (uint32_t)(e >> 32);\n"
+    s += "        O[2 * k] = (uint32_t)o;      O[2 * k + 1] = (uint32_t)(o >> 32);\n"
     s += "    }\n"
     s += emit(MUL)
     s += "#pragma unroll\n    for (int k = 0; k < 8; k++) r[k] = E[k];\n"
