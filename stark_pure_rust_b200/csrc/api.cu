@@ -237,7 +237,7 @@ static int plan_bits(uint32_t log_n, uint32_t *bits) {
         bits[0] = 0;
         return 1;
     }
-    const uint32_t maxb = NTT_LOG_TILE - 3;     // keep >= 8 contiguous columns per tile row
+    const uint32_t maxb = 8;                    // 2^8 rows x 4 contiguous columns (128 B) at the widest
     int m = (int)((log_n + maxb - 1) / maxb);
     uint32_t base = log_n / m, rem = log_n % m;
     for (int i = 0; i < m; i++) bits[i] = base + ((uint32_t)i < rem ? 1 : 0);
@@ -289,7 +289,7 @@ static int ntt_dev_tw(sb_ctx *ctx, const uint4 *d_src, size_t len_in, size_t src
         P.n_prev = (uint32_t)p;
         for (int i = 0; i < p; i++) P.prev_bits[i] = bits[i];
         memcpy(P.n_inv, ninv.l, 32);
-        if (bits[p] > NTT_LOG_TILE - 3) return fail(ctx, SB_ERR_ARG, "internal: pass width %u", bits[p]);
+        if (bits[p] > 8) return fail(ctx, SB_ERR_ARG, "internal: pass width %u", bits[p]);
         KLAUNCH(SB_KIND_NTT_PASS, ntt_launch_pass(ctx->stream, bits[p], P));
         log_outer += bits[p];
     }

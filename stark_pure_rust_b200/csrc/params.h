@@ -11,7 +11,7 @@ struct fp {
 };
 
 #ifndef NTT_LOG_TILE
-#define NTT_LOG_TILE 11            // 2048 elements = 64 KiB of shared memory per CTA
+#define NTT_LOG_TILE 10            // 1024 elements = 32 KiB of shared memory per CTA, 128 threads, 4 CTAs per SM
 #endif
 #define NTT_MAX_PASSES 6
 
