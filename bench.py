@@ -400,6 +400,9 @@ def run_gpu(args):
         "breakdown": {"lde_ms": lde_ms, "ntt_elems_per_s": Cn * N / (lde_ms * 1e-3),
                       "merkle8_ms": m8_ms, "merkle1_ms": m1_ms,
                       "merkle_hashes_per_s": (comp8 + comp1) / ((m8_ms + m1_ms) * 1e-3),
+                      # Blake2s compression = 805 ALU-pipe instructions (SASS count) at 64 lanes/clk/SM (tools/pipe_bench.cu)
+                      "merkle_alu_roof_hashes_per_s": 148 * 64 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 805.0,
+                      "merkle_alu_frac": (comp8 + comp1) / ((m8_ms + m1_ms) * 1e-3) / (148 * 64 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 805.0),
                       "fri_ms": fri_ms, "fri_layers": int(n_layers),
                       "kernel_ms_per_step": {k: v[1] / args.steps for k, v in prof.items()},
                       "kernel_launches_per_step": {k: v[0] / args.steps for k, v in prof.items()}},

@@ -238,6 +238,16 @@ static int plan_bits(uint32_t log_n, uint32_t *bits) {
         return 1;
     }
     const uint32_t maxb = 8;                    // 2^8 rows x 4 contiguous columns (128 B) at the widest
+    if (const char *e = getenv("SB_NTT_PLAN")) {   // experiment hook: "21:8,8,5" forces the passes of 2^21-point transforms
+        unsigned ln = 0, b[NTT_MAX_PASSES] = {0};
+        int cnt = sscanf(e, "%u:%u,%u,%u,%u,%u,%u", &ln, &b[0], &b[1], &b[2], &b[3], &b[4], &b[5]) - 1;
+        unsigned sum = 0;
+        for (int i = 0; i < cnt; i++) sum += b[i];
+        if (cnt > 0 && ln == log_n && sum == log_n) {
+            for (int i = 0; i < cnt; i++) bits[i] = b[i];
+            return cnt;
+        }
+    }
     int m = (int)((log_n + maxb - 1) / maxb);
     uint32_t base = log_n / m, rem = log_n % m;
     for (int i = 0; i < m; i++) bits[i] = base + ((uint32_t)i < rem ? 1 : 0);
