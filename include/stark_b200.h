@@ -43,6 +43,7 @@ extern "C" {
 #define SB_ERR_ARG (-3)         /* size / alignment / range violation (reference: assert!)     */
 #define SB_ERR_ROOT (-4)        /* root_of_unity is not a primitive 2^log_n-th root of unity   */
 #define SB_ERR_OOM (-5)         /* device allocation failed                                    */
+#define SB_ERR_VERIFY (-6)      /* a proof was rejected (reference verifier: assert / unwrap panic) */
 
 typedef struct sb_ctx sb_ctx;
 typedef struct sb_tree sb_tree;
@@ -192,6 +193,18 @@ int sb_stark_proof_stage_ms(const sb_stark_proof *p, double ms[5]);
 /* serde_json::to_string(&StarkProof) (utils.rs:122-130, run.rs:549): malloc'd, free with sb_free_string. */
 char *sb_stark_proof_json(const sb_stark_proof *p, size_t *len);
 void sb_stark_proof_free(sb_stark_proof *p);
+
+/* verify_r1cs_proof (r1cs-stark/src/verify.rs:13-258; fri/src/fri.rs:226-404; merkle_tree.rs:25-58).  Uses the public
+ * members of `trace` (original_steps, coefficients, flag0..2, permuted_indices, public wires and their first uses);
+ * witness_trace / computational_trace may be NULL.  SB_OK = accepted, SB_ERR_VERIFY = rejected (sb_last_error names the
+ * failed check), other codes = malformed input.  The six interpolated columns the reference evaluates with eval_poly_at are
+ * extended on the device instead (same field elements). */
+int sb_verify_r1cs(sb_ctx *ctx, const sb_trace *trace, const sb_stark_proof *proof);
+/* serde_json::from_reader::<StarkProof> (run.rs:578): parses the text sb_stark_proof_json writes. */
+int sb_stark_proof_from_json(const char *text, size_t len, sb_stark_proof **out);
+/* verify_with_file_path (run.rs:556-590): r1cs + witness (for the public wires) + proof.json.  verify_ms (may be NULL):
+ * [0] host front end + JSON parse, [1] sb_verify_r1cs wall clock. */
+int sb_verify_files(sb_ctx *ctx, const char *r1cs_path, const char *wtns_path, const char *proof_path, double verify_ms[2]);
 
 /* prove_with_file_path (r1cs-stark/src/run.rs:528-554): parse <r1cs> (circom2bellman_core/src/reader.rs:4-89) and
  * <wtns> (r1cs-stark/src/reader.rs:7-42), arrange the traces (run.rs:109-308, :390-419), prove on the device and

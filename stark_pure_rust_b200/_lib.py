@@ -11,7 +11,7 @@ _LIB_PATH = os.path.join(HERE, "libstark_b200.so")
 _HEADER = os.path.join(HERE, "..", "include", "stark_b200.h")
 
 SB_OK = 0
-ERRORS = {-1: "SB_ERR_NO_DEVICE", -2: "SB_ERR_CUDA", -3: "SB_ERR_ARG", -4: "SB_ERR_ROOT", -5: "SB_ERR_OOM"}
+ERRORS = {-1: "SB_ERR_NO_DEVICE", -2: "SB_ERR_CUDA", -3: "SB_ERR_ARG", -4: "SB_ERR_ROOT", -5: "SB_ERR_OOM", -6: "SB_ERR_VERIFY"}
 
 
 class StarkB200Error(RuntimeError):
@@ -96,6 +96,9 @@ def load():
         "sb_stark_proof_stage_ms": (i32, [vp, C.POINTER(C.c_double)]),
         "sb_stark_proof_json": (vp, [vp, szp]),
         "sb_stark_proof_free": (None, [vp]),
+        "sb_verify_r1cs": (i32, [vp, vp, vp]),
+        "sb_stark_proof_from_json": (i32, [C.c_char_p, sz, C.POINTER(vp)]),
+        "sb_verify_files": (i32, [vp, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_double)]),
         "sb_prove_files": (i32, [vp, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_double)]),
         "sb_set_extended_domain": (i32, [vp, i32]),
         "sb_pipe_peak": (i32, [vp, i32, C.POINTER(C.c_double)]),

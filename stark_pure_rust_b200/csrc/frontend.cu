@@ -157,9 +157,11 @@ struct Trace {
 };
 
 // run.rs:109-281, :283-308, :390-419
-const char *build_trace(sb_ctx *ctx, const R1cs &r, const std::vector<hfp::el> &witness, Trace &t) {
+// with_witness = false (verifier, run.rs:454-526): only the public part is built -- coefficients, flags, permutation,
+// public wires and their first uses; `witness` then only needs the public wires
+const char *build_trace(sb_ctx *ctx, const R1cs &r, const std::vector<hfp::el> &witness, Trace &t, bool with_witness = true) {
     const size_t n_wires = r.n_wires, nc = r.n_constraints;
-    if (witness.size() < n_wires || n_wires == 0) return "witness shorter than the circuit's wire count";
+    if ((with_witness && witness.size() < n_wires) || n_wires == 0) return "witness shorter than the circuit's wire count";
     const size_t a = r.row_off[nc], os = 3 * a;
     if (a == 0) return "circuit has no constraint rows";
     hfp::el *arena = (hfp::el *)pinned_arena(ctx, 6 * os * sizeof(hfp::el));
@@ -186,15 +188,17 @@ const char *build_trace(sb_ctx *ctx, const R1cs &r, const std::vector<hfp::el> &
                             w = 0;
                         }
                         const hfp::el cf = hfp::from_bytes_le32(term + 4);     // T::from_bytes_le(value), run.rs:156
-                        run = hfp::add(run, hfp::mul(cf, witness[w]));
+                        if (with_witness) run = hfp::add(run, hfp::mul(cf, witness[w]));
                         t.coef[pos] = cf;
                     } else {                                           // padding row: LAST wire, coefficient 0 (run.rs:165-176)
                         w = (uint32_t)(n_wires - 1);
                         t.coef[pos] = hfp::ZERO;
                     }
                     wire_at[pos] = w;
-                    t.wit[pos] = witness[w];
-                    t.comp[pos] = run;
+                    if (with_witness) {
+                        t.wit[pos] = witness[w];
+                        t.comp[pos] = run;
+                    }
                 }
             }
         }
@@ -307,5 +311,56 @@ extern "C" int sb_prove_files(sb_ctx *ctx, const char *r1cs_path, const char *wt
         stage_ms[6] = t3 - t2;
     }
     sb_stark_proof_free(proof);
+    return rc;
+}
+
+// verify_with_file_path (run.rs:556-590): the public wires are the head of the witness file (run.rs:582-585)
+extern "C" int sb_verify_files(sb_ctx *ctx, const char *r1cs_path, const char *wtns_path, const char *proof_path, double verify_ms[2]) {
+    if (!ctx || !r1cs_path || !wtns_path || !proof_path) return SB_ERR_ARG;
+    auto now = []() {
+        struct timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    };
+    const double t0 = now();
+    std::vector<uint8_t> rb, wb, pb;
+    if (!slurp(r1cs_path, rb)) return fail(ctx, SB_ERR_ARG, "cannot read %s", r1cs_path);
+    if (!slurp(wtns_path, wb)) return fail(ctx, SB_ERR_ARG, "cannot read %s", wtns_path);
+    if (!slurp(proof_path, pb)) return fail(ctx, SB_ERR_ARG, "cannot read %s", proof_path);
+    R1cs r;
+    std::vector<hfp::el> witness;
+    const char *e = read_r1cs(rb, r);
+    if (e) return fail(ctx, SB_ERR_ARG, "%s: %s", r1cs_path, e);
+    if (memcmp(r.prime, BN254_FR_LE, 32) != 0) return fail(ctx, SB_ERR_ARG, "%s: field is not BN254 Fr (run.rs:344-350)", r1cs_path);
+    e = read_witness(wb, witness);
+    if (e) return fail(ctx, SB_ERR_ARG, "%s: %s", wtns_path, e);
+    if (witness.empty() || !hfp::eq(witness[0], hfp::ONE)) return fail(ctx, SB_ERR_ARG, "public_wires[0] must be 1 (run.rs:479)");
+    Trace t;
+    e = build_trace(ctx, r, witness, t, false);
+    if (e) return fail(ctx, SB_ERR_ARG, "%s", e);
+    sb_stark_proof *proof = nullptr;
+    if (sb_stark_proof_from_json((const char *)pb.data(), pb.size(), &proof) != SB_OK)
+        return fail(ctx, SB_ERR_ARG, "%s: not a serialised StarkProof", proof_path);
+    sb_trace st;
+    memset(&st, 0, sizeof st);
+    st.original_steps = t.os;
+    st.coefficients = (const uint64_t *)t.coef;
+    st.flag0 = (const uint64_t *)t.f0;
+    st.flag1 = (const uint64_t *)t.f1;
+    st.flag2 = (const uint64_t *)t.f2;
+    st.permuted_indices = t.perm.data();
+    st.n_public = t.pub.size();
+    st.public_wires = (const uint64_t *)t.pub.data();
+    st.n_pfi = t.pfi_k.size();
+    st.pfi_k = t.pfi_k.data();
+    st.pfi_w = t.pfi_w.data();
+    const double t1 = now();
+    int rc = sb_verify_r1cs(ctx, &st, proof);
+    const double t2 = now();
+    sb_stark_proof_free(proof);
+    if (verify_ms) {
+        verify_ms[0] = t1 - t0;
+        verify_ms[1] = t2 - t1;
+    }
     return rc;
 }

@@ -1,7 +1,6 @@
 // r1cs-stark <r1cs> <wtns> <proof.json> -- the reference binary's command line (r1cs-stark/src/main.rs:4-11) on the
-// B200 backend: prove and write proof.json (compact serde_json layout, run.rs:549-551).  The reference then also
-// re-verifies the proof on the CPU (run.rs:618-622); verification is outside the accelerated path and is left to
-// the reference's verifier (or the oracle's restatement of it).
+// B200 backend: prove, write proof.json (compact serde_json layout, run.rs:549-551), then verify what was written like the
+// reference's run_with_file_path does (run.rs:592-626).
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -27,6 +26,15 @@ int main(int argc, char **argv) {
     }
     printf("Produced STARK proof: front end %.3f ms, GPU prove %.3f ms (LDE %.3f, m_tree %.3f, FRI %.3f, rest %.3f), JSON %.3f ms\n",
            ms[5], ms[4], ms[0], ms[1], ms[2], ms[3], ms[6]);
+    // run_with_file_path (run.rs:592-626) verifies what it has just written
+    double vms[2] = {0, 0};
+    rc = sb_verify_files(ctx, argv[1], argv[2], argv[3], vms);
+    if (rc != SB_OK) {
+        fprintf(stderr, "r1cs-stark: proof rejected: %s (error %d)\n", sb_last_error(ctx), rc);
+        sb_destroy(ctx);
+        return 1;
+    }
+    printf("Done proof verification: front end + JSON parse %.3f ms, verify %.3f ms\n", vms[0], vms[1]);
     sb_destroy(ctx);
     return 0;
 }

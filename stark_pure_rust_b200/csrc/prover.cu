@@ -451,3 +451,459 @@ extern "C" char *sb_stark_proof_json(const sb_stark_proof *p, size_t *len) {
     return r;
 }
 extern "C" void sb_stark_proof_free(sb_stark_proof *p) { delete p; }
+
+// =====================================================================================================================
+// Verifier (r1cs-stark/src/verify.rs:13-258, fri/src/fri.rs:226-404, commitment/src/merkle_tree.rs:25-58): SURVEY.md 8f
+// next-3.  The reference verifier interpolates K, F0, F1, F2 and the two index columns and evaluates them at the 80
+// spot-check points with eval_poly_at (O(80 S) products) plus three N-point transforms; here the six columns are
+// extended on the device by the same LDE the prover uses and read at the 80 positions (identical field elements).
+// Merkle branches, the FRI layer checks and the constraint equations are O(proof size) scalar work on the host.
+// Returns SB_OK when the proof is accepted and SB_ERR_VERIFY (reference: assert / unwrap panic) otherwise.
+// =====================================================================================================================
+namespace {
+
+bool branch_ok(const uint8_t root[32], size_t index, const uint8_t *leaf, size_t leaf_bytes, const uint8_t *nodes, size_t depth) {
+    uint8_t h[32], buf[64];
+    b2s::hash_bytes(h, leaf, leaf_bytes);                         // merkle_tree.rs:26
+    for (size_t l = 0; l < depth; l++) {                          // merkle_tree.rs:27-41
+        const uint8_t *sib = nodes + 32 * l;
+        if (index & 1) { memcpy(buf, sib, 32); memcpy(buf + 32, h, 32); } else { memcpy(buf, h, 32); memcpy(buf + 32, sib, 32); }
+        b2s::hash_bytes(h, buf, 64);
+        index >>= 1;
+    }
+    return memcmp(h, root, 32) == 0;
+}
+
+hfp::el sub(const hfp::el &a, const hfp::el &b) { return hfp::add(a, hfp::neg(b)); }
+
+// value at x of the polynomial of degree < n through (xs[i], ys[i]) (poly_utils.rs:409-439 + eval_poly_at)
+hfp::el lagrange_eval(const std::vector<hfp::el> &xs, const std::vector<hfp::el> &ys, const hfp::el &x) {
+    hfp::el acc = hfp::ZERO;
+    for (size_t i = 0; i < xs.size(); i++) {
+        hfp::el num = hfp::ONE, den = hfp::ONE;
+        for (size_t j = 0; j < xs.size(); j++) {
+            if (i == j) continue;
+            num = hfp::mul(num, sub(x, xs[j]));
+            den = hfp::mul(den, sub(xs[i], xs[j]));
+        }
+        acc = hfp::add(acc, hfp::mul(ys[i], hfp::mul(num, hfp::inv(den))));
+    }
+    return acc;
+}
+
+// fri.rs:244-404
+int fri_verify_host(sb_ctx *ctx, const sb_fri_proof *pr, const uint8_t values_root[32], hfp::el w, size_t n, size_t bound, uint32_t excl) {
+    if (!pr || pr->layers.empty()) return fail(ctx, SB_ERR_VERIFY, "FRI proof is empty");
+    uint8_t root[32];
+    memcpy(root, values_root, 32);
+    for (size_t li = 0; li + 1 < pr->layers.size(); li++) {
+        const FriLayer &L = pr->layers[li];
+        if (L.is_last) return fail(ctx, SB_ERR_VERIFY, "FRI proofs must consist of Middle layers except the last element (fri.rs:279)");
+        if (n < 4) return fail(ctx, SB_ERR_VERIFY, "FRI layer %zu: domain exhausted", li);
+        const size_t q = n / 4;
+        const hfp::el special_x = hfp::from_bytes_le32(root);                      // fri.rs:285
+        uint32_t ys[FRI_QUERIES];
+        if (pseudorandom_indices(L.root2, 32, (uint32_t)q, FRI_QUERIES, excl, ys, ctx->extended_domain) != SB_OK)
+            return fail(ctx, SB_ERR_VERIFY, "FRI layer %zu: sampler rejects column length %zu", li, q);
+        uint32_t dq = 0, dn = 0;
+        while (((size_t)1 << dq) < q) dq++;
+        while (((size_t)1 << dn) < n) dn++;
+        if (L.n_column != FRI_QUERIES || L.n_poly != 4 * FRI_QUERIES || L.depth_column != dq || L.depth_poly != dn ||
+            L.column_leaves.size() != FRI_QUERIES * 32 || L.poly_leaves.size() != 4 * FRI_QUERIES * 32 ||
+            L.column_nodes.size() != FRI_QUERIES * dq * 32 || L.poly_nodes.size() != 4 * FRI_QUERIES * dn * 32)
+            return fail(ctx, SB_ERR_VERIFY, "FRI layer %zu: malformed branches", li);
+        const hfp::el iota = hfp::pow_u64(w, q);                                    // quartic roots of unity, fri.rs:263-268
+        for (size_t i = 0; i < FRI_QUERIES; i++) {
+            if (!branch_ok(L.root2, ys[i], &L.column_leaves[32 * i], 32, &L.column_nodes[i * dq * 32], dq))
+                return fail(ctx, SB_ERR_VERIFY, "FRI layer %zu: column branch %zu does not match root2 (fri.rs:310)", li, i);
+            std::vector<hfp::el> xc(4), row(4);
+            hfp::el x = hfp::pow_u64(w, ys[i]);
+            for (size_t j = 0; j < 4; j++) {
+                const size_t pos = j * q + ys[i];                                   // fri.rs:301-307
+                if (!branch_ok(root, pos, &L.poly_leaves[(4 * i + j) * 32], 32, &L.poly_nodes[(4 * i + j) * dn * 32], dn))
+                    return fail(ctx, SB_ERR_VERIFY, "FRI layer %zu: poly branch %zu does not match the layer root (fri.rs:311)", li, 4 * i + j);
+                xc[j] = x;
+                row[j] = hfp::from_bytes_le32(&L.poly_leaves[(4 * i + j) * 32]);
+                x = hfp::mul(x, iota);
+            }
+            // fri.rs:340-346: the four row values and the column value lie on one polynomial of degree < 4
+            if (!hfp::eq(lagrange_eval(xc, row, special_x), hfp::from_bytes_le32(&L.column_leaves[32 * i])))
+                return fail(ctx, SB_ERR_VERIFY, "FRI layer %zu: query %zu is not on the degree-<4 interpolant (fri.rs:345)", li, i);
+        }
+        memcpy(root, L.root2, 32);
+        w = hfp::sqr(hfp::sqr(w));
+        n = q;
+        bound /= 4;
+    }
+    const FriLayer &last = pr->layers.back();
+    if (!last.is_last) return fail(ctx, SB_ERR_VERIFY, "the last element of FRI proofs must be Last (fri.rs:362)");
+    if (bound < FRI_MIN_DEG_DIRECT / 2) return fail(ctx, SB_ERR_VERIFY, "the degree of direct checking is too low (fri.rs:355)");
+    const size_t m = last.last.size() / 32;
+    if (m != n || m <= bound) return fail(ctx, SB_ERR_VERIFY, "FRI last layer holds %zu values, expected %zu > %zu (fri.rs:366)", m, n, bound);
+    // fri.rs:374-383: the Merkle root of the last values matches
+    {
+        std::vector<uint8_t> lv(m * 32);
+        for (size_t i = 0; i < m; i++) b2s::hash_bytes(&lv[32 * i], &last.last[32 * i], 32);
+        for (size_t w2 = m; w2 > 1; w2 /= 2)
+            for (size_t i = 0; i < w2 / 2; i++) {
+                uint8_t buf[64];
+                memcpy(buf, &lv[64 * i], 64);
+                b2s::hash_bytes(&lv[32 * i], buf, 64);
+            }
+        if (memcmp(lv.data(), root, 32) != 0) return fail(ctx, SB_ERR_VERIFY, "FRI last layer does not hash to the previous root2 (fri.rs:383)");
+    }
+    // fri.rs:385-401: degree check on the points that are not multiples of `excl`
+    std::vector<size_t> pts;
+    for (size_t pos = 0; pos < m; pos++)
+        if (excl == 0 || pos % excl != 0) pts.push_back(pos);
+    if (pts.size() < bound) return fail(ctx, SB_ERR_VERIFY, "FRI last layer: not enough points");
+    std::vector<hfp::el> xv(bound), yv(bound);
+    std::vector<hfp::el> pw(m);
+    pw[0] = hfp::ONE;
+    for (size_t i = 1; i < m; i++) pw[i] = hfp::mul(pw[i - 1], w);
+    for (size_t i = 0; i < bound; i++) {
+        xv[i] = pw[pts[i]];
+        yv[i] = hfp::from_bytes_le32(&last.last[32 * pts[i]]);
+    }
+    for (size_t i = bound; i < pts.size(); i++)
+        if (!hfp::eq(lagrange_eval(xv, yv, pw[pts[i]]), hfp::from_bytes_le32(&last.last[32 * pts[i]])))
+            return fail(ctx, SB_ERR_VERIFY, "FRI last layer is not of degree < %zu (fri.rs:399)", bound);
+    return SB_OK;
+}
+
+}  // namespace
+
+extern "C" int sb_verify_r1cs(sb_ctx *ctx, const sb_trace *t, const sb_stark_proof *proof) {
+    if (!ctx || !t || !proof) return SB_ERR_ARG;
+    const size_t os = t->original_steps;
+    if (os == 0 || os % 3 != 0) return fail(ctx, SB_ERR_ARG, "original_steps %zu must be a positive multiple of 3", os);   // verify.rs:27
+    if (!t->coefficients || !t->flag0 || !t->flag1 || !t->flag2 || !t->permuted_indices) return fail(ctx, SB_ERR_ARG, "missing public array");
+    const uint32_t log_steps = log2_ceil_quirk(os - 1);                      // verify.rs:29-33
+    const size_t S = (size_t)1 << log_steps;
+    if (S < 8) return fail(ctx, SB_ERR_ARG, "traces shorter than 8 steps are not supported");
+    const uint32_t log_prec = log_steps + LOG_EXTENSION_FACTOR;
+    if (log_prec > 28) return fail(ctx, SB_ERR_ARG, "precision 2^%u exceeds the field's two-adicity (verify.rs:38)", log_prec);
+    const size_t N = S * EXTENSION_FACTOR, sk = EXTENSION_FACTOR, o3 = os / 3;
+    if (N >= ((size_t)1 << 24)) return fail(ctx, SB_ERR_ARG, "precision 2^%u: the sampler asserts modulus < 2^24", log_prec);
+    if (proof->depth != log_prec) return fail(ctx, SB_ERR_VERIFY, "proof was made for precision 2^%zu, the circuit needs 2^%u", proof->depth, log_prec);
+    const size_t V = SPOT_CHECK_SECURITY_FACTOR;
+    if (proof->main_leaves.size() != 4 * V * 256 || proof->main_nodes.size() != 4 * V * log_prec * 32 || proof->lc_leaves.size() != V * 32 ||
+        proof->lc_nodes.size() != V * log_prec * 32)
+        return fail(ctx, SB_ERR_VERIFY, "malformed branches");
+    int rc = SB_OK;
+#define VTRY(expr) do { rc = (expr); if (rc != SB_OK) return rc; } while (0)
+#define VCU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, SB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
+
+    // verify.rs:55-66 g2 and xs
+    hfp::el g2;
+    {
+        uint64_t e[4] = {hfp::PMOD[0] - 1, hfp::PMOD[1], hfp::PMOD[2], hfp::PMOD[3]};
+        for (uint32_t i = 0; i < log_prec; i++) {
+            for (int k = 0; k < 3; k++) e[k] = (e[k] >> 1) | (e[k + 1] << 63);
+            e[3] >>= 1;
+        }
+        g2 = hfp::pow_limbs(hfp::from_u64(7), e, 4);
+    }
+    const uint4 *xs;
+    uint32_t tw_log_n, tw_stride;
+    VTRY(get_table(ctx, g2, log_prec, &xs, &tw_log_n, &tw_stride, true));
+
+    // verify.rs:83-87 low-degree proof of l
+    VTRY(fri_verify_host(ctx, proof->fri, proof->l_root, g2, N, N / 4, (uint32_t)sk));
+
+    // verify.rs:89-118 positions and branches
+    uint32_t pos32[SPOT_CHECK_SECURITY_FACTOR];
+    if (pseudorandom_indices(proof->l_root, 32, (uint32_t)N, V, (uint32_t)sk, pos32, false) != SB_OK) return fail(ctx, SB_ERR_ARG, "sampler rejected precision %zu", N);
+    std::vector<size_t> aug(4 * V);
+    for (size_t i = 0; i < V; i++) {
+        const size_t j = pos32[i];
+        aug[4 * i] = j;
+        aug[4 * i + 1] = (j + N - sk) % N;
+        aug[4 * i + 2] = (j + o3 * sk) % N;
+        aug[4 * i + 3] = (j + o3 * 2 * sk) % N;
+    }
+    for (size_t i = 0; i < 4 * V; i++)
+        if (!branch_ok(proof->m_root, aug[i], &proof->main_leaves[256 * i], 256, &proof->main_nodes[i * log_prec * 32], log_prec))
+            return fail(ctx, SB_ERR_VERIFY, "main branch %zu does not match m_root (verify.rs:115)", i);
+    for (size_t i = 0; i < V; i++)
+        if (!branch_ok(proof->l_root, pos32[i], &proof->lc_leaves[32 * i], 32, &proof->lc_nodes[i * log_prec * 32], log_prec))
+            return fail(ctx, SB_ERR_VERIFY, "linear combination branch %zu does not match l_root (verify.rs:117)", i);
+
+    // verify.rs:72-80, 127-136: K F0 F1 F2 idx pidx extended to the N-point domain on the device, read at the positions
+    DevBuf in6(ctx), ev6(ctx), perm_d(ctx), dpos(ctx), dgath(ctx);
+    VTRY(in6.alloc(6 * S * 32));
+    VTRY(ev6.alloc(6 * N * 32));
+    VTRY(perm_d.alloc(S * 8));
+    auto in_col = [&](int c) { return (uint4 *)in6.p + 2 * (size_t)c * S; };
+    VCU(cudaMemsetAsync(in6.p, 0, 6 * S * 32, ctx->stream));
+    const uint64_t *srcs[4] = {t->coefficients, t->flag0, t->flag1, t->flag2};
+    for (int c = 0; c < 4; c++) VCU(cudaMemcpyAsync(in_col(c), srcs[c], os * 32, cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<unsigned long long> perm(S);
+    for (size_t i = 0; i < os; i++) {
+        if (t->permuted_indices[i] >= S) return fail(ctx, SB_ERR_ARG, "permuted index out of range");
+        perm[i] = t->permuted_indices[i];
+    }
+    for (size_t i = os; i < S; i++) perm[i] = i;                                   // verify.rs:41-42
+    VCU(cudaMemcpyAsync(perm_d.p, perm.data(), S * 8, cudaMemcpyHostToDevice, ctx->stream));
+    pw_u64_to_fp_kernel<<<nblk(S), 128, 0, ctx->stream>>>(nullptr, in_col(4), S);
+    pw_u64_to_fp_kernel<<<nblk(S), 128, 0, ctx->stream>>>((const unsigned long long *)perm_d.p, in_col(5), S);
+    ctx->launches += 2;
+    VTRY(lde_dev(ctx, in_col(0), 6, S, S, g2, log_steps, LOG_EXTENSION_FACTOR, (uint4 *)ev6.p));
+    // gather: 6 columns + xs at the V positions, xs at the public wires' first uses, xs[N - sk]
+    const size_t np = t->n_pfi;
+    std::vector<unsigned long long> gidx;
+    for (int c = 0; c < 6; c++)
+        for (size_t i = 0; i < V; i++) gidx.push_back((unsigned long long)c * N + pos32[i]);
+    const size_t n_ev = gidx.size();
+    std::vector<unsigned long long> xidx;
+    for (size_t i = 0; i < V; i++) xidx.push_back(pos32[i]);
+    for (size_t i = 0; i < np; i++) {
+        if (t->pfi_w[i] >= S || t->pfi_k[i] >= t->n_public) return fail(ctx, SB_ERR_ARG, "public_first_indices out of range");
+        xidx.push_back(sk * t->pfi_w[i]);
+    }
+    xidx.push_back(N - sk);
+    std::vector<hfp::el> ev(n_ev), xv(xidx.size());
+    VTRY(dpos.alloc((n_ev + xidx.size()) * 8));
+    VTRY(dgath.alloc((n_ev + xidx.size()) * 32));
+    VCU(cudaMemcpyAsync(dpos.p, gidx.data(), n_ev * 8, cudaMemcpyHostToDevice, ctx->stream));
+    VCU(cudaMemcpyAsync((uint8_t *)dpos.p + n_ev * 8, xidx.data(), xidx.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->launches += merkle_launch_gather_bytes(ctx->stream, (const uint8_t *)ev6.p, 32, (const unsigned long long *)dpos.p, (uint32_t)n_ev, (uint8_t *)dgath.p);
+    ctx->launches += merkle_launch_gather_bytes(ctx->stream, (const uint8_t *)xs, 32, (const unsigned long long *)dpos.p + n_ev, (uint32_t)xidx.size(),
+                                                (uint8_t *)dgath.p + n_ev * 32);
+    VCU(cudaMemcpyAsync(ev.data(), dgath.p, n_ev * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    VCU(cudaMemcpyAsync(xv.data(), (uint8_t *)dgath.p + n_ev * 32, xidx.size() * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    VCU(cudaStreamSynchronize(ctx->stream));
+    VCU(cudaGetLastError());
+    auto col_at = [&](int c, size_t i) { return ev[(size_t)c * V + i]; };
+
+    // verify.rs:152-173 boundary data and challenges
+    std::vector<hfp::el> pub_x(np), pub_y(np);
+    for (size_t i = 0; i < np; i++) {
+        pub_x[i] = xv[V + i];
+        pub_y[i] = hfp::from_limbs(t->public_wires + 4 * t->pfi_k[i]);
+    }
+    const hfp::el x_last = xv[V + np];
+    hfp::el r[3], k[11];
+    {
+        uint32_t idx[24];
+        if (pseudorandom_indices(proof->a_root, 32, (uint32_t)N, 24, 0, idx, false) != SB_OK) return fail(ctx, SB_ERR_ARG, "sampler rejected precision %zu", N);
+        for (int i = 0; i < 3; i++) {
+            uint8_t b[32];
+            for (int j = 0; j < 8; j++) {
+                uint32_t v = idx[8 * i + j];
+                b[4 * j] = (uint8_t)(v >> 24); b[4 * j + 1] = (uint8_t)(v >> 16); b[4 * j + 2] = (uint8_t)(v >> 8); b[4 * j + 3] = (uint8_t)v;
+            }
+            r[i] = hfp::from_bytes_le32(b);
+        }
+        k[0] = hfp::ONE;
+        for (int i = 1; i < 11; i++) {
+            uint8_t msg[33], h[32], le[32];
+            memcpy(msg, proof->m_root, 32);
+            msg[32] = (uint8_t)i;
+            b2s::hash_bytes(h, msg, 33);
+            for (int b = 0; b < 32; b++) le[b] = h[31 - b];
+            k[i] = hfp::from_bytes_le32(le);
+        }
+    }
+
+    // verify.rs:175-252 the spot checks
+    for (size_t i = 0; i < V; i++) {
+        const hfp::el x = xv[i];
+        auto leaf = [&](size_t br, size_t f) { return hfp::from_bytes_le32(&proof->main_leaves[256 * (4 * i + br) + 32 * f]); };
+        const hfp::el p_x = leaf(0, 0), p_prev = leaf(1, 0), p_w = leaf(2, 0), p_2w = leaf(3, 0);
+        const hfp::el a_x = leaf(0, 1), a_prev = leaf(1, 1), s_x = leaf(0, 2);
+        const hfp::el d1 = leaf(0, 3), d2 = leaf(0, 4), d3 = leaf(0, 5), b2 = leaf(0, 6), b3 = leaf(0, 7);
+        const hfp::el x_s = hfp::pow_u64(x, S);                                          // verify.rs:234
+        const hfp::el z = sub(x_s, hfp::ONE);                                            // z_evaluations[pos], utils.rs:173-178
+        const hfp::el k_x = col_at(0, i), f0 = col_at(1, i), f1 = col_at(2, i), f2 = col_at(3, i);
+        if (!hfp::eq(hfp::mul(f0, sub(sub(p_x, hfp::mul(f1, p_prev)), hfp::mul(k_x, s_x))), hfp::mul(z, d1)))
+            return fail(ctx, SB_ERR_VERIFY, "spot check %zu: Q1(x) != Z(x) D1(x) (verify.rs:205)", i);
+        if (!hfp::eq(hfp::mul(f2, sub(p_2w, hfp::mul(p_x, p_w))), hfp::mul(z, d2)))
+            return fail(ctx, SB_ERR_VERIFY, "spot check %zu: Q2(x) != Z(x) D2(x) (verify.rs:211)", i);
+        const hfp::el t2 = hfp::mul(r[2], s_x);
+        const hfp::el vn = hfp::add(hfp::add(r[0], hfp::mul(r[1], col_at(4, i))), t2);
+        const hfp::el vd = hfp::add(hfp::add(r[0], hfp::mul(r[1], col_at(5, i))), t2);
+        if (!hfp::eq(sub(hfp::mul(a_x, vd), hfp::mul(a_prev, vn)), hfp::mul(z, d3)))
+            return fail(ctx, SB_ERR_VERIFY, "spot check %zu: Q3(x) != Z(x) D3(x) (verify.rs:220)", i);
+        hfp::el zb2 = hfp::ONE;
+        for (size_t j = 0; j < np; j++) zb2 = hfp::mul(zb2, sub(x, pub_x[j]));           // verify.rs:223-226
+        const hfp::el i2 = np ? lagrange_eval(pub_x, pub_y, x) : hfp::ZERO;
+        if (!hfp::eq(sub(s_x, i2), hfp::mul(zb2, b2))) return fail(ctx, SB_ERR_VERIFY, "spot check %zu: S(x) - I2(x) != Zb2(x) B2(x) (verify.rs:228)", i);
+        if (!hfp::eq(sub(a_x, hfp::ONE), hfp::mul(sub(x, x_last), b3)))                 // I3 = 1 (utils.rs:458-463)
+            return fail(ctx, SB_ERR_VERIFY, "spot check %zu: A(x) - I3(x) != Zb3(x) B3(x) (verify.rs:232)", i);
+        const hfp::el l_x = hfp::from_bytes_le32(&proof->lc_leaves[32 * i]);
+        hfp::el acc = hfp::mul(k[0], d1);
+        acc = hfp::add(acc, hfp::mul(k[1], d2));
+        acc = hfp::add(acc, hfp::mul(k[2], d3));
+        acc = hfp::add(acc, hfp::mul(k[3], p_x));
+        acc = hfp::add(acc, hfp::mul(hfp::mul(k[4], p_x), x_s));
+        acc = hfp::add(acc, hfp::mul(k[5], b2));
+        acc = hfp::add(acc, hfp::mul(hfp::mul(k[6], b2), x_s));
+        acc = hfp::add(acc, hfp::mul(k[7], b3));
+        acc = hfp::add(acc, hfp::mul(hfp::mul(k[8], b3), x_s));
+        acc = hfp::add(acc, hfp::mul(k[9], a_x));
+        acc = hfp::add(acc, hfp::mul(k[10], s_x));
+        if (!hfp::eq(l_x, acc)) return fail(ctx, SB_ERR_VERIFY, "spot check %zu: linear combination mismatch (verify.rs:237)", i);
+    }
+    return SB_OK;
+#undef VTRY
+#undef VCU
+}
+
+// ---- serde_json reader for StarkProof (run.rs:578 serde_json::from_reader; the layout sb_stark_proof_json writes) ------
+namespace {
+struct JsonIn {
+    const char *p, *end;
+    bool ok = true;
+    void ws() { while (p < end && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) p++; }
+    bool eat(char c) {
+        ws();
+        if (p < end && *p == c) { p++; return true; }
+        return false;
+    }
+    void need(char c) { if (!eat(c)) ok = false; }
+    bool key(const char *name) {                       // "name":
+        ws();
+        const size_t n = strlen(name);
+        if ((size_t)(end - p) < n + 3 || *p != '"' || memcmp(p + 1, name, n) != 0 || p[n + 1] != '"') { ok = false; return false; }
+        p += n + 2;
+        need(':');
+        return ok;
+    }
+    bool bytes(std::vector<uint8_t> &out) {            // [1,2,3] appended
+        need('[');
+        if (eat(']')) return ok;
+        while (ok) {
+            ws();
+            unsigned v = 0;
+            int digits = 0;
+            while (p < end && *p >= '0' && *p <= '9' && digits < 4) { v = v * 10 + (unsigned)(*p - '0'); p++; digits++; }
+            if (!digits || v > 255) { ok = false; break; }
+            out.push_back((uint8_t)v);
+            if (eat(',')) continue;
+            need(']');
+            break;
+        }
+        return ok;
+    }
+    // [{"leaf":[..],"nodes":[[..],..]},..]
+    bool branches(std::vector<uint8_t> &leaves, std::vector<uint8_t> &nodes, size_t &count, size_t &leaf_bytes, size_t &depth) {
+        count = 0; leaf_bytes = 0; depth = 0;
+        need('[');
+        if (eat(']')) return ok;
+        while (ok) {
+            need('{');
+            key("leaf");
+            const size_t l0 = leaves.size();
+            bytes(leaves);
+            const size_t lb = leaves.size() - l0;
+            need(',');
+            key("nodes");
+            need('[');
+            size_t d = 0;
+            if (!eat(']')) {
+                while (ok) {
+                    const size_t n0 = nodes.size();
+                    bytes(nodes);
+                    if (nodes.size() - n0 != 32) ok = false;
+                    d++;
+                    if (eat(',')) continue;
+                    need(']');
+                    break;
+                }
+            }
+            need('}');
+            if (count == 0) { leaf_bytes = lb; depth = d; } else if (lb != leaf_bytes || d != depth) ok = false;
+            count++;
+            if (eat(',')) continue;
+            need(']');
+            break;
+        }
+        return ok;
+    }
+};
+}  // namespace
+
+extern "C" int sb_stark_proof_from_json(const char *text, size_t len, sb_stark_proof **out) {
+    if (!text || !out) return SB_ERR_ARG;
+    JsonIn j{text, text + len};
+    sb_stark_proof *p = new sb_stark_proof();
+    p->fri = new sb_fri_proof();
+    auto root = [&](const char *name, uint8_t dst[32]) {
+        std::vector<uint8_t> v;
+        j.key(name);
+        j.bytes(v);
+        if (v.size() != 32) j.ok = false; else memcpy(dst, v.data(), 32);
+    };
+    j.need('{');
+    root("m_root", p->m_root); j.need(',');
+    root("l_root", p->l_root); j.need(',');
+    root("a_root", p->a_root); j.need(',');
+    size_t cnt = 0, lb = 0, depth = 0, depth2 = 0;
+    j.key("main_branches");
+    j.branches(p->main_leaves, p->main_nodes, cnt, lb, depth);
+    if (cnt && lb != 256) j.ok = false;
+    j.need(',');
+    j.key("linear_comb_branches");
+    j.branches(p->lc_leaves, p->lc_nodes, cnt, lb, depth2);
+    if ((cnt && lb != 32) || depth2 != depth) j.ok = false;
+    p->depth = depth;
+    j.need(',');
+    j.key("fri_proof");
+    j.need('[');
+    if (!j.eat(']')) {
+        while (j.ok) {
+            FriLayer L;
+            j.need('{');
+            j.ws();
+            if (j.p + 6 < j.end && memcmp(j.p, "\"Last\"", 6) == 0) {
+                j.key("Last");
+                j.need('{');
+                j.key("last");
+                j.need('[');
+                if (!j.eat(']')) {
+                    while (j.ok) {
+                        const size_t n0 = L.last.size();
+                        j.bytes(L.last);
+                        if (L.last.size() - n0 != 32) j.ok = false;
+                        if (j.eat(',')) continue;
+                        j.need(']');
+                        break;
+                    }
+                }
+                j.need('}');
+                L.is_last = true;
+            } else {
+                j.key("Middle");
+                j.need('{');
+                std::vector<uint8_t> v;
+                j.key("root2");
+                j.bytes(v);
+                if (v.size() != 32) j.ok = false; else memcpy(L.root2, v.data(), 32);
+                j.need(',');
+                size_t lb2 = 0;
+                j.key("column_branches");
+                j.branches(L.column_leaves, L.column_nodes, L.n_column, lb2, L.depth_column);
+                if (L.n_column && lb2 != 32) j.ok = false;
+                j.need(',');
+                j.key("poly_branches");
+                j.branches(L.poly_leaves, L.poly_nodes, L.n_poly, lb2, L.depth_poly);
+                if (L.n_poly && lb2 != 32) j.ok = false;
+                j.need('}');
+            }
+            j.need('}');
+            p->fri->layers.push_back(std::move(L));
+            if (j.eat(',')) continue;
+            j.need(']');
+            break;
+        }
+    }
+    j.need('}');
+    j.ws();
+    if (!j.ok || j.p != j.end) {
+        delete p;
+        return SB_ERR_ARG;
+    }
+    *out = p;
+    return SB_OK;
+}

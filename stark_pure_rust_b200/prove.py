@@ -65,3 +65,12 @@ def prove_with_file_path(r1cs_path, wtns_path, proof_path, ctx=None):
     ctx.check(ctx.lib.sb_prove_files(ctx.h, str(r1cs_path).encode(), str(wtns_path).encode(),
                                      str(proof_path).encode() if proof_path else None, ms))
     return list(ms)
+
+
+def verify_with_file_path(r1cs_path, wtns_path, proof_path, ctx=None):
+    """run.rs:556-590.  Returns [front end + parse ms, verify ms]; raises StarkB200Error(SB_ERR_VERIFY) when the proof is
+    rejected (the reference panics)."""
+    ctx = ctx or default_context()
+    ms = (C.c_double * 2)()
+    ctx.check(ctx.lib.sb_verify_files(ctx.h, str(r1cs_path).encode(), str(wtns_path).encode(), str(proof_path).encode(), ms))
+    return list(ms)

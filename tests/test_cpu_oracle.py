@@ -206,3 +206,28 @@ def test_bench_reference_arm_runs():
     assert r.returncode == 0, r.stderr
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+
+
+def test_proof_json_reader_round_trip(oracle, tmp_path):
+    """sb_stark_proof_from_json (serde_json::from_reader::<StarkProof>, run.rs:578) followed by sb_stark_proof_json
+    reproduces the oracle's proof.json byte for byte; malformed text is refused.  Host only: no GPU needed."""
+    import ctypes as C
+    from stark_pure_rust_b200 import _lib
+    L = _lib.load()
+    d = os.path.join(ROOT, "tests", "golden", "circuits")
+    path = str(tmp_path / "compute.json")
+    rc, _ = oracle.prove_files(os.path.join(d, "compute.r1cs"), os.path.join(d, "compute.wtns"), path)
+    assert rc == 0
+    text = open(path, "rb").read()
+    h = C.c_void_p()
+    assert L.sb_stark_proof_from_json(text, len(text), C.byref(h)) == 0
+    n = C.c_size_t()
+    s = L.sb_stark_proof_json(h, C.byref(n))
+    try:
+        assert C.string_at(s, n.value) == text
+    finally:
+        L.sb_free_string(s)
+        L.sb_stark_proof_free(h)
+    for bad in (text[:-1], text.replace(b'"l_root"', b'"x_root"'), text.replace(b"[", b"[256,", 1), b"{}", b""):
+        h = C.c_void_p()
+        assert L.sb_stark_proof_from_json(bad, len(bad), C.byref(h)) == -3

@@ -505,3 +505,83 @@ def test_synthetic_sha256_scale_prove_matches_golden(ctx, tmp_path):
     sb.prove.prove_with_file_path(prefix + ".r1cs", prefix + ".wtns", out, ctx=ctx)
     assert hashlib.sha256(open(out, "rb").read()).hexdigest() == gold["proof_json_sha256"]
     assert os.path.getsize(out) == gold["proof_json_bytes"]
+
+
+# ---- verifier (verify.rs:13-258, fri.rs:226-404): SURVEY.md 8f next-3 ------------------------------------------
+def _prove_files(ctx, name, tmp_path):
+    import os
+    import stark_pure_rust_b200 as sb
+    from conftest import ROOT
+    d = os.path.join(ROOT, "tests", "golden", "circuits")
+    out = str(tmp_path / (name + ".proof.json"))
+    sb.prove.prove_with_file_path(os.path.join(d, name + ".r1cs"), os.path.join(d, name + ".wtns"), out, ctx=ctx)
+    return os.path.join(d, name + ".r1cs"), os.path.join(d, name + ".wtns"), out
+
+
+@pytest.mark.parametrize("name", ["compute", "poseidon3_test"])
+def test_verifier_accepts_and_rejects(ctx, name, tmp_path):
+    """the device-assisted verifier accepts the prover's proof.json and rejects every single-byte tampering tried:
+    roots, a main-branch leaf, a Merkle sibling, an FRI column value, an FRI root2, a last-layer value"""
+    import json
+    import stark_pure_rust_b200 as sb
+    r1cs, wtns, out = _prove_files(ctx, name, tmp_path)
+    ms = sb.prove.verify_with_file_path(r1cs, wtns, out, ctx=ctx)
+    assert ms[1] > 0
+    proof = json.load(open(out))
+
+    def tampered(mutate):
+        p = json.loads(json.dumps(proof))
+        mutate(p)
+        path = str(tmp_path / "bad.json")
+        json.dump(p, open(path, "w"), separators=(",", ":"))
+        with pytest.raises(sb.StarkB200Error) as e:
+            sb.prove.verify_with_file_path(r1cs, wtns, path, ctx=ctx)
+        assert e.value.code == -6, e.value
+        return str(e.value)
+
+    def flip(lst, i=0):
+        lst[i] = (lst[i] + 1) % 256
+
+    assert "m_root" in tampered(lambda p: flip(p["m_root"]))
+    tampered(lambda p: flip(p["l_root"]))
+    assert "Q3" in tampered(lambda p: flip(p["a_root"]))
+    assert "main branch" in tampered(lambda p: flip(p["main_branches"][5]["leaf"], 40))
+    assert "main branch" in tampered(lambda p: flip(p["main_branches"][0]["nodes"][2], 7))
+    assert "linear combination branch" in tampered(lambda p: flip(p["linear_comb_branches"][3]["leaf"], 1))
+    assert "FRI" in tampered(lambda p: flip(p["fri_proof"][0]["Middle"]["column_branches"][2]["leaf"], 3))
+    assert "FRI" in tampered(lambda p: flip(p["fri_proof"][0]["Middle"]["root2"], 9))
+    assert "FRI" in tampered(lambda p: flip(p["fri_proof"][-1]["Last"]["last"][5], 0))
+    # a consistent-looking change that only the constraint equations catch: swap d1 and d2 inside a leaf of position 0
+    def swap_fields(p):
+        leaf = p["main_branches"][0]["leaf"]
+        leaf[96:128], leaf[128:160] = leaf[128:160], leaf[96:128]
+    assert "main branch" in tampered(swap_fields)
+
+
+def test_verifier_rejects_other_circuit_and_public_inputs(ctx, oracle, tmp_path):
+    """a valid proof of one circuit does not verify against another circuit's r1cs or against changed public wires"""
+    import os
+    import sys
+    import stark_pure_rust_b200 as sb
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_r1cs
+    pa, pb = str(tmp_path / "a"), str(tmp_path / "b")
+    wit, cons = gen_r1cs.generate(300, 3.0, 2, 1)
+    gen_r1cs.write_files(pa, wit, cons, 2)
+    out = str(tmp_path / "a.json")
+    sb.prove.prove_with_file_path(pa + ".r1cs", pa + ".wtns", out, ctx=ctx)
+    sb.prove.verify_with_file_path(pa + ".r1cs", pa + ".wtns", out, ctx=ctx)
+    # same structure, different public input value: the boundary check S(x) - I2(x) = Zb2(x) B2(x) fails
+    wit2 = list(wit)
+    wit2[1] = (wit2[1] + 1) % gen_r1cs.P
+    gen_r1cs.write_files(pb, wit2, cons, 2)
+    with pytest.raises(sb.StarkB200Error) as e:
+        sb.prove.verify_with_file_path(pa + ".r1cs", pb + ".wtns", out, ctx=ctx)
+    assert e.value.code == -6 and "I2" in str(e.value)
+    # different circuit of the same size class
+    wit3, cons3 = gen_r1cs.generate(300, 3.0, 2, 2)
+    gen_r1cs.write_files(pb, wit3, cons3, 2)
+    with pytest.raises(sb.StarkB200Error) as e:
+        sb.prove.verify_with_file_path(pb + ".r1cs", pb + ".wtns", out, ctx=ctx)
+    assert e.value.code in (-6, -3)
