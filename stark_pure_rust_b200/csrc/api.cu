@@ -3,6 +3,8 @@
 // vector work needs a live context, and sb_init fails without a compute-capability-10 device.
 #include "internal.h"
 
+#include <algorithm>
+
 // ------------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------------
@@ -50,6 +52,8 @@ extern "C" void sb_destroy(sb_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (auto &t : ctx->tables) cudaFree(t.d);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     prof_collect(ctx);
     for (auto e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -399,10 +403,53 @@ extern "C" int sb_lde_batch(sb_ctx *ctx, const uint64_t *cols, size_t n_cols, si
     DevBuf in(ctx), o(ctx);
     TRY(in.alloc(n_cols * col_len * 32));
     TRY(o.alloc(n_cols * N * 32));
-    CU(cudaMemcpyAsync(in.p, cols, n_cols * col_len * 32, cudaMemcpyHostToDevice, ctx->stream));
-    TRY(lde_dev(ctx, (const uint4 *)in.p, n_cols, col_len, col_len, hfp::from_limbs(root_big), log_s, log_ext, (uint4 *)o.p));
-    CU(cudaMemcpyAsync(out, o.p, n_cols * N * 32, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    const hfp::el root = hfp::from_limbs(root_big);
+    const size_t G = 2;                                  // columns per pipeline stage
+    if (n_cols < 2 * G || N < ((size_t)1 << 18)) {
+        CU(cudaMemcpyAsync(in.p, cols, n_cols * col_len * 32, cudaMemcpyHostToDevice, ctx->stream));
+        TRY(lde_dev(ctx, (const uint4 *)in.p, n_cols, col_len, col_len, root, log_s, log_ext, (uint4 *)o.p));
+        CU(cudaMemcpyAsync(out, o.p, n_cols * N * 32, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        return SB_OK;
+    }
+    // Large batches: upload of group g+1, transform of group g and download of group g-1 overlap (three streams).  The
+    // download (32 N bytes per column) is the long pole over PCIe; the transform hides behind it.  Needs pinned host buffers
+    // to overlap (pageable ones are staged by the driver and serialise, still correct).
+    if (!ctx->h2d_stream) CU(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+    if (!ctx->d2h_stream) CU(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+    const size_t n_groups = (n_cols + G - 1) / G;
+    std::vector<cudaEvent_t> up(n_groups), done(n_groups);
+    cudaEvent_t ready;
+    CU(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    CU(cudaEventRecord(ready, ctx->stream));             // the allocations above are ordered on ctx->stream
+    CU(cudaStreamWaitEvent(ctx->h2d_stream, ready, 0));
+    CU(cudaStreamWaitEvent(ctx->d2h_stream, ready, 0));
+    int rc = SB_OK;
+    for (size_t g = 0; g < n_groups; g++) {
+        cudaEventCreateWithFlags(&up[g], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&done[g], cudaEventDisableTiming);
+        const size_t c0 = g * G, nc = std::min(G, n_cols - c0);
+        cudaMemcpyAsync((uint8_t *)in.p + c0 * col_len * 32, (const uint8_t *)cols + c0 * col_len * 32, nc * col_len * 32,
+                        cudaMemcpyHostToDevice, ctx->h2d_stream);
+        cudaEventRecord(up[g], ctx->h2d_stream);
+    }
+    for (size_t g = 0; g < n_groups && rc == SB_OK; g++) {
+        const size_t c0 = g * G, nc = std::min(G, n_cols - c0);
+        cudaStreamWaitEvent(ctx->stream, up[g], 0);
+        rc = lde_dev(ctx, (const uint4 *)in.p + 2 * c0 * col_len, nc, col_len, col_len, root, log_s, log_ext, (uint4 *)o.p + 2 * c0 * N);
+        cudaEventRecord(done[g], ctx->stream);
+        cudaStreamWaitEvent(ctx->d2h_stream, done[g], 0);
+        cudaMemcpyAsync((uint8_t *)out + c0 * N * 32, (const uint8_t *)o.p + c0 * N * 32, nc * N * 32, cudaMemcpyDeviceToHost, ctx->d2h_stream);
+    }
+    cudaError_t e1 = cudaStreamSynchronize(ctx->d2h_stream), e2 = cudaStreamSynchronize(ctx->h2d_stream), e3 = cudaStreamSynchronize(ctx->stream);
+    for (size_t g = 0; g < n_groups; g++) {
+        cudaEventDestroy(up[g]);
+        cudaEventDestroy(done[g]);
+    }
+    cudaEventDestroy(ready);
+    if (rc != SB_OK) return rc;
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+        return fail(ctx, SB_ERR_CUDA, "sb_lde_batch pipeline: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
     return SB_OK;
 }
 

@@ -34,6 +34,8 @@ struct sb_ctx {
     size_t table_cache_bytes = (size_t)8 << 30;   // soft cap of the twiddle-table cache (SB_TABLE_CACHE_BYTES)
     char err[512] = {0};
     bool extended_domain = false;      // sb_set_extended_domain: FRI layers beyond the reference sampler's 2^24 limit
+    // copy streams of the host-buffer entry points (sb_lde_batch pipelines upload / transform / download), created on demand
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     // pinned host staging arena (front end -> sb_prove_r1cs uploads); grows on demand, freed in sb_destroy
     void *pinned = nullptr;
     size_t pinned_bytes = 0;

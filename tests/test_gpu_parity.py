@@ -92,7 +92,7 @@ def test_best_fft_errors(ctx, oracle):
     assert e.value.code == -4
 
 
-@pytest.mark.parametrize("log_s,n_cols,col_len", [(4, 1, 16), (4, 3, 15), (10, 10, 1024), (13, 6, 6684), (15, 2, 1 << 15)])
+@pytest.mark.parametrize("log_s,n_cols,col_len", [(4, 1, 16), (4, 3, 15), (10, 10, 1024), (13, 6, 6684), (15, 2, 1 << 15), (15, 5, 30000)])
 def test_lde_batch(ctx, oracle, log_s, n_cols, col_len):
     """prove.rs:100-124: best_fft(inv_best_fft(col, g1, log_s), g2, log_s + 3); out[8j] == col[j]"""
     import stark_pure_rust_b200 as sb
