@@ -679,8 +679,8 @@ extern "C" int sb_tree_root(const sb_tree *t, uint8_t root[32]) {
     return SB_OK;
 }
 extern "C" void sb_tree_free(sb_ctx *ctx, sb_tree *t) {
-    (void)ctx;
-    free_tree(t);      // stream-ordered: work already queued on the tree's stream finishes first
+    if (t && ctx) t->stream = ctx->stream;   // the context's stream may have been replaced since the tree was built (sb_set_stream)
+    free_tree(t);      // stream-ordered: work already queued on the stream finishes first
 }
 
 // ------------------------------------------------------------------------------------------------

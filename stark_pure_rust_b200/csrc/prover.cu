@@ -476,17 +476,32 @@ bool branch_ok(const uint8_t root[32], size_t index, const uint8_t *leaf, size_t
 
 hfp::el sub(const hfp::el &a, const hfp::el &b) { return hfp::add(a, hfp::neg(b)); }
 
-// value at x of the polynomial of degree < n through (xs[i], ys[i]) (poly_utils.rs:409-439 + eval_poly_at)
+// value at x of the polynomial of degree < n through (xs[i], ys[i]) (poly_utils.rs:409-439 + eval_poly_at); the n
+// denominators share one field inversion (Montgomery's trick)
 hfp::el lagrange_eval(const std::vector<hfp::el> &xs, const std::vector<hfp::el> &ys, const hfp::el &x) {
-    hfp::el acc = hfp::ZERO;
-    for (size_t i = 0; i < xs.size(); i++) {
-        hfp::el num = hfp::ONE, den = hfp::ONE;
-        for (size_t j = 0; j < xs.size(); j++) {
+    const size_t n = xs.size();
+    if (n == 0) return hfp::ZERO;
+    std::vector<hfp::el> num(n), den(n), pre(n);
+    for (size_t i = 0; i < n; i++) {
+        num[i] = hfp::ONE;
+        den[i] = hfp::ONE;
+        for (size_t j = 0; j < n; j++) {
             if (i == j) continue;
-            num = hfp::mul(num, sub(x, xs[j]));
-            den = hfp::mul(den, sub(xs[i], xs[j]));
+            num[i] = hfp::mul(num[i], sub(x, xs[j]));
+            den[i] = hfp::mul(den[i], sub(xs[i], xs[j]));
         }
-        acc = hfp::add(acc, hfp::mul(ys[i], hfp::mul(num, hfp::inv(den))));
+    }
+    hfp::el run = hfp::ONE;
+    for (size_t i = 0; i < n; i++) {
+        pre[i] = run;
+        run = hfp::mul(run, den[i]);
+    }
+    hfp::el inv = hfp::inv(run);          // the points are distinct, so no denominator is zero
+    hfp::el acc = hfp::ZERO;
+    for (size_t i = n; i-- > 0;) {
+        const hfp::el di = hfp::mul(inv, pre[i]);
+        inv = hfp::mul(inv, den[i]);
+        acc = hfp::add(acc, hfp::mul(ys[i], hfp::mul(num[i], di)));
     }
     return acc;
 }

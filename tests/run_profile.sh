@@ -9,6 +9,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
 echo "launch list rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:ntt_pass_kernel -s 6 -c 6 -f -o gpurun_out/prof_ntt_${TAG} $CMD > gpurun_out/ncu_full_ntt_${TAG}.log 2>&1
 echo "ntt full rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:merkle_leaves_cols -s 11 -c 2 -f -o gpurun_out/prof_merkle_${TAG} $CMD > gpurun_out/ncu_full_merkle_${TAG}.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:merkle_leaves_cols -s 2 -c 2 -f -o gpurun_out/prof_merkle_${TAG} $CMD > gpurun_out/ncu_full_merkle_${TAG}.log 2>&1
 echo "merkle full rc=$?"
 tail -2 gpurun_out/ncu_full_ntt_${TAG}.log
