@@ -297,7 +297,7 @@ static int ntt_dev_tw(sb_ctx *ctx, const uint4 *d_src, size_t len_in, size_t src
         P.coset_log = coset_log;
         {   // interleave polynomials when a tile never straddles two of them (the coset transforms also in the last
             // pass: the CTAs that fill the same output lines then run together)
-            const unsigned long long cpp = 1ull << (log_n - bits[p]), cc = (1ull << NTT_LOG_TILE) >> bits[p];
+            const unsigned long long cpp = 1ull << (log_n - bits[p]), cc = (1ull << NTT_LOG_TILE_FOR(bits[p])) >> bits[p];
             P.n_polys = (n_batch > 1 && (!last || coset_m1) && cpp % cc == 0 && n_batch < (1u << 20)) ? (uint32_t)n_batch : 0;
         }
         P.n_prev = (uint32_t)p;

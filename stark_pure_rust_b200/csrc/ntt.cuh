@@ -104,7 +104,7 @@ __device__ __forceinline__ unsigned long long ntt_digitrev_inv(const NttPassPara
 }
 
 template <int B, int LOG_TILE>
-__global__ void __launch_bounds__((1 << LOG_TILE) / 8, 4) ntt_pass_kernel(const __grid_constant__ NttPassParams P) {
+__global__ void __launch_bounds__((1 << LOG_TILE) / 8, LOG_TILE >= 11 ? 2 : 4) ntt_pass_kernel(const __grid_constant__ NttPassParams P) {
     constexpr int TILE = 1 << LOG_TILE, NT = TILE / 8, R = 1 << B, CC = TILE >> B, PITCH = CC + 1;
     extern __shared__ uint4 smem[];
     uint4 *slo = smem, *shi = smem + R * PITCH;

@@ -5,18 +5,18 @@
 
 template <int B>
 static size_t ntt_smem_bytes() {
-    constexpr int R = 1 << B, CC = (1 << NTT_LOG_TILE) >> B, PITCH = CC + 1;
+    constexpr int R = 1 << B, CC = (1 << NTT_LOG_TILE_FOR(B)) >> B, PITCH = CC + 1;
     return (size_t)(2 * R * PITCH + 2 * (R / 2 > 0 ? R / 2 : 1)) * sizeof(uint4);
 }
 template <int B>
 static cudaError_t ntt_set_attr_one() {
-    return cudaFuncSetAttribute(ntt_pass_kernel<B, NTT_LOG_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    return cudaFuncSetAttribute(ntt_pass_kernel<B, NTT_LOG_TILE_FOR(B)>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)ntt_smem_bytes<B>());
 }
 template <int B>
 static int ntt_launch_one(cudaStream_t stream, const NttPassParams &P) {
-    constexpr int TILE = 1 << NTT_LOG_TILE, CC = TILE >> B;
+    constexpr int TILE = 1 << NTT_LOG_TILE_FOR(B), CC = TILE >> B;
     unsigned long long grid = (P.n_cols_total + CC - 1) / CC;
-    ntt_pass_kernel<B, NTT_LOG_TILE><<<(unsigned)grid, TILE / 8, ntt_smem_bytes<B>(), stream>>>(P);
+    ntt_pass_kernel<B, NTT_LOG_TILE_FOR(B)><<<(unsigned)grid, TILE / 8, ntt_smem_bytes<B>(), stream>>>(P);
     return 1;
 }
