@@ -13,6 +13,22 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
+def fri_layers_from_json(text):
+    """serde text of Vec<FriProof> -> the layout of stark_pure_rust_b200.fri.unpack_proof"""
+    import json
+    from stark_pure_rust_b200.merkle import Proof
+    out = []
+    for layer in json.loads(text):
+        if "Last" in layer:
+            out.append({"Last": {"last": [bytes(v) for v in layer["Last"]["last"]]}})
+        else:
+            m = layer["Middle"]
+            conv = lambda bs: [Proof(bytes(b["leaf"]), [bytes(x) for x in b["nodes"]]) for b in bs]
+            out.append({"Middle": {"root2": bytes(m["root2"]), "column_branches": conv(m["column_branches"]),
+                                   "poly_branches": conv(m["poly_branches"])}})
+    return out
+
+
 class OracleBackend:
     """same duck type as sharded.CudaBackend, CPU tensors + oracle arithmetic"""
 
@@ -73,6 +89,33 @@ class OracleBackend:
         vals = field.from_mont(self._np(x).reshape(-1, 4))
         out = [v * pow(w, ((row0 + i // cols) * (i % cols)) % (1 << log_n), field.P) % field.P for i, v in enumerate(vals)]
         x.copy_(self.from_numpy(field.to_mont(out)).reshape(rows, cols, 4))
+
+    def fri_fold(self, vals, root_limbs, values_root):
+        """fri.rs:135-164 with Python big ints: Lagrange through the four row points, evaluated at special_x"""
+        from stark_pure_rust_b200 import field
+        Pm = field.P
+        v = field.from_mont(self._np(vals))
+        n, q = len(v), len(v) // 4
+        w = field.from_mont(np.asarray(root_limbs, dtype=np.uint64).reshape(1, 4))[0]
+        sx = int.from_bytes(values_root, "little") % Pm
+        iota = pow(w, q, Pm)
+        out = []
+        for i in range(q):
+            xs = [pow(w, i, Pm) * pow(iota, j, Pm) % Pm for j in range(4)]
+            acc = 0
+            for a in range(4):
+                num = den = 1
+                for b in range(4):
+                    if a != b:
+                        num = num * (sx - xs[b]) % Pm
+                        den = den * (xs[a] - xs[b]) % Pm
+                acc = (acc + v[i + q * a] * num * pow(den, -1, Pm)) % Pm
+            out.append(acc)
+        return self.from_numpy(field.to_mont(out))
+
+    def fri_rest(self, col, root_limbs, max_deg_plus_1, excl, tree):
+        text, _ = self.ob.prove_low_degree_json(self._np(col), np.asarray(root_limbs, dtype=np.uint64), max_deg_plus_1, excl, verify=False)
+        return fri_layers_from_json(text)
 
     def root_tensor(self, root):
         return self.torch.frombuffer(bytearray(root), dtype=self.torch.uint8).clone()
@@ -145,6 +188,52 @@ def _ntt_worker(rank, world, port, log_n, ret):
             ret.put(all(flags))
     finally:
         dist.destroy_process_group()
+
+
+def _fri_worker(rank, world, port, log_n, ret):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from conftest import random_elems
+        import oracle_bind as ob
+        from stark_pure_rust_b200 import field, sharded
+        be = OracleBackend()
+        n = 1 << log_n
+        w = field.root_of_unity(log_n)
+        coeffs = random_elems(n // 8, 1234)
+        values = ob.best_fft(coeffs, field.mont_scalar(w), log_n)          # degree < n/8 <= n/4
+        lo, hi = sharded.row_range(n, world, rank)
+        rows = be.from_numpy(values).reshape(1, n, 4)[:, lo:hi]
+        sc = sharded.ShardedCommitter(be, dist)
+        tree = sc.commit_rows(rows, [0], n)
+        owner = world - 1
+        vals = be.from_numpy(values) if rank == owner else None
+        proof = sharded.prove_low_degree_sharded(be, tree, vals, owner, w, n, n // 4, 8, dist, replicate=True)
+        if rank == 0:
+            text, ok = ob.prove_low_degree_json(values, field.mont_scalar(w), n // 4, 8)
+            ret.put(bool(ok) and proof == fri_layers_from_json(text))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_fri_matches_single_process(world):
+    """prove_low_degree_sharded (layer 0 on the row-sharded values tree, the rest on the owner) under gloo: the assembled
+    proof equals the oracle's prove_low_degree of the whole vector"""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000) + world * 13
+    procs = [ctx.Process(target=_fri_worker, args=(r, world, port, 9, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    assert ret.get(timeout=5) is True
 
 
 @pytest.mark.parametrize("world,log_n", [(2, 6), (2, 9), (4, 8)])
