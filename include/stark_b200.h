@@ -212,6 +212,13 @@ int sb_verify_files(sb_ctx *ctx, const char *r1cs_path, const char *wtns_path, c
  * [3] rest of the GPU pipeline [4] sb_prove_r1cs wall clock [5] host front end [6] JSON + file write. */
 int sb_prove_files(sb_ctx *ctx, const char *r1cs_path, const char *wtns_path, const char *proof_path, double stage_ms[7]);
 
+/* The host front end alone (run.rs:109-308, :390-419; circom2bellman_core/src/reader.rs:4-89; r1cs-stark/src/reader.rs:7-42):
+ * parses the two files and builds the arguments of mk_r1cs_proof in host memory.  Needs no device and no context.  *view
+ * points into *out and stays valid until sb_host_trace_free. */
+typedef struct sb_host_trace sb_host_trace;
+int sb_trace_from_files(const char *r1cs_path, const char *wtns_path, sb_host_trace **out, const sb_trace **view);
+void sb_host_trace_free(sb_host_trace *h);
+
 /* ---- unit-test hook for the device field library (no reference counterpart: ff_derive's arithmetic is
  * generated code) ---- element-wise op on n raw 256-bit values, no range checks.
  * op: 0 Montgomery product (lazy, < 2p), 1 add, 2 sub, 3 a+2p-b, 4 canonicalise, 5 halve, 6 from Montgomery,

@@ -152,7 +152,7 @@ const char *read_witness(const std::vector<uint8_t> &buf, std::vector<hfp::el> &
 struct Trace {
     size_t os = 0;
     hfp::el *wit = nullptr, *comp = nullptr, *coef = nullptr, *f0 = nullptr, *f1 = nullptr, *f2 = nullptr;
-    std::vector<hfp::el> pub;
+    std::vector<hfp::el> pub, heap;
     std::vector<size_t> perm, pfi_k, pfi_w;
 };
 
@@ -164,7 +164,13 @@ const char *build_trace(sb_ctx *ctx, const R1cs &r, const std::vector<hfp::el> &
     if ((with_witness && witness.size() < n_wires) || n_wires == 0) return "witness shorter than the circuit's wire count";
     const size_t a = r.row_off[nc], os = 3 * a;
     if (a == 0) return "circuit has no constraint rows";
-    hfp::el *arena = (hfp::el *)pinned_arena(ctx, 6 * os * sizeof(hfp::el));
+    hfp::el *arena;
+    if (ctx) {
+        arena = (hfp::el *)pinned_arena(ctx, 6 * os * sizeof(hfp::el));
+    } else {                      // host-only use (sb_trace_from_files): ordinary memory owned by the Trace
+        t.heap.resize(6 * os);
+        arena = t.heap.data();
+    }
     if (!arena) return "cannot allocate the pinned staging arena";
     t.os = os;
     t.coef = arena; t.f0 = arena + os; t.f1 = arena + 2 * os; t.f2 = arena + 3 * os; t.wit = arena + 4 * os; t.comp = arena + 5 * os;
@@ -364,3 +370,44 @@ extern "C" int sb_verify_files(sb_ctx *ctx, const char *r1cs_path, const char *w
     }
     return rc;
 }
+
+// The arguments run.rs:390-419 hands to mk_r1cs_proof, built on the host alone (no device, no context): lets the front
+// end be checked without a GPU and lets a caller keep the trace around for several sb_prove_r1cs / sb_verify_r1cs calls.
+struct sb_host_trace {
+    Trace t;
+    sb_trace view;
+};
+extern "C" int sb_trace_from_files(const char *r1cs_path, const char *wtns_path, sb_host_trace **out, const sb_trace **view) {
+    if (!r1cs_path || !wtns_path || !out || !view) return SB_ERR_ARG;
+    std::vector<uint8_t> rb, wb;
+    if (!slurp(r1cs_path, rb) || !slurp(wtns_path, wb)) return SB_ERR_ARG;
+    R1cs r;
+    std::vector<hfp::el> witness;
+    if (read_r1cs(rb, r) || memcmp(r.prime, BN254_FR_LE, 32) != 0) return SB_ERR_ARG;
+    if (read_witness(wb, witness) || witness.empty() || !hfp::eq(witness[0], hfp::ONE)) return SB_ERR_ARG;
+    sb_host_trace *h = new sb_host_trace();
+    if (build_trace(nullptr, r, witness, h->t)) {
+        delete h;
+        return SB_ERR_ARG;
+    }
+    const Trace &t = h->t;
+    sb_trace &st = h->view;
+    memset(&st, 0, sizeof st);
+    st.original_steps = t.os;
+    st.witness_trace = (const uint64_t *)t.wit;
+    st.computational_trace = (const uint64_t *)t.comp;
+    st.coefficients = (const uint64_t *)t.coef;
+    st.flag0 = (const uint64_t *)t.f0;
+    st.flag1 = (const uint64_t *)t.f1;
+    st.flag2 = (const uint64_t *)t.f2;
+    st.permuted_indices = t.perm.data();
+    st.n_public = t.pub.size();
+    st.public_wires = (const uint64_t *)t.pub.data();
+    st.n_pfi = t.pfi_k.size();
+    st.pfi_k = t.pfi_k.data();
+    st.pfi_w = t.pfi_w.data();
+    *out = h;
+    *view = &h->view;
+    return SB_OK;
+}
+extern "C" void sb_host_trace_free(sb_host_trace *h) { delete h; }

@@ -74,3 +74,30 @@ def verify_with_file_path(r1cs_path, wtns_path, proof_path, ctx=None):
     ms = (C.c_double * 2)()
     ctx.check(ctx.lib.sb_verify_files(ctx.h, str(r1cs_path).encode(), str(wtns_path).encode(), str(proof_path).encode(), ms))
     return list(ms)
+
+
+def trace_from_files(r1cs_path, wtns_path):
+    """the host front end alone (run.rs:109-308, :390-419 and the two readers): the arguments of mk_r1cs_proof as numpy
+    copies.  Needs no GPU."""
+    from ._lib import StarkB200Error, load
+    lib = load()
+    h, view = C.c_void_p(), C.c_void_p()
+    rc = lib.sb_trace_from_files(str(r1cs_path).encode(), str(wtns_path).encode(), C.byref(h), C.byref(view))
+    if rc != 0:
+        raise StarkB200Error(rc, "cannot build the trace of %s / %s" % (r1cs_path, wtns_path))
+    try:
+        t = C.cast(view, C.POINTER(SbTrace)).contents
+        n = t.original_steps
+
+        def fp(p, cnt):
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint64)), shape=(cnt, 4)).copy() if cnt else np.zeros((0, 4), dtype=np.uint64)
+
+        def sz(p, cnt):
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_size_t)), shape=(cnt,)).copy() if cnt else np.zeros(0, dtype=np.uint64)
+
+        return {"original_steps": n, "witness_trace": fp(t.witness_trace, n), "computational_trace": fp(t.computational_trace, n),
+                "coefficients": fp(t.coefficients, n), "flag0": fp(t.flag0, n), "flag1": fp(t.flag1, n), "flag2": fp(t.flag2, n),
+                "permuted_indices": sz(t.permuted_indices, n), "public_wires": fp(t.public_wires, t.n_public),
+                "pfi_k": sz(t.pfi_k, t.n_pfi), "pfi_w": sz(t.pfi_w, t.n_pfi)}
+    finally:
+        lib.sb_host_trace_free(h)

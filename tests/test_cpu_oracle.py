@@ -231,3 +231,42 @@ def test_proof_json_reader_round_trip(oracle, tmp_path):
     for bad in (text[:-1], text.replace(b'"l_root"', b'"x_root"'), text.replace(b"[", b"[256,", 1), b"{}", b""):
         h = C.c_void_p()
         assert L.sb_stark_proof_from_json(bad, len(bad), C.byref(h)) == -3
+
+
+@pytest.mark.parametrize("name", ["compute", "poseidon3_test"])
+def test_host_front_end_matches_oracle(oracle, name):
+    """the product's parsers + trace arrangement (csrc/frontend.cu, threaded, in-place r1cs decode) against the oracle's
+    restatement of run.rs:109-452 on the bundled circuits: every array of the mk_r1cs_proof arguments is identical"""
+    import stark_pure_rust_b200 as sb
+    d = os.path.join(ROOT, "tests", "golden", "circuits")
+    got = sb.prove.trace_from_files(os.path.join(d, name + ".r1cs"), os.path.join(d, name + ".wtns"))
+    want = oracle.trace_from_files(os.path.join(d, name + ".r1cs"), os.path.join(d, name + ".wtns"))
+    assert got["original_steps"] == want["original_steps"]
+    for k in ("witness_trace", "computational_trace", "coefficients", "flag0", "flag1", "flag2", "permuted_indices", "public_wires", "pfi_k", "pfi_w"):
+        assert np.array_equal(got[k], want[k]), k
+
+
+def test_host_front_end_synthetic_and_errors(oracle, tmp_path):
+    """seeded synthetic circuits (multi-term C, linear constraints, padding rows, 60 public inputs) and malformed files"""
+    import stark_pure_rust_b200 as sb
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_r1cs
+    for n_constraints, avg_terms, seed, n_pub in ((40, 2.0, 3, 2), (1200, 4.0, 7, 2), (400, 3.0, 11, 60)):
+        prefix = str(tmp_path / ("syn%d" % seed))
+        wit, cons = gen_r1cs.generate(n_constraints, avg_terms, n_pub, seed)
+        gen_r1cs.write_files(prefix, wit, cons, n_pub)
+        got = sb.prove.trace_from_files(prefix + ".r1cs", prefix + ".wtns")
+        want = oracle.trace_from_files(prefix + ".r1cs", prefix + ".wtns")
+        for k in want:
+            assert np.array_equal(got[k], want[k]), (seed, k)
+    bad = tmp_path / "bad.r1cs"
+    bad.write_bytes(b"r1cs" + bytes(40))
+    d = os.path.join(ROOT, "tests", "golden", "circuits")
+    with pytest.raises(sb.StarkB200Error):
+        sb.prove.trace_from_files(bad, os.path.join(d, "compute.wtns"))
+    with pytest.raises(sb.StarkB200Error):
+        sb.prove.trace_from_files(os.path.join(d, "compute.r1cs"), bad)
+    trunc = tmp_path / "trunc.r1cs"
+    trunc.write_bytes(open(os.path.join(d, "poseidon3_test.r1cs"), "rb").read()[:5000])
+    with pytest.raises(sb.StarkB200Error):
+        sb.prove.trace_from_files(trunc, os.path.join(d, "poseidon3_test.wtns"))
