@@ -200,6 +200,10 @@ void sb_stark_proof_free(sb_stark_proof *p);
  * failed check), other codes = malformed input.  The six interpolated columns the reference evaluates with eval_poly_at are
  * extended on the device instead (same field elements). */
 int sb_verify_r1cs(sb_ctx *ctx, const sb_trace *trace, const sb_stark_proof *proof);
+/* verify_low_degree_proof (fri/src/fri.rs:226-404) on the serde_json text of Vec<FriProof> (what sb_fri_proof_json writes):
+ * merkle_root = root of the tree over the n values, root_of_unity of order n.  Host only; ctx may be NULL. */
+int sb_fri_verify_json(sb_ctx *ctx, const char *text, size_t len, const uint8_t merkle_root[32], const uint64_t root_of_unity[4],
+                       size_t n, size_t max_deg_plus_1, uint32_t exclude_multiples_of);
 /* serde_json::from_reader::<StarkProof> (run.rs:578): parses the text sb_stark_proof_json writes. */
 int sb_stark_proof_from_json(const char *text, size_t len, sb_stark_proof **out);
 /* verify_with_file_path (run.rs:556-590): r1cs + witness (for the public wires) + proof.json.  verify_ms (may be NULL):

@@ -98,6 +98,7 @@ def load():
         "sb_stark_proof_free": (None, [vp]),
         "sb_verify_r1cs": (i32, [vp, vp, vp]),
         "sb_stark_proof_from_json": (i32, [C.c_char_p, sz, C.POINTER(vp)]),
+        "sb_fri_verify_json": (i32, [vp, C.c_char_p, sz, vp, vp, sz, sz, u32]),
         "sb_verify_files": (i32, [vp, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_double)]),
         "sb_trace_from_files": (i32, [C.c_char_p, C.c_char_p, C.POINTER(vp), C.POINTER(vp)]),
         "sb_host_trace_free": (None, [vp]),

@@ -839,6 +839,57 @@ struct JsonIn {
 };
 }  // namespace
 
+// [{"Middle":{"root2":..,"column_branches":..,"poly_branches":..}},..,{"Last":{"last":[[..],..]}}]  (fri.rs:16-26)
+static void parse_fri_layers(JsonIn &j, sb_fri_proof *fri) {
+    j.need('[');
+    if (j.eat(']')) return;
+    while (j.ok) {
+        FriLayer L;
+        j.need('{');
+        j.ws();
+        if (j.p + 6 < j.end && memcmp(j.p, "\"Last\"", 6) == 0) {
+            j.key("Last");
+            j.need('{');
+            j.key("last");
+            j.need('[');
+            if (!j.eat(']')) {
+                while (j.ok) {
+                    const size_t n0 = L.last.size();
+                    j.bytes(L.last);
+                    if (L.last.size() - n0 != 32) j.ok = false;
+                    if (j.eat(',')) continue;
+                    j.need(']');
+                    break;
+                }
+            }
+            j.need('}');
+            L.is_last = true;
+        } else {
+            j.key("Middle");
+            j.need('{');
+            std::vector<uint8_t> v;
+            j.key("root2");
+            j.bytes(v);
+            if (v.size() != 32) j.ok = false; else memcpy(L.root2, v.data(), 32);
+            j.need(',');
+            size_t lb2 = 0;
+            j.key("column_branches");
+            j.branches(L.column_leaves, L.column_nodes, L.n_column, lb2, L.depth_column);
+            if (L.n_column && lb2 != 32) j.ok = false;
+            j.need(',');
+            j.key("poly_branches");
+            j.branches(L.poly_leaves, L.poly_nodes, L.n_poly, lb2, L.depth_poly);
+            if (L.n_poly && lb2 != 32) j.ok = false;
+            j.need('}');
+        }
+        j.need('}');
+        fri->layers.push_back(std::move(L));
+        if (j.eat(',')) continue;
+        j.need(']');
+        break;
+    }
+}
+
 extern "C" int sb_stark_proof_from_json(const char *text, size_t len, sb_stark_proof **out) {
     if (!text || !out) return SB_ERR_ARG;
     JsonIn j{text, text + len};
@@ -865,54 +916,7 @@ extern "C" int sb_stark_proof_from_json(const char *text, size_t len, sb_stark_p
     p->depth = depth;
     j.need(',');
     j.key("fri_proof");
-    j.need('[');
-    if (!j.eat(']')) {
-        while (j.ok) {
-            FriLayer L;
-            j.need('{');
-            j.ws();
-            if (j.p + 6 < j.end && memcmp(j.p, "\"Last\"", 6) == 0) {
-                j.key("Last");
-                j.need('{');
-                j.key("last");
-                j.need('[');
-                if (!j.eat(']')) {
-                    while (j.ok) {
-                        const size_t n0 = L.last.size();
-                        j.bytes(L.last);
-                        if (L.last.size() - n0 != 32) j.ok = false;
-                        if (j.eat(',')) continue;
-                        j.need(']');
-                        break;
-                    }
-                }
-                j.need('}');
-                L.is_last = true;
-            } else {
-                j.key("Middle");
-                j.need('{');
-                std::vector<uint8_t> v;
-                j.key("root2");
-                j.bytes(v);
-                if (v.size() != 32) j.ok = false; else memcpy(L.root2, v.data(), 32);
-                j.need(',');
-                size_t lb2 = 0;
-                j.key("column_branches");
-                j.branches(L.column_leaves, L.column_nodes, L.n_column, lb2, L.depth_column);
-                if (L.n_column && lb2 != 32) j.ok = false;
-                j.need(',');
-                j.key("poly_branches");
-                j.branches(L.poly_leaves, L.poly_nodes, L.n_poly, lb2, L.depth_poly);
-                if (L.n_poly && lb2 != 32) j.ok = false;
-                j.need('}');
-            }
-            j.need('}');
-            p->fri->layers.push_back(std::move(L));
-            if (j.eat(',')) continue;
-            j.need(']');
-            break;
-        }
-    }
+    parse_fri_layers(j, p->fri);
     j.need('}');
     j.ws();
     if (!j.ok || j.p != j.end) {
@@ -921,4 +925,18 @@ extern "C" int sb_stark_proof_from_json(const char *text, size_t len, sb_stark_p
     }
     *out = p;
     return SB_OK;
+}
+
+// verify_low_degree_proof (fri.rs:226-404) on the serde text of Vec<FriProof>: host only, needs no device.  ctx may be NULL
+// (then the sampler keeps the reference's 2^24 limit and no error text is recorded).
+extern "C" int sb_fri_verify_json(sb_ctx *ctx, const char *text, size_t len, const uint8_t merkle_root[32], const uint64_t root_of_unity[4],
+                                  size_t n, size_t max_deg_plus_1, uint32_t exclude_multiples_of) {
+    if (!text || !merkle_root || !root_of_unity) return SB_ERR_ARG;
+    JsonIn j{text, text + len};
+    sb_fri_proof fri;
+    parse_fri_layers(j, &fri);
+    j.ws();
+    if (!j.ok || j.p != j.end) return SB_ERR_ARG;
+    sb_ctx scratch;               // only err / extended_domain are touched by the host verifier
+    return fri_verify_host(ctx ? ctx : &scratch, &fri, merkle_root, hfp::from_limbs(root_of_unity), n, max_deg_plus_1, exclude_multiples_of);
 }

@@ -69,3 +69,17 @@ def unpack_proof(ctx, h):
                                "column_branches": branches(cl, cn, nc.value, dc.value),
                                "poly_branches": branches(pl, pn, npo.value, dp.value)}})
     return out
+
+
+def verify_low_degree_proof(merkle_root, root_of_unity, proof_json, max_deg_plus_1, exclude_multiples_of, n, ctx=None):
+    """fri.rs:226-404 on the serde text of Vec<FriProof>.  Host-side check (no GPU needed when ctx is None).  Returns True,
+    or raises StarkB200Error(SB_ERR_VERIFY) where the reference asserts."""
+    from ._lib import StarkB200Error, load
+    lib = ctx.lib if ctx is not None else load()
+    text = proof_json.encode() if isinstance(proof_json, str) else bytes(proof_json)
+    root = _root_limbs(root_of_unity)
+    mr = np.frombuffer(bytes(merkle_root), dtype=np.uint8).copy()
+    rc = lib.sb_fri_verify_json(ctx.h if ctx is not None else None, text, len(text), _ptr(mr), _ptr(root), n, max_deg_plus_1, exclude_multiples_of)
+    if rc != 0:
+        raise StarkB200Error(rc, lib.sb_last_error(ctx.h).decode(errors="replace") if ctx is not None else "FRI proof rejected")
+    return True

@@ -270,3 +270,42 @@ def test_host_front_end_synthetic_and_errors(oracle, tmp_path):
     trunc.write_bytes(open(os.path.join(d, "poseidon3_test.r1cs"), "rb").read()[:5000])
     with pytest.raises(sb.StarkB200Error):
         sb.prove.trace_from_files(trunc, os.path.join(d, "poseidon3_test.wtns"))
+
+
+def test_product_fri_verifier_on_oracle_proofs(oracle):
+    """sb_fri_verify_json (the product's restatement of fri.rs:226-404, host only) accepts the oracle prover's proofs of
+    low-degree vectors, and rejects tampered proofs, a wrong Merkle root and a tighter degree bound (the reference prover
+    itself panics on a vector that is not of low degree, so that case cannot be produced)"""
+    import json
+    import stark_pure_rust_b200 as sb
+    from stark_pure_rust_b200 import field
+    for log_n, deg_log in ((7, 4), (10, 7), (12, 9)):
+        n = 1 << log_n
+        w = field.root_of_unity(log_n)
+        wl = field.mont_scalar(w)
+        values = oracle.best_fft(random_elems(1 << deg_log, 600 + log_n), wl, log_n)
+        text, ok = oracle.prove_low_degree_json(values, wl, n // 4, 8)
+        assert ok
+        root, _ = oracle.merkle_gen_proofs(oracle.fp_to_bytes_le(values).tobytes(), 32, n, [])
+        assert sb.fri.verify_low_degree_proof(root, w, text, n // 4, 8, n)
+        proof = json.loads(text)
+
+        def rejected(p, mroot=root, bound=n // 4):
+            with pytest.raises(sb.StarkB200Error) as e:
+                sb.fri.verify_low_degree_proof(mroot, w, json.dumps(p, separators=(",", ":")), bound, 8, n)
+            return e.value.code == -6
+
+        assert rejected(proof, mroot=bytes(32))
+        if len(proof) > 1:
+            p = json.loads(text); p[0]["Middle"]["column_branches"][0]["leaf"][0] ^= 1
+            assert rejected(p)
+            p = json.loads(text); p[0]["Middle"]["poly_branches"][7]["nodes"][0][3] ^= 1
+            assert rejected(p)
+            p = json.loads(text); p[0]["Middle"]["root2"][31] ^= 0x80
+            assert rejected(p)
+        p = json.loads(text); p[-1]["Last"]["last"][3][0] ^= 1
+        assert rejected(p)
+        p = json.loads(text); p[-1]["Last"]["last"].pop()
+        assert rejected(p)
+        # the same proof does not pass for a tighter degree bound
+        assert rejected(proof, bound=n // 16)
