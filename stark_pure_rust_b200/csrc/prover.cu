@@ -698,6 +698,8 @@ extern "C" int sb_verify_r1cs(sb_ctx *ctx, const sb_trace *t, const sb_stark_pro
         pub_y[i] = hfp::from_limbs(t->public_wires + 4 * t->pfi_k[i]);
     }
     const hfp::el x_last = xv[V + np];
+    std::vector<hfp::el> interp2;                                              // calc_i2_polynomial once (verify.rs:152), Horner per position
+    host_lagrange(interp2, pub_x, pub_y);
     hfp::el r[3], k[11];
     {
         uint32_t idx[24];
@@ -742,7 +744,8 @@ extern "C" int sb_verify_r1cs(sb_ctx *ctx, const sb_trace *t, const sb_stark_pro
             return fail(ctx, SB_ERR_VERIFY, "spot check %zu: Q3(x) != Z(x) D3(x) (verify.rs:220)", i);
         hfp::el zb2 = hfp::ONE;
         for (size_t j = 0; j < np; j++) zb2 = hfp::mul(zb2, sub(x, pub_x[j]));           // verify.rs:223-226
-        const hfp::el i2 = np ? lagrange_eval(pub_x, pub_y, x) : hfp::ZERO;
+        hfp::el i2 = hfp::ZERO;
+        for (size_t j = np; j-- > 0;) i2 = hfp::add(hfp::mul(i2, x), interp2[j]);          // eval_poly_at (verify.rs:227)
         if (!hfp::eq(sub(s_x, i2), hfp::mul(zb2, b2))) return fail(ctx, SB_ERR_VERIFY, "spot check %zu: S(x) - I2(x) != Zb2(x) B2(x) (verify.rs:228)", i);
         if (!hfp::eq(sub(a_x, hfp::ONE), hfp::mul(sub(x, x_last), b3)))                 // I3 = 1 (utils.rs:458-463)
             return fail(ctx, SB_ERR_VERIFY, "spot check %zu: A(x) - I3(x) != Zb3(x) B3(x) (verify.rs:232)", i);

@@ -233,7 +233,7 @@ def test_proof_json_reader_round_trip(oracle, tmp_path):
         assert L.sb_stark_proof_from_json(bad, len(bad), C.byref(h)) == -3
 
 
-@pytest.mark.parametrize("name", ["compute", "poseidon3_test"])
+@pytest.mark.parametrize("name", ["compute", "poseidon3_test", "bits", "pedersen_test"])
 def test_host_front_end_matches_oracle(oracle, name):
     """the product's parsers + trace arrangement (csrc/frontend.cu, threaded, in-place r1cs decode) against the oracle's
     restatement of run.rs:109-452 on the bundled circuits: every array of the mk_r1cs_proof arguments is identical"""

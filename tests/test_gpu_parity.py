@@ -585,3 +585,21 @@ def test_verifier_rejects_other_circuit_and_public_inputs(ctx, oracle, tmp_path)
     with pytest.raises(sb.StarkB200Error) as e:
         sb.prove.verify_with_file_path(pb + ".r1cs", pb + ".wtns", out, ctx=ctx)
     assert e.value.code in (-6, -3)
+
+
+@pytest.mark.parametrize("name", ["bits", "pedersen_test"])
+def test_other_bundled_circuits_match_golden(ctx, name, tmp_path):
+    """the reference's two other bundled circuits (r1cs-stark/tests: bits has 1062 public wires -> the NTT path of the boundary
+    polynomials and an O(n^2) host interpolation; pedersen_test has precision 2^18): proof.json hash equals the oracle's
+    (tests/golden/vectors.json; the same hashes as SURVEY.md Appendix C's independent model), and the verifier accepts it"""
+    import json
+    import os
+    import stark_pure_rust_b200 as sb
+    from conftest import ROOT
+    d = os.path.join(ROOT, "tests", "golden", "circuits")
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "vectors.json")))["proofs"][name]
+    out = str(tmp_path / "proof.json")
+    sb.prove.prove_with_file_path(os.path.join(d, name + ".r1cs"), os.path.join(d, name + ".wtns"), out, ctx=ctx)
+    assert hashlib.sha256(open(out, "rb").read()).hexdigest() == gold["proof_json_sha256"]
+    assert os.path.getsize(out) == gold["proof_json_bytes"]
+    sb.prove.verify_with_file_path(os.path.join(d, name + ".r1cs"), os.path.join(d, name + ".wtns"), out, ctx=ctx)
