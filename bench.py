@@ -502,6 +502,22 @@ def run_prove_extras(ctx, args, large_only=False, sync=None):
         r["identical_proof_json"] = ob.sha256_file(os.path.join(tmp, "oracle.json")) == ob.sha256_file(os.path.join(tmp, "proof.json"))
     r["precision"] = 1 << 16
     out["poseidon3_test"] = r
+    if not large_only:
+        # the reference's two other bundled circuits; the oracle needs 7 s (pedersen_test) and 34 s (bits: O(N n_pub) with 1062
+        # public wires) on the host, so bits' CPU time is only taken with --prove-cpu-large
+        gold = json.load(open(os.path.join(ROOT, "tests", "golden", "vectors.json")))["proofs"]
+        for name, prec in (("pedersen_test", 1 << 18), ("bits", 1 << 17)):
+            r = gpu_prove(os.path.join(d, name + ".r1cs"), os.path.join(d, name + ".wtns"))
+            import hashlib
+            r["proof_matches_golden"] = hashlib.sha256(open(os.path.join(tmp, "proof.json"), "rb").read()).hexdigest() == gold[name]["proof_json_sha256"]
+            if not args.no_cpu and (name != "bits" or args.prove_cpu_large):
+                import oracle_bind as ob
+                t0 = time.perf_counter()
+                ob.prove_files(os.path.join(d, name + ".r1cs"), os.path.join(d, name + ".wtns"), os.path.join(tmp, "oracle.json"), verify=False)
+                r["cpu_s"] = time.perf_counter() - t0
+                r["cpu_cores"] = os.cpu_count()
+            r["precision"] = prec
+            out[name] = r
     import gen_r1cs
     wit, cons = gen_r1cs.generate(30000, 8.0, 2, 1)
     info = gen_r1cs.write_files(os.path.join(tmp, "syn"), wit, cons, 2)
