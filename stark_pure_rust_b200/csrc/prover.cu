@@ -4,6 +4,9 @@
 #include "internal.h"
 #include "pointwise.cuh"
 
+#include <algorithm>
+#include <thread>
+
 static const uint32_t EXTENSION_FACTOR = 8, LOG_EXTENSION_FACTOR = 3;    // utils.rs:134-135
 static const size_t SPOT_CHECK_SECURITY_FACTOR = 80;                     // utils.rs:136
 
@@ -47,12 +50,17 @@ static int prefix_product(sb_ctx *ctx, const uint4 *in, uint4 *out, size_t n) {
 }
 
 // host: coefficients of the interpolant through (xs[i], ys[i]) (poly_utils.rs:409-439) and of
-// prod (X - xs[i]) (poly_utils.rs:362-373).  O(n^2) scalar work, n = number of public wires in use.
+// prod (X - xs[i]) (poly_utils.rs:362-373).  O(n^2) scalar work, n = number of public wires in use (1062 for the
+// reference's `bits` circuit): the n synthetic divisions run on host threads, the denominators share one inversion.
 static void host_zpoly(std::vector<hfp::el> &root, const std::vector<hfp::el> &xs) {
-    root.assign(1, hfp::ONE);
-    for (const auto &x : xs) {
-        root.insert(root.begin(), hfp::ZERO);                       // multiply by X
-        for (size_t j = 0; j + 1 < root.size(); j++) root[j] = hfp::add(root[j], hfp::neg(hfp::mul(root[j + 1], x)));
+    root.assign(xs.size() + 1, hfp::ZERO);
+    root[0] = hfp::ONE;
+    size_t deg = 0;
+    for (const auto &x : xs) {                                      // multiply by (X - x), in place from the top down
+        root[deg + 1] = root[deg];
+        for (size_t j = deg; j > 0; j--) root[j] = hfp::add(root[j - 1], hfp::neg(hfp::mul(root[j], x)));
+        root[0] = hfp::neg(hfp::mul(root[0], x));
+        deg++;
     }
 }
 static void host_lagrange(std::vector<hfp::el> &out, const std::vector<hfp::el> &xs, const std::vector<hfp::el> &ys) {
@@ -61,16 +69,55 @@ static void host_lagrange(std::vector<hfp::el> &out, const std::vector<hfp::el> 
     if (!n) return;
     std::vector<hfp::el> root;
     host_zpoly(root, xs);                                          // degree n, root[n] = 1
-    std::vector<hfp::el> num(n);
+    unsigned hw = std::thread::hardware_concurrency();
+    const size_t T = std::max<size_t>(1, std::min<size_t>(std::min<unsigned>(hw ? hw : 1, 16), n / 64));
+    // pass 1: denominators denom_i = (root / (X - x_i))(x_i) = root'(x_i)
+    std::vector<hfp::el> denom(n);
+    auto run = [&](auto body) {
+        if (T == 1) { body((size_t)0, n); return; }
+        std::vector<std::thread> th;
+        for (size_t t = 0; t < T; t++) th.emplace_back([=]() { body(n * t / T, n * (t + 1) / T); });
+        for (auto &x : th) x.join();
+    };
+    run([&](size_t lo, size_t hi) {
+        std::vector<hfp::el> num(n);
+        for (size_t i = lo; i < hi; i++) {
+            num[n - 1] = root[n];
+            for (size_t j = n - 1; j-- > 0;) num[j] = hfp::add(root[j + 1], hfp::mul(num[j + 1], xs[i]));
+            hfp::el d = hfp::ZERO;
+            for (size_t j = n; j-- > 0;) d = hfp::add(hfp::mul(d, xs[i]), num[j]);
+            denom[i] = d;
+        }
+    });
+    // one inversion for all denominators (distinct points: none is zero)
+    std::vector<hfp::el> pre(n), scale(n);
+    hfp::el acc = hfp::ONE;
     for (size_t i = 0; i < n; i++) {
-        // num = root / (X - xs[i]) by synthetic division, denom = num(xs[i])
-        num[n - 1] = root[n];
-        for (size_t j = n - 1; j-- > 0;) num[j] = hfp::add(root[j + 1], hfp::mul(num[j + 1], xs[i]));
-        hfp::el denom = hfp::ZERO;
-        for (size_t j = n; j-- > 0;) denom = hfp::add(hfp::mul(denom, xs[i]), num[j]);
-        hfp::el scale = hfp::mul(ys[i], hfp::inv(denom));
-        for (size_t j = 0; j < n; j++) out[j] = hfp::add(out[j], hfp::mul(num[j], scale));
+        pre[i] = acc;
+        acc = hfp::mul(acc, denom[i]);
     }
+    hfp::el inv = hfp::inv(acc);
+    for (size_t i = n; i-- > 0;) {
+        scale[i] = hfp::mul(ys[i], hfp::mul(inv, pre[i]));          // y_i / denom_i
+        inv = hfp::mul(inv, denom[i]);
+    }
+    // pass 2: out = sum_i scale_i * root / (X - x_i); every thread sums its share, the shares are added at the end
+    std::vector<std::vector<hfp::el>> part(T, std::vector<hfp::el>(n, hfp::ZERO));
+    std::vector<size_t> owner_lo(T);
+    for (size_t t = 0; t < T; t++) owner_lo[t] = n * t / T;
+    run([&](size_t lo, size_t hi) {
+        size_t t = 0;
+        while (t + 1 < T && owner_lo[t + 1] <= lo) t++;
+        std::vector<hfp::el> num(n);
+        std::vector<hfp::el> &o = part[t];
+        for (size_t i = lo; i < hi; i++) {
+            num[n - 1] = root[n];
+            for (size_t j = n - 1; j-- > 0;) num[j] = hfp::add(root[j + 1], hfp::mul(num[j + 1], xs[i]));
+            for (size_t j = 0; j < n; j++) o[j] = hfp::add(o[j], hfp::mul(num[j], scale[i]));
+        }
+    });
+    for (size_t t = 0; t < T; t++)
+        for (size_t j = 0; j < n; j++) out[j] = hfp::add(out[j], part[t][j]);
 }
 
 static void put_const(uint32_t (&dst)[8], const hfp::el &v) { memcpy(dst, v.l, 32); }
