@@ -63,12 +63,14 @@ static void host_zpoly(std::vector<hfp::el> &root, const std::vector<hfp::el> &x
         deg++;
     }
 }
-static void host_lagrange(std::vector<hfp::el> &out, const std::vector<hfp::el> &xs, const std::vector<hfp::el> &ys) {
+static void host_lagrange(std::vector<hfp::el> &out, const std::vector<hfp::el> &xs, const std::vector<hfp::el> &ys,
+                          std::vector<hfp::el> *root_out = nullptr) {
     const size_t n = xs.size();
     out.assign(n, hfp::ZERO);
+    std::vector<hfp::el> root_local;
+    std::vector<hfp::el> &root = root_out ? *root_out : root_local;
+    host_zpoly(root, xs);                                          // degree n, root[n] = 1 (the vanishing polynomial, also wanted by the caller)
     if (!n) return;
-    std::vector<hfp::el> root;
-    host_zpoly(root, xs);                                          // degree n, root[n] = 1
     unsigned hw = std::thread::hardware_concurrency();
     const size_t T = std::max<size_t>(1, std::min<size_t>(std::min<unsigned>(hw ? hw : 1, 16), n / 64));
     // pass 1: denominators denom_i = (root / (X - x_i))(x_i) = root'(x_i)
@@ -341,8 +343,7 @@ extern "C" int sb_prove_r1cs(sb_ctx *ctx, const sb_trace *t, sb_stark_proof **ou
             PCU(cudaMemcpyAsync(xv.data(), dx.p, np * 32, cudaMemcpyDeviceToHost, ctx->stream));
             PCU(cudaStreamSynchronize(ctx->stream));
         }
-        host_lagrange(interp, xv, yv);
-        host_zpoly(zroot, xv);
+        host_lagrange(interp, xv, yv, &zroot);
         DevBuf coef(ctx), i2b(ctx);
         PTRY(coef.alloc((2 * np + 1) * 32));
         uint4 *zb2 = q_col(B2_), *zb3 = q_col(B3_);          // B2_ and B3_ are adjacent: one 2N batch inverse
