@@ -260,9 +260,25 @@ static int plan_bits(uint32_t log_n, uint32_t *bits) {
 
 // coset_log > 0: the coset transforms of a low-degree extension (see NttPassParams); `root` is then the root of the
 // 2^log_n-point transform (W^(2^coset_log)) and the table must be the extended domain's (tw of W).
+// The cluster variant of the coset transforms' last pass (NttPassParams::cluster) applies when that pass is not also the first
+// one, eight cosets are asked for and a tile never straddles two polynomials.  It is bit-exact (the LDE parity tests pass with
+// it) but measured SLOWER on B200 -- LDE 2^21 -> 2^24 x 10: 34.9 ms against 33.3 ms with strided stores + the coset-0 copy:
+// seven CTAs in lockstep around two cluster barriers and latency-bound DSMEM reads cost more than the coalesced stores save --
+// so it is opt-in (SB_CLUSTER=1) and kept as the starting point for a pipelined version.
+static bool coset_cluster_ok(uint32_t log_n, uint32_t coset_log) {
+    static const bool on = getenv("SB_CLUSTER") != nullptr;
+    if (!on || coset_log != 3) return false;
+    uint32_t bits[NTT_MAX_PASSES];
+    const int m = plan_bits(log_n, bits);
+    if (m < 2) return false;
+    const uint32_t b = bits[m - 1];
+    const unsigned long long cpp = 1ull << (log_n - b), cc = (1ull << NTT_LOG_TILE_FOR(b)) >> b;
+    return cpp % cc == 0;
+}
+
 static int ntt_dev_tw(sb_ctx *ctx, const uint4 *d_src, size_t len_in, size_t src_stride, uint4 *d_dst, size_t dst_stride,
                       size_t n_polys, uint32_t log_n, int inverse, const uint4 *tw, uint32_t tw_log_n, uint32_t log_stride,
-                      uint32_t coset_log) {
+                      uint32_t coset_log, const uint4 *c0_src = nullptr, size_t c0_stride = 0, size_t c0_len = 0) {
     const size_t n = (size_t)1 << log_n;
     if (len_in > n) return fail(ctx, SB_ERR_ARG, "vector of %zu elements does not fit a 2^%u transform", len_in, log_n);
     if (n_polys == 0) return SB_OK;
@@ -295,6 +311,12 @@ static int ntt_dev_tw(sb_ctx *ctx, const uint4 *d_src, size_t len_in, size_t src
         P.tw_log_stride = log_stride;
         P.coset_m1 = coset_m1;
         P.coset_log = coset_log;
+        if (last && c0_src && coset_cluster_ok(log_n, coset_log)) {
+            P.cluster = 1;
+            P.c0_src = c0_src;
+            P.c0_stride = c0_stride;
+            P.c0_len = c0_len;
+        }
         {   // interleave polynomials when a tile never straddles two of them (the coset transforms also in the last
             // pass: the CTAs that fill the same output lines then run together)
             const unsigned long long cpp = 1ull << (log_n - bits[p]), cc = (1ull << NTT_LOG_TILE_FOR(bits[p])) >> bits[p];
@@ -383,8 +405,13 @@ int lde_dev(sb_ctx *ctx, const uint4 *d_cols, size_t n_cols, size_t col_len, siz
     DevBuf coef(ctx);
     TRY(coef.alloc(n_cols * S * 32));
     TRY(ntt_dev_tw(ctx, d_cols, col_len, col_stride, (uint4 *)coef.p, S, n_cols, log_s, 1, tw, tw_log_n, log_stride + log_ext, 0));
-    KLAUNCH(SB_KIND_OTHER, lde_launch_coset0(ctx->stream, d_cols, col_len, col_stride, d_out, N, S, log_ext, n_cols));
-    TRY(ntt_dev_tw(ctx, (const uint4 *)coef.p, S, S, d_out, N, n_cols, log_s, 0, tw, tw_log_n, log_stride + log_ext, log_ext));
+    if (coset_cluster_ok(log_s, log_ext)) {      // the last pass writes coset 0 too (it reads it from d_cols)
+        TRY(ntt_dev_tw(ctx, (const uint4 *)coef.p, S, S, d_out, N, n_cols, log_s, 0, tw, tw_log_n, log_stride + log_ext, log_ext, d_cols,
+                       col_stride, col_len));
+    } else {
+        KLAUNCH(SB_KIND_OTHER, lde_launch_coset0(ctx->stream, d_cols, col_len, col_stride, d_out, N, S, log_ext, n_cols));
+        TRY(ntt_dev_tw(ctx, (const uint4 *)coef.p, S, S, d_out, N, n_cols, log_s, 0, tw, tw_log_n, log_stride + log_ext, log_ext));
+    }
     return SB_OK;
 }
 

@@ -19,6 +19,8 @@
 //
 // Bound: 32-bit integer pipe (IMAD carry chains); HBM traffic is 64 B per element per pass.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "fp.cuh"
 #include "params.h"
 
@@ -166,6 +168,34 @@ __global__ void __launch_bounds__((1 << LOG_TILE) / 8, LOG_TILE >= 11 ? 2 : 4) n
 
     // ---- butterflies ----
     ntt_rounds<B, B, LOG_TILE>(slo, shi, wlo, whi);
+
+    // ---- cluster variant of the coset transforms' last pass: see NttPassParams::cluster ----
+    if (P.last && P.cluster) {
+        namespace cg = cooperative_groups;
+        cg::cluster_group cluster = cg::this_cluster();
+        cluster.sync();                                   // every coset's tile is complete in its CTA's shared memory
+        const uint32_t rank = cluster.block_rank(), E = P.coset_m1 + 1;        // rank = coset - 1
+        const unsigned long long poly = blk_col0 >> log_cpp, gl0 = blk_col0 & ((1ull << log_cpp) - 1);
+        const unsigned long long col = poly / P.coset_m1;
+        const uint32_t my_rows = (R - rank + P.coset_m1 - 1) / P.coset_m1;      // rows kk = rank, rank + 7, ...
+        const uint32_t per_row = CC * E;
+        for (uint32_t w = threadIdx.x; w < my_rows * per_row; w += NT) {
+            const uint32_t kk = rank + (w / per_row) * P.coset_m1;
+            const uint32_t j = (w % per_row) / E, rr = w % E;                   // consecutive lanes: consecutive output elements
+            const unsigned long long e = gl0 + j + ((unsigned long long)kk << P.log_outer);
+            fp v;
+            if (rr == 0) {
+                v = e < P.c0_len ? fp_canon(fp_ldg(P.c0_src, col * P.c0_stride + e)) : fp_zero();
+            } else {
+                const uint32_t r = B ? (__brev(kk) >> (32 - B)) : 0;
+                const uint4 *rlo = cluster.map_shared_rank(slo, rr - 1), *rhi = cluster.map_shared_rank(shi, rr - 1);
+                v = fp_canon(fp_from_u4(rlo[r * PITCH + j], rhi[r * PITCH + j]));
+            }
+            fp_stg(P.dst, col * P.dst_stride + (e << P.coset_log) + rr, v);
+        }
+        cluster.sync();                                   // nobody leaves while its shared memory is still being read
+        return;
+    }
 
     // ---- store tile (row r of the tile holds output k = bitrev_B(r)) ----
     fp ninv;

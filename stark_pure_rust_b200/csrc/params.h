@@ -40,6 +40,13 @@ struct NttPassParams {
     // W^(j r) (W = the extended domain's root, w = W^(2^coset_log)); the last pass writes output k to element
     // k * 2^coset_log + r of `column`.  coset_m1 == 0: plain transform.
     uint32_t coset_m1, coset_log;
+    // last pass of the coset transforms, cluster variant (cluster == 1): the launch groups the coset_m1 = 7 CTAs that hold the same
+    // tile of the seven cosets of one column into one thread-block cluster; after the butterflies they read each other's
+    // shared memory (DSMEM) so that every CTA writes whole 2^coset_log-element groups out[8k .. 8k+7] -- 256 B contiguous
+    // instead of one 32-byte element per 256 B -- and coset 0 (the input column itself) is filled in by the writer.
+    uint32_t cluster;
+    const uint4 *c0_src;           // the LDE's input columns (coset 0)
+    unsigned long long c0_stride, c0_len;
 };
 
 struct MerkleColsParams {
