@@ -51,6 +51,13 @@ typedef struct sb_fri_proof sb_fri_proof;
 
 /* ---- context ------------------------------------------------------------------------------ */
 int sb_init(int device, sb_ctx **out);
+/* One context over n_devices GPUs of the node (1, 2, 4 or 8; one process, peer access over NVLink / NVSwitch; fails with
+ * SB_ERR_NO_DEVICE when a pair has no peer access).  devices[0] is the primary device: every single-device entry point
+ * runs there.  sb_prove_r1cs / sb_prove_files and the sb_ext_* chain spread ONE job over all devices: the
+ * r1cs-stark binary proves on N GPUs with `r1cs-stark <r1cs> <wtns> <proof.json> --gpus N`.  An ordinal may be listed more
+ * than once (logical devices on one GPU: the sharded code path without the speed-up; how it is tested on a 1-GPU box). */
+int sb_init_multi(const int *devices, int n_devices, sb_ctx **out);
+int sb_device_count(const sb_ctx *ctx);
 void sb_destroy(sb_ctx *ctx);
 const char *sb_last_error(const sb_ctx *ctx);
 /* Use an external CUDA stream (cudaStream_t passed as void*, e.g. torch's current stream). */
@@ -171,6 +178,31 @@ char *sb_fri_proof_json(const sb_fri_proof *p);
 void sb_free_string(char *s);
 void sb_fri_proof_free(sb_fri_proof *p);
 
+/* ---- the LDE -> commit -> FRI chain with the extended columns kept on the device(s) (prove.rs:100-124, :235-264, :324-332,
+ * :367), the building blocks of sb_prove_r1cs.  Columns are stored coset-major: the value at position 8 k + r of the
+ * extended domain lives in coset array r at index k, and a context of g devices gives device d the cosets
+ * [8 d / g, 8 (d + 1) / g) of every column.  All shifts of the prover are whole steps (multiples of 8), so pointwise work,
+ * leaf hashing and the first FRI fold stay on the device that holds the data; S-point coefficient vectors (once per
+ * column) and 32-byte digests are all that crosses NVLink.  Results (roots, openings, proofs, sb_ext_read) are identical to
+ * the natural-order single-GPU entry points above.  log_ext must be 3 (EXTENSION_FACTOR = 8, utils.rs:134). */
+typedef struct sb_ext sb_ext;
+int sb_ext_create(sb_ctx *ctx, size_t n_cols, uint32_t log_s, uint32_t log_ext, sb_ext **out);
+void sb_ext_free(sb_ctx *ctx, sb_ext *e);
+int sb_ext_devices(const sb_ext *e);       /* devices the columns are spread over (1 for domains below 2^13) */
+/* host columns [first, first + count) (count x col_len elements, col_len <= 2^log_s, zero padded like inv_best_fft) ->
+ * the device that runs the column's inverse transform (column c: device c mod g) */
+int sb_ext_load(sb_ctx *ctx, sb_ext *e, size_t first, size_t count, const uint64_t *cols, size_t col_len);
+/* best_fft(inv_best_fft(col, root^8, log_s), root, log_s + 3) for the loaded columns [first, first + count) */
+int sb_ext_extend(sb_ctx *ctx, sb_ext *e, size_t first, size_t count);
+/* MerkleProofInPlace over the rows of the given columns (leaf i = to_bytes_le(col_ids[0][i]) || ...); per-device subtrees,
+ * top finished on the host.  sb_merkle_open / sb_tree_* / sb_tree_free work on the returned tree. */
+int sb_ext_commit(sb_ctx *ctx, const sb_ext *e, const size_t *col_ids, size_t n_ids, uint8_t root[32], sb_tree **tree);
+/* prove_low_degree(column, root, max_deg_plus_1, exclude_multiples_of); values_tree = sb_ext_commit of that column or NULL */
+int sb_ext_fri_prove(sb_ctx *ctx, const sb_ext *e, size_t col, const sb_tree *values_tree, size_t max_deg_plus_1,
+                     uint32_t exclude_multiples_of, sb_fri_proof **out);
+/* one extended column in natural order (2^(log_s+3) elements) to the host */
+int sb_ext_read(sb_ctx *ctx, const sb_ext *e, size_t col, uint64_t *out);
+
 /* ---- the caller of the hot path: mk_r1cs_proof (r1cs-stark/src/prove.rs:14-378), device resident -------- */
 /* Same arguments as the reference function (prove.rs:14-26); n_constraints / n_wires only feed an assert there.
  * All field vectors are Montgomery limbs; traces / coefficients / flags have original_steps elements. */
@@ -188,7 +220,8 @@ typedef struct sb_stark_proof sb_stark_proof;
  * precision beyond the sampler's 2^24 or the field's two-adicity). */
 int sb_prove_r1cs(sb_ctx *ctx, const sb_trace *trace, sb_stark_proof **out);
 int sb_stark_proof_roots(const sb_stark_proof *p, uint8_t m_root[32], uint8_t l_root[32], uint8_t a_root[32]);
-/* CUDA-event stage times of that proof: [0] LDE/NTT, [1] m_tree commit, [2] FRI, [3] the rest, [4] total (ms). */
+/* Stage times of that proof (host clock, every device waited for at the stage boundaries): [0] inputs + LDEs, [1] m_tree
+ * commit, [2] FRI, [3] the rest (pointwise stage, accumulator, l_tree, openings), [4] total (ms). */
 int sb_stark_proof_stage_ms(const sb_stark_proof *p, double ms[5]);
 /* serde_json::to_string(&StarkProof) (utils.rs:122-130, run.rs:549): malloc'd, free with sb_free_string. */
 char *sb_stark_proof_json(const sb_stark_proof *p, size_t *len);

@@ -47,6 +47,16 @@ def load():
     szp = C.POINTER(C.c_size_t)
     proto = {
         "sb_init": (i32, [i32, C.POINTER(vp)]),
+        "sb_init_multi": (i32, [C.POINTER(i32), i32, C.POINTER(vp)]),
+        "sb_device_count": (i32, [vp]),
+        "sb_ext_create": (i32, [vp, sz, u32, u32, C.POINTER(vp)]),
+        "sb_ext_free": (None, [vp, vp]),
+        "sb_ext_devices": (i32, [vp]),
+        "sb_ext_load": (i32, [vp, vp, sz, sz, vp, sz]),
+        "sb_ext_extend": (i32, [vp, vp, sz, sz]),
+        "sb_ext_commit": (i32, [vp, vp, szp, sz, vp, C.POINTER(vp)]),
+        "sb_ext_fri_prove": (i32, [vp, vp, sz, vp, sz, u32, C.POINTER(vp)]),
+        "sb_ext_read": (i32, [vp, vp, sz, vp]),
         "sb_destroy": (None, [vp]),
         "sb_last_error": (C.c_char_p, [vp]),
         "sb_set_stream": (i32, [vp, vp]),
@@ -130,16 +140,27 @@ def _ptr(a):
 
 
 class Context:
-    """one per GPU (sb_ctx).  Raises StarkB200Error(SB_ERR_NO_DEVICE) without a B200."""
+    """sb_ctx: one GPU (device = ordinal) or several GPUs of the node driven by one process (devices = list of ordinals,
+    1 / 2 / 4 / 8 entries, the first one is the primary; an ordinal may repeat -- logical devices on one GPU).
+    Raises StarkB200Error(SB_ERR_NO_DEVICE) without a B200."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, devices=None):
         self.lib = load()
         h = C.c_void_p()
-        rc = self.lib.sb_init(device, C.byref(h))
-        if rc != SB_OK:
-            raise StarkB200Error(rc, "sb_init(device=%d) failed: a CUDA device of compute capability 10.x is required" % device)
+        if devices is not None:
+            devices = [int(d) for d in devices]
+            arr = (C.c_int * len(devices))(*devices)
+            rc = self.lib.sb_init_multi(arr, len(devices), C.byref(h))
+            if rc != SB_OK:
+                raise StarkB200Error(rc, "sb_init_multi(%s) failed: 1/2/4/8 CUDA devices of compute capability 10.x with peer access are required" % devices)
+            device = devices[0]
+        else:
+            rc = self.lib.sb_init(device, C.byref(h))
+            if rc != SB_OK:
+                raise StarkB200Error(rc, "sb_init(device=%d) failed: a CUDA device of compute capability 10.x is required" % device)
         self.h = h
         self.device = device
+        self.devices = devices or [device]
 
     def close(self):
         if getattr(self, "h", None):

@@ -8,7 +8,7 @@
 // ------------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------------
-extern "C" int sb_init(int device, sb_ctx **out) {
+int ctx_create(int device, sb_ctx **out) {
     if (!out) return SB_ERR_ARG;
     *out = nullptr;
     int count = 0;
@@ -16,7 +16,9 @@ extern "C" int sb_init(int device, sb_ctx **out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SB_ERR_NO_DEVICE;
     if (prop.major != 10) return SB_ERR_NO_DEVICE;   // kernels are built for sm_100a only
-    if (cudaSetDevice(device) != cudaSuccess) return SB_ERR_NO_DEVICE;
+    DevGuard g(device);
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != device) return SB_ERR_NO_DEVICE;
     sb_ctx *ctx = new sb_ctx();
     ctx->device = device;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -42,13 +44,74 @@ extern "C" int sb_init(int device, sb_ctx **out) {
         sb_destroy(ctx);
         return SB_ERR_NO_DEVICE;
     }
+    ctx->dev.push_back(ctx);
     *out = ctx;
     return SB_OK;
 }
 
+extern "C" int sb_init(int device, sb_ctx **out) {
+    try {
+        return ctx_create(device, out);
+    } catch (...) {
+        return SB_ERR_OOM;
+    }
+}
+
+// One context over several GPUs of the node (one process, peer access over NVLink / NVSwitch).  devices[0] is the primary
+// device: every single-device entry point runs there; sb_prove_r1cs / sb_prove_files and the sb_ext_* calls spread their
+// work over all of them.  n_devices must be 1, 2, 4 or 8.  The same ordinal may appear more than once (logical devices
+// sharing one GPU: same code path, no speed-up -- that is how the sharded logic is tested on a single-GPU box).
+extern "C" int sb_init_multi(const int *devices, int n_devices, sb_ctx **out) {
+    if (!out || !devices) return SB_ERR_ARG;
+    *out = nullptr;
+    if (n_devices != 1 && n_devices != 2 && n_devices != 4 && n_devices != 8) return SB_ERR_ARG;
+    try {
+        sb_ctx *root = nullptr;
+        int rc = ctx_create(devices[0], &root);
+        if (rc != SB_OK) return rc;
+        for (int i = 1; i < n_devices; i++) {
+            sb_ctx *c = nullptr;
+            rc = ctx_create(devices[i], &c);
+            if (rc != SB_OK) {
+                sb_destroy(root);
+                return rc;
+            }
+            c->primary = root;
+            root->dev.push_back(c);
+        }
+        for (int i = 0; i < n_devices; i++)          // peer access between every pair of distinct GPUs
+            for (int j = 0; j < n_devices; j++) {
+                if (devices[i] == devices[j]) continue;
+                int can = 0;
+                if (cudaDeviceCanAccessPeer(&can, devices[i], devices[j]) != cudaSuccess || !can) {
+                    fail(root, SB_ERR_NO_DEVICE, "no peer access from device %d to device %d", devices[i], devices[j]);
+                    fprintf(stderr, "stark_b200: %s\n", root->err);
+                    sb_destroy(root);
+                    return SB_ERR_NO_DEVICE;
+                }
+                DevGuard g(devices[i]);
+                cudaError_t e = cudaDeviceEnablePeerAccess(devices[j], 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                    sb_destroy(root);
+                    return SB_ERR_NO_DEVICE;
+                }
+                cudaGetLastError();
+            }
+        *out = root;
+        return SB_OK;
+    } catch (...) {
+        return SB_ERR_OOM;
+    }
+}
+extern "C" int sb_device_count(const sb_ctx *ctx) { return ctx ? ctx->n_dev() : 0; }
+
 extern "C" void sb_destroy(sb_ctx *ctx) {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
+    for (size_t i = 1; i < ctx->dev.size(); i++) {
+        ctx->dev[i]->dev.clear();
+        sb_destroy(ctx->dev[i]);
+    }
+    DevGuard g(ctx);
     cudaStreamSynchronize(ctx->stream);
     for (auto &t : ctx->tables) cudaFree(t.d);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -80,80 +143,121 @@ void *pinned_arena(sb_ctx *ctx, size_t bytes) {
 extern "C" const char *sb_last_error(const sb_ctx *ctx) { return ctx ? ctx->err : "no context"; }
 
 extern "C" int sb_set_stream(sb_ctx *ctx, void *s) {
+    return guarded(ctx, [&]() -> int {
     if (!ctx) return SB_ERR_ARG;
     CU(cudaStreamSynchronize(ctx->stream));
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     ctx->stream = (cudaStream_t)s;
     ctx->own_stream = false;
     return SB_OK;
+    });
 }
 extern "C" int sb_sync(sb_ctx *ctx) {
+    return guarded(ctx, [&]() -> int {
     if (!ctx) return SB_ERR_ARG;
     CU(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 1; i < ctx->dev.size(); i++) CU(cudaStreamSynchronize(ctx->dev[i]->stream));
     return SB_OK;
+    });
 }
 extern "C" int sb_timer_start(sb_ctx *ctx) {
+    return guarded(ctx, [&]() -> int {
     if (!ctx) return SB_ERR_ARG;
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
     return SB_OK;
+    });
 }
 extern "C" int sb_timer_stop(sb_ctx *ctx, float *ms) {
+    return guarded(ctx, [&]() -> int {
     if (!ctx || !ms) return SB_ERR_ARG;
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
     CU(cudaEventSynchronize(ctx->ev1));
     CU(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
     return SB_OK;
+    });
 }
-extern "C" uint64_t sb_launch_count(const sb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" uint64_t sb_launch_count(const sb_ctx *ctx) {
+    if (!ctx) return 0;
+    uint64_t n = ctx->launches;
+    for (size_t i = 1; i < ctx->dev.size(); i++) n += ctx->dev[i]->launches;
+    return n;
+}
 extern "C" int sb_profile(sb_ctx *ctx, int enable) {
+    return guarded(ctx, [&]() -> int {
     if (!ctx) return SB_ERR_ARG;
-    prof_collect(ctx);
-    ctx->prof = enable != 0;
-    for (int k = 0; k < SB_KIND_COUNT; k++) ctx->prof_ms[k] = 0, ctx->prof_n[k] = 0;
+    for (sb_ctx *c : ctx->dev) {
+        DevGuard g(c);
+        prof_collect(c);
+        c->prof = enable != 0;
+        for (int k = 0; k < SB_KIND_COUNT; k++) c->prof_ms[k] = 0, c->prof_n[k] = 0;
+    }
     return SB_OK;
+    });
 }
+// multi-device contexts: launches and milliseconds are summed over the devices
 extern "C" int sb_profile_read(sb_ctx *ctx, int kind, uint64_t *launches, double *total_ms) {
+    return guarded(ctx, [&]() -> int {
     if (!ctx || kind < 0 || kind >= SB_KIND_COUNT) return SB_ERR_ARG;
-    CU(cudaStreamSynchronize(ctx->stream));
-    prof_collect(ctx);
-    if (launches) *launches = ctx->prof_n[kind];
-    if (total_ms) *total_ms = ctx->prof_ms[kind];
+    uint64_t n = 0;
+    double ms = 0;
+    for (sb_ctx *c : ctx->dev) {
+        DevGuard g(c);
+        CU(cudaStreamSynchronize(c->stream));
+        prof_collect(c);
+        n += c->prof_n[kind];
+        ms += c->prof_ms[kind];
+    }
+    if (launches) *launches = n;
+    if (total_ms) *total_ms = ms;
     return SB_OK;
+    });
 }
 
 extern "C" int sb_dev_alloc(sb_ctx *ctx, size_t bytes, void **p) {
+    return guarded(ctx, [&]() -> int {
     if (!ctx || !p) return SB_ERR_ARG;
     CU(cudaSetDevice(ctx->device));
     CU(cudaMalloc(p, bytes ? bytes : 16));
     return SB_OK;
+    });
 }
 extern "C" int sb_dev_free(sb_ctx *ctx, void *p) {
+    return guarded(ctx, [&]() -> int {
     if (!ctx) return SB_ERR_ARG;
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaFree(p));
     return SB_OK;
+    });
 }
 extern "C" int sb_h2d(sb_ctx *ctx, void *d, const void *s, size_t bytes) {
+    return guarded(ctx, [&]() -> int {
     if (!ctx) return SB_ERR_ARG;
     CU(cudaMemcpyAsync(d, s, bytes, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return SB_OK;
+    });
 }
 extern "C" int sb_d2h(sb_ctx *ctx, void *d, const void *s, size_t bytes) {
+    return guarded(ctx, [&]() -> int {
     if (!ctx) return SB_ERR_ARG;
     CU(cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return SB_OK;
+    });
 }
 extern "C" int sb_host_alloc_pinned(sb_ctx *ctx, size_t bytes, void **p) {
+    return guarded(ctx, [&]() -> int {
     if (!ctx || !p) return SB_ERR_ARG;
     CU(cudaMallocHost(p, bytes ? bytes : 16));
     return SB_OK;
+    });
 }
 extern "C" int sb_host_free_pinned(sb_ctx *ctx, void *p) {
+    return guarded(ctx, [&]() -> int {
     if (!ctx) return SB_ERR_ARG;
     CU(cudaFreeHost(p));
     return SB_OK;
+    });
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -258,34 +362,26 @@ static int plan_bits(uint32_t log_n, uint32_t *bits) {
     return m;
 }
 
-// coset_log > 0: the coset transforms of a low-degree extension (see NttPassParams); `root` is then the root of the
-// 2^log_n-point transform (W^(2^coset_log)) and the table must be the extended domain's (tw of W).
-// The cluster variant of the coset transforms' last pass (NttPassParams::cluster) applies when that pass is not also the first
-// one, eight cosets are asked for and a tile never straddles two polynomials.  It is bit-exact (the LDE parity tests pass with
-// it) but measured SLOWER on B200 -- LDE 2^21 -> 2^24 x 10: 34.9 ms against 33.3 ms with strided stores + the coset-0 copy:
-// seven CTAs in lockstep around two cluster barriers and latency-bound DSMEM reads cost more than the coalesced stores save --
-// so it is opt-in (SB_CLUSTER=1) and kept as the starting point for a pipelined version.
-static bool coset_cluster_ok(uint32_t log_n, uint32_t coset_log) {
-    static const bool on = getenv("SB_CLUSTER") != nullptr;
-    if (!on || coset_log != 3) return false;
-    uint32_t bits[NTT_MAX_PASSES];
-    const int m = plan_bits(log_n, bits);
-    if (m < 2) return false;
-    const uint32_t b = bits[m - 1];
-    const unsigned long long cpp = 1ull << (log_n - b), cc = (1ull << NTT_LOG_TILE_FOR(b)) >> b;
-    return cpp % cc == 0;
-}
-
-static int ntt_dev_tw(sb_ctx *ctx, const uint4 *d_src, size_t len_in, size_t src_stride, uint4 *d_dst, size_t dst_stride,
-                      size_t n_polys, uint32_t log_n, int inverse, const uint4 *tw, uint32_t tw_log_n, uint32_t log_stride,
-                      uint32_t coset_log, const uint4 *c0_src = nullptr, size_t c0_stride = 0, size_t c0_len = 0) {
+// cs != NULL: the coset transforms of a low-degree extension (see NttPassParams); the transform's root is then
+// W^(2^log_ext) and the table must be the extended domain's (tw of W).
+int ntt_dev_tw(sb_ctx *ctx, const uint4 *d_src, size_t len_in, size_t src_stride, uint4 *d_dst, size_t dst_stride,
+               size_t n_polys, uint32_t log_n, int inverse, const uint4 *tw, uint32_t tw_log_n, uint32_t log_stride,
+               const CosetSpec *cs) {
     const size_t n = (size_t)1 << log_n;
     if (len_in > n) return fail(ctx, SB_ERR_ARG, "vector of %zu elements does not fit a 2^%u transform", len_in, log_n);
     if (n_polys == 0) return SB_OK;
-    const uint32_t coset_m1 = coset_log ? (1u << coset_log) - 1 : 0;
-    const size_t n_batch = coset_m1 ? n_polys * coset_m1 : n_polys;       // transforms in flight
+    const uint32_t coset_cnt = cs ? cs->cnt : 0;
+    if (cs && (cs->cnt == 0 || cs->r0 + cs->cnt > (1u << cs->log_ext))) return fail(ctx, SB_ERR_ARG, "internal: coset range");
+    const size_t n_batch = coset_cnt ? n_polys * coset_cnt : n_polys;       // transforms in flight
     uint32_t bits[NTT_MAX_PASSES];
     const int m = plan_bits(log_n, bits);
+    uint32_t store = cs ? cs->store : NTT_STORE_PLAIN;
+    if (store == NTT_STORE_GATHER) {
+        // all eight cosets of a tile in one CTA: needs a last pass of its own and at least one sub-transform per eight tile columns
+        const uint32_t b = bits[m - 1];
+        const unsigned long long cpp = 1ull << (log_n - b), cc = (1ull << NTT_LOG_TILE_FOR(b)) >> b;
+        if (m < 2 || cs->log_ext != 3 || cs->r0 != 1 || cs->cnt != 7 || cc < 8 || cpp < cc / 8 || !cs->c0_src) store = NTT_STORE_INTERLEAVED;
+    }
     DevBuf work(ctx);
     if (m > 1) TRY(work.alloc(n_batch * n * 32));
     hfp::el ninv = hfp::inv(hfp::from_u64((uint64_t)n));
@@ -309,18 +405,22 @@ static int ntt_dev_tw(sb_ctx *ctx, const uint4 *d_src, size_t len_in, size_t src
         P.inverse = inverse ? 1 : 0;
         P.tw_log_n = tw_log_n;
         P.tw_log_stride = log_stride;
-        P.coset_m1 = coset_m1;
-        P.coset_log = coset_log;
-        if (last && c0_src && coset_cluster_ok(log_n, coset_log)) {
-            P.cluster = 1;
-            P.c0_src = c0_src;
-            P.c0_stride = c0_stride;
-            P.c0_len = c0_len;
+        if (cs) {
+            P.coset_cnt = cs->cnt;
+            P.coset_r0 = cs->r0;
+            P.coset_log = cs->log_ext;
+            P.coset_store = store;
+            P.coset_dst_cpd = cs->dst_cpd ? cs->dst_cpd : cs->cnt;
+            P.coset_dst_r0 = cs->dst_cpd ? cs->dst_r0 : cs->r0;
+            P.c0_src = cs->c0_src;
+            P.c0_stride = cs->c0_stride;
+            P.c0_len = cs->c0_len;
         }
-        {   // interleave polynomials when a tile never straddles two of them (the coset transforms also in the last
+        {   // interleave polynomials when a tile never straddles two of them (the interleaved coset store also in the last
             // pass: the CTAs that fill the same output lines then run together)
             const unsigned long long cpp = 1ull << (log_n - bits[p]), cc = (1ull << NTT_LOG_TILE_FOR(bits[p])) >> bits[p];
-            P.n_polys = (n_batch > 1 && (!last || coset_m1) && cpp % cc == 0 && n_batch < (1u << 20)) ? (uint32_t)n_batch : 0;
+            const bool il_last = last && store == NTT_STORE_INTERLEAVED;
+            P.n_polys = (n_batch > 1 && (!last || il_last) && cpp % cc == 0 && n_batch < (1u << 20)) ? (uint32_t)n_batch : 0;
         }
         P.n_prev = (uint32_t)p;
         for (int i = 0; i < p; i++) P.prev_bits[i] = bits[i];
@@ -330,6 +430,11 @@ static int ntt_dev_tw(sb_ctx *ctx, const uint4 *d_src, size_t len_in, size_t src
         log_outer += bits[p];
     }
     CU(cudaGetLastError());
+    if (cs && cs->store == NTT_STORE_GATHER && store != NTT_STORE_GATHER) {
+        // fallback for tiny transforms: coset 0 (the input column itself) by a copy kernel
+        KLAUNCH(SB_KIND_OTHER, lde_launch_coset0(ctx->stream, cs->c0_src, cs->c0_len, cs->c0_stride, d_dst, dst_stride, n, cs->log_ext, n_polys));
+        CU(cudaGetLastError());
+    }
     return SB_OK;
 }
 
@@ -341,20 +446,23 @@ int ntt_dev(sb_ctx *ctx, const uint4 *d_src, size_t len_in, size_t src_stride, u
     const uint4 *tw;
     uint32_t tw_log_n, log_stride;
     TRY(get_table(ctx, root, log_n, &tw, &tw_log_n, &log_stride));
-    return ntt_dev_tw(ctx, d_src, len_in, src_stride, d_dst, dst_stride, n_polys, log_n, inverse, tw, tw_log_n, log_stride, 0);
+    return ntt_dev_tw(ctx, d_src, len_in, src_stride, d_dst, dst_stride, n_polys, log_n, inverse, tw, tw_log_n, log_stride, nullptr);
 }
 
 extern "C" int sb_ntt_dev(sb_ctx *ctx, const uint64_t *d_src, size_t len_in, size_t src_stride, uint64_t *d_dst,
                           size_t dst_stride, size_t n_polys, const uint64_t root[4], uint32_t log_n, int inverse) {
+    return guarded(ctx, [&]() -> int {
     if (!ctx || !d_src || !d_dst || !root) return SB_ERR_ARG;
     if (d_src == d_dst) return fail(ctx, SB_ERR_ARG, "sb_ntt_dev is out of place");
     return ntt_dev(ctx, (const uint4 *)d_src, len_in, src_stride, (uint4 *)d_dst, dst_stride, n_polys, hfp::from_limbs(root),
                    log_n, inverse);
+    });
 }
 
 // four-step twiddle step of a transform split over several GPUs (sharded.py::distributed_ntt)
 extern "C" int sb_twiddle_mul_dev(sb_ctx *ctx, uint64_t *d_vals, size_t rows, size_t cols, size_t row0, const uint64_t root[4],
                                   uint32_t log_n, int inverse) {
+    return guarded(ctx, [&]() -> int {
     if (!ctx || !d_vals || !root) return SB_ERR_ARG;
     if (log_n > 28) return fail(ctx, SB_ERR_ARG, "log_n %u exceeds the field's two-adicity 28", log_n);
     const uint4 *tw;
@@ -363,9 +471,11 @@ extern "C" int sb_twiddle_mul_dev(sb_ctx *ctx, uint64_t *d_vals, size_t rows, si
     KLAUNCH(SB_KIND_OTHER, twiddle_mul_launch(ctx->stream, (uint4 *)d_vals, rows, cols, row0, tw, tw_log_n, log_stride, log_n, inverse ? 1 : 0));
     CU(cudaGetLastError());
     return SB_OK;
+    });
 }
 
 extern "C" int sb_ntt(sb_ctx *ctx, uint64_t *vals, size_t len_in, const uint64_t root[4], uint32_t log_n, int inverse) {
+    return guarded(ctx, [&]() -> int {
     if (!ctx || !vals || !root) return SB_ERR_ARG;
     if (log_n > 28) return fail(ctx, SB_ERR_ARG, "log_n %u exceeds the field's two-adicity 28", log_n);
     const size_t n = (size_t)1 << log_n;
@@ -378,6 +488,7 @@ extern "C" int sb_ntt(sb_ctx *ctx, uint64_t *vals, size_t len_in, const uint64_t
     CU(cudaMemcpyAsync(vals, b.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return SB_OK;
+    });
 }
 
 // Low-degree extension (prove.rs:100-124: best_fft(inv_best_fft(col, W^E, log_s), W, log_s + log_ext), E = 2^log_ext).
@@ -404,26 +515,35 @@ int lde_dev(sb_ctx *ctx, const uint4 *d_cols, size_t n_cols, size_t col_len, siz
     }
     DevBuf coef(ctx);
     TRY(coef.alloc(n_cols * S * 32));
-    TRY(ntt_dev_tw(ctx, d_cols, col_len, col_stride, (uint4 *)coef.p, S, n_cols, log_s, 1, tw, tw_log_n, log_stride + log_ext, 0));
-    if (coset_cluster_ok(log_s, log_ext)) {      // the last pass writes coset 0 too (it reads it from d_cols)
-        TRY(ntt_dev_tw(ctx, (const uint4 *)coef.p, S, S, d_out, N, n_cols, log_s, 0, tw, tw_log_n, log_stride + log_ext, log_ext, d_cols,
-                       col_stride, col_len));
+    TRY(ntt_dev_tw(ctx, d_cols, col_len, col_stride, (uint4 *)coef.p, S, n_cols, log_s, 1, tw, tw_log_n, log_stride + log_ext, nullptr));
+    CosetSpec cs;
+    cs.log_ext = log_ext;
+    cs.r0 = 1;
+    cs.cnt = (1u << log_ext) - 1;
+    cs.c0_src = d_cols;
+    cs.c0_stride = col_stride;
+    cs.c0_len = col_len;
+    if (log_ext == 3) {
+        cs.store = NTT_STORE_GATHER;           // the last pass writes whole 256-byte groups, coset 0 included
     } else {
+        cs.store = NTT_STORE_INTERLEAVED;
         KLAUNCH(SB_KIND_OTHER, lde_launch_coset0(ctx->stream, d_cols, col_len, col_stride, d_out, N, S, log_ext, n_cols));
-        TRY(ntt_dev_tw(ctx, (const uint4 *)coef.p, S, S, d_out, N, n_cols, log_s, 0, tw, tw_log_n, log_stride + log_ext, log_ext));
     }
-    return SB_OK;
+    return ntt_dev_tw(ctx, (const uint4 *)coef.p, S, S, d_out, N, n_cols, log_s, 0, tw, tw_log_n, log_stride + log_ext, &cs);
 }
 
 extern "C" int sb_lde_batch_dev(sb_ctx *ctx, const uint64_t *d_cols, size_t n_cols, size_t col_len, size_t col_stride,
                                 const uint64_t root_big[4], uint32_t log_s, uint32_t log_ext, uint64_t *d_out) {
+    return guarded(ctx, [&]() -> int {
     if (!ctx || !d_cols || !d_out || !root_big) return SB_ERR_ARG;
     return lde_dev(ctx, (const uint4 *)d_cols, n_cols, col_len, col_stride, hfp::from_limbs(root_big), log_s, log_ext,
                    (uint4 *)d_out);
+    });
 }
 
 extern "C" int sb_lde_batch(sb_ctx *ctx, const uint64_t *cols, size_t n_cols, size_t col_len, const uint64_t root_big[4],
                             uint32_t log_s, uint32_t log_ext, uint64_t *out) {
+    return guarded(ctx, [&]() -> int {
     if (!ctx || !cols || !out || !root_big) return SB_ERR_ARG;
     if (log_s + log_ext > 28) return fail(ctx, SB_ERR_ARG, "extended domain 2^%u exceeds two-adicity 28", log_s + log_ext);
     const size_t N = (size_t)1 << (log_s + log_ext);
@@ -478,13 +598,17 @@ extern "C" int sb_lde_batch(sb_ctx *ctx, const uint64_t *cols, size_t n_cols, si
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
         return fail(ctx, SB_ERR_CUDA, "sb_lde_batch pipeline: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
     return SB_OK;
+    });
 }
 
 extern "C" int sb_powers_dev(sb_ctx *ctx, const uint64_t root[4], size_t n, uint64_t *d_out) {
+    return guarded(ctx, [&]() -> int {
     if (!ctx || !root || !d_out) return SB_ERR_ARG;
     return powers_into(ctx, hfp::from_limbs(root), n, (uint4 *)d_out);
+    });
 }
 extern "C" int sb_powers(sb_ctx *ctx, const uint64_t root[4], size_t n, uint64_t *out) {
+    return guarded(ctx, [&]() -> int {
     if (!ctx || !root || !out) return SB_ERR_ARG;
     DevBuf b(ctx);
     TRY(b.alloc(n * 32));
@@ -492,9 +616,11 @@ extern "C" int sb_powers(sb_ctx *ctx, const uint64_t root[4], size_t n, uint64_t
     CU(cudaMemcpyAsync(out, b.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return SB_OK;
+    });
 }
 
 extern "C" int sb_batch_inverse_dev(sb_ctx *ctx, uint64_t *d_vals, size_t n) {
+    return guarded(ctx, [&]() -> int {
     if (!ctx || !d_vals) return SB_ERR_ARG;
     if (n == 0) return SB_OK;
     DevBuf scratch(ctx);
@@ -502,8 +628,10 @@ extern "C" int sb_batch_inverse_dev(sb_ctx *ctx, uint64_t *d_vals, size_t n) {
     KLAUNCH(SB_KIND_OTHER, batch_inverse_launch(ctx->stream, (uint4 *)d_vals, (uint4 *)scratch.p, n));
     CU(cudaGetLastError());
     return SB_OK;
+    });
 }
 extern "C" int sb_batch_inverse(sb_ctx *ctx, uint64_t *vals, size_t n) {
+    return guarded(ctx, [&]() -> int {
     if (!ctx || !vals) return SB_ERR_ARG;
     DevBuf b(ctx);
     TRY(b.alloc(n * 32));
@@ -512,6 +640,7 @@ extern "C" int sb_batch_inverse(sb_ctx *ctx, uint64_t *vals, size_t n) {
     CU(cudaMemcpyAsync(vals, b.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return SB_OK;
+    });
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -519,6 +648,15 @@ extern "C" int sb_batch_inverse(sb_ctx *ctx, uint64_t *vals, size_t n) {
 // ------------------------------------------------------------------------------------------------
 void free_tree(sb_tree *t) {
     if (!t) return;
+    if (t->sh) {
+        for (int d = 0; d < t->sh->g; d++) {
+            DevGuard g(t->sh->devices[d]);
+            if (t->sh->low[d]) cudaFreeAsync(t->sh->low[d], t->sh->streams[d]);
+            if (t->sh->sub[d]) cudaFreeAsync(t->sh->sub[d], t->sh->streams[d]);
+        }
+        delete t->sh;
+    }
+    DevGuard g(t->device);
     if (t->d_nodes) cudaFreeAsync(t->d_nodes, t->stream);
     if (t->d_leaves) cudaFreeAsync(t->d_leaves, t->stream);
     delete t;
@@ -531,6 +669,7 @@ static void launch_leaves(sb_ctx *ctx, sb_tree *t, uint32_t lv) {
         P.nodes = t->d_nodes;
         P.n = t->n;
         P.nc = (uint32_t)t->n_cols;
+        P.coset_log_s = 0;
         KLAUNCH(SB_KIND_MERKLE_LEAVES, merkle_launch_leaves_cols(ctx->stream, lv, P));
     } else {
         MerkleBytesParams P;
@@ -542,7 +681,22 @@ static void launch_leaves(sb_ctx *ctx, sb_tree *t, uint32_t lv) {
     }
 }
 
-// hashes the leaves and every level; leaves the root in t->root (one 32-byte D2H + sync).
+// levels above `level` (already present in t->d_nodes); fetch_root: leaves the root in t->root (one 32-byte D2H + sync)
+int merkle_finish(sb_ctx *ctx, sb_tree *t, uint32_t level, bool fetch_root) {
+    while (level < t->depth) {
+        const uint32_t lv = t->depth - level < 3 ? t->depth - level : 3;
+        KLAUNCH(SB_KIND_MERKLE_NODES, merkle_launch_nodes(ctx->stream, lv, t->d_nodes, t->n, level));
+        level += lv;
+    }
+    CU(cudaGetLastError());
+    if (fetch_root) {
+        CU(cudaMemcpyAsync(t->root, (const uint8_t *)t->d_nodes + (2 * t->n - 2) * 32, 32, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return SB_OK;
+}
+
+// hashes the leaves and every level; leaves the root in t->root.
 // fold != NULL: the leaves are produced by the FRI fold of *fold (fused kernel), which also writes the column t->cols[0].
 static int merkle_build(sb_ctx *ctx, sb_tree *t, const FriFoldParams *fold = nullptr) {
     uint32_t level = t->depth < 3 ? t->depth : 3;
@@ -551,18 +705,10 @@ static int merkle_build(sb_ctx *ctx, sb_tree *t, const FriFoldParams *fold = nul
     } else {
         launch_leaves(ctx, t, level);
     }
-    while (level < t->depth) {
-        const uint32_t lv = t->depth - level < 3 ? t->depth - level : 3;
-        KLAUNCH(SB_KIND_MERKLE_NODES, merkle_launch_nodes(ctx->stream, lv, t->d_nodes, t->n, level));
-        level += lv;
-    }
-    CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(t->root, (const uint8_t *)t->d_nodes + (2 * t->n - 2) * 32, 32, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    return SB_OK;
+    return merkle_finish(ctx, t, level, true);
 }
 
-static int tree_new(sb_ctx *ctx, size_t n, size_t leaf_bytes, sb_tree **out) {
+int tree_new(sb_ctx *ctx, size_t n, size_t leaf_bytes, sb_tree **out) {
     if (!is_pow2(n)) return fail(ctx, SB_ERR_ARG, "leaf count %zu is not a power of two", n);   // merkle_proof_in_place.rs:113
     if (n > ((size_t)1 << 30)) return fail(ctx, SB_ERR_ARG, "tree too large");
     sb_tree *t = new sb_tree();
@@ -570,6 +716,7 @@ static int tree_new(sb_ctx *ctx, size_t n, size_t leaf_bytes, sb_tree **out) {
     t->depth = ilog2(n);
     t->leaf_bytes = leaf_bytes;
     t->stream = ctx->stream;
+    t->device = ctx->device;
     cudaError_t e = cudaMallocAsync(&t->d_nodes, (2 * n - 1) * 32, ctx->stream);
     if (e != cudaSuccess) {
         delete t;
@@ -580,6 +727,7 @@ static int tree_new(sb_ctx *ctx, size_t n, size_t leaf_bytes, sb_tree **out) {
 }
 
 extern "C" int sb_merkle_commit(sb_ctx *ctx, const void *leaves, size_t leaf_bytes, size_t n, uint8_t root[32], sb_tree **tree) {
+    return guarded(ctx, [&]() -> int {
     if (!ctx || !tree) return SB_ERR_ARG;
     if (!leaves && n * leaf_bytes) return fail(ctx, SB_ERR_ARG, "leaves is NULL");
     if (leaf_bytes >= ((size_t)1 << 31)) return fail(ctx, SB_ERR_ARG, "leaf too long");
@@ -599,6 +747,7 @@ extern "C" int sb_merkle_commit(sb_ctx *ctx, const void *leaves, size_t leaf_byt
     if (root) memcpy(root, t->root, 32);
     *tree = t;
     return SB_OK;
+    });
 }
 
 // byte leaves already on the device; the tree takes ownership of d_leaves (allocated with cudaMallocAsync)
@@ -652,13 +801,16 @@ static int commit_fold(sb_ctx *ctx, const FriFoldParams &F, sb_tree **tree) {
 
 extern "C" int sb_merkle_commit_cols_dev(sb_ctx *ctx, const uint64_t *const *d_cols, size_t n_cols, size_t n, uint8_t root[32],
                                          sb_tree **tree) {
+    return guarded(ctx, [&]() -> int {
     if (!ctx || !d_cols || !tree) return SB_ERR_ARG;
     TRY(commit_cols(ctx, (const uint4 *const *)d_cols, n_cols, n, tree));
     if (root) memcpy(root, (*tree)->root, 32);
     return SB_OK;
+    });
 }
 
 extern "C" int sb_merkle_open(sb_ctx *ctx, const sb_tree *t, const size_t *idx, size_t n_idx, uint8_t *leaves_out, uint8_t *nodes_out) {
+    return guarded(ctx, [&]() -> int {
     if (!ctx || !t || (!idx && n_idx)) return SB_ERR_ARG;
     if (n_idx == 0) return SB_OK;
     if (n_idx > ((size_t)1 << 24)) return fail(ctx, SB_ERR_ARG, "too many openings");
@@ -670,6 +822,43 @@ extern "C" int sb_merkle_open(sb_ctx *ctx, const sb_tree *t, const size_t *idx, 
     DevBuf d_idx(ctx), d_nodes(ctx), d_leaves(ctx);
     TRY(d_idx.alloc(n_idx * 8));
     CU(cudaMemcpyAsync(d_idx.p, h.data(), n_idx * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (t->sh) {
+        // sharded tree: one gather kernel on this (the primary) device reads the shards through peer pointers; the top
+        // log2 g levels are appended from the host copy
+        const TreeShards &sh = *t->sh;
+        const uint32_t dlow = sh.lv + sh.log_s;
+        ExtOpenParams P;
+        memset(&P, 0, sizeof P);
+        for (int d = 0; d < sh.g; d++) {
+            P.low[d] = sh.low[d];
+            P.sub[d] = sh.sub[d];
+            for (int c = 0; c < 8; c++) P.cols[d][c] = sh.cols[d][c];
+        }
+        P.nc = (uint32_t)t->n_cols; P.log_s = sh.log_s; P.cpd = sh.cpd; P.lv = sh.lv; P.g = (uint32_t)sh.g;
+        std::vector<uint8_t> low_nodes;
+        if (nodes_out && dlow) TRY(d_nodes.alloc(n_idx * dlow * 32));
+        if (leaves_out) TRY(d_leaves.alloc(n_idx * t->leaf_bytes));
+        KLAUNCH(SB_KIND_OPEN, merkle_launch_open_ext(ctx->stream, P, (const unsigned long long *)d_idx.p, (uint32_t)n_idx,
+                                                     nodes_out && dlow ? (uint4 *)d_nodes.p : nullptr, leaves_out ? (uint4 *)d_leaves.p : nullptr));
+        if (nodes_out && dlow) {
+            low_nodes.resize(n_idx * dlow * 32);
+            CU(cudaMemcpyAsync(low_nodes.data(), d_nodes.p, low_nodes.size(), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        if (leaves_out) CU(cudaMemcpyAsync(leaves_out, d_leaves.p, n_idx * t->leaf_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (nodes_out) {
+            for (size_t q = 0; q < n_idx; q++) {
+                uint8_t *o = nodes_out + q * t->depth * 32;
+                if (dlow) memcpy(o, low_nodes.data() + q * dlow * 32, dlow * 32);
+                for (uint32_t l = dlow; l < t->depth; l++) {
+                    const size_t m = (idx[q] >> l) ^ 1;
+                    memcpy(o + l * 32, sh.top.data() + (merkle_level_off((size_t)sh.g, l - dlow) + m) * 32, 32);
+                }
+            }
+        }
+        return SB_OK;
+    }
     if (nodes_out && t->depth) {
         TRY(d_nodes.alloc(n_idx * t->depth * 32));
         const size_t tot = n_idx * t->depth;
@@ -685,6 +874,7 @@ extern "C" int sb_merkle_open(sb_ctx *ctx, const sb_tree *t, const size_t *idx, 
             P.nodes = nullptr;
             P.n = t->n;
             P.nc = (uint32_t)t->n_cols;
+            P.coset_log_s = t->coset_log_s;
             KLAUNCH(SB_KIND_OPEN, merkle_launch_open_leaves_cols(ctx->stream, P, (const unsigned long long *)d_idx.p, (uint32_t)n_idx,
                                                             (uint4 *)d_leaves.p));
         } else {
@@ -696,6 +886,7 @@ extern "C" int sb_merkle_open(sb_ctx *ctx, const sb_tree *t, const size_t *idx, 
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(ctx->stream));
     return SB_OK;
+    });
 }
 
 extern "C" size_t sb_tree_width(const sb_tree *t) { return t ? t->n : 0; }
@@ -706,7 +897,8 @@ extern "C" int sb_tree_root(const sb_tree *t, uint8_t root[32]) {
     return SB_OK;
 }
 extern "C" void sb_tree_free(sb_ctx *ctx, sb_tree *t) {
-    if (t && ctx) t->stream = ctx->stream;   // the context's stream may have been replaced since the tree was built (sb_set_stream)
+    DevGuard g(ctx);
+    if (t && ctx && t->device == ctx->device) t->stream = ctx->stream;   // the context's stream may have been replaced since the tree was built (sb_set_stream)
     free_tree(t);      // stream-ordered: work already queued on the stream finishes first
 }
 
@@ -754,7 +946,7 @@ extern "C" int sb_pseudorandom_indices_ctx(const sb_ctx *ctx, const uint8_t *see
 }
 extern "C" int sb_set_extended_domain(sb_ctx *ctx, int enable) {
     if (!ctx) return SB_ERR_ARG;
-    ctx->extended_domain = enable != 0;
+    for (sb_ctx *c : ctx->dev) c->extended_domain = enable != 0;
     return SB_OK;
 }
 
@@ -870,6 +1062,7 @@ int fri_prove_dev(sb_ctx *ctx, const uint4 *d_vals, size_t n, const hfp::el &roo
 // subtrees live on several GPUs and only needs the column from this GPU
 extern "C" int sb_fri_fold_dev(sb_ctx *ctx, const uint64_t *d_vals, size_t n, const uint64_t root[4], const uint8_t values_root[32],
                                uint64_t *d_col) {
+    return guarded(ctx, [&]() -> int {
     if (!ctx || !d_vals || !root || !values_root || !d_col) return SB_ERR_ARG;
     if (!is_pow2(n) || n < 4) return fail(ctx, SB_ERR_ARG, "FRI fold needs a power-of-two number of values >= 4, got %zu", n);
     const uint4 *tw;
@@ -887,17 +1080,21 @@ extern "C" int sb_fri_fold_dev(sb_ctx *ctx, const uint64_t *d_vals, size_t n, co
     KLAUNCH(SB_KIND_FRI_FOLD, fri_launch_fold(ctx->stream, P));
     CU(cudaGetLastError());
     return SB_OK;
+    });
 }
 
 extern "C" int sb_fri_prove_dev(sb_ctx *ctx, const uint64_t *d_vals, size_t n, const uint64_t root[4], size_t max_deg_plus_1,
                                 uint32_t excl, const sb_tree *values_tree, sb_fri_proof **out) {
+    return guarded(ctx, [&]() -> int {
     if (!ctx || !d_vals || !root || !out) return SB_ERR_ARG;
     if (values_tree && (values_tree->n != n || values_tree->leaf_bytes != 32)) return fail(ctx, SB_ERR_ARG, "values_tree does not match the values");
     return fri_prove_dev(ctx, (const uint4 *)d_vals, n, hfp::from_limbs(root), max_deg_plus_1, excl, values_tree, out);
+    });
 }
 
 extern "C" int sb_fri_prove(sb_ctx *ctx, const uint64_t *vals, size_t n, const uint64_t root[4], size_t max_deg_plus_1, uint32_t excl,
                             sb_fri_proof **out) {
+    return guarded(ctx, [&]() -> int {
     if (!ctx || !vals || !root || !out) return SB_ERR_ARG;
     void *d = nullptr;
     CU(cudaMallocAsync(&d, n * 32 ? n * 32 : 16, ctx->stream));
@@ -907,6 +1104,7 @@ extern "C" int sb_fri_prove(sb_ctx *ctx, const uint64_t *vals, size_t n, const u
     cudaFreeAsync(d, ctx->stream);
     cudaStreamSynchronize(ctx->stream);
     return rc;
+    });
 }
 
 extern "C" size_t sb_fri_n_layers(const sb_fri_proof *p) { return p ? p->layers.size() : 0; }
@@ -942,17 +1140,20 @@ extern "C" int sb_fri_layer_root(const sb_fri_proof *p, size_t i, uint8_t root[3
 void json_bytes(std::string &s, const uint8_t *b, size_t n) {
     // serde_json prints a Vec<u8> / BlakeDigest(Vec<u8>) as an array of decimal integers.  Written straight into the
     // string's buffer (at most 4 characters per byte): the proof is megabytes of these.
-    static char tab[256][4];
-    static uint8_t len[256];
-    static bool init = false;
-    if (!init) {
-        for (int v = 0; v < 256; v++) {
-            char t[8];
-            len[v] = (uint8_t)snprintf(t, sizeof t, "%d,", v);
-            memcpy(tab[v], t, 4);
+    struct Tab {
+        char tab[256][4];
+        uint8_t len[256];
+        Tab() {
+            for (int v = 0; v < 256; v++) {
+                char t[8];
+                len[v] = (uint8_t)snprintf(t, sizeof t, "%d,", v);
+                memcpy(tab[v], t, 4);
+            }
         }
-        init = true;
-    }
+    };
+    static const Tab T;            // C++11 magic static: initialised once, thread-safe
+    const auto &tab = T.tab;
+    const auto &len = T.len;
     const size_t at = s.size();
     s.resize(at + 4 * n + 2);
     char *w = &s[at];
@@ -1019,6 +1220,7 @@ extern "C" void sb_fri_proof_free(sb_fri_proof *p) { delete p; }
 
 // element-wise field op on raw 256-bit limbs (no range checks): unit-test hook for the device field library
 extern "C" int sb_fp_vec_op(sb_ctx *ctx, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n) {
+    return guarded(ctx, [&]() -> int {
     if (!ctx || !a || !b || !out) return SB_ERR_ARG;
     DevBuf da(ctx), db(ctx), dout(ctx);
     TRY(da.alloc(n * 32));
@@ -1031,11 +1233,13 @@ extern "C" int sb_fp_vec_op(sb_ctx *ctx, int op, const uint64_t *a, const uint64
     CU(cudaMemcpyAsync(out, dout.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return SB_OK;
+    });
 }
 
 // Measured issue-rate ceilings for bench.py's integer roofline: a register-only kernel of independent chains, timed with
 // CUDA events on the context's stream (best of 5).  which = 0: Montgomery products per second, 1: IMAD.WIDE.U32 per second.
 extern "C" int sb_pipe_peak(sb_ctx *ctx, int which, double *ops_per_s) {
+    return guarded(ctx, [&]() -> int {
     if (!ctx || !ops_per_s || which < 0 || which > 1) return SB_ERR_ARG;
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, ctx->device));
@@ -1065,4 +1269,5 @@ extern "C" int sb_pipe_peak(sb_ctx *ctx, int which, double *ops_per_s) {
     CU(cudaGetLastError());
     *ops_per_s = best;
     return SB_OK;
+    });
 }

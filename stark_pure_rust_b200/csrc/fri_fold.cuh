@@ -4,10 +4,10 @@
 #include "fp.cuh"
 #include "params.h"
 
-__device__ __forceinline__ fp fri_fold_row(const FriFoldParams &P, size_t i, const fp &sx, const fp &iota_inv) {
-    const size_t q = P.n >> 2;
+// y0..y3 = values[i + j q], j < 4 (q = n / 4): the degree-<4 interpolant through (x iota^j, y_j) evaluated at special_x
+__device__ __forceinline__ fp fri_fold_vals(const FriFoldParams &P, size_t i, const fp &y0, const fp &y1, const fp &y2, const fp &y3,
+                                            const fp &sx, const fp &iota_inv) {
     const unsigned long long nT = 1ull << P.tw_log_n;
-    fp y0 = fp_ldg(P.vals, i), y1 = fp_ldg(P.vals, i + q), y2 = fp_ldg(P.vals, i + 2 * q), y3 = fp_ldg(P.vals, i + 3 * q);
     fp xinv = fp_ldg_ro(P.tw, (nT - ((unsigned long long)i << P.tw_log_stride)) & (nT - 1));
     fp z = fp_mul(sx, xinv);
     fp a = fp_add(y0, y2), b = fp_sub(y0, y2), c = fp_add(y1, y3);
@@ -22,3 +22,8 @@ __device__ __forceinline__ fp fri_fold_row(const FriFoldParams &P, size_t i, con
     return fp_canon(r);
 }
 
+__device__ __forceinline__ fp fri_fold_row(const FriFoldParams &P, size_t i, const fp &sx, const fp &iota_inv) {
+    const size_t q = P.n >> 2;
+    fp y0 = fp_ldg(P.vals, i), y1 = fp_ldg(P.vals, i + q), y2 = fp_ldg(P.vals, i + 2 * q), y3 = fp_ldg(P.vals, i + 3 * q);
+    return fri_fold_vals(P, i, y0, y1, y2, y3, sx, iota_inv);
+}

@@ -107,6 +107,9 @@ const char *read_r1cs(const std::vector<uint8_t> &buf, R1cs &r) {
     if (p.u32() != 2) return "second r1cs section must be the constraints";
     p.u64();
     if (!p.ok) return "truncated r1cs header";
+    // the third section maps every wire to a u64 label (reader.rs:66-74), so a well-formed file holds 8 bytes per wire:
+    // bounds n_wires before anything is sized by it (the verifier has no witness to compare it with)
+    if ((uint64_t)r.n_wires * 8 > buf.size()) return "r1cs header declares more wires than the file can describe";
     if ((size_t)r.n_constraints * 12 > p.left) return "truncated r1cs constraints";
     r.factors.resize((size_t)3 * r.n_constraints);
     r.row_off.assign((size_t)r.n_constraints + 1, 0);
@@ -261,6 +264,7 @@ const char *build_trace(sb_ctx *ctx, const R1cs &r, const std::vector<hfp::el> &
 // proof_path may be NULL (timing only).  stage_ms (may be NULL): [0] LDE [1] m_tree [2] FRI [3] rest [4] GPU total,
 // [5] host front end (parse + trace arrangement), [6] JSON serialisation + write.
 extern "C" int sb_prove_files(sb_ctx *ctx, const char *r1cs_path, const char *wtns_path, const char *proof_path, double stage_ms[7]) {
+    return guarded(ctx, [&]() -> int {
     if (!ctx || !r1cs_path || !wtns_path) return SB_ERR_ARG;
     auto now = []() {
         struct timespec ts;
@@ -318,10 +322,12 @@ extern "C" int sb_prove_files(sb_ctx *ctx, const char *r1cs_path, const char *wt
     }
     sb_stark_proof_free(proof);
     return rc;
+    });
 }
 
 // verify_with_file_path (run.rs:556-590): the public wires are the head of the witness file (run.rs:582-585)
 extern "C" int sb_verify_files(sb_ctx *ctx, const char *r1cs_path, const char *wtns_path, const char *proof_path, double verify_ms[2]) {
+    return guarded(ctx, [&]() -> int {
     if (!ctx || !r1cs_path || !wtns_path || !proof_path) return SB_ERR_ARG;
     auto now = []() {
         struct timespec ts;
@@ -369,6 +375,7 @@ extern "C" int sb_verify_files(sb_ctx *ctx, const char *r1cs_path, const char *w
         verify_ms[1] = t2 - t1;
     }
     return rc;
+    });
 }
 
 // The arguments run.rs:390-419 hands to mk_r1cs_proof, built on the host alone (no device, no context): lets the front
@@ -378,6 +385,7 @@ struct sb_host_trace {
     sb_trace view;
 };
 extern "C" int sb_trace_from_files(const char *r1cs_path, const char *wtns_path, sb_host_trace **out, const sb_trace **view) {
+    return guarded((sb_ctx *)nullptr, [&]() -> int {
     if (!r1cs_path || !wtns_path || !out || !view) return SB_ERR_ARG;
     std::vector<uint8_t> rb, wb;
     if (!slurp(r1cs_path, rb) || !slurp(wtns_path, wb)) return SB_ERR_ARG;
@@ -409,5 +417,6 @@ extern "C" int sb_trace_from_files(const char *r1cs_path, const char *wtns_path,
     *out = h;
     *view = &h->view;
     return SB_OK;
+    });
 }
 extern "C" void sb_host_trace_free(sb_host_trace *h) { delete h; }

@@ -7,6 +7,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -46,6 +48,13 @@ struct sb_ctx {
     std::vector<cudaEvent_t> prof_pool;
     double prof_ms[SB_KIND_COUNT] = {0};
     uint64_t prof_n[SB_KIND_COUNT] = {0};
+    // multi-device contexts (sb_init_multi): the primary context is dev[0] and owns one sub-context per further device;
+    // every sub-context is a full context (own stream, table cache, profile counters) whose `primary` points back.
+    // Plain sb_init contexts have dev = {this}.  Two entries may name the same physical GPU (logical devices: the
+    // sharded code paths then run unchanged on a single-GPU box).
+    std::vector<sb_ctx *> dev;
+    sb_ctx *primary = nullptr;
+    int n_dev() const { return dev.empty() ? 1 : (int)dev.size(); }
 };
 
 static cudaEvent_t prof_event(sb_ctx *ctx) {
@@ -105,6 +114,41 @@ static int fail(sb_ctx *ctx, int code, const char *fmt, ...) {
             return fail(ctx, e_ == cudaErrorMemoryAllocation ? SB_ERR_OOM : SB_ERR_CUDA, "%s: %s (%s:%d)", #call, \
                         cudaGetErrorString(e_), __FILE__, __LINE__);                                \
     } while (0)
+// Every extern "C" entry point runs its body through guarded(): (1) the context's device becomes the calling thread's
+// current device for the duration of the call (the current device is per host thread: a context for device != 0 used from
+// a worker thread, two contexts in one process, or torch switching devices would otherwise launch on the wrong GPU) and is
+// restored afterwards; (2) no C++ exception crosses the C ABI (std::bad_alloc from a vector sized by untrusted input
+// becomes SB_ERR_OOM, anything else SB_ERR_ARG).
+struct DevGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DevGuard(const sb_ctx *ctx) {
+        if (!ctx) return;
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != ctx->device) switched = cudaSetDevice(ctx->device) == cudaSuccess;
+    }
+    explicit DevGuard(int device) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+    }
+    ~DevGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+    DevGuard(const DevGuard &) = delete;
+    DevGuard &operator=(const DevGuard &) = delete;
+};
+template <class F>
+static int guarded(sb_ctx *ctx, F &&body) {
+    DevGuard g(ctx);
+    try {
+        return body();
+    } catch (const std::bad_alloc &) {
+        return fail(ctx, SB_ERR_OOM, "host allocation failed");
+    } catch (const std::exception &e) {
+        return fail(ctx, SB_ERR_ARG, "exception: %s", e.what());
+    } catch (...) {
+        return fail(ctx, SB_ERR_ARG, "unknown exception");
+    }
+}
+
 #define TRY(expr)                \
     do {                         \
         int rc_ = (expr);        \
@@ -131,6 +175,21 @@ struct DevBuf {   // stream-ordered scratch
     DevBuf &operator=(const DevBuf &) = delete;
 };
 
+// Tree over coset-major columns spread over g devices (ext.cu): device d hashes the leaves of its cosets and keeps the
+// lv = log2(cosets per device) lowest levels of those; the level-lv digests are written straight into the memory of the
+// device that owns their node range, which builds the subtree over its S level-lv digests; the top log2 g levels are
+// finished on the host from the g subtree roots.
+struct TreeShards {
+    int g = 1;
+    uint32_t lv = 0, log_s = 0, cpd = 8;
+    uint4 *low[SB_MAX_DEV] = {0};          // per device: levels 0 .. lv-1 of its own leaves (NULL when lv == 0)
+    uint4 *sub[SB_MAX_DEV] = {0};          // per device: 2S - 1 digests, standard layout over its S level-lv digests
+    const uint4 *cols[SB_MAX_DEV][8] = {{0}};   // per device: (column, coset 0, k = 0) of the committed columns
+    cudaStream_t streams[SB_MAX_DEV] = {0};
+    int devices[SB_MAX_DEV] = {0};
+    std::vector<uint8_t> top;              // host: (2g - 1) digests over the subtree roots, standard layout
+};
+
 struct sb_tree {
     size_t n = 0;
     uint32_t depth = 0;
@@ -139,8 +198,11 @@ struct sb_tree {
     uint8_t *d_leaves = nullptr;   // owned copy of byte leaves (NULL for column-backed trees)
     int n_cols = 0;
     const uint4 *cols[8] = {0};
+    uint32_t coset_log_s = 0;      // != 0: the columns are coset-major (leaf i = element (i & 7) * 2^coset_log_s + (i >> 3))
     uint8_t root[32] = {0};
     cudaStream_t stream = nullptr; // allocations are stream-ordered (pool) on the owning context's stream
+    int device = 0;
+    TreeShards *sh = nullptr;      // != NULL: the levels live in the shards (d_nodes == NULL)
 };
 
 static bool is_pow2(size_t n) { return n && !(n & (n - 1)); }
@@ -179,15 +241,54 @@ void *pinned_arena(sb_ctx *ctx, size_t bytes);
 // dense: the caller indexes the table directly (the prover's `xs`), so a strided view of a larger cached table will not do
 int get_table(sb_ctx *ctx, const hfp::el &w, uint32_t log_n, const uint4 **tw, uint32_t *tw_log_n, uint32_t *log_stride,
               bool dense = false);
+// coset transforms of a low-degree extension by 2^log_ext (NttPassParams): cosets r0 .. r0 + cnt - 1 of every polynomial
+struct CosetSpec {
+    uint32_t log_ext = 3, r0 = 1, cnt = 7;
+    uint32_t store = NTT_STORE_PLAIN;
+    uint32_t dst_cpd = 0, dst_r0 = 0;  // NTT_STORE_PLAIN: (column, coset) lands at polynomial slot column * dst_cpd + coset - dst_r0 (0: dst_cpd = cnt, dst_r0 = r0)
+    const uint4 *c0_src = nullptr;     // NTT_STORE_GATHER: the input columns (coset 0 of the output)
+    size_t c0_stride = 0, c0_len = 0;
+};
+int ntt_dev_tw(sb_ctx *ctx, const uint4 *d_src, size_t len_in, size_t src_stride, uint4 *d_dst, size_t dst_stride, size_t n_polys,
+               uint32_t log_n, int inverse, const uint4 *tw, uint32_t tw_log_n, uint32_t log_stride, const CosetSpec *cs);
 int ntt_dev(sb_ctx *ctx, const uint4 *d_src, size_t len_in, size_t src_stride, uint4 *d_dst, size_t dst_stride, size_t n_polys,
             const hfp::el &root, uint32_t log_n, int inverse);
 int lde_dev(sb_ctx *ctx, const uint4 *d_cols, size_t n_cols, size_t col_len, size_t col_stride, const hfp::el &root_big,
             uint32_t log_s, uint32_t log_ext, uint4 *d_out);
+int ctx_create(int device, sb_ctx **out);
 void free_tree(sb_tree *t);
+int tree_new(sb_ctx *ctx, size_t n, size_t leaf_bytes, sb_tree **out);
+int merkle_finish(sb_ctx *ctx, sb_tree *t, uint32_t level, bool fetch_root);
 int commit_bytes_owned(sb_ctx *ctx, uint8_t *d_leaves, size_t leaf_bytes, size_t n, sb_tree **tree);
 int commit_cols(sb_ctx *ctx, const uint4 *const *d_cols, size_t n_cols, size_t n, sb_tree **tree);
 int fri_prove_dev(sb_ctx *ctx, const uint4 *d_vals, size_t n, const hfp::el &root, size_t max_deg_plus_1, uint32_t excl,
                   const sb_tree *values_tree, sb_fri_proof **out);
+// ---- ext.cu: columns of the extended domain in coset-major layout, spread over the context's devices --------------------
+// Device d of g holds cosets r0 = d * cpd .. r0 + cpd - 1 (cpd = 8 / g) of EVERY column: element (c, r, k) -- the value at
+// position 8 k + r of column c -- lives at buf[d][((c * cpd + r - r0) << log_s) + k].  Every shift the prover applies is a
+// multiple of 8 (prove.rs: previous step, +o3 steps, the FRI fold's quarter turns), so pointwise kernels, leaf hashing and
+// the first FRI fold never leave a device; only coefficients (once per column) and 32-byte digests cross NVLink.
+struct sb_ext {
+    sb_ctx *root = nullptr;
+    int g = 1;
+    uint32_t log_s = 0, cpd = 8, lv = 3;
+    size_t S = 0, N = 0, n_cols = 0, n_lde = 0;       // the first n_lde columns have input / coefficient staging (ext_extend)
+    hfp::el g2;                                 // root of unity of the extended domain (order N)
+    uint4 *buf[SB_MAX_DEV] = {0};               // n_cols * cpd * S elements
+    uint4 *coef[SB_MAX_DEV] = {0};              // n_lde * S coefficients (every device holds every column's)
+    uint4 *in[SB_MAX_DEV] = {0};                // n_lde * S input staging; column c is read on device owner[c]
+    std::vector<int> owner;
+    uint4 *col(int d, size_t c) const { return buf[d] + 2 * ((c * cpd) << log_s); }
+    uint4 *input(size_t c) const { return in[owner[c]] + 2 * (c << log_s); }
+};
+int ext_create(sb_ctx *root, size_t n_cols, size_t n_lde, uint32_t log_s, sb_ext **out);
+void ext_free(sb_ext *e);
+int ext_extend(sb_ext *e, size_t first, size_t count);
+int ext_commit(const sb_ext *e, const size_t *col_ids, size_t n_ids, sb_tree **tree);
+int ext_fri_prove(const sb_ext *e, size_t col, const sb_tree *values_tree, size_t max_deg_plus_1, uint32_t excl, sb_fri_proof **out);
+int ext_to_natural(const sb_ext *e, size_t col, uint4 *d_out);
+int sync_all(sb_ctx *root);
+
 void json_bytes(std::string &s, const uint8_t *b, size_t n);
 void json_branches(std::string &s, const uint8_t *leaves, size_t leaf_bytes, const uint8_t *nodes, size_t depth, size_t count);
 void fri_proof_json_into(std::string &s, const sb_fri_proof *p);

@@ -9,6 +9,8 @@ struct NttPassParams;
 struct MerkleColsParams;
 struct MerkleBytesParams;
 struct FriFoldParams;
+struct ExtLeavesParams;
+struct ExtOpenParams;
 struct fp;
 
 // ntt_b*.cu
@@ -25,6 +27,11 @@ int merkle_launch_open(cudaStream_t stream, const uint4 *nodes, unsigned long lo
                        const unsigned long long *idx, uint32_t n_idx, uint4 *out);
 int merkle_launch_open_leaves_cols(cudaStream_t stream, const MerkleColsParams &P, const unsigned long long *idx,
                                    uint32_t n_idx, uint4 *out);
+int merkle_launch_leaves_ext(cudaStream_t stream, const ExtLeavesParams &P);
+int merkle_launch_leaves_fold_ext(cudaStream_t stream, const FriFoldParams &F, uint4 *nodes);
+int merkle_launch_open_ext(cudaStream_t stream, const ExtOpenParams &P, const unsigned long long *idx, uint32_t n_idx, uint4 *nodes_out,
+                           uint4 *leaves_out);
+int ext_launch_to_natural(cudaStream_t stream, const ExtOpenParams &P, uint4 *out);
 int merkle_launch_gather_bytes(cudaStream_t stream, const uint8_t *leaves, size_t leaf_bytes,
                                const unsigned long long *idx, uint32_t n_idx, uint8_t *out);
 // fri.cu

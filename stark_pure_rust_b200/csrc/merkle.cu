@@ -55,6 +55,44 @@ int merkle_launch_open_leaves_cols(cudaStream_t s, const MerkleColsParams &P, co
     return 1;
 }
 
+int merkle_launch_leaves_ext(cudaStream_t s, const ExtLeavesParams &P) {
+    const unsigned b = blocks128((size_t)1 << P.log_s);
+    switch (P.lv) {
+        case 0: merkle_leaves_ext_kernel<0><<<b, 128, 0, s>>>(P); break;
+        case 1: merkle_leaves_ext_kernel<1><<<b, 128, 0, s>>>(P); break;
+        case 2: merkle_leaves_ext_kernel<2><<<b, 128, 0, s>>>(P); break;
+        default: merkle_leaves_ext_kernel<3><<<b, 128, 0, s>>>(P); break;
+    }
+    return 1;
+}
+int merkle_launch_leaves_fold_ext(cudaStream_t s, const FriFoldParams &F, uint4 *nodes) {
+    const unsigned b = blocks128(((size_t)1 << F.log_s) >> 2);
+    switch (F.lv) {
+        case 0: merkle_leaves_fold_ext_kernel<0><<<b, 128, 0, s>>>(F, nodes); break;
+        case 1: merkle_leaves_fold_ext_kernel<1><<<b, 128, 0, s>>>(F, nodes); break;
+        case 2: merkle_leaves_fold_ext_kernel<2><<<b, 128, 0, s>>>(F, nodes); break;
+        default: merkle_leaves_fold_ext_kernel<3><<<b, 128, 0, s>>>(F, nodes); break;
+    }
+    return 1;
+}
+int merkle_launch_open_ext(cudaStream_t s, const ExtOpenParams &P, const unsigned long long *idx, uint32_t n_idx, uint4 *nodes_out,
+                           uint4 *leaves_out) {
+    int n = 0;
+    if (nodes_out && P.lv + P.log_s) {
+        merkle_open_ext_kernel<<<blocks128((size_t)n_idx * (P.lv + P.log_s)), 128, 0, s>>>(P, idx, n_idx, nodes_out);
+        n++;
+    }
+    if (leaves_out) {
+        merkle_open_leaves_ext_kernel<<<blocks128((size_t)n_idx * P.nc), 128, 0, s>>>(P, idx, n_idx, leaves_out);
+        n++;
+    }
+    return n;
+}
+int ext_launch_to_natural(cudaStream_t s, const ExtOpenParams &P, uint4 *out) {
+    ext_to_natural_kernel<<<(unsigned)((((size_t)8 << P.log_s) + 255) / 256), 256, 0, s>>>(P, out);
+    return 1;
+}
+
 __global__ void gather_leaf_bytes_kernel(const uint8_t *leaves, size_t leaf_bytes, const unsigned long long *idx, uint32_t n_idx,
                                          uint8_t *out) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -19,8 +19,6 @@
 //
 // Bound: 32-bit integer pipe (IMAD carry chains); HBM traffic is 64 B per element per pass.
 #pragma once
-#include <cooperative_groups.h>
-
 #include "fp.cuh"
 #include "params.h"
 
@@ -56,13 +54,15 @@ __device__ __forceinline__ void ntt_round_regs(fp (&x)[1 << Q], uint32_t low, co
     }
 }
 
+// skip0: tile columns j with j % 8 == 0 carry no transform (NTT_STORE_GATHER: the coset-0 slots)
 template <int B, int S, int Q, int LOG_TILE>
-__device__ __forceinline__ void ntt_round(uint4 *slo, uint4 *shi, const uint4 *wlo, const uint4 *whi) {
+__device__ __forceinline__ void ntt_round(uint4 *slo, uint4 *shi, const uint4 *wlo, const uint4 *whi, bool skip0) {
     constexpr int TILE = 1 << LOG_TILE, NT = TILE / 8, CC = TILE >> B, PITCH = CC + 1;
     constexpr int GROUPS = TILE >> Q;
 #pragma unroll 1
     for (int g = threadIdx.x; g < GROUPS; g += NT) {
         const int j = g % CC;
+        if (skip0 && (j & 7) == 0) continue;
         const uint32_t rb = g / CC;                          // row index with the Q round bits removed
         const uint32_t low = rb & ((1u << S) - 1), high = rb >> S;
         const uint32_t base = (high << (S + Q)) | low;
@@ -84,12 +84,12 @@ __device__ __forceinline__ void ntt_round(uint4 *slo, uint4 *shi, const uint4 *w
 
 // all rounds of a 2^B sub-transform: first round takes B mod 3 bits (if any), the rest 3 each
 template <int B, int HI, int LOG_TILE>
-__device__ __forceinline__ void ntt_rounds(uint4 *slo, uint4 *shi, const uint4 *wlo, const uint4 *whi) {
+__device__ __forceinline__ void ntt_rounds(uint4 *slo, uint4 *shi, const uint4 *wlo, const uint4 *whi, bool skip0) {
     if constexpr (HI > 0) {
         constexpr int Q = (HI % 3) ? (HI % 3) : 3;
-        ntt_round<B, HI - Q, Q, LOG_TILE>(slo, shi, wlo, whi);
+        ntt_round<B, HI - Q, Q, LOG_TILE>(slo, shi, wlo, whi, skip0);
         __syncthreads();
-        ntt_rounds<B, HI - Q, LOG_TILE>(slo, shi, wlo, whi);
+        ntt_rounds<B, HI - Q, LOG_TILE>(slo, shi, wlo, whi, skip0);
     }
 }
 
@@ -112,10 +112,15 @@ __global__ void __launch_bounds__((1 << LOG_TILE) / 8, LOG_TILE >= 11 ? 2 : 4) n
     uint4 *slo = smem, *shi = smem + R * PITCH;
     uint4 *wlo = shi + R * PITCH, *whi = wlo + (R / 2 > 0 ? R / 2 : 1);
 
-    const unsigned long long n = 1ull << P.log_n;
     const uint32_t log_cpp = P.log_n - B;                     // log2(columns per polynomial)
+    const bool gather = P.last && P.coset_store == NTT_STORE_GATHER;      // uniform over the grid
     unsigned long long blk_col0 = (unsigned long long)blockIdx.x * CC;
-    if (P.n_polys) {   // tile-major order (host guarantees CC divides the columns of one polynomial)
+    unsigned long long g_col = 0, g_gl0 = 0;                  // gather: the column and the first sub-transform of this CTA
+    if (gather) {             // CC / 8 adjacent sub-transforms x 8 cosets of one column (host guarantees 8 <= CC <= 8 * columns per polynomial)
+        const unsigned long long tiles = (1ull << log_cpp) / (CC / 8);
+        g_col = blockIdx.x / tiles;
+        g_gl0 = (blockIdx.x % tiles) * (CC / 8);
+    } else if (P.n_polys) {   // tile-major order (host guarantees CC divides the columns of one polynomial)
         const unsigned long long poly = blockIdx.x % P.n_polys, tile = blockIdx.x / P.n_polys;
         blk_col0 = (poly << log_cpp) + tile * CC;
     }
@@ -132,32 +137,45 @@ __global__ void __launch_bounds__((1 << LOG_TILE) / 8, LOG_TILE >= 11 ? 2 : 4) n
     for (int idx = threadIdx.x; idx < TILE; idx += NT) {
         int r, j;
         if (!P.last) { j = idx % CC; r = idx / CC; } else { r = idx % R; j = idx / R; }
-        const unsigned long long g = blk_col0 + j;
         uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
-        if (g < P.n_cols_total) {
-            const unsigned long long poly = g >> log_cpp, gl = g & ((1ull << log_cpp) - 1);
-            unsigned long long e;
-            if (!P.last) {
-                const unsigned long long o = gl >> P.log_inner, c = gl & ((1ull << P.log_inner) - 1);
-                e = (o << (B + P.log_inner)) + ((unsigned long long)r << P.log_inner) + c;
-            } else {
-                e = (ntt_digitrev_inv(P, gl) << B) + r;
+        if (gather) {
+            const uint32_t rr = j & 7;
+            if (rr) {         // coset rr of column g_col is polynomial g_col * 7 + rr - 1 of the batch
+                const unsigned long long e = (ntt_digitrev_inv(P, g_gl0 + (j >> 3)) << B) + r;
+                const uint4 *s = P.src + 2 * ((g_col * 7 + rr - 1) * P.src_stride + e);
+                lo = s[0];
+                hi = s[1];
             }
-            if (!P.first || e < P.len_in) {
-                if (P.first && P.coset_m1) {
-                    // coefficient e of column poly / coset_m1, scaled onto coset r: c_e * W^(e r)
-                    const unsigned long long col = poly / P.coset_m1, rr = poly % P.coset_m1 + 1;
-                    const uint4 *s = P.src + 2 * (col * P.src_stride + e);
-                    fp v = fp_from_u4(s[0], s[1]);
-                    const unsigned long long nT = 1ull << P.tw_log_n;
-                    const unsigned long long ti = ((e * rr) << (P.tw_log_stride - P.coset_log)) & (nT - 1);
-                    v = fp_mul(v, fp_ldg_ro(P.tw, ti));
-                    lo = fp_lo(v);
-                    hi = fp_hi(v);
+        } else {
+            const unsigned long long g = blk_col0 + j;
+            if (g < P.n_cols_total) {
+                const unsigned long long poly = g >> log_cpp, gl = g & ((1ull << log_cpp) - 1);
+                unsigned long long e;
+                if (!P.last) {
+                    const unsigned long long o = gl >> P.log_inner, c = gl & ((1ull << P.log_inner) - 1);
+                    e = (o << (B + P.log_inner)) + ((unsigned long long)r << P.log_inner) + c;
                 } else {
-                    const uint4 *s = P.src + 2 * (poly * P.src_stride + e);
-                    lo = s[0];
-                    hi = s[1];
+                    e = (ntt_digitrev_inv(P, gl) << B) + r;
+                }
+                if (!P.first || e < P.len_in) {
+                    if (P.first && P.coset_cnt) {
+                        // coefficient e of column poly / coset_cnt, scaled onto coset rr: c_e * W^(e rr)
+                        const unsigned long long col = poly / P.coset_cnt, rr = poly % P.coset_cnt + P.coset_r0;
+                        const uint4 *s = P.src + 2 * (col * P.src_stride + e);
+                        lo = s[0];
+                        hi = s[1];
+                        if (rr) {
+                            const unsigned long long nT = 1ull << P.tw_log_n;
+                            const unsigned long long ti = ((e * rr) << (P.tw_log_stride - P.coset_log)) & (nT - 1);
+                            fp v = fp_mul(fp_from_u4(lo, hi), fp_ldg_ro(P.tw, ti));
+                            lo = fp_lo(v);
+                            hi = fp_hi(v);
+                        }
+                    } else {
+                        const uint4 *s = P.src + 2 * (poly * P.src_stride + e);
+                        lo = s[0];
+                        hi = s[1];
+                    }
                 }
             }
         }
@@ -167,35 +185,7 @@ __global__ void __launch_bounds__((1 << LOG_TILE) / 8, LOG_TILE >= 11 ? 2 : 4) n
     __syncthreads();
 
     // ---- butterflies ----
-    ntt_rounds<B, B, LOG_TILE>(slo, shi, wlo, whi);
-
-    // ---- cluster variant of the coset transforms' last pass: see NttPassParams::cluster ----
-    if (P.last && P.cluster) {
-        namespace cg = cooperative_groups;
-        cg::cluster_group cluster = cg::this_cluster();
-        cluster.sync();                                   // every coset's tile is complete in its CTA's shared memory
-        const uint32_t rank = cluster.block_rank(), E = P.coset_m1 + 1;        // rank = coset - 1
-        const unsigned long long poly = blk_col0 >> log_cpp, gl0 = blk_col0 & ((1ull << log_cpp) - 1);
-        const unsigned long long col = poly / P.coset_m1;
-        const uint32_t my_rows = (R - rank + P.coset_m1 - 1) / P.coset_m1;      // rows kk = rank, rank + 7, ...
-        const uint32_t per_row = CC * E;
-        for (uint32_t w = threadIdx.x; w < my_rows * per_row; w += NT) {
-            const uint32_t kk = rank + (w / per_row) * P.coset_m1;
-            const uint32_t j = (w % per_row) / E, rr = w % E;                   // consecutive lanes: consecutive output elements
-            const unsigned long long e = gl0 + j + ((unsigned long long)kk << P.log_outer);
-            fp v;
-            if (rr == 0) {
-                v = e < P.c0_len ? fp_canon(fp_ldg(P.c0_src, col * P.c0_stride + e)) : fp_zero();
-            } else {
-                const uint32_t r = B ? (__brev(kk) >> (32 - B)) : 0;
-                const uint4 *rlo = cluster.map_shared_rank(slo, rr - 1), *rhi = cluster.map_shared_rank(shi, rr - 1);
-                v = fp_canon(fp_from_u4(rlo[r * PITCH + j], rhi[r * PITCH + j]));
-            }
-            fp_stg(P.dst, col * P.dst_stride + (e << P.coset_log) + rr, v);
-        }
-        cluster.sync();                                   // nobody leaves while its shared memory is still being read
-        return;
-    }
+    ntt_rounds<B, B, LOG_TILE>(slo, shi, wlo, whi, gather);
 
     // ---- store tile (row r of the tile holds output k = bitrev_B(r)) ----
     fp ninv;
@@ -205,9 +195,18 @@ __global__ void __launch_bounds__((1 << LOG_TILE) / 8, LOG_TILE >= 11 ? 2 : 4) n
     for (int idx = threadIdx.x; idx < TILE; idx += NT) {
         const int j = idx % CC;
         const uint32_t kk = idx / CC;
+        const uint32_t r = B ? (__brev(kk) >> (32 - B)) : 0;
+        if (gather) {         // lanes j = 0..7 write out[8 e .. 8 e + 7] of one output position e: 256 contiguous bytes
+            const uint32_t rr = j & 7;
+            const unsigned long long e = g_gl0 + (j >> 3) + ((unsigned long long)kk << P.log_outer);
+            fp v;
+            if (rr) v = fp_from_u4(slo[r * PITCH + j], shi[r * PITCH + j]);
+            else v = e < P.c0_len ? fp_ldg(P.c0_src, g_col * P.c0_stride + e) : fp_zero();
+            fp_stg(P.dst, g_col * P.dst_stride + (e << 3) + rr, fp_canon(v));
+            continue;
+        }
         const unsigned long long g = blk_col0 + j;
         if (g >= P.n_cols_total) continue;
-        const uint32_t r = B ? (__brev(kk) >> (32 - B)) : 0;
         fp v = fp_from_u4(slo[r * PITCH + j], shi[r * PITCH + j]);
         const unsigned long long poly = g >> log_cpp, gl = g & ((1ull << log_cpp) - 1);
         unsigned long long e;
@@ -222,13 +221,13 @@ __global__ void __launch_bounds__((1 << LOG_TILE) / 8, LOG_TILE >= 11 ? 2 : 4) n
             if (P.inverse) v = fp_mul(v, ninv);
             v = fp_canon(v);
         }
-        (void)n;
-        if (P.last && P.coset_m1) {
-            const unsigned long long col = poly / P.coset_m1, rr = poly % P.coset_m1 + 1;
+        if (P.last && P.coset_store == NTT_STORE_INTERLEAVED) {
+            const unsigned long long col = poly / P.coset_cnt, rr = poly % P.coset_cnt + P.coset_r0;
             fp_stg(P.dst, col * P.dst_stride + (e << P.coset_log) + rr, v);
         } else {
-            fp_stg(P.dst, poly * P.dst_stride + e, v);
+            unsigned long long dp = poly;
+            if (P.last && P.coset_cnt) dp = (poly / P.coset_cnt) * P.coset_dst_cpd + (poly % P.coset_cnt + P.coset_r0 - P.coset_dst_r0);
+            fp_stg(P.dst, dp * P.dst_stride + e, v);
         }
     }
 }
-

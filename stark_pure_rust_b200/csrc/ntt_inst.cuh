@@ -17,22 +17,8 @@ template <int B>
 static int ntt_launch_one(cudaStream_t stream, const NttPassParams &P) {
     constexpr int TILE = 1 << NTT_LOG_TILE_FOR(B), CC = TILE >> B;
     unsigned long long grid = (P.n_cols_total + CC - 1) / CC;
-    if (P.cluster) {          // the coset_m1 consecutive CTAs of one (column, tile) form a cluster
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)grid, 1, 1);
-        cfg.blockDim = dim3(TILE / 8, 1, 1);
-        cfg.dynamicSmemBytes = ntt_smem_bytes<B>();
-        cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = P.coset_m1;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        cudaLaunchKernelEx(&cfg, ntt_pass_kernel<B, NTT_LOG_TILE_FOR(B)>, P);
-        return 1;
-    }
+    if (P.last && P.coset_store == NTT_STORE_GATHER)     // one CTA = CC / 8 sub-transforms x 8 cosets; n_cols_total counts the 7 computed cosets
+        grid = P.n_cols_total / 7 * 8 / CC;
     ntt_pass_kernel<B, NTT_LOG_TILE_FOR(B)><<<(unsigned)grid, TILE / 8, ntt_smem_bytes<B>(), stream>>>(P);
     return 1;
 }

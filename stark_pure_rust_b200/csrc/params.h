@@ -35,25 +35,63 @@ struct NttPassParams {
     uint32_t n_prev;               // last pass: widths of the earlier passes, in order
     uint32_t prev_bits[NTT_MAX_PASSES];
     uint32_t n_inv[8];             // Montgomery form of n^-1 (inverse transform, last pass)
-    // coset mode (low-degree extension by 2^coset_log, lde_dev): the batch holds (column, r) pairs, r = 1 .. 2^coset_log - 1
-    // (polynomial id = column * coset_m1 + r - 1).  The first pass reads coefficient j of `column` and scales it by
-    // W^(j r) (W = the extended domain's root, w = W^(2^coset_log)); the last pass writes output k to element
-    // k * 2^coset_log + r of `column`.  coset_m1 == 0: plain transform.
-    uint32_t coset_m1, coset_log;
-    // last pass of the coset transforms, cluster variant (cluster == 1): the launch groups the coset_m1 = 7 CTAs that hold the same
-    // tile of the seven cosets of one column into one thread-block cluster; after the butterflies they read each other's
-    // shared memory (DSMEM) so that every CTA writes whole 2^coset_log-element groups out[8k .. 8k+7] -- 256 B contiguous
-    // instead of one 32-byte element per 256 B -- and coset 0 (the input column itself) is filled in by the writer.
-    uint32_t cluster;
-    const uint4 *c0_src;           // the LDE's input columns (coset 0)
+    // coset mode (low-degree extension by 2^coset_log): the batch holds (column, coset) pairs, polynomial id =
+    // column * coset_cnt + (coset - coset_r0) for cosets coset_r0 .. coset_r0 + coset_cnt - 1.  The first pass reads
+    // coefficient j of `column` and scales it by W^(j * coset) (W = the extended domain's root, w = W^(2^coset_log)).
+    // coset_cnt == 0: plain transform.  The last pass stores according to coset_store:
+    //   NTT_STORE_PLAIN       polynomial-major like a plain transform: output k of (column, coset) at
+    //                         dst[polynomial * dst_stride + k] -- the coset-major layout of the prover (ext.cu)
+    //   NTT_STORE_INTERLEAVED natural order of the extended domain: element k * 2^coset_log + coset of `column`
+    //   NTT_STORE_GATHER      natural order as well, but one CTA holds the SAME tile of all 2^coset_log cosets of one
+    //                         column (tile columns = (sub-transform, coset) pairs, coset minor), so every output row is
+    //                         2^coset_log contiguous elements (256 B) instead of one 32-byte element per 256 B; the coset-0
+    //                         slots carry the input column itself (c0_src), which makes the separate copy kernel unnecessary.
+    //                         Needs coset_log == 3, coset_r0 == 1, coset_cnt == 7 and at least two passes.
+    uint32_t coset_cnt, coset_r0, coset_log, coset_store;
+    uint32_t coset_dst_cpd, coset_dst_r0;   // NTT_STORE_PLAIN: (column, coset) is stored as polynomial column * coset_dst_cpd + coset - coset_dst_r0
+    const uint4 *c0_src;           // NTT_STORE_GATHER: the LDE's input columns (coset 0)
     unsigned long long c0_stride, c0_len;
 };
+#define NTT_STORE_PLAIN 0
+#define NTT_STORE_INTERLEAVED 1
+#define NTT_STORE_GATHER 2
 
 struct MerkleColsParams {
     const uint4 *cols[8];
     uint4 *nodes;
     unsigned long long n;          // leaves (power of two)
     uint32_t nc;                   // columns per leaf, 1..8
+    uint32_t coset_log_s;          // != 0 (openings only): coset-major columns, leaf i = element (i & 7) << coset_log_s | i >> 3
+};
+
+#define SB_MAX_DEV 8
+
+// Leaf hashing of coset-major columns on ONE device of a g-device context (merkle_leaves_ext_kernel): the device holds
+// cosets r0 .. r0 + cpd - 1 (r0 = d * cpd, cpd = 8 / g = 2^lv) of every column as arrays of S = 2^log_s values; leaf
+// 8 k + r of the tree is the row (col_0[r][k], ..., col_{nc-1}[r][k]).  Thread k hashes its cpd adjacent leaves and reduces
+// them lv levels.  Destinations: `single` != NULL -> a standard tree array over N = 8 S leaves (all levels there: one
+// device, or device 0 gathering everything); otherwise levels < lv go to this device's `low` array and the level-lv
+// digest of node k g + d goes to the subtree array of the device that owns that node range, sub[k / (S / g)].
+struct ExtLeavesParams {
+    const uint4 *cols[8];
+    uint4 *low;
+    uint4 *sub[SB_MAX_DEV];
+    uint4 *single;
+    uint32_t nc, log_s, cpd, lv, d, g;
+};
+// offset (in digests) of level l < lv inside a device's `low` array: levels 0 .. l-1 hold S * (cpd >> l') digests each
+__host__ __device__ inline size_t ext_low_off(uint32_t log_s, uint32_t cpd, uint32_t l) {
+    size_t off = 0;
+    for (uint32_t i = 0; i < l; i++) off += ((size_t)(cpd >> i)) << log_s;
+    return off;
+}
+
+// Openings of a sharded tree, gathered by one kernel on the primary device through peer pointers
+struct ExtOpenParams {
+    const uint4 *low[SB_MAX_DEV];
+    const uint4 *sub[SB_MAX_DEV];
+    const uint4 *cols[SB_MAX_DEV][8];
+    uint32_t nc, log_s, cpd, lv, g;
 };
 
 struct MerkleBytesParams {
@@ -75,4 +113,9 @@ struct FriFoldParams {
     unsigned long long n;
     uint32_t tw_log_n, tw_log_stride;   // layer root w = w_T^(2^tw_log_stride)
     uint32_t special_x[8];         // Montgomery
+    // coset-major input (merkle_leaves_fold_ext_kernel): vals = this device's cosets r0 .. r0 + cpd - 1 of the layer's
+    // values, 2^log_s each (n = 8 * 2^log_s); row i = 8 k + r reads vals[(r - r0) * S + k + j S / 4], j < 4.  The folded
+    // column is written in natural order to `col` and its tree (standard layout, n / 4 leaves) to `nodes`, both on the
+    // primary device.
+    uint32_t log_s, cpd, lv, d, g;
 };

@@ -10,6 +10,23 @@
 #include "fp.cuh"
 #include "params.h"
 
+// Layout: every N-point column is coset-major and sharded by cosets (sb_ext, internal.h).  A kernel launch covers ONE device's
+// cosets r0 .. r0 + cpd - 1: thread t < cpd * S handles coset r = r0 + (t >> log_s) at step k = t & (S - 1), i.e. domain
+// position j = 8 k + r, and element t of every column pointer (which points at that device's block of the column).  The
+// prover's shifts are whole steps: position j - 8 is (r, k - 1), j + 8 o3 is (r, k + o3), all mod S inside the same coset.
+struct PwView {
+    uint32_t log_s, r0;
+    unsigned long long n;            // cpd << log_s
+};
+#define PW_DECODE(V)                                                          \
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;           \
+    if (t >= (V).n) return;                                                   \
+    const size_t S_ = (size_t)1 << (V).log_s, k_ = t & (S_ - 1), cb_ = t - k_; \
+    const uint32_t r_ = (V).r0 + (uint32_t)(t >> (V).log_s);                  \
+    const size_t j_ = (k_ << 3) + r_;                                         \
+    (void)j_; (void)cb_;
+#define PW_SHIFT(steps) (cb_ + ((k_ + (steps)) & (S_ - 1)))
+
 struct PwConsts {
     uint32_t inv_z8[8][8];     // multi_inv(z)[j] for j mod 8
     uint32_t pw8[8][8];        // (g2^S)^(j mod 8)
@@ -55,23 +72,22 @@ __global__ void pw_a_leaves_kernel(const unsigned long long *perm, const uint4 *
 struct PwQ12Params {
     const uint4 *k, *f0, *f1, *f2, *s, *p;
     uint4 *d1, *d2;
-    unsigned long long n, o3sk;      // o3sk = (original_steps / 3) * sk
+    PwView v;
+    unsigned long long o3;           // original_steps / 3
     int *err;                        // set when q != 0 where inv_z == 0 (reference: assert, utils.rs:379-418)
 };
 __global__ void __launch_bounds__(128) pw_q12_kernel(const __grid_constant__ PwQ12Params P, const __grid_constant__ PwConsts Cst) {
-    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= P.n) return;
-    const size_t N = P.n;
-    fp pj = fp_ldg(P.p, j);
-    fp t1 = fp_mul(fp_ldg(P.f1, j), fp_ldg(P.p, (j + N - 8) % N));
-    fp t2 = fp_mul(fp_ldg(P.k, j), fp_ldg(P.s, j));
-    fp q1 = fp_mul(fp_sub(fp_sub(pj, t1), t2), fp_ldg(P.f0, j));
-    fp t3 = fp_mul(pj, fp_ldg(P.p, (j + P.o3sk) % N));
-    fp q2 = fp_mul(fp_sub(fp_ldg(P.p, (j + 2 * P.o3sk) % N), t3), fp_ldg(P.f2, j));
-    fp iz = pw_const(Cst.inv_z8[j & 7]);
-    if ((j & 7) == 0 && !(pw_is_zero(q1) && pw_is_zero(q2))) atomicExch(P.err, 1);
-    fp_stg(P.d1, j, fp_canon(fp_mul(q1, iz)));
-    fp_stg(P.d2, j, fp_canon(fp_mul(q2, iz)));
+    PW_DECODE(P.v)
+    fp pj = fp_ldg(P.p, t);
+    fp t1 = fp_mul(fp_ldg(P.f1, t), fp_ldg(P.p, PW_SHIFT(S_ - 1)));
+    fp t2 = fp_mul(fp_ldg(P.k, t), fp_ldg(P.s, t));
+    fp q1 = fp_mul(fp_sub(fp_sub(pj, t1), t2), fp_ldg(P.f0, t));
+    fp t3 = fp_mul(pj, fp_ldg(P.p, PW_SHIFT(P.o3)));
+    fp q2 = fp_mul(fp_sub(fp_ldg(P.p, PW_SHIFT(2 * P.o3)), t3), fp_ldg(P.f2, t));
+    fp iz = pw_const(Cst.inv_z8[r_]);
+    if (r_ == 0 && !(pw_is_zero(q1) && pw_is_zero(q2))) atomicExch(P.err, 1);
+    fp_stg(P.d1, t, fp_canon(fp_mul(q1, iz)));
+    fp_stg(P.d2, t, fp_canon(fp_mul(q2, iz)));
 }
 
 // accumulator factors (utils.rs:293-339): nmr_j = r0 + r1*j + r2*w_j, dnm_j = r0 + r1*perm[j] + r2*w_j
@@ -153,63 +169,57 @@ __global__ void __launch_bounds__(128) pw_mul_kernel(const uint4 *a, const uint4
 struct PwQ3Params {
     const uint4 *a, *s, *idx, *pidx;
     uint4 *d3;
-    unsigned long long n;
+    PwView v;
     int *err;
 };
 __global__ void __launch_bounds__(128) pw_q3_kernel(const __grid_constant__ PwQ3Params P, const __grid_constant__ PwConsts Cst) {
-    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= P.n) return;
-    const size_t N = P.n;
+    PW_DECODE(P.v)
     fp r0 = pw_const(Cst.r[0]), r1 = pw_const(Cst.r[1]), r2 = pw_const(Cst.r[2]);
-    fp t2 = fp_mul(r2, fp_ldg(P.s, j));
-    fp vn = fp_add(fp_add(r0, fp_mul(r1, fp_ldg(P.idx, j))), t2);
-    fp vd = fp_add(fp_add(r0, fp_mul(r1, fp_ldg(P.pidx, j))), t2);
-    fp u = fp_mul(fp_ldg(P.a, j), vd);
-    fp v = fp_mul(fp_ldg(P.a, (j + N - 8) % N), vn);
+    fp t2 = fp_mul(r2, fp_ldg(P.s, t));
+    fp vn = fp_add(fp_add(r0, fp_mul(r1, fp_ldg(P.idx, t))), t2);
+    fp vd = fp_add(fp_add(r0, fp_mul(r1, fp_ldg(P.pidx, t))), t2);
+    fp u = fp_mul(fp_ldg(P.a, t), vd);
+    fp v = fp_mul(fp_ldg(P.a, PW_SHIFT(S_ - 1)), vn);
     fp q3 = fp_sub(u, v);
-    if ((j & 7) == 0 && !pw_is_zero(q3)) atomicExch(P.err, 1);
-    fp_stg(P.d3, j, fp_canon(fp_mul(q3, pw_const(Cst.inv_z8[j & 7]))));
+    if (r_ == 0 && !pw_is_zero(q3)) atomicExch(P.err, 1);
+    fp_stg(P.d3, t, fp_canon(fp_mul(q3, pw_const(Cst.inv_z8[r_]))));
 }
 
 // zb3[j] = xs[j] - xs[N - sk] (utils.rs:458-474), written behind zb2 so that one batch inverse serves both
-__global__ void __launch_bounds__(128) pw_zb3_kernel(const uint4 *xs, uint4 *zb3, unsigned long long n, const __grid_constant__ PwConsts Cst) {
-    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    fp_stg(zb3, j, fp_canon(fp_sub(fp_ldg(xs, j), pw_const(Cst.x_last))));
+__global__ void __launch_bounds__(128) pw_zb3_kernel(const uint4 *xs, uint4 *zb3, PwView V, const __grid_constant__ PwConsts Cst) {
+    PW_DECODE(V)
+    fp_stg(zb3, t, fp_canon(fp_sub(fp_ldg(xs, j_), pw_const(Cst.x_last))));
 }
 
 // out[j] = sum_k coef[k] xs[j]^k (Horner): the boundary polynomials i2 / zb2 when only a few public wires are in use
-// (prove.rs:216-224 evaluates them point by point as well; for many public wires an N-point NTT of the same
-// coefficients is used instead -- identical field elements either way)
-__global__ void __launch_bounds__(128) pw_poly_eval_kernel(const uint4 *xs, const uint4 *coef, uint32_t n_coef, uint4 *out,
-                                                           unsigned long long n) {
-    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    const fp x = fp_ldg(xs, j);
+// (prove.rs:216-224 evaluates them point by point as well; for many public wires the coset transforms of the same
+// coefficients are used instead -- identical field elements either way)
+__global__ void __launch_bounds__(128) pw_poly_eval_kernel(const uint4 *xs, const uint4 *coef, uint32_t n_coef, uint4 *out, PwView V) {
+    PW_DECODE(V)
+    const fp x = fp_ldg(xs, j_);
     fp acc = fp_ldg_ro(coef, n_coef - 1);
     for (uint32_t k = n_coef - 1; k-- > 0;) acc = fp_add(fp_mul(acc, x), fp_ldg_ro(coef, k));
-    fp_stg(out, j, fp_canon(acc));
+    fp_stg(out, t, fp_canon(acc));
 }
 
 // b2 = (s - i2) * inv(zb2), b3 = (a - 1) * inv(zb3)  (utils.rs:477-524); in place over the inverse arrays
 struct PwB23Params {
     const uint4 *s, *a, *i2;     // i2 == NULL: the interpolant is the zero polynomial (no public wire in use)
     uint4 *inv_zb2, *inv_zb3;    // in: inverses, out: b2, b3
-    unsigned long long n;
+    PwView v;
     int *err;
 };
 __global__ void __launch_bounds__(128) pw_b23_kernel(const __grid_constant__ PwB23Params P, const __grid_constant__ PwConsts Cst) {
-    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= P.n) return;
-    fp i2 = P.i2 ? fp_ldg(P.i2, j) : fp_zero();
-    fp df2 = fp_sub(fp_ldg(P.s, j), i2);
-    fp inv2 = fp_ldg(P.inv_zb2, j);
+    PW_DECODE(P.v)
+    fp i2 = P.i2 ? fp_ldg(P.i2, t) : fp_zero();
+    fp df2 = fp_sub(fp_ldg(P.s, t), i2);
+    fp inv2 = fp_ldg(P.inv_zb2, t);
     if (pw_is_zero(inv2) && !pw_is_zero(df2)) atomicExch(P.err, 2);     // utils.rs:489
-    fp_stg(P.inv_zb2, j, fp_canon(fp_mul(df2, inv2)));
-    fp df3 = fp_sub(fp_ldg(P.a, j), pw_const(Cst.one));
-    fp inv3 = fp_ldg(P.inv_zb3, j);
+    fp_stg(P.inv_zb2, t, fp_canon(fp_mul(df2, inv2)));
+    fp df3 = fp_sub(fp_ldg(P.a, t), pw_const(Cst.one));
+    fp inv3 = fp_ldg(P.inv_zb3, t);
     if (pw_is_zero(inv3) && !pw_is_zero(df3)) atomicExch(P.err, 3);     // utils.rs:514
-    fp_stg(P.inv_zb3, j, fp_canon(fp_mul(df3, inv3)));
+    fp_stg(P.inv_zb3, t, fp_canon(fp_mul(df3, inv3)));
 }
 
 // l[j] = k0 d1 + k1 d2 + k2 d3 + k3 p + k4 p X + k5 b2 + k6 b2 X + k7 b3 + k8 b3 X + k9 a + k10 s,  X = (g2^S)^j
@@ -217,23 +227,22 @@ __global__ void __launch_bounds__(128) pw_b23_kernel(const __grid_constant__ PwB
 struct PwLParams {
     const uint4 *d1, *d2, *d3, *p, *b2, *b3, *a, *s;
     uint4 *l;
-    unsigned long long n;
+    PwView v;
 };
 __global__ void __launch_bounds__(128) pw_l_kernel(const __grid_constant__ PwLParams P, const __grid_constant__ PwConsts Cst) {
-    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= P.n) return;
-    fp X = pw_const(Cst.pw8[j & 7]);
-    fp pj = fp_ldg(P.p, j), b2 = fp_ldg(P.b2, j), b3 = fp_ldg(P.b3, j);
-    fp acc = fp_mul(fp_ldg(P.d1, j), pw_const(Cst.k[0]));
-    acc = fp_add(acc, fp_mul(fp_ldg(P.d2, j), pw_const(Cst.k[1])));
-    acc = fp_add(acc, fp_mul(fp_ldg(P.d3, j), pw_const(Cst.k[2])));
+    PW_DECODE(P.v)
+    fp X = pw_const(Cst.pw8[r_]);
+    fp pj = fp_ldg(P.p, t), b2 = fp_ldg(P.b2, t), b3 = fp_ldg(P.b3, t);
+    fp acc = fp_mul(fp_ldg(P.d1, t), pw_const(Cst.k[0]));
+    acc = fp_add(acc, fp_mul(fp_ldg(P.d2, t), pw_const(Cst.k[1])));
+    acc = fp_add(acc, fp_mul(fp_ldg(P.d3, t), pw_const(Cst.k[2])));
     acc = fp_add(acc, fp_mul(pj, pw_const(Cst.k[3])));
     acc = fp_add(acc, fp_mul(fp_mul(pj, pw_const(Cst.k[4])), X));
     acc = fp_add(acc, fp_mul(b2, pw_const(Cst.k[5])));
     acc = fp_add(acc, fp_mul(fp_mul(b2, pw_const(Cst.k[6])), X));
     acc = fp_add(acc, fp_mul(b3, pw_const(Cst.k[7])));
     acc = fp_add(acc, fp_mul(fp_mul(b3, pw_const(Cst.k[8])), X));
-    acc = fp_add(acc, fp_mul(fp_ldg(P.a, j), pw_const(Cst.k[9])));
-    acc = fp_add(acc, fp_mul(fp_ldg(P.s, j), pw_const(Cst.k[10])));
-    fp_stg(P.l, j, fp_canon(acc));
+    acc = fp_add(acc, fp_mul(fp_ldg(P.a, t), pw_const(Cst.k[9])));
+    acc = fp_add(acc, fp_mul(fp_ldg(P.s, t), pw_const(Cst.k[10])));
+    fp_stg(P.l, t, fp_canon(acc));
 }

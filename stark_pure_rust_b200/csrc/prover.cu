@@ -124,7 +124,12 @@ static void host_lagrange(std::vector<hfp::el> &out, const std::vector<hfp::el> 
 
 static void put_const(uint32_t (&dst)[8], const hfp::el &v) { memcpy(dst, v.l, 32); }
 
+// mk_r1cs_proof on the devices of `ctx` (one, or the several of sb_init_multi).  Every N-point column is coset-major and
+// sharded by cosets (sb_ext): pointwise kernels, leaf hashing and the first FRI fold run where the data is, the trees are
+// built as per-device subtrees with the top finished on the host, and only S-point coefficient vectors and 32-byte digests
+// cross NVLink.  The S-point accumulator chain (prefix products) runs on the device that holds the witness column.
 extern "C" int sb_prove_r1cs(sb_ctx *ctx, const sb_trace *t, sb_stark_proof **out) {
+    return guarded(ctx, [&]() -> int {
     if (!ctx || !t || !out) return SB_ERR_ARG;
     const size_t os = t->original_steps;
     if (os == 0 || os % 3 != 0) return fail(ctx, SB_ERR_ARG, "original_steps %zu must be a positive multiple of 3", os);   // :33
@@ -132,115 +137,130 @@ extern "C" int sb_prove_r1cs(sb_ctx *ctx, const sb_trace *t, sb_stark_proof **ou
         return fail(ctx, SB_ERR_ARG, "missing trace array");
     // :37-53 sizes
     const uint32_t log_steps = log2_ceil_quirk(os - 1);
-    size_t S = (size_t)1 << log_steps;
+    const size_t S = (size_t)1 << log_steps;
     if (S < 8) return fail(ctx, SB_ERR_ARG, "traces shorter than 8 steps hit the reference's unpatched log_steps (prove.rs:39-41)");
     const uint32_t log_prec = log_steps + LOG_EXTENSION_FACTOR;
     if (log_prec > 28) return fail(ctx, SB_ERR_ARG, "precision 2^%u exceeds the field's two-adicity (prove.rs:51-53)", log_prec);
     const size_t N = S * EXTENSION_FACTOR, sk = EXTENSION_FACTOR, o3 = os / 3;
     if (N >= ((size_t)1 << 24)) return fail(ctx, SB_ERR_ARG, "precision 2^%u: the sampler asserts modulus < 2^24 (fri/src/utils.rs:88)", log_prec);
     if (os > S) return fail(ctx, SB_ERR_ARG, "internal: steps < original_steps");
+    for (size_t i = 0; i < os; i++)
+        if (t->permuted_indices[i] >= S) return fail(ctx, SB_ERR_ARG, "permuted index out of range");
+    const size_t np = t->n_pfi;
+    if (np + 1 > S) return fail(ctx, SB_ERR_ARG, "more public wires than steps");
+    for (size_t i = 0; i < np; i++)
+        if (t->pfi_w[i] >= S || t->pfi_k[i] >= t->n_public) return fail(ctx, SB_ERR_ARG, "public_first_indices out of range");
 
-    cudaEvent_t ev[8];
-    for (auto &e : ev) cudaEventCreate(&e);
-    auto mark = [&](int i) { cudaEventRecord(ev[i], ctx->stream); };
+    // columns: nine low-degree extensions (prove.rs:100-124, :160-167, :183-184), six quotient / combination columns, I2
+    enum { K_ = 0, F0_, F1_, F2_, S_, P_, IDX_, PIDX_, A_, D1_, D2_, D3_, B2_, B3_, L_, I2_, N_COLS };
+    sb_ext *E = nullptr;
+    TRY(ext_create(ctx, N_COLS, A_ + 1, log_steps, &E));
+    const int g = E->g;
+    const uint32_t cpd = E->cpd;
+    const int dS = E->owner[S_];               // the device with the witness column runs the accumulator chain
+    E->owner[A_] = dS;
     sb_stark_proof *proof = new sb_stark_proof();
     proof->depth = log_prec;
     std::vector<sb_tree *> trees;
-    int rc = SB_OK;
+    struct PerDev {
+        void *perm = nullptr, *err = nullptr, *coef = nullptr, *amini = nullptr, *aleaves = nullptr;
+    } pd[SB_MAX_DEV];
     struct Cleanup {
+        sb_ctx *root;
+        sb_ext *&E;
         std::vector<sb_tree *> &trees;
-        cudaEvent_t *ev;
+        PerDev *pd;
+        sb_stark_proof *&proof;
+        bool ok = false;
         ~Cleanup() {
             for (auto x : trees) free_tree(x);
-            for (int i = 0; i < 8; i++) cudaEventDestroy(ev[i]);
+            for (int d = 0; d < root->n_dev(); d++) {
+                sb_ctx *c = root->dev[d];
+                DevGuard dg(c);
+                for (void *p : {pd[d].perm, pd[d].err, pd[d].coef, pd[d].amini, pd[d].aleaves})
+                    if (p) cudaFreeAsync(p, c->stream);
+            }
+            ext_free(E);
+            if (!ok) delete proof;
         }
-    } cleanup{trees, ev};
-#define PTRY(expr)                 \
-    do {                           \
-        rc = (expr);               \
-        if (rc != SB_OK) {         \
-            delete proof;          \
-            return rc;             \
-        }                          \
-    } while (0)
-#define PCU(call)                                                                                              \
+    } cleanup{ctx, E, trees, pd, proof};
+#define DCU(call)                                                                                              \
     do {                                                                                                       \
         cudaError_t e_ = (call);                                                                               \
-        if (e_ != cudaSuccess) {                                                                               \
-            delete proof;                                                                                      \
-            return fail(ctx, SB_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-        }                                                                                                      \
+        if (e_ != cudaSuccess) return fail(ctx, e_ == cudaErrorMemoryAllocation ? SB_ERR_OOM : SB_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
-
-    // :71-94 roots of unity: g2 = 7^((p-1)/N); the N-entry power table doubles as `xs`
-    hfp::el g2;
-    {
-        uint64_t e[4] = {hfp::PMOD[0] - 1, hfp::PMOD[1], hfp::PMOD[2], hfp::PMOD[3]};   // (p - 1) >> log_prec
-        for (uint32_t i = 0; i < log_prec; i++) {
-            for (int k = 0; k < 3; k++) e[k] = (e[k] >> 1) | (e[k + 1] << 63);
-            e[3] >>= 1;
-        }
-        g2 = hfp::pow_limbs(hfp::from_u64(7), e, 4);
-    }
-    const uint4 *xs;
-    uint32_t tw_log_n, tw_stride;
-    PTRY(get_table(ctx, g2, log_prec, &xs, &tw_log_n, &tw_stride, true));
-    if (tw_stride != 0) {
-        delete proof;
-        return fail(ctx, SB_ERR_ARG, "internal: power table of g2 must have stride 1");
-    }
-    auto host_xs = [&](size_t i, hfp::el *v) -> cudaError_t {   // xs[i] fetched from the device table (a few scalars only)
-        cudaError_t e = cudaMemcpyAsync(v, (const uint8_t *)xs + 32 * i, 32, cudaMemcpyDeviceToHost, ctx->stream);
-        return e == cudaSuccess ? cudaStreamSynchronize(ctx->stream) : e;
+    auto now = []() {
+        struct timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
     };
-
-    // ---- device buffers ------------------------------------------------------------------------------
-    // in8: the eight S-point input columns K F0 F1 F2 S P idx pidx (zero padded, :55-68, :105-113)
-    // ev : nine N-point LDE columns, same order + A;  q : d1 d2 d3 b2 b3 l
-    DevBuf in8(ctx), evb(ctx), qb(ctx), perm_d(ctx), amini(ctx), err_d(ctx);
-    PTRY(in8.alloc(8 * S * 32));
-    PTRY(evb.alloc(9 * N * 32));
-    PTRY(qb.alloc(6 * N * 32));
-    PTRY(perm_d.alloc(S * 8));
-    PTRY(amini.alloc(3 * S * 32));
-    PTRY(err_d.alloc(sizeof(int)));
-    auto in_col = [&](int c) { return (uint4 *)in8.p + 2 * (size_t)c * S; };
-    auto ev_col = [&](int c) { return (uint4 *)evb.p + 2 * (size_t)c * N; };
-    auto q_col = [&](int c) { return (uint4 *)qb.p + 2 * (size_t)c * N; };
-    enum { K_ = 0, F0_, F1_, F2_, S_, P_, IDX_, PIDX_, A_ };
-    enum { D1_ = 0, D2_, D3_, B2_, B3_, L_ };
-
-    mark(0);
-    PCU(cudaMemsetAsync(in8.p, 0, 8 * S * 32, ctx->stream));
-    PCU(cudaMemsetAsync(err_d.p, 0, sizeof(int), ctx->stream));
-    const uint64_t *srcs[6] = {t->coefficients, t->flag0, t->flag1, t->flag2, t->witness_trace, t->computational_trace};
-    for (int c = 0; c < 6; c++) PCU(cudaMemcpyAsync(in_col(c), srcs[c], os * 32, cudaMemcpyHostToDevice, ctx->stream));
-    std::vector<unsigned long long> perm(S);
-    for (size_t i = 0; i < os; i++) {
-        if (t->permuted_indices[i] >= S) {
-            delete proof;
-            return fail(ctx, SB_ERR_ARG, "permuted index out of range");
-        }
-        perm[i] = t->permuted_indices[i];
+    // stage times: host clock at points where every device has been waited for
+    double tm[8];
+    int n_tm = 0;
+    auto mark = [&]() -> int {
+        TRY(sync_all(ctx));
+        tm[n_tm++] = now();
+        return SB_OK;
+    };
+    auto sub_err = [&](sb_ctx *c, int rc) {           // an error recorded on a sub-context is reported on the primary
+        if (c != ctx) fail(ctx, rc, "%s", c->err);
+        return rc;
+    };
+    const hfp::el g2 = E->g2;                  // :71-94: g2 = 7^((p-1)/N); its power table doubles as `xs`
+    const uint4 *xs[SB_MAX_DEV];
+    for (int d = 0; d < g; d++) {
+        sb_ctx *c = ctx->dev[d];
+        DevGuard dg(c);
+        uint32_t tw_log_n, tw_stride;
+        int rc = get_table(c, g2, log_prec, &xs[d], &tw_log_n, &tw_stride, true);
+        if (rc != SB_OK) return sub_err(c, rc);
+        if (tw_stride != 0) return fail(ctx, SB_ERR_ARG, "internal: power table of g2 must have stride 1");
+        DCU(cudaMallocAsync(&pd[d].err, sizeof(int), c->stream));
+        DCU(cudaMemsetAsync(pd[d].err, 0, sizeof(int), c->stream));
     }
-    for (size_t i = os; i < S; i++) perm[i] = i;                                                    // :55-56
-    PCU(cudaMemcpyAsync(perm_d.p, perm.data(), S * 8, cudaMemcpyHostToDevice, ctx->stream));
-    pw_u64_to_fp_kernel<<<nblk(S), 128, 0, ctx->stream>>>(nullptr, in_col(IDX_), S);                 // :160-163
-    pw_u64_to_fp_kernel<<<nblk(S), 128, 0, ctx->stream>>>((const unsigned long long *)perm_d.p, in_col(PIDX_), S);
-    ctx->launches += 2;
+    TRY(mark());
 
-    // :100-124, :160-167 the eight LDEs in one batch
-    PTRY(lde_dev(ctx, in_col(0), 8, S, S, g2, log_steps, LOG_EXTENSION_FACTOR, ev_col(0)));
-    mark(1);
+    // ---- inputs: every column goes to the device that runs its inverse transform (:55-68, :105-113, :160-163) ----------
+    const uint64_t *srcs[6] = {t->coefficients, t->flag0, t->flag1, t->flag2, t->witness_trace, t->computational_trace};
+    for (int c = 0; c < 6; c++) {
+        sb_ctx *o = ctx->dev[E->owner[c]];
+        DevGuard dg(o);
+        DCU(cudaMemcpyAsync(E->input(c), srcs[c], os * 32, cudaMemcpyHostToDevice, o->stream));      // the tail stays zero (ext_create)
+    }
+    std::vector<unsigned long long> perm(S);
+    for (size_t i = 0; i < os; i++) perm[i] = t->permuted_indices[i];
+    for (size_t i = os; i < S; i++) perm[i] = i;                                                    // :55-56
+    for (int d : {E->owner[PIDX_], dS}) {
+        if (pd[d].perm) continue;
+        sb_ctx *c = ctx->dev[d];
+        DevGuard dg(c);
+        DCU(cudaMallocAsync(&pd[d].perm, S * 8, c->stream));
+        DCU(cudaMemcpyAsync(pd[d].perm, perm.data(), S * 8, cudaMemcpyHostToDevice, c->stream));
+    }
+    {
+        sb_ctx *c = ctx->dev[E->owner[IDX_]];
+        DevGuard dg(c);
+        pw_u64_to_fp_kernel<<<nblk(S), 128, 0, c->stream>>>(nullptr, E->input(IDX_), S);
+        c->launches++;
+    }
+    {
+        sb_ctx *c = ctx->dev[E->owner[PIDX_]];
+        DevGuard dg(c);
+        pw_u64_to_fp_kernel<<<nblk(S), 128, 0, c->stream>>>((const unsigned long long *)pd[E->owner[PIDX_]].perm, E->input(PIDX_), S);
+        c->launches++;
+    }
+    // :100-124, :160-167 the eight LDEs
+    TRY(ext_extend(E, 0, 8));
+    TRY(mark());
 
     // ---- constants of the pointwise stage ---------------------------------------------------------------
     PwConsts Cst;
     memset(&Cst, 0, sizeof Cst);
-    hfp::el gs, x_last;
-    PCU(host_xs(S, &gs));                   // g2^S: primitive 8th root of unity (:287-290)
-    PCU(host_xs(N - sk, &x_last));          // utils.rs:459
     {
-        hfp::el pw = hfp::ONE;
+        hfp::el gs, x_last, pw = hfp::ONE;
+        DCU(cudaMemcpyAsync(&gs, (const uint8_t *)xs[0] + 32 * S, 32, cudaMemcpyDeviceToHost, ctx->stream));             // g2^S: primitive 8th root (:287-290)
+        DCU(cudaMemcpyAsync(&x_last, (const uint8_t *)xs[0] + 32 * (N - sk), 32, cudaMemcpyDeviceToHost, ctx->stream)); // utils.rs:459
+        DCU(cudaStreamSynchronize(ctx->stream));
         for (int i = 0; i < 8; i++) {
             put_const(Cst.pw8[i], pw);
             hfp::el z = hfp::add(pw, hfp::neg(hfp::ONE));                   // z[j] = g2^(jS) - 1 (utils.rs:173-178)
@@ -250,39 +270,46 @@ extern "C" int sb_prove_r1cs(sb_ctx *ctx, const sb_trace *t, sb_stark_proof **ou
         put_const(Cst.one, hfp::ONE);
         put_const(Cst.x_last, x_last);
     }
+    auto view = [&](int d) {
+        PwView v;
+        v.log_s = log_steps;
+        v.r0 = (uint32_t)d * cpd;
+        v.n = (unsigned long long)cpd << log_steps;
+        return v;
+    };
+    const unsigned pw_blocks = nblk((size_t)cpd << log_steps);
 
     // :133-151 + :203-214 (d1, d2)
-    {
+    for (int d = 0; d < g; d++) {
+        sb_ctx *c = ctx->dev[d];
+        DevGuard dg(c);
         PwQ12Params P;
-        P.k = ev_col(K_); P.f0 = ev_col(F0_); P.f1 = ev_col(F1_); P.f2 = ev_col(F2_); P.s = ev_col(S_); P.p = ev_col(P_);
-        P.d1 = q_col(D1_); P.d2 = q_col(D2_);
-        P.n = N; P.o3sk = o3 * sk; P.err = (int *)err_d.p;
-        pw_q12_kernel<<<nblk(N), 128, 0, ctx->stream>>>(P, Cst);
-        ctx->launches++;
+        P.k = E->col(d, K_); P.f0 = E->col(d, F0_); P.f1 = E->col(d, F1_); P.f2 = E->col(d, F2_); P.s = E->col(d, S_); P.p = E->col(d, P_);
+        P.d1 = E->col(d, D1_); P.d2 = E->col(d, D2_);
+        P.v = view(d); P.o3 = o3; P.err = (int *)pd[d].err;
+        pw_q12_kernel<<<pw_blocks, 128, 0, c->stream>>>(P, Cst);
+        c->launches++;
     }
 
-    // :171 a_root (utils.rs:250-270): S leaves of 40 bytes
+    // :171 a_root (utils.rs:250-270): S leaves of 40 bytes, on the device that holds the witness column
     sb_tree *a_tree = nullptr;
     {
-        uint8_t *d_leaves = nullptr;
-        PCU(cudaMallocAsync(&d_leaves, S * 40, ctx->stream));
-        pw_a_leaves_kernel<<<nblk(S), 128, 0, ctx->stream>>>((const unsigned long long *)perm_d.p, in_col(S_), (uint32_t *)d_leaves, S);
-        ctx->launches++;
-        rc = commit_bytes_owned(ctx, d_leaves, 40, S, &a_tree);
-        if (rc != SB_OK) {
-            delete proof;
-            return rc;
-        }
+        sb_ctx *c = ctx->dev[dS];
+        DevGuard dg(c);
+        DCU(cudaMallocAsync(&pd[dS].aleaves, S * 40, c->stream));
+        pw_a_leaves_kernel<<<nblk(S), 128, 0, c->stream>>>((const unsigned long long *)pd[dS].perm, E->input(S_), (uint32_t *)pd[dS].aleaves, S);
+        c->launches++;
+        uint8_t *leaves = (uint8_t *)pd[dS].aleaves;
+        pd[dS].aleaves = nullptr;                       // the tree takes ownership
+        int rc = commit_bytes_owned(c, leaves, 40, S, &a_tree);
+        if (rc != SB_OK) return sub_err(c, rc);
         trees.push_back(a_tree);
         memcpy(proof->a_root, a_tree->root, 32);
     }
     // :172 r = get_random_ff_values(a_root, precision, 3, 0) (utils.rs:272-290)
     {
         uint32_t idx[24];
-        if (sb_pseudorandom_indices(proof->a_root, 32, (uint32_t)N, 24, 0, idx) != SB_OK) {
-            delete proof;
-            return fail(ctx, SB_ERR_ARG, "sampler rejected precision %zu", N);
-        }
+        if (sb_pseudorandom_indices(proof->a_root, 32, (uint32_t)N, 24, 0, idx) != SB_OK) return fail(ctx, SB_ERR_ARG, "sampler rejected precision %zu", N);
         for (int i = 0; i < 3; i++) {
             uint8_t b[32];
             for (int j = 0; j < 8; j++) {     // utils.rs:29-38: each u32 big-endian, the 32 bytes then read little-endian
@@ -294,108 +321,113 @@ extern "C" int sb_prove_r1cs(sb_ctx *ctx, const sb_trace *t, sb_stark_proof **ou
     }
     // :175-184 accumulator (utils.rs:293-339) and its LDE
     {
-        uint4 *nmr = (uint4 *)amini.p, *dnm = nmr + 2 * S, *am = dnm + 2 * S;
-        pw_acc_terms_kernel<<<nblk(S), 128, 0, ctx->stream>>>((const unsigned long long *)perm_d.p, in_col(S_), nmr, dnm, S, Cst);
-        ctx->launches++;
-        PTRY(prefix_product(ctx, nmr, nmr, S));
-        PTRY(prefix_product(ctx, dnm, dnm, S));
-        PTRY(sb_batch_inverse_dev(ctx, (uint64_t *)dnm, S));
-        pw_mul_kernel<<<nblk(S), 128, 0, ctx->stream>>>(nmr, dnm, am, S);
-        ctx->launches++;
-        mark(2);
-        PTRY(lde_dev(ctx, am, 1, S, S, g2, log_steps, LOG_EXTENSION_FACTOR, ev_col(A_)));
-        mark(3);
+        sb_ctx *c = ctx->dev[dS];
+        DevGuard dg(c);
+        DCU(cudaMallocAsync(&pd[dS].amini, 2 * S * 32, c->stream));
+        uint4 *nmr = (uint4 *)pd[dS].amini, *dnm = nmr + 2 * S;
+        pw_acc_terms_kernel<<<nblk(S), 128, 0, c->stream>>>((const unsigned long long *)pd[dS].perm, E->input(S_), nmr, dnm, S, Cst);
+        c->launches++;
+        int rc = prefix_product(c, nmr, nmr, S);
+        if (rc == SB_OK) rc = prefix_product(c, dnm, dnm, S);
+        if (rc == SB_OK) rc = sb_batch_inverse_dev(c, (uint64_t *)dnm, S);
+        if (rc != SB_OK) return sub_err(c, rc);
+        pw_mul_kernel<<<nblk(S), 128, 0, c->stream>>>(nmr, dnm, E->input(A_), S);
+        c->launches++;
     }
+    TRY(mark());
+    TRY(ext_extend(E, A_, 1));
+    TRY(mark());
     // :192-214 d3
-    {
+    for (int d = 0; d < g; d++) {
+        sb_ctx *c = ctx->dev[d];
+        DevGuard dg(c);
         PwQ3Params P;
-        P.a = ev_col(A_); P.s = ev_col(S_); P.idx = ev_col(IDX_); P.pidx = ev_col(PIDX_);
-        P.d3 = q_col(D3_); P.n = N; P.err = (int *)err_d.p;
-        pw_q3_kernel<<<nblk(N), 128, 0, ctx->stream>>>(P, Cst);
-        ctx->launches++;
+        P.a = E->col(d, A_); P.s = E->col(d, S_); P.idx = E->col(d, IDX_); P.pidx = E->col(d, PIDX_);
+        P.d3 = E->col(d, D3_); P.v = view(d); P.err = (int *)pd[d].err;
+        pw_q3_kernel<<<pw_blocks, 128, 0, c->stream>>>(P, Cst);
+        c->launches++;
     }
-    // :216-232 boundary quotients.  i2 and zb2 are polynomials of degree < n_pub evaluated on the whole domain:
-    // the reference does that with eval_poly_at / a product per point (O(N n_pub)); an N-point NTT of the same
-    // coefficients gives the same field elements.
+    // :216-232 boundary quotients.  i2 and zb2 are polynomials of degree <= n_pub evaluated on the whole domain: the
+    // reference does that with eval_poly_at / a product per point (O(N n_pub)); coset transforms of the same coefficients
+    // (or Horner per point for a handful of public wires) give the same field elements.
     {
-        const size_t np = t->n_pfi;
-        if (np + 1 > N) {
-            delete proof;
-            return fail(ctx, SB_ERR_ARG, "more public wires than domain points");
-        }
         std::vector<hfp::el> xv(np), yv(np), interp, zroot;
-        for (size_t i = 0; i < np; i++) {       // utils.rs:421-435
-            if (t->pfi_w[i] >= S || t->pfi_k[i] >= t->n_public) {
-                delete proof;
-                return fail(ctx, SB_ERR_ARG, "public_first_indices out of range");
-            }
-            yv[i] = hfp::from_limbs(t->public_wires + 4 * t->pfi_k[i]);
-        }
+        for (size_t i = 0; i < np; i++) yv[i] = hfp::from_limbs(t->public_wires + 4 * t->pfi_k[i]);   // utils.rs:421-435
         if (np) {
             std::vector<unsigned long long> pos(np);
             for (size_t i = 0; i < np; i++) pos[i] = sk * t->pfi_w[i];
             DevBuf dpos(ctx), dx(ctx);
-            PTRY(dpos.alloc(np * 8));
-            PTRY(dx.alloc(np * 32));
-            PCU(cudaMemcpyAsync(dpos.p, pos.data(), np * 8, cudaMemcpyHostToDevice, ctx->stream));
-            ctx->launches += merkle_launch_gather_bytes(ctx->stream, (const uint8_t *)xs, 32, (const unsigned long long *)dpos.p, (uint32_t)np,
-                                                        (uint8_t *)dx.p);
-            PCU(cudaMemcpyAsync(xv.data(), dx.p, np * 32, cudaMemcpyDeviceToHost, ctx->stream));
-            PCU(cudaStreamSynchronize(ctx->stream));
+            TRY(dpos.alloc(np * 8));
+            TRY(dx.alloc(np * 32));
+            DCU(cudaMemcpyAsync(dpos.p, pos.data(), np * 8, cudaMemcpyHostToDevice, ctx->stream));
+            ctx->launches += merkle_launch_gather_bytes(ctx->stream, (const uint8_t *)xs[0], 32, (const unsigned long long *)dpos.p, (uint32_t)np, (uint8_t *)dx.p);
+            DCU(cudaMemcpyAsync(xv.data(), dx.p, np * 32, cudaMemcpyDeviceToHost, ctx->stream));
+            DCU(cudaStreamSynchronize(ctx->stream));
         }
         host_lagrange(interp, xv, yv, &zroot);
-        DevBuf coef(ctx), i2b(ctx);
-        PTRY(coef.alloc((2 * np + 1) * 32));
-        uint4 *zb2 = q_col(B2_), *zb3 = q_col(B3_);          // B2_ and B3_ are adjacent: one 2N batch inverse
-        if (np) PCU(cudaMemcpyAsync(coef.p, interp.data(), np * 32, cudaMemcpyHostToDevice, ctx->stream));
-        PCU(cudaMemcpyAsync((uint8_t *)coef.p + np * 32, zroot.data(), (np + 1) * 32, cudaMemcpyHostToDevice, ctx->stream));
-        const bool horner = np + 1 <= 24;      // ~np products per point against the ~log2(N)/2 + 2 of a transform
-        if (np) {
-            PTRY(i2b.alloc(N * 32));
+        const bool horner = np + 1 <= 24;      // ~np products per point against the ~log2(S)/2 + 2 of a transform
+        for (int d = 0; d < g; d++) {
+            sb_ctx *c = ctx->dev[d];
+            DevGuard dg(c);
+            DCU(cudaMallocAsync(&pd[d].coef, (2 * np + 1) * 32, c->stream));
+            uint4 *ci = (uint4 *)pd[d].coef, *cz = ci + 2 * np;
+            if (np) DCU(cudaMemcpyAsync(ci, interp.data(), np * 32, cudaMemcpyHostToDevice, c->stream));
+            DCU(cudaMemcpyAsync(cz, zroot.data(), (np + 1) * 32, cudaMemcpyHostToDevice, c->stream));
+            uint4 *zb2 = E->col(d, B2_), *zb3 = E->col(d, B3_);          // adjacent columns: one batch inverse over both
             if (horner) {
-                pw_poly_eval_kernel<<<nblk(N), 128, 0, ctx->stream>>>(xs, (const uint4 *)coef.p, (uint32_t)np, (uint4 *)i2b.p, N);
-                ctx->launches++;
+                if (np) {
+                    pw_poly_eval_kernel<<<pw_blocks, 128, 0, c->stream>>>(xs[d], ci, (uint32_t)np, E->col(d, I2_), view(d));
+                    c->launches++;
+                }
+                pw_poly_eval_kernel<<<pw_blocks, 128, 0, c->stream>>>(xs[d], cz, (uint32_t)np + 1, zb2, view(d));
+                c->launches++;
             } else {
-                PTRY(ntt_dev(ctx, (const uint4 *)coef.p, np, np, (uint4 *)i2b.p, N, 1, g2, log_prec, 0));
+                CosetSpec cs;
+                cs.log_ext = LOG_EXTENSION_FACTOR;
+                cs.store = NTT_STORE_PLAIN;
+                cs.r0 = (uint32_t)d * cpd;
+                cs.cnt = cpd;
+                int rc = ntt_dev_tw(c, ci, np, np, E->col(d, I2_), S, 1, log_steps, 0, xs[d], log_prec, LOG_EXTENSION_FACTOR, &cs);
+                if (rc == SB_OK) rc = ntt_dev_tw(c, cz, np + 1, np + 1, zb2, S, 1, log_steps, 0, xs[d], log_prec, LOG_EXTENSION_FACTOR, &cs);
+                if (rc != SB_OK) return sub_err(c, rc);
             }
+            pw_zb3_kernel<<<pw_blocks, 128, 0, c->stream>>>(xs[d], zb3, view(d), Cst);
+            c->launches++;
+            int rc = sb_batch_inverse_dev(c, (uint64_t *)zb2, 2 * ((size_t)cpd << log_steps));
+            if (rc != SB_OK) return sub_err(c, rc);
+            PwB23Params P;
+            P.s = E->col(d, S_); P.a = E->col(d, A_); P.i2 = np ? E->col(d, I2_) : nullptr;
+            P.inv_zb2 = zb2; P.inv_zb3 = zb3; P.v = view(d); P.err = (int *)pd[d].err;
+            pw_b23_kernel<<<pw_blocks, 128, 0, c->stream>>>(P, Cst);
+            c->launches++;
         }
-        if (horner) {
-            pw_poly_eval_kernel<<<nblk(N), 128, 0, ctx->stream>>>(xs, (const uint4 *)coef.p + 2 * np, (uint32_t)np + 1, zb2, N);
-            ctx->launches++;
-        } else {
-            PTRY(ntt_dev(ctx, (const uint4 *)coef.p + 2 * np, np + 1, np + 1, zb2, N, 1, g2, log_prec, 0));
-        }
-        pw_zb3_kernel<<<nblk(N), 128, 0, ctx->stream>>>(xs, zb3, N, Cst);
-        ctx->launches++;
-        PTRY(sb_batch_inverse_dev(ctx, (uint64_t *)zb2, 2 * N));
-        PwB23Params P;
-        P.s = ev_col(S_); P.a = ev_col(A_); P.i2 = np ? (const uint4 *)i2b.p : nullptr;
-        P.inv_zb2 = zb2; P.inv_zb3 = zb3; P.n = N; P.err = (int *)err_d.p;
-        pw_b23_kernel<<<nblk(N), 128, 0, ctx->stream>>>(P, Cst);
-        ctx->launches++;
     }
     // the reference's asserts (utils.rs:379-418, :489, :514) -> error code
     {
-        int err = 0;
-        PCU(cudaMemcpyAsync(&err, err_d.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        PCU(cudaStreamSynchronize(ctx->stream));
-        PCU(cudaGetLastError());
-        if (err) {
-            delete proof;
-            return fail(ctx, SB_ERR_ARG, err == 1 ? "invalid D1/D2/D3: the witness does not satisfy the constraints (utils.rs:379-418)"
-                                                  : (err == 2 ? "invalid B2: public wires do not match the trace (utils.rs:489)" : "invalid B3 (utils.rs:514)"));
+        int err[SB_MAX_DEV] = {0};
+        for (int d = 0; d < g; d++) {
+            sb_ctx *c = ctx->dev[d];
+            DevGuard dg(c);
+            DCU(cudaMemcpyAsync(&err[d], pd[d].err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            DCU(cudaGetLastError());
         }
+        TRY(mark());
+        int bad = 0;
+        for (int d = 0; d < g; d++)
+            if (err[d] && (!bad || err[d] < bad)) bad = err[d];
+        if (bad)
+            return fail(ctx, SB_ERR_ARG, bad == 1 ? "invalid D1/D2/D3: the witness does not satisfy the constraints (utils.rs:379-418)"
+                                                  : (bad == 2 ? "invalid B2: public wires do not match the trace (utils.rs:489)" : "invalid B3 (utils.rs:514)"));
     }
-    mark(4);
     // :235-264 m_tree over p a s d1 d2 d3 b2 b3
     sb_tree *m_tree = nullptr;
     {
-        const uint4 *cols[8] = {ev_col(P_), ev_col(A_), ev_col(S_), q_col(D1_), q_col(D2_), q_col(D3_), q_col(B2_), q_col(B3_)};
-        PTRY(commit_cols(ctx, cols, 8, N, &m_tree));
+        const size_t ids[8] = {P_, A_, S_, D1_, D2_, D3_, B2_, B3_};
+        TRY(ext_commit(E, ids, 8, &m_tree));
         trees.push_back(m_tree);
         memcpy(proof->m_root, m_tree->root, 32);
     }
-    mark(5);
+    TRY(mark());
     // :274-283 k[i] = int_BE(blake(m_root || i)) mod p
     put_const(Cst.k[0], hfp::ONE);
     for (int i = 1; i < 11; i++) {
@@ -407,28 +439,28 @@ extern "C" int sb_prove_r1cs(sb_ctx *ctx, const sb_trace *t, sb_stark_proof **ou
         put_const(Cst.k[i], hfp::from_bytes_le32(le));
     }
     // :287-322 l
-    {
+    for (int d = 0; d < g; d++) {
+        sb_ctx *c = ctx->dev[d];
+        DevGuard dg(c);
         PwLParams P;
-        P.d1 = q_col(D1_); P.d2 = q_col(D2_); P.d3 = q_col(D3_); P.p = ev_col(P_); P.b2 = q_col(B2_); P.b3 = q_col(B3_);
-        P.a = ev_col(A_); P.s = ev_col(S_); P.l = q_col(L_); P.n = N;
-        pw_l_kernel<<<nblk(N), 128, 0, ctx->stream>>>(P, Cst);
-        ctx->launches++;
+        P.d1 = E->col(d, D1_); P.d2 = E->col(d, D2_); P.d3 = E->col(d, D3_); P.p = E->col(d, P_); P.b2 = E->col(d, B2_); P.b3 = E->col(d, B3_);
+        P.a = E->col(d, A_); P.s = E->col(d, S_); P.l = E->col(d, L_); P.v = view(d);
+        pw_l_kernel<<<pw_blocks, 128, 0, c->stream>>>(P, Cst);
+        c->launches++;
     }
     // :324-332 l_tree
     sb_tree *l_tree = nullptr;
     {
-        const uint4 *cols[1] = {q_col(L_)};
-        PTRY(commit_cols(ctx, cols, 1, N, &l_tree));
+        const size_t ids[1] = {L_};
+        TRY(ext_commit(E, ids, 1, &l_tree));
         trees.push_back(l_tree);
         memcpy(proof->l_root, l_tree->root, 32);
     }
     // :337-362 spot-check positions and openings
     {
         uint32_t pos32[SPOT_CHECK_SECURITY_FACTOR];
-        if (sb_pseudorandom_indices(proof->l_root, 32, (uint32_t)N, SPOT_CHECK_SECURITY_FACTOR, (uint32_t)sk, pos32) != SB_OK) {
-            delete proof;
+        if (sb_pseudorandom_indices(proof->l_root, 32, (uint32_t)N, SPOT_CHECK_SECURITY_FACTOR, (uint32_t)sk, pos32) != SB_OK)
             return fail(ctx, SB_ERR_ARG, "sampler rejected precision %zu", N);
-        }
         std::vector<size_t> positions(SPOT_CHECK_SECURITY_FACTOR), aug(4 * SPOT_CHECK_SECURITY_FACTOR);
         for (size_t i = 0; i < SPOT_CHECK_SECURITY_FACTOR; i++) {
             const size_t j = positions[i] = pos32[i];
@@ -439,27 +471,27 @@ extern "C" int sb_prove_r1cs(sb_ctx *ctx, const sb_trace *t, sb_stark_proof **ou
         }
         proof->lc_leaves.resize(positions.size() * 32);
         proof->lc_nodes.resize(positions.size() * log_prec * 32);
-        PTRY(sb_merkle_open(ctx, l_tree, positions.data(), positions.size(), proof->lc_leaves.data(), proof->lc_nodes.data()));
+        TRY(sb_merkle_open(ctx, l_tree, positions.data(), positions.size(), proof->lc_leaves.data(), proof->lc_nodes.data()));
         proof->main_leaves.resize(aug.size() * 256);
         proof->main_nodes.resize(aug.size() * log_prec * 32);
-        PTRY(sb_merkle_open(ctx, m_tree, aug.data(), aug.size(), proof->main_leaves.data(), proof->main_nodes.data()));
+        TRY(sb_merkle_open(ctx, m_tree, aug.data(), aug.size(), proof->main_leaves.data(), proof->main_nodes.data()));
     }
-    mark(6);
+    TRY(mark());
     // :367 FRI on l with the committed l_tree
-    PTRY(fri_prove_dev(ctx, q_col(L_), N, g2, N / 4, (uint32_t)sk, l_tree, &proof->fri));
-    mark(7);
-    PCU(cudaStreamSynchronize(ctx->stream));
-    float ms;
-    auto span = [&](int a, int b) { return cudaEventElapsedTime(&ms, ev[a], ev[b]) == cudaSuccess ? (double)ms : 0.0; };
-    proof->stage_ms[0] = span(0, 1) + span(2, 3);
-    proof->stage_ms[1] = span(4, 5);
-    proof->stage_ms[2] = span(6, 7);
-    proof->stage_ms[4] = span(0, 7);
+    TRY(ext_fri_prove(E, L_, l_tree, N / 4, (uint32_t)sk, &proof->fri));
+    TRY(mark());
+    // marks: 0 start, 1 inputs + eight LDEs, 2 a_tree + accumulator, 3 LDE of A, 4 pointwise stage checked, 5 m_tree, 6 l + l_tree +
+    // openings, 7 FRI (host clock; every device has been waited for at each mark)
+    proof->stage_ms[0] = (tm[1] - tm[0]) + (tm[3] - tm[2]);
+    proof->stage_ms[1] = tm[5] - tm[4];
+    proof->stage_ms[2] = tm[7] - tm[6];
+    proof->stage_ms[4] = tm[7] - tm[0];
     proof->stage_ms[3] = proof->stage_ms[4] - proof->stage_ms[0] - proof->stage_ms[1] - proof->stage_ms[2];
+    cleanup.ok = true;
     *out = proof;
     return SB_OK;
-#undef PTRY
-#undef PCU
+#undef DCU
+    });
 }
 
 extern "C" int sb_stark_proof_roots(const sb_stark_proof *p, uint8_t m_root[32], uint8_t l_root[32], uint8_t a_root[32]) {
@@ -637,6 +669,7 @@ int fri_verify_host(sb_ctx *ctx, const sb_fri_proof *pr, const uint8_t values_ro
 }  // namespace
 
 extern "C" int sb_verify_r1cs(sb_ctx *ctx, const sb_trace *t, const sb_stark_proof *proof) {
+    return guarded(ctx, [&]() -> int {
     if (!ctx || !t || !proof) return SB_ERR_ARG;
     const size_t os = t->original_steps;
     if (os == 0 || os % 3 != 0) return fail(ctx, SB_ERR_ARG, "original_steps %zu must be a positive multiple of 3", os);   // verify.rs:27
@@ -814,6 +847,7 @@ extern "C" int sb_verify_r1cs(sb_ctx *ctx, const sb_trace *t, const sb_stark_pro
     return SB_OK;
 #undef VTRY
 #undef VCU
+    });
 }
 
 // ---- serde_json reader for StarkProof (run.rs:578 serde_json::from_reader; the layout sb_stark_proof_json writes) ------
@@ -942,6 +976,7 @@ static void parse_fri_layers(JsonIn &j, sb_fri_proof *fri) {
 }
 
 extern "C" int sb_stark_proof_from_json(const char *text, size_t len, sb_stark_proof **out) {
+    return guarded((sb_ctx *)nullptr, [&]() -> int {
     if (!text || !out) return SB_ERR_ARG;
     JsonIn j{text, text + len};
     sb_stark_proof *p = new sb_stark_proof();
@@ -976,12 +1011,14 @@ extern "C" int sb_stark_proof_from_json(const char *text, size_t len, sb_stark_p
     }
     *out = p;
     return SB_OK;
+    });
 }
 
 // verify_low_degree_proof (fri.rs:226-404) on the serde text of Vec<FriProof>: host only, needs no device.  ctx may be NULL
 // (then the sampler keeps the reference's 2^24 limit and no error text is recorded).
 extern "C" int sb_fri_verify_json(sb_ctx *ctx, const char *text, size_t len, const uint8_t merkle_root[32], const uint64_t root_of_unity[4],
                                   size_t n, size_t max_deg_plus_1, uint32_t exclude_multiples_of) {
+    return guarded(ctx, [&]() -> int {
     if (!text || !merkle_root || !root_of_unity) return SB_ERR_ARG;
     JsonIn j{text, text + len};
     sb_fri_proof fri;
@@ -990,4 +1027,5 @@ extern "C" int sb_fri_verify_json(sb_ctx *ctx, const char *text, size_t len, con
     if (!j.ok || j.p != j.end) return SB_ERR_ARG;
     sb_ctx scratch;               // only err / extended_domain are touched by the host verifier
     return fri_verify_host(ctx ? ctx : &scratch, &fri, merkle_root, hfp::from_limbs(root_of_unity), n, max_deg_plus_1, exclude_multiples_of);
+    });
 }

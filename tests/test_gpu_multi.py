@@ -1,0 +1,197 @@
+"""ONE job over several devices behind the C ABI (sb_init_multi, sb_ext_*, sb_prove_r1cs): every result must
+equal the single-GPU / oracle result bit for bit.
+
+The sharded code path is selected by the number of devices in the context, not by the number of physical GPUs: a context may
+list the same ordinal several times (logical devices on one GPU), so the whole partitioning / peer-store / subtree / top-of-
+tree / opening logic for g = 2, 4, 8 is exercised on a single-GPU box; the *_real_gpus tests repeat it on distinct GPUs when
+the box has them."""
+import ctypes as C
+import hashlib
+import json
+import os
+import threading
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, random_elems
+
+pytestmark = pytest.mark.gpu
+
+
+def n_gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.fixture(scope="module", params=[1, 2, 4, 8])
+def mctx(request):
+    import stark_pure_rust_b200 as sb
+    c = sb.Context(devices=[0] * request.param)
+    yield c
+    c.close()
+
+
+def _ext_chain(ctx, oracle, log_s, n_cols, col_len, seed):
+    import stark_pure_rust_b200 as sb
+    from stark_pure_rust_b200 import field
+    S, N = 1 << log_s, 8 << log_s
+    g2, g1 = oracle.root_of_unity(log_s + 3), oracle.root_of_unity(log_s)
+    cols = random_elems(n_cols * col_len, seed).reshape(n_cols, col_len, 4)
+    e = sb.ext.ExtColumns(n_cols, log_s, ctx=ctx)
+    e.load(0, cols)
+    e.extend()
+    want = []
+    for c in range(n_cols):
+        padded = np.zeros((S, 4), dtype=np.uint64)
+        padded[:col_len] = cols[c]
+        want.append(oracle.best_fft(oracle.best_fft(padded, g1, log_s, inverse=True), g2, log_s + 3))
+        assert np.array_equal(e.read(c), want[c]), "LDE column %d" % c
+    # prove.rs:235-264: tree over the rows of up to eight columns
+    k = min(8, n_cols)
+    ids = list(range(k))
+    rows = np.concatenate([oracle.fp_to_bytes_le(want[c]).reshape(N, 1, 32) for c in ids], axis=1).tobytes()
+    idx = [0, N - 1, 5, 5, N // 2 + 3, N // 8 - 1, N // 8, 7 * N // 8 + 1] + [int(x) for x in np.random.default_rng(seed).integers(0, N, 24)]
+    root_want, nodes_want = oracle.merkle_gen_proofs(rows, 32 * k, N, idx)
+    root, tree = e.commit(ids)
+    assert root == root_want
+    proofs = e.open(tree, idx)
+    for q, i in enumerate(idx):
+        assert proofs[q].leaf == rows[i * 32 * k:(i + 1) * 32 * k], "leaf %d" % i
+        assert b"".join(proofs[q].nodes) == nodes_want[q].tobytes(), "path %d" % i
+    e.free_tree(tree)
+    # prove.rs:324-332 + :367: one-column tree and the low-degree proof on it, with and without the committed tree
+    last = n_cols - 1
+    root1, tree1 = e.commit([last])
+    r1_want, _ = oracle.merkle_gen_proofs(oracle.fp_to_bytes_le(want[last]).tobytes(), 32, N, [])
+    assert root1 == r1_want
+    text_want, ok = oracle.prove_low_degree_json(want[last], g2, N // 4, 8)
+    assert ok
+    assert e.fri_prove(last, N // 4, 8, tree=tree1, as_json=True) == text_want
+    assert e.fri_prove(last, N // 4, 8, tree=None, as_json=True) == text_want
+    e.free_tree(tree1)
+    e.close()
+
+
+@pytest.mark.parametrize("log_s,n_cols,col_len", [(10, 3, 1024), (11, 9, 2000), (13, 8, 6684), (5, 2, 32), (3, 1, 8)])
+def test_ext_chain_matches_oracle(mctx, oracle, log_s, n_cols, col_len):
+    _ext_chain(mctx, oracle, log_s, n_cols, col_len, 9000 + log_s + n_cols)
+
+
+def test_ext_direct_fri_and_errors(mctx, oracle):
+    """max_deg_plus_1 <= 16: the proof is the values themselves (fri.rs:88-112), gathered in natural order"""
+    import stark_pure_rust_b200 as sb
+    log_s = 10
+    N = 8 << log_s
+    g2 = oracle.root_of_unity(log_s + 3)
+    col = np.zeros((1, 16, 4), dtype=np.uint64)
+    col[0] = random_elems(16, 31)
+    e = sb.ext.ExtColumns(1, log_s, ctx=mctx)
+    e.load(0, col)
+    e.extend()
+    vals = e.read(0)
+    text_want, ok = oracle.prove_low_degree_json(vals, g2, 16, 8)
+    assert e.fri_prove(0, 16, 8, as_json=True) == text_want
+    with pytest.raises(sb.StarkB200Error):
+        e.commit([3])
+    with pytest.raises(sb.StarkB200Error):
+        e.load(0, np.zeros((2, 8, 4), dtype=np.uint64))
+    e.close()
+
+
+@pytest.mark.parametrize("name", ["compute", "poseidon3_test", "pedersen_test"])
+def test_prove_sharded_matches_golden(mctx, name, tmp_path):
+    """mk_r1cs_proof over g (logical) devices: proof.json byte-identical to the oracle's (golden hashes)"""
+    import stark_pure_rust_b200 as sb
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "vectors.json")))["proofs"][name]
+    d = os.path.join(ROOT, "tests", "golden", "circuits")
+    out = str(tmp_path / "proof.json")
+    sb.prove.prove_with_file_path(os.path.join(d, name + ".r1cs"), os.path.join(d, name + ".wtns"), out, ctx=mctx)
+    assert hashlib.sha256(open(out, "rb").read()).hexdigest() == gold["proof_json_sha256"]
+    sb.prove.verify_with_file_path(os.path.join(d, name + ".r1cs"), os.path.join(d, name + ".wtns"), out, ctx=mctx)
+
+
+def test_prove_sharded_many_public_wires(mctx, oracle, tmp_path):
+    """the coset-transform path of the boundary polynomials (more than 23 public wires) on every device count"""
+    import sys
+    import stark_pure_rust_b200 as sb
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_r1cs
+    prefix = str(tmp_path / "syn")
+    wit, cons = gen_r1cs.generate(1500, 3.0, 60, 5)
+    gen_r1cs.write_files(prefix, wit, cons, 60)
+    out, want = str(tmp_path / "proof.json"), str(tmp_path / "oracle.json")
+    rc, _ = oracle.prove_files(prefix + ".r1cs", prefix + ".wtns", want, verify=False)
+    assert rc == 0
+    sb.prove.prove_with_file_path(prefix + ".r1cs", prefix + ".wtns", out, ctx=mctx)
+    assert open(out, "rb").read() == open(want, "rb").read()
+
+
+def test_prove_sharded_rejects_bad_witness(mctx, tmp_path):
+    import stark_pure_rust_b200 as sb
+    d = os.path.join(ROOT, "tests", "golden", "circuits")
+    w = bytearray(open(os.path.join(d, "poseidon3_test.wtns"), "rb").read())
+    w[-40] ^= 1
+    bad = str(tmp_path / "bad.wtns")
+    open(bad, "wb").write(bytes(w))
+    with pytest.raises(sb.StarkB200Error):
+        sb.prove.prove_with_file_path(os.path.join(d, "poseidon3_test.r1cs"), bad, None, ctx=mctx)
+
+
+# ---- distinct GPUs (run with gpurun --gpus N) ---------------------------------------------------------------------------
+@pytest.mark.parametrize("g", [2, 4, 8])
+def test_ext_chain_real_gpus(oracle, g):
+    if n_gpus() < g:
+        pytest.skip("needs %d GPUs" % g)
+    import stark_pure_rust_b200 as sb
+    ctx = sb.Context(devices=list(range(g)))
+    try:
+        _ext_chain(ctx, oracle, 13, 9, 6684, 77)
+        _ext_chain(ctx, oracle, 10, 8, 1024, 78)
+    finally:
+        ctx.close()
+
+
+@pytest.mark.parametrize("g", [2, 4, 8])
+def test_prove_real_gpus(g, tmp_path):
+    if n_gpus() < g:
+        pytest.skip("needs %d GPUs" % g)
+    import stark_pure_rust_b200 as sb
+    ctx = sb.Context(devices=list(range(g)))
+    try:
+        gold = json.load(open(os.path.join(ROOT, "tests", "golden", "vectors.json")))["proofs"]
+        d = os.path.join(ROOT, "tests", "golden", "circuits")
+        out = str(tmp_path / "proof.json")
+        for name in ("poseidon3_test", "pedersen_test", "bits"):
+            sb.prove.prove_with_file_path(os.path.join(d, name + ".r1cs"), os.path.join(d, name + ".wtns"), out, ctx=ctx)
+            assert hashlib.sha256(open(out, "rb").read()).hexdigest() == gold[name]["proof_json_sha256"], name
+    finally:
+        ctx.close()
+
+
+def test_context_used_from_another_thread():
+    """the current CUDA device is per host thread; every entry point must select the context's device itself.
+    A context on the last GPU is created here and used from a fresh thread (whose current device is 0)."""
+    import stark_pure_rust_b200 as sb
+    from stark_pure_rust_b200 import field
+    dev = n_gpus() - 1
+    ctx = sb.Context(dev)
+    v = random_elems(1 << 12, 5)
+    w = field.root_of_unity(12)
+    res = {}
+
+    def work():
+        try:
+            import torch
+            if dev:
+                torch.cuda.set_device(0)
+            y = sb.fft.best_fft(v, w, 12, ctx=ctx)
+            res["ok"] = np.array_equal(sb.fft.inv_best_fft(y, w, 12, ctx=ctx), v)
+        except Exception as ex:      # noqa: BLE001
+            res["err"] = repr(ex)
+
+    th = threading.Thread(target=work)
+    th.start()
+    th.join()
+    ctx.close()
+    assert res.get("ok"), res

@@ -485,6 +485,80 @@ def test_full_size_2_24_properties(ctx):
     assert _fri_verify_python(proof, rootv.tobytes(), g2i, N, N // 4, 8)
 
 
+def test_full_size_2_24_golden(ctx):
+    """Byte-level parity at the headline size (BASELINE.json configs[1], N = 2^24): sha256 of best_fft / inv_best_fft at 2^22
+    and 2^24, of every column of the 8-column LDE 2^21 -> 2^24, the 8-column Merkle root + openings, the 1-column root and
+    the serde JSON of prove_low_degree, against digests the CPU oracle produced once (tests/golden/make_golden_large.py)."""
+    import json
+    import os
+    import stark_pure_rust_b200 as sb
+    from stark_pure_rust_b200 import field
+    from stark_pure_rust_b200._lib import _ptr
+    from conftest import ROOT
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "vectors_large.json")))
+    sha = lambda b: hashlib.sha256(bytes(b)).hexdigest()
+    for e in gold["ntt"]:
+        k = e["log_n"]
+        v = random_elems(1 << k, e["seed"])
+        w = field.root_of_unity(k)
+        assert sha(sb.fft.best_fft(v, w, k, ctx=ctx).tobytes()) == e["fwd_sha256"], "best_fft 2^%d" % k
+        assert sha(sb.fft.inv_best_fft(v, w, k, ctx=ctx).tobytes()) == e["inv_sha256"], "inv_best_fft 2^%d" % k
+    log_s, L, nc = gold["log_s"], gold["log_n"], gold["n_cols"]
+    S, N = 1 << log_s, 1 << L
+    g2 = field.mont_scalar(field.root_of_unity(L))
+    cols = random_elems(nc * S, gold["lde"]["seed"]).reshape(nc, S, 4)
+    d_cols = ctx.to_device(cols)
+    d_ext = ctx.alloc(nc * N * 32)
+    ctx.check(ctx.lib.sb_lde_batch_dev(ctx.h, C.c_void_p(d_cols), nc, S, S, _ptr(g2), log_s, L - log_s, C.c_void_p(d_ext)))
+    one = np.empty((N, 4), dtype=np.uint64)
+    for c in range(nc):
+        ctx.d2h(one, d_ext + c * N * 32)
+        assert sha(one.tobytes()) == gold["lde"]["col_sha256"][c], "LDE column %d" % c
+    ptrs = (C.c_void_p * nc)(*[d_ext + c * N * 32 for c in range(nc)])
+    root, tree = np.empty(32, dtype=np.uint8), C.c_void_p()
+    ctx.check(ctx.lib.sb_merkle_commit_cols_dev(ctx.h, ptrs, nc, N, _ptr(root), C.byref(tree)))
+    assert root.tobytes().hex() == gold["merkle8"]["root"]
+    idx = np.array(gold["merkle8"]["open"], dtype=np.uint64)
+    lv, nd = np.empty(idx.size * 32 * nc, dtype=np.uint8), np.empty(idx.size * L * 32, dtype=np.uint8)
+    ctx.check(ctx.lib.sb_merkle_open(ctx.h, tree, idx.ctypes.data_as(C.POINTER(C.c_size_t)), idx.size, _ptr(lv), _ptr(nd)))
+    assert sha(nd.tobytes()) == gold["merkle8"]["nodes_sha256"] and sha(lv.tobytes()) == gold["merkle8"]["leaves_sha256"]
+    ctx.lib.sb_tree_free(ctx.h, tree)
+    p1 = (C.c_void_p * 1)(d_ext + (nc - 1) * N * 32)
+    ctx.check(ctx.lib.sb_merkle_commit_cols_dev(ctx.h, p1, 1, N, _ptr(root), C.byref(tree)))
+    assert root.tobytes().hex() == gold["merkle1"]["root"]
+    pr = C.c_void_p()
+    ctx.check(ctx.lib.sb_fri_prove_dev(ctx.h, C.c_void_p(p1[0]), N, _ptr(g2), N // 4, 8, tree, C.byref(pr)))
+    txt = ctx.lib.sb_fri_proof_json(pr)
+    text = C.string_at(txt)
+    ctx.lib.sb_free_string(txt)
+    ctx.lib.sb_fri_proof_free(pr)
+    ctx.lib.sb_tree_free(ctx.h, tree)
+    ctx.free(d_cols)
+    ctx.free(d_ext)
+    assert len(text) == gold["fri"]["json_len"] and sha(text) == gold["fri"]["json_sha256"]
+
+
+@pytest.mark.parametrize("name", ["compute", "poseidon3_test"])
+def test_product_verifier_on_oracle_proof_files(ctx, oracle, name, tmp_path):
+    """the product verifier (sb_verify_files: verify.rs:13-258) is fed whole proof.json files written by the ORACLE's prover,
+    and rejects them after a one-byte change"""
+    import os
+    import stark_pure_rust_b200 as sb
+    from conftest import ROOT
+    d = os.path.join(ROOT, "tests", "golden", "circuits")
+    r1cs, wtns, out = os.path.join(d, name + ".r1cs"), os.path.join(d, name + ".wtns"), str(tmp_path / "oracle_proof.json")
+    rc, _ = oracle.prove_files(r1cs, wtns, out, verify=False)
+    assert rc == 0
+    sb.prove.verify_with_file_path(r1cs, wtns, out, ctx=ctx)
+    text = open(out).read()
+    k = text.index('"l_root":[') + len('"l_root":[')
+    digit = text[k]
+    bad = text[:k] + ("1" if digit != "1" else "2") + text[k + 1:]
+    open(out, "w").write(bad)
+    with pytest.raises(sb.StarkB200Error):
+        sb.prove.verify_with_file_path(r1cs, wtns, out, ctx=ctx)
+
+
 def test_synthetic_sha256_scale_prove_matches_golden(ctx, tmp_path):
     """BASELINE.json configs[3] stand-in (tools/gen_r1cs.py 30000 constraints, avg 8 terms, seed 1: 955086 steps, precision
     2^23): proof.json hash equals the CPU oracle's, recorded in tests/golden/vectors.json (the oracle needs ~70 s on 16
