@@ -139,6 +139,18 @@ def run_cpu(args, as_reference_arm):
     ob.lib()
     cores = os.cpu_count() or 1
     log_n = args.cpu_log_n
+    if log_n <= 0:
+        # largest domain whose (warmup + steps) repetitions fit the time budget, extrapolated from one step at 2^18
+        # (cost per element grows ~ log n: factor 4.3 per two bits)
+        probe = random_elems(args.cols << 15, 0xC0FFEE).reshape(args.cols, 1 << 15, 4)
+        t0 = time.perf_counter()
+        cpu_step(ob, probe, 18, cores)
+        t18 = time.perf_counter() - t0
+        reps = (args.steps + min(args.warmup, 1)) if as_reference_arm else 1
+        budget = args.cpu_budget_s if as_reference_arm else 30.0
+        log_n = 18
+        while log_n < min(args.log_n, 24) and t18 * (2.15 ** (log_n + 1 - 18)) * reps <= budget:
+            log_n += 1
     cols = random_elems(args.cols << (log_n - 3), 0xC0FFEE).reshape(args.cols, 1 << (log_n - 3), 4)
     times = []
     steps = args.steps if as_reference_arm else 1
@@ -153,7 +165,7 @@ def run_cpu(args, as_reference_arm):
     value = args.cols * (1 << log_n) / dt
     sample = "same step at L=%d (C=%d columns): %.2f s per step on %d host threads (NTT threaded like parallel_fft, Merkle/FRI single-threaded like the reference)" % (
         log_n, args.cols, dt, cores)
-    return value, dt, {"value": value, "unit": "elems/s", "cores": cores, "kind": "port", "sample": sample}
+    return value, dt, {"value": value, "unit": "elems/s", "cores": cores, "kind": "port", "sample": sample, "log_n": log_n}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -165,6 +177,40 @@ def pinned_array(ctx, shape, dtype):
     ctx.check(ctx.lib.sb_host_alloc_pinned(ctx.h, max(n, 16), C.byref(p)))
     buf = (C.c_uint8 * max(n, 16)).from_address(p.value)
     return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape), p
+
+
+def gpu_step_ms(ctx, L, Cn, reps=5):
+    """device-resident step (LDE + two trees + FRI) at domain 2^L, CUDA-event timed"""
+    from stark_pure_rust_b200 import field
+    from stark_pure_rust_b200._lib import _ptr
+    lib = ctx.lib
+    log_s, N, S = L - 3, 1 << L, 1 << (L - 3)
+    g2 = field.mont_scalar(field.root_of_unity(L))
+    d_cols = ctx.to_device(random_elems(Cn * S, 0xB200).reshape(Cn, S, 4))
+    d_out = ctx.alloc(Cn * N * 32)
+    k_tree = min(8, Cn)
+    p8 = (C.c_void_p * k_tree)(*[d_out + i * N * 32 for i in range(k_tree)])
+    p1 = (C.c_void_p * 1)(d_out + (Cn - 1) * N * 32)
+    root = np.empty(32, dtype=np.uint8)
+
+    def step():
+        ctx.check(lib.sb_lde_batch_dev(ctx.h, C.c_void_p(d_cols), Cn, S, S, _ptr(g2), log_s, 3, C.c_void_p(d_out)))
+        tm, tl, pr = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        ctx.check(lib.sb_merkle_commit_cols_dev(ctx.h, p8, k_tree, N, _ptr(root), C.byref(tm)))
+        ctx.check(lib.sb_merkle_commit_cols_dev(ctx.h, p1, 1, N, _ptr(root), C.byref(tl)))
+        ctx.check(lib.sb_fri_prove_dev(ctx.h, C.c_void_p(p1[0]), N, _ptr(g2), N // 4, 8, tl, C.byref(pr)))
+        lib.sb_fri_proof_free(pr)
+        lib.sb_tree_free(ctx.h, tm)
+        lib.sb_tree_free(ctx.h, tl)
+
+    step()
+    ctx.timer_start()
+    for _ in range(reps):
+        step()
+    ms = ctx.timer_stop() / reps
+    ctx.free(d_cols)
+    ctx.free(d_out)
+    return ms
 
 
 def run_gpu(args):
@@ -182,6 +228,10 @@ def run_gpu(args):
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # CPU-side control group: ranks > 0 wait on it while rank 0 drives all GPUs through the C ABI (an NCCL barrier would
+        # keep a spinning kernel on their GPUs)
+        import datetime
+        ctrl = dist.new_group(backend="gloo", timeout=datetime.timedelta(minutes=60))
     ctx = sb.Context(local_rank)
     lib = ctx.lib
     L, Cn = args.log_n, args.cols
@@ -287,7 +337,7 @@ def run_gpu(args):
         barrier()
         t0 = time.perf_counter()
         ctx.timer_start()
-        e2e_steps = max(1, min(args.steps, 3))
+        e2e_steps = args.steps
         for _ in range(e2e_steps):
             step_host()
         e2e_ms = ctx.timer_stop()
@@ -320,6 +370,22 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         prove_multi = {key: dict(p[key], gpu_s_max_over_ranks=float(t[0]), proofs_per_s_all_gpus=world / float(t[0]),
                                  note="one proof per GPU, concurrently; every process runs its own host front end")}
+    multi = None
+    if world > 1 and not args.no_sharded:
+        # ONE job over all GPUs (strong scaling), driven by rank 0 through the C ABI; everybody else frees its GPU's memory first
+        ctx.free(d_cols)
+        ctx.free(d_out)
+        ctx.close()
+        import torch
+        torch.cuda.empty_cache()
+        dist.barrier(group=ctrl)
+        if rank == 0:
+            try:
+                multi = run_multi_records(args, world)
+            except BaseException as ex:      # noqa: BLE001 -- the record says so; the headline line still goes out
+                multi = {"error": repr(ex)}
+        dist.barrier(group=ctrl)
+        ctx = sb.Context(local_rank)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -377,6 +443,7 @@ def run_gpu(args):
                         "achieved uses SURVEY 8d's count ((n/2) log2 n per transform); the coset LDE executes fewer products than that count, "
                         "executed_frac is the pipe's real load"}
 
+    int_pipe["independent_probe"] = independent_pipe_probe(clocks.get("sm_mhz") or 1965.0)
     total_elems = world * Cn * N
     value = total_elems / (step_ms * 1e-3)
     prove = sweep = None
@@ -409,22 +476,62 @@ def run_gpu(args):
         "roofline": {"bound": "hbm", "kernel": "ntt_pass_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "avg_launch_ms": avg_launch_ms, "algorithmic_bytes_per_launch": alg_bytes_per_launch,
-                     "note": "integer-pipe bound kernel (8x32-bit Montgomery IMAD chains); the HBM fraction is reported because the contract asks for hbm|tensor; see int_pipe"},
+                     "primary_bound": "int32 multiplier pipe (IMAD.WIDE.U32 issue rate): the kernel is not HBM-bound",
+                     "primary_frac": int_pipe["executed_frac"], "primary_achieved": int_pipe["executed_per_s"], "primary_peak": int_pipe["peak"],
+                     "primary_unit": "executed Montgomery products/s",
+                     "note": "the contract's roofline object is bytes over the measured HBM peak; the bound that applies is the integer multiplier, whose fraction "
+                             "(EXECUTED products over the measured issue-rate ceiling) is primary_frac; details in int_pipe"},
         "int_pipe": int_pipe,
     }
     if prove:
         out["prove"] = prove
+    if multi:
+        out.update(multi)
     if sweep:
         out["sweep"] = sweep
     if e2e:
-        out["e2e"] = {"value": total_elems / (e2e["ms"] * 1e-3), "unit": "elems/s", "ms_per_step": e2e["ms"],
-                      "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"])}
+        # the three reference-shaped calls are synchronous and each moves its whole argument / result across PCIe, so the copies of
+        # one step cannot overlap each other beyond what happens inside a call: the floor is bytes / link rate
+        link = 55e9
+        out["e2e"] = {"value": total_elems / (e2e["ms"] * 1e-3), "unit": "elems/s", "ms_per_step": e2e["ms"], "steps": args.steps,
+                      "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]),
+                      "pcie_gbs_achieved_both_directions": (e2e["h2d"] + e2e["d2h"]) / (e2e["ms"] * 1e-3) / 1e9,
+                      "pcie_floor_ms_at_55gbs_per_direction_serialised": (e2e["h2d"] + e2e["d2h"]) / link * 1e3,
+                      "note": "sb_lde_batch overlaps its upload / transform / download, sb_merkle_commit hashes chunk k while chunk k+1 uploads; what remains is PCIe "
+                              "transfer time of the by-value Vec<Fp> signatures (best_fft returns the vector, MerkleProofInPlace::update takes the packed rows). "
+                              "The resident pipeline behind sb_prove_r1cs / sb_ext_* moves 0.2 GB per 2^23 proof instead."}
     if world == 1 and not args.no_cpu:
         _, _, cb = run_cpu(args, False)
         out["cpu_baseline"] = cb
+        # like for like: the same step at the CPU sample's size on the GPU (resident), next to the cross-size headline ratio
+        Lc = cb["log_n"]
+        gl = gpu_step_ms(ctx, Lc, Cn)
+        out["same_config"] = {"log_n": Lc, "cols": Cn, "gpu_ms_per_step": gl, "gpu_elems_per_s": Cn * (1 << Lc) / (gl * 1e-3),
+                              "cpu_elems_per_s": cb["value"], "speedup": Cn * (1 << Lc) / (gl * 1e-3) / cb["value"],
+                              "note": "GPU resident step and CPU oracle step at the SAME domain 2^%d; the headline value is measured at 2^%d (cross-size)" % (Lc, L)}
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def independent_pipe_probe(sm_mhz):
+    """tools/pipe_bench.cu (a stand-alone microbenchmark, not the library's own probe): IMAD.WIDE issue rate -> Montgomery products/s.
+    The text goes to profiles/pipe_bench_r02.txt."""
+    exe = os.path.join(ROOT, "tools", "bin", "pipe_bench")
+    if not os.path.exists(exe):
+        return None
+    try:
+        txt = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout
+        open(os.path.join(ROOT, "profiles", "pipe_bench_r02.txt"), "w").write(txt)
+        best = 0.0
+        for line in txt.splitlines():
+            if line.startswith("mad.lo.cc+madc.hi.cc pair") or line.startswith("IMAD.WIDE.U32") or line.startswith("mul.wide.u32"):
+                best = max(best, float(line.split("warps/SM")[1].split()[1]))
+        # one Montgomery product = 128 IMAD.WIDE.U32 (64 for a*b, 64 for m*p)
+        return {"imad_wide_lanes_per_clk_per_sm": best, "products_per_s": best * 148 * sm_mhz * 1e6 / 128.0,
+                "source": "tools/pipe_bench.cu (stand-alone), best IMAD.WIDE-class rate over 16 / 32 warps per SM"}
+    except Exception as ex:      # noqa: BLE001
+        return {"error": repr(ex)}
 
 
 def run_sweep(ctx, args):
@@ -752,6 +859,111 @@ def run_gpu_sharded_ntt(args):
         dist.destroy_process_group()
 
 
+def run_multi_records(args, n_dev):
+    """ONE job over n_dev GPUs through the C ABI (sb_init_multi; one process drives all devices with peer access over
+    NVLink / NVSwitch).  Called on rank 0 only; the other ranks have released their GPUs' memory and wait on a CPU barrier.
+      sharded        BASELINE.json configs[4]: LDE of 8 columns 2^23 -> 2^26, Merkle over the 256-byte rows, one-column tree,
+                     FRI -- columns coset-major and sharded by cosets, per-device subtrees, top of the tree on the host
+      prove_sharded  BASELINE.json configs[3]: ONE proof of the sha256_2_test-scale circuit (2^23) on n_dev GPUs
+    Each record carries the same job timed on ONE device in the same run and asserts in-run that roots / FRI proof /
+    proof.json equal the single-device (and golden) results: the driver's box is the only place with n_dev real GPUs."""
+    import hashlib
+    import tempfile
+    import stark_pure_rust_b200 as sb
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    out = {}
+    sha = lambda b: hashlib.sha256(bytes(b)).hexdigest()
+    ctxs = {1: sb.Context(devices=[0]), n_dev: sb.Context(devices=list(range(n_dev)))}
+
+    # ---- sharded commitment + FRI ------------------------------------------------------------------------------------
+    L, nc = args.sharded_log_n, 8
+    log_s, N, S = L - 3, 1 << L, 1 << (L - 3)
+    base = random_elems(1 << 20, 0x26)
+    reps = max(1, S >> 20)
+    res = {}
+    for g, ctx in ctxs.items():
+        lib = ctx.lib
+        if L > 26:
+            raise SystemExit("sharded_log_n too large")
+        ctx.check(lib.sb_set_extended_domain(ctx.h, 1))
+        h_cols, hp = pinned_array(ctx, (nc, S, 4), np.uint64)
+        for c in range(nc):
+            h_cols[c] = np.roll(np.tile(base, (reps, 1))[:S], 977 * c, axis=0)
+        e = sb.ext.ExtColumns(nc, log_s, ctx=ctx)
+        e.load(0, h_cols)
+
+        def step(upload):
+            if upload:
+                e.load(0, h_cols)
+            e.extend()
+            rm, tm_ = e.commit(list(range(nc)))
+            rl, tl = e.commit([nc - 1])
+            text = e.fri_prove(nc - 1, N // 4, 8, tree=tl, as_json=True)
+            e.free_tree(tm_)
+            e.free_tree(tl)
+            return rm, rl, text
+
+        rm, rl, text = step(False)
+        times = {}
+        for name, upload in (("resident", False), ("e2e", True)):
+            ctx.sync()
+            l0 = ctx.launch_count()
+            t0 = time.perf_counter()
+            for _ in range(args.sharded_steps):
+                step(upload)
+            times[name] = (time.perf_counter() - t0) * 1e3 / args.sharded_steps
+            times[name + "_launches"] = (ctx.launch_count() - l0) // args.sharded_steps
+        res[g] = {"m_root": rm.hex(), "l_root": rl.hex(), "fri_json_sha256": sha(text.encode()), **times}
+        e.close()
+        lib.sb_host_free_pinned(ctx.h, hp)
+    same = all(res[1][k] == res[n_dev][k] for k in ("m_root", "l_root", "fri_json_sha256"))
+    assert same, "sharded commitment over %d GPUs differs from the single-GPU result: %r" % (n_dev, res)
+    out["sharded"] = {
+        "workload": "ONE job: LDE 2^%d->2^%d x %d cols + Merkle(8 cols, 256 B leaves) + Merkle(1 col) + FRI(2^%d), coset-sharded over %d GPUs behind the C ABI (sb_ext_*)" % (log_s, L, nc, L, n_dev),
+        "scaling": "strong", "n_gpus": n_dev, "steps": args.sharded_steps,
+        "ms_per_step": res[n_dev]["resident"], "ms_per_step_1gpu": res[1]["resident"], "speedup_vs_1gpu": res[1]["resident"] / res[n_dev]["resident"],
+        "elems_per_s": nc * N / (res[n_dev]["resident"] * 1e-3),
+        "e2e_ms_per_step": res[n_dev]["e2e"], "e2e_ms_per_step_1gpu": res[1]["e2e"], "h2d_bytes_per_step": nc * S * 32,
+        "gpu_launches_per_step": res[n_dev]["resident_launches"],
+        "parity": {"equal_to_1gpu": same, "m_root": res[n_dev]["m_root"], "l_root": res[n_dev]["l_root"], "fri_json_sha256": res[n_dev]["fri_json_sha256"],
+                   "note": "domain 2^26 is beyond the reference sampler's 2^24 (sb_set_extended_domain): the parity target is the single-GPU natural-order path, itself oracle-checked up to 2^24"},
+    }
+
+    # ---- one proof over n_dev GPUs -------------------------------------------------------------------------------------
+    import gen_r1cs
+    tmp = tempfile.mkdtemp(prefix="sb_bench_multi_")
+    wit, cons = gen_r1cs.generate(30000, 8.0, 2, 1)
+    info = gen_r1cs.write_files(os.path.join(tmp, "syn"), wit, cons, 2)
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "vectors.json")))["proofs"]["synthetic_30000_8_2_1"]
+    pres = {}
+    for g, ctx in ctxs.items():
+        best = None
+        for _ in range(4):
+            t0 = time.perf_counter()
+            ms = sb.prove.prove_with_file_path(os.path.join(tmp, "syn.r1cs"), os.path.join(tmp, "syn.wtns"), os.path.join(tmp, "proof.json"), ctx=ctx)
+            wall = time.perf_counter() - t0
+            if best is None or ms[4] < best[1][4]:
+                best = (wall, ms)
+        digest = sha(open(os.path.join(tmp, "proof.json"), "rb").read())
+        pres[g] = {"wall_s": best[0], "device_ms": best[1][4], "stage_ms": {"lde": best[1][0], "m_tree": best[1][1], "fri": best[1][2], "rest": best[1][3]},
+                   "host_front_end_ms": best[1][5], "json_ms": best[1][6], "proof_json_sha256": digest}
+        assert digest == gold["proof_json_sha256"], "proof.json on %d GPU(s) differs from the oracle's golden hash" % g
+    sb.prove.verify_with_file_path(os.path.join(tmp, "syn.r1cs"), os.path.join(tmp, "syn.wtns"), os.path.join(tmp, "proof.json"), ctx=ctxs[n_dev])
+    out["prove_sharded"] = {
+        "workload": "ONE proof of the sha256_2_test-scale synthetic circuit (%d steps, precision 2^23) over %d GPUs (sb_prove_files on an sb_init_multi context)" % (info["original_steps"], n_dev),
+        "scaling": "strong", "n_gpus": n_dev, "device_ms": pres[n_dev]["device_ms"], "device_ms_1gpu": pres[1]["device_ms"],
+        "speedup_vs_1gpu": pres[1]["device_ms"] / pres[n_dev]["device_ms"], "wall_s": pres[n_dev]["wall_s"], "wall_s_1gpu": pres[1]["wall_s"],
+        "stage_ms": pres[n_dev]["stage_ms"], "stage_ms_1gpu": pres[1]["stage_ms"],
+        "host_front_end_ms": pres[n_dev]["host_front_end_ms"], "json_ms": pres[n_dev]["json_ms"],
+        "parity": {"proof_json_sha256": pres[n_dev]["proof_json_sha256"], "equals_oracle_golden": True, "verified_by_product_verifier": True},
+    }
+    import shutil
+    shutil.rmtree(tmp, ignore_errors=True)
+    for c in ctxs.values():
+        c.close()
+    return out
+
+
 def ntt_plan(log_n, maxb=8):
     if log_n == 0:
         return [0]
@@ -767,13 +979,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--log-n", type=int, default=24)
     ap.add_argument("--cols", type=int, default=10)
-    ap.add_argument("--cpu-log-n", type=int, default=20)
+    ap.add_argument("--cpu-log-n", type=int, default=0, help="domain of the CPU arm; 0 = the largest that fits --cpu-budget-s (reference arm) / 30 s (cpu_baseline)")
+    ap.add_argument("--cpu-budget-s", type=float, default=600.0)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sweep", action="store_true", help="skip the 2^16..2^24 fft / inv_fft / LDE sweep")
     ap.add_argument("--no-prove", action="store_true", help="skip the prove-sec-per-circuit extras")
     ap.add_argument("--prove-cpu-large", action="store_true", help="also time the CPU oracle on the 2^23 synthetic circuit (~70 s)")
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the one-job-over-all-GPUs records (sharded, prove_sharded)")
+    ap.add_argument("--sharded-log-n", type=int, default=26, help="domain of the sharded record (BASELINE.json configs[4]: 2^26)")
+    ap.add_argument("--sharded-steps", type=int, default=3)
     ap.add_argument("--mode", default="replicas", choices=["replicas", "sharded", "sharded-ntt"],
                     help="replicas: every GPU runs its own batch (weak scaling, default); sharded: ONE job over all GPUs (strong scaling)")
     args = ap.parse_args()
@@ -788,7 +1004,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64x4 (254-bit Montgomery, integer)",
             "data": "synthetic (seeded uniform field elements)",
             "config": {"workload": "LDE 2^%d->2^%d x %d cols + Merkle(8 cols) + Merkle(1 col) + FRI: bounded sample of the L=%d workload" % (
-                args.cpu_log_n - 3, args.cpu_log_n, args.cols, args.log_n), "log_n": args.cpu_log_n, "cols": args.cols},
+                cb["log_n"] - 3, cb["log_n"], args.cols, args.log_n), "log_n": cb["log_n"], "cols": args.cols},
             "cpu_baseline": cb,
             "e2e": {"value": value, "unit": "elems/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "the Rust reference cannot be built here (no cargo/rustc); this is the C restatement in oracle/ (kind=port)"}))

@@ -122,6 +122,10 @@ extern "C" void sb_destroy(sb_ctx *ctx) {
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    {   // hand the cached scratch of the stream-ordered pool back to the driver (another process may want this GPU's memory)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    }
     delete ctx;
 }
 
@@ -364,6 +368,16 @@ static int plan_bits(uint32_t log_n, uint32_t *bits) {
 
 // cs != NULL: the coset transforms of a low-degree extension (see NttPassParams); the transform's root is then
 // W^(2^log_ext) and the table must be the extended domain's (tw of W).
+// kernel variant (radix of the register rounds); SB_NTT_MAXQ overrides the default for experiments
+static uint32_t ntt_maxq() {
+    static const uint32_t v = []() {
+        const char *e = getenv("SB_NTT_MAXQ");
+        const int q = e ? atoi(e) : 3;
+        return (uint32_t)(q >= 0 && q <= 3 ? q : 3);
+    }();
+    return v;
+}
+
 int ntt_dev_tw(sb_ctx *ctx, const uint4 *d_src, size_t len_in, size_t src_stride, uint4 *d_dst, size_t dst_stride,
                size_t n_polys, uint32_t log_n, int inverse, const uint4 *tw, uint32_t tw_log_n, uint32_t log_stride,
                const CosetSpec *cs) {
@@ -375,13 +389,7 @@ int ntt_dev_tw(sb_ctx *ctx, const uint4 *d_src, size_t len_in, size_t src_stride
     const size_t n_batch = coset_cnt ? n_polys * coset_cnt : n_polys;       // transforms in flight
     uint32_t bits[NTT_MAX_PASSES];
     const int m = plan_bits(log_n, bits);
-    uint32_t store = cs ? cs->store : NTT_STORE_PLAIN;
-    if (store == NTT_STORE_GATHER) {
-        // all eight cosets of a tile in one CTA: needs a last pass of its own and at least one sub-transform per eight tile columns
-        const uint32_t b = bits[m - 1];
-        const unsigned long long cpp = 1ull << (log_n - b), cc = (1ull << NTT_LOG_TILE_FOR(b)) >> b;
-        if (m < 2 || cs->log_ext != 3 || cs->r0 != 1 || cs->cnt != 7 || cc < 8 || cpp < cc / 8 || !cs->c0_src) store = NTT_STORE_INTERLEAVED;
-    }
+    const uint32_t store = cs ? cs->store : NTT_STORE_PLAIN;
     DevBuf work(ctx);
     if (m > 1) TRY(work.alloc(n_batch * n * 32));
     hfp::el ninv = hfp::inv(hfp::from_u64((uint64_t)n));
@@ -412,9 +420,6 @@ int ntt_dev_tw(sb_ctx *ctx, const uint4 *d_src, size_t len_in, size_t src_stride
             P.coset_store = store;
             P.coset_dst_cpd = cs->dst_cpd ? cs->dst_cpd : cs->cnt;
             P.coset_dst_r0 = cs->dst_cpd ? cs->dst_r0 : cs->r0;
-            P.c0_src = cs->c0_src;
-            P.c0_stride = cs->c0_stride;
-            P.c0_len = cs->c0_len;
         }
         {   // interleave polynomials when a tile never straddles two of them (the interleaved coset store also in the last
             // pass: the CTAs that fill the same output lines then run together)
@@ -425,16 +430,12 @@ int ntt_dev_tw(sb_ctx *ctx, const uint4 *d_src, size_t len_in, size_t src_stride
         P.n_prev = (uint32_t)p;
         for (int i = 0; i < p; i++) P.prev_bits[i] = bits[i];
         memcpy(P.n_inv, ninv.l, 32);
+        P.maxq = ntt_maxq();
         if (bits[p] > 8) return fail(ctx, SB_ERR_ARG, "internal: pass width %u", bits[p]);
         KLAUNCH(SB_KIND_NTT_PASS, ntt_launch_pass(ctx->stream, bits[p], P));
         log_outer += bits[p];
     }
     CU(cudaGetLastError());
-    if (cs && cs->store == NTT_STORE_GATHER && store != NTT_STORE_GATHER) {
-        // fallback for tiny transforms: coset 0 (the input column itself) by a copy kernel
-        KLAUNCH(SB_KIND_OTHER, lde_launch_coset0(ctx->stream, cs->c0_src, cs->c0_len, cs->c0_stride, d_dst, dst_stride, n, cs->log_ext, n_polys));
-        CU(cudaGetLastError());
-    }
     return SB_OK;
 }
 
@@ -516,19 +517,15 @@ int lde_dev(sb_ctx *ctx, const uint4 *d_cols, size_t n_cols, size_t col_len, siz
     DevBuf coef(ctx);
     TRY(coef.alloc(n_cols * S * 32));
     TRY(ntt_dev_tw(ctx, d_cols, col_len, col_stride, (uint4 *)coef.p, S, n_cols, log_s, 1, tw, tw_log_n, log_stride + log_ext, nullptr));
+    // (Tried: one CTA holding the same tile of all eight cosets so that every output row is 256 contiguous bytes and the copy
+    // kernel disappears.  Measured slower on B200, LDE 2^21 -> 2^24 x 10: 35.8 against 33.5 ms -- the eight-column tile carries
+    // seven transforms, so every butterfly round runs with 1/8 of its lanes idle, which costs more than the stores gain.)
     CosetSpec cs;
     cs.log_ext = log_ext;
     cs.r0 = 1;
     cs.cnt = (1u << log_ext) - 1;
-    cs.c0_src = d_cols;
-    cs.c0_stride = col_stride;
-    cs.c0_len = col_len;
-    if (log_ext == 3) {
-        cs.store = NTT_STORE_GATHER;           // the last pass writes whole 256-byte groups, coset 0 included
-    } else {
-        cs.store = NTT_STORE_INTERLEAVED;
-        KLAUNCH(SB_KIND_OTHER, lde_launch_coset0(ctx->stream, d_cols, col_len, col_stride, d_out, N, S, log_ext, n_cols));
-    }
+    cs.store = NTT_STORE_INTERLEAVED;
+    KLAUNCH(SB_KIND_OTHER, lde_launch_coset0(ctx->stream, d_cols, col_len, col_stride, d_out, N, S, log_ext, n_cols));
     return ntt_dev_tw(ctx, (const uint4 *)coef.p, S, S, d_out, N, n_cols, log_s, 0, tw, tw_log_n, log_stride + log_ext, &cs);
 }
 
@@ -677,6 +674,8 @@ static void launch_leaves(sb_ctx *ctx, sb_tree *t, uint32_t lv) {
         P.nodes = t->d_nodes;
         P.n = t->n;
         P.leaf_bytes = (uint32_t)t->leaf_bytes;
+        P.first = 0;
+        P.count = t->n;
         KLAUNCH(SB_KIND_MERKLE_LEAVES, merkle_launch_leaves_bytes(ctx->stream, lv, P));
     }
 }
@@ -738,8 +737,46 @@ extern "C" int sb_merkle_commit(sb_ctx *ctx, const void *leaves, size_t leaf_byt
         free_tree(t);
         return fail(ctx, SB_ERR_OOM, "cudaMalloc(leaves): %s", cudaGetErrorString(e));
     }
-    e = n * leaf_bytes ? cudaMemcpyAsync(t->d_leaves, leaves, n * leaf_bytes, cudaMemcpyHostToDevice, ctx->stream) : cudaSuccess;
-    int rc = e == cudaSuccess ? merkle_build(ctx, t) : fail(ctx, SB_ERR_CUDA, "H2D leaves: %s", cudaGetErrorString(e));
+    int rc = SB_OK;
+    const size_t total = n * leaf_bytes;
+    const size_t CHUNK_BYTES = (size_t)64 << 20;
+    if (total >= 4 * CHUNK_BYTES && t->depth >= 13) {
+        // Large trees: the upload of chunk k + 1 overlaps the leaf hashing (+ 3 levels) of chunk k (two streams); only the last
+        // chunk's hashing and the upper levels remain after the transfer.  Chunks are multiples of 1024 leaves (one CTA's share).
+        size_t chunk = CHUNK_BYTES / leaf_bytes;
+        chunk = chunk < 1024 ? 1024 : (chunk & ~(size_t)1023);
+        if (!ctx->h2d_stream) CU(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+        cudaEvent_t ready, up;
+        CU(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+        CU(cudaEventRecord(ready, ctx->stream));             // the allocations above are ordered on ctx->stream
+        CU(cudaStreamWaitEvent(ctx->h2d_stream, ready, 0));
+        std::vector<cudaEvent_t> ups;
+        for (size_t first = 0; first < n && e == cudaSuccess; first += chunk) {
+            const size_t cnt = std::min(chunk, n - first);
+            e = cudaMemcpyAsync(t->d_leaves + first * leaf_bytes, (const uint8_t *)leaves + first * leaf_bytes, cnt * leaf_bytes, cudaMemcpyHostToDevice, ctx->h2d_stream);
+            if (e != cudaSuccess) break;
+            cudaEventCreateWithFlags(&up, cudaEventDisableTiming);
+            cudaEventRecord(up, ctx->h2d_stream);
+            ups.push_back(up);
+            cudaStreamWaitEvent(ctx->stream, up, 0);
+            MerkleBytesParams P;
+            P.leaves = t->d_leaves;
+            P.nodes = t->d_nodes;
+            P.n = t->n;
+            P.leaf_bytes = (uint32_t)leaf_bytes;
+            P.first = first;
+            P.count = cnt;
+            KLAUNCH(SB_KIND_MERKLE_LEAVES, merkle_launch_leaves_bytes(ctx->stream, 3, P));
+        }
+        if (e == cudaSuccess) rc = merkle_finish(ctx, t, 3, true);
+        else rc = fail(ctx, SB_ERR_CUDA, "H2D leaves: %s", cudaGetErrorString(e));
+        cudaStreamSynchronize(ctx->h2d_stream);
+        for (auto ev : ups) cudaEventDestroy(ev);
+        cudaEventDestroy(ready);
+    } else {
+        e = total ? cudaMemcpyAsync(t->d_leaves, leaves, total, cudaMemcpyHostToDevice, ctx->stream) : cudaSuccess;
+        rc = e == cudaSuccess ? merkle_build(ctx, t) : fail(ctx, SB_ERR_CUDA, "H2D leaves: %s", cudaGetErrorString(e));
+    }
     if (rc != SB_OK) {
         free_tree(t);
         return rc;

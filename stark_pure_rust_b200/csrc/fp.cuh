@@ -135,13 +135,11 @@ __device__ __forceinline__ fp fp_half(const fp &a) {
     r.l[7] = t.l[7] >> 1;
     return r;
 }
-// Montgomery -> canonical integer (< p): a / R mod p
+// Montgomery -> canonical integer (< p): a / R mod p, for any a < 2^256 (the dedicated reduction: half the wide multiplies
+// of a product by the raw integer 1; the leaf kernels run one per committed element)
 __device__ __forceinline__ fp fp_from_mont(const fp &a) {
-    fp one;
-#pragma unroll
-    for (int i = 0; i < 8; i++) one.l[i] = (i == 0);
     fp r;
-    fpgen::mont_mul(r.l, a.l, one.l);   // <= p
+    fpgen::redc(r.l, a.l);              // <= p
     return fp_canon(r);
 }
 // canonical integer (any value < 2^256 - p) -> Montgomery, canonical representative

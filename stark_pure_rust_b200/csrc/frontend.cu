@@ -151,12 +151,14 @@ const char *read_witness(const std::vector<uint8_t> &buf, std::vector<hfp::el> &
 }
 
 // the six original_steps-long vectors mk_r1cs_proof takes, carved out of the context's pinned staging arena so that
-// their upload runs at PCIe speed; perm / public data are small and stay in ordinary vectors
+// their upload runs at PCIe speed (the copy permutation sits behind them in the same arena); public data are small and stay
+// in ordinary vectors
 struct Trace {
     size_t os = 0;
     hfp::el *wit = nullptr, *comp = nullptr, *coef = nullptr, *f0 = nullptr, *f1 = nullptr, *f2 = nullptr;
     std::vector<hfp::el> pub, heap;
-    std::vector<size_t> perm, pfi_k, pfi_w;
+    size_t *perm = nullptr;                     // original_steps entries, in the arena (or perm_heap)
+    std::vector<size_t> perm_heap, pfi_k, pfi_w;
 };
 
 // run.rs:109-281, :283-308, :390-419
@@ -169,10 +171,13 @@ const char *build_trace(sb_ctx *ctx, const R1cs &r, const std::vector<hfp::el> &
     if (a == 0) return "circuit has no constraint rows";
     hfp::el *arena;
     if (ctx) {
-        arena = (hfp::el *)pinned_arena(ctx, 6 * os * sizeof(hfp::el));
+        arena = (hfp::el *)pinned_arena(ctx, 6 * os * sizeof(hfp::el) + os * sizeof(size_t));
+        if (arena) t.perm = (size_t *)(arena + 6 * os);
     } else {                      // host-only use (sb_trace_from_files): ordinary memory owned by the Trace
         t.heap.resize(6 * os);
         arena = t.heap.data();
+        t.perm_heap.assign(os, 0);
+        t.perm = t.perm_heap.data();
     }
     if (!arena) return "cannot allocate the pinned staging arena";
     t.os = os;
@@ -231,7 +236,7 @@ const char *build_trace(sb_ctx *ctx, const R1cs &r, const std::vector<hfp::el> &
     // perm[first use] = last use, perm[use j] = use j-1
     const size_t NONE = (size_t)-1;
     std::vector<size_t> first(n_wires, NONE), prev(n_wires, NONE);
-    t.perm.assign(os, 0);
+    memset(t.perm, 0, os * sizeof(size_t));
     for (size_t c = 0; c < nc; c++) {
         const size_t off = r.row_off[c], n = r.row_off[c + 1] - off;
         for (int k = 0; k < 3; k++) {
@@ -294,7 +299,7 @@ extern "C" int sb_prove_files(sb_ctx *ctx, const char *r1cs_path, const char *wt
     st.flag0 = (const uint64_t *)t.f0;
     st.flag1 = (const uint64_t *)t.f1;
     st.flag2 = (const uint64_t *)t.f2;
-    st.permuted_indices = t.perm.data();
+    st.permuted_indices = t.perm;
     st.n_public = t.pub.size();
     st.public_wires = (const uint64_t *)t.pub.data();
     st.n_pfi = t.pfi_k.size();
@@ -360,7 +365,7 @@ extern "C" int sb_verify_files(sb_ctx *ctx, const char *r1cs_path, const char *w
     st.flag0 = (const uint64_t *)t.f0;
     st.flag1 = (const uint64_t *)t.f1;
     st.flag2 = (const uint64_t *)t.f2;
-    st.permuted_indices = t.perm.data();
+    st.permuted_indices = t.perm;
     st.n_public = t.pub.size();
     st.public_wires = (const uint64_t *)t.pub.data();
     st.n_pfi = t.pfi_k.size();
@@ -408,7 +413,7 @@ extern "C" int sb_trace_from_files(const char *r1cs_path, const char *wtns_path,
     st.flag0 = (const uint64_t *)t.f0;
     st.flag1 = (const uint64_t *)t.f1;
     st.flag2 = (const uint64_t *)t.f2;
-    st.permuted_indices = t.perm.data();
+    st.permuted_indices = t.perm;
     st.n_public = t.pub.size();
     st.public_wires = (const uint64_t *)t.pub.data();
     st.n_pfi = t.pfi_k.size();

@@ -246,8 +246,6 @@ struct CosetSpec {
     uint32_t log_ext = 3, r0 = 1, cnt = 7;
     uint32_t store = NTT_STORE_PLAIN;
     uint32_t dst_cpd = 0, dst_r0 = 0;  // NTT_STORE_PLAIN: (column, coset) lands at polynomial slot column * dst_cpd + coset - dst_r0 (0: dst_cpd = cnt, dst_r0 = r0)
-    const uint4 *c0_src = nullptr;     // NTT_STORE_GATHER: the input columns (coset 0 of the output)
-    size_t c0_stride = 0, c0_len = 0;
 };
 int ntt_dev_tw(sb_ctx *ctx, const uint4 *d_src, size_t len_in, size_t src_stride, uint4 *d_dst, size_t dst_stride, size_t n_polys,
                uint32_t log_n, int inverse, const uint4 *tw, uint32_t tw_log_n, uint32_t log_stride, const CosetSpec *cs);

@@ -26,7 +26,7 @@ int merkle_launch_leaves_fold(cudaStream_t s, uint32_t lv, const FriFoldParams &
     return 1;
 }
 int merkle_launch_leaves_bytes(cudaStream_t s, uint32_t lv, const MerkleBytesParams &P) {
-    const unsigned b = blocks128(P.n >> lv);
+    const unsigned b = blocks128((P.count + ((size_t)1 << lv) - 1) >> lv);
     switch (lv) {
         case 0: merkle_leaves_bytes_kernel<0><<<b, 128, 0, s>>>(P); break;
         case 1: merkle_leaves_bytes_kernel<1><<<b, 128, 0, s>>>(P); break;

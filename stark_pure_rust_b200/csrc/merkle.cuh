@@ -188,11 +188,11 @@ __device__ __forceinline__ void merkle_leaf_from_bytes(uint32_t (&out)[8], const
 template <int LV>
 __global__ void __launch_bounds__(MERKLE_THREADS, 4) merkle_leaves_bytes_kernel(const __grid_constant__ MerkleBytesParams P) {
     __shared__ uint32_t sd_all[MERKLE_SMEM_WORDS(LV)];
-    const size_t base = ((size_t)blockIdx.x * MERKLE_THREADS) << LV;
+    const size_t base = P.first + (((size_t)blockIdx.x * MERKLE_THREADS) << LV), end = P.first + P.count;
 #pragma unroll 1
     for (int i = 0; i < (1 << LV); i++) {
         const uint32_t l = i * MERKLE_THREADS + threadIdx.x;
-        if (base + l < P.n) {
+        if (base + l < end) {
             uint32_t h[8];
             merkle_leaf_from_bytes(h, P.leaves + (base + l) * (size_t)P.leaf_bytes, P.leaf_bytes);
             digest_store(P.nodes, base + l, h);
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(MERKLE_THREADS, 4) merkle_leaves_bytes_kernel(
     }
     __syncthreads();
     const size_t first = base + ((size_t)threadIdx.x << LV);
-    if (first < P.n) merkle_reduce_smem<LV>(sd_all + threadIdx.x, P.nodes, P.n, 0, first);
+    if (first < end) merkle_reduce_smem<LV>(sd_all + threadIdx.x, P.nodes, P.n, 0, first);
 }
 
 // ---- inner levels: each thread lifts 2^LV nodes of level `level` LV levels up -----------------

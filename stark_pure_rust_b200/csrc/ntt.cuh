@@ -54,15 +54,13 @@ __device__ __forceinline__ void ntt_round_regs(fp (&x)[1 << Q], uint32_t low, co
     }
 }
 
-// skip0: tile columns j with j % 8 == 0 carry no transform (NTT_STORE_GATHER: the coset-0 slots)
 template <int B, int S, int Q, int LOG_TILE>
-__device__ __forceinline__ void ntt_round(uint4 *slo, uint4 *shi, const uint4 *wlo, const uint4 *whi, bool skip0) {
+__device__ __forceinline__ void ntt_round(uint4 *slo, uint4 *shi, const uint4 *wlo, const uint4 *whi) {
     constexpr int TILE = 1 << LOG_TILE, NT = TILE / 8, CC = TILE >> B, PITCH = CC + 1;
     constexpr int GROUPS = TILE >> Q;
 #pragma unroll 1
     for (int g = threadIdx.x; g < GROUPS; g += NT) {
         const int j = g % CC;
-        if (skip0 && (j & 7) == 0) continue;
         const uint32_t rb = g / CC;                          // row index with the Q round bits removed
         const uint32_t low = rb & ((1u << S) - 1), high = rb >> S;
         const uint32_t base = (high << (S + Q)) | low;
@@ -82,14 +80,53 @@ __device__ __forceinline__ void ntt_round(uint4 *slo, uint4 *shi, const uint4 *w
     }
 }
 
-// all rounds of a 2^B sub-transform: first round takes B mod 3 bits (if any), the rest 3 each
-template <int B, int HI, int LOG_TILE>
-__device__ __forceinline__ void ntt_rounds(uint4 *slo, uint4 *shi, const uint4 *wlo, const uint4 *whi, bool skip0) {
+// all rounds of a 2^B sub-transform: first round takes B mod MAXQ bits (if any), the rest MAXQ each (radix 2^MAXQ in
+// registers between shared-memory round trips).  MAXQ = 3 has the fewest round trips but inlines 12 Montgomery products per
+// round (the whole kernel: 133 KB of SASS, at the size of the instruction cache); MAXQ = 2 / 1 trade round trips for code
+// size and registers (more resident CTAs).
+template <int B, int HI, int LOG_TILE, int MAXQ>
+__device__ __forceinline__ void ntt_rounds(uint4 *slo, uint4 *shi, const uint4 *wlo, const uint4 *whi) {
     if constexpr (HI > 0) {
-        constexpr int Q = (HI % 3) ? (HI % 3) : 3;
-        ntt_round<B, HI - Q, Q, LOG_TILE>(slo, shi, wlo, whi, skip0);
+        constexpr int Q = (HI % MAXQ) ? (HI % MAXQ) : MAXQ;
+        ntt_round<B, HI - Q, Q, LOG_TILE>(slo, shi, wlo, whi);
         __syncthreads();
-        ntt_rounds<B, HI - Q, LOG_TILE>(slo, shi, wlo, whi, skip0);
+        ntt_rounds<B, HI - Q, LOG_TILE, MAXQ>(slo, shi, wlo, whi);
+    }
+}
+
+// MAXQ = 0: radix-2 stages rolled into ONE loop with the stage as a run-time value (a single inlined product for all stages
+// with non-trivial twiddles, ~30 KB of SASS for the whole kernel, 64 registers); B shared-memory round trips per tile.
+template <int B, int LOG_TILE>
+__device__ __forceinline__ void ntt_rounds_rolled(uint4 *slo, uint4 *shi, const uint4 *wlo, const uint4 *whi) {
+    constexpr int TILE = 1 << LOG_TILE, NT = TILE / 8, CC = TILE >> B, PITCH = CC + 1, GROUPS = TILE / 2;
+    if constexpr (B > 1) {
+#pragma unroll 1
+        for (int S = B - 1; S >= 1; S--) {
+#pragma unroll 2
+            for (int g = threadIdx.x; g < GROUPS; g += NT) {
+                const int j = g % CC;
+                const uint32_t rb = g / CC, low = rb & ((1u << S) - 1), high = rb >> S;
+                const int i0 = ((high << (S + 1)) | low) * PITCH + j, i1 = i0 + (PITCH << S);
+                const fp a = fp_from_u4(slo[i0], shi[i0]), c = fp_from_u4(slo[i1], shi[i1]);
+                const uint32_t expo = low << (B - 1 - S);
+                const fp x0 = fp_add(a, c), x1 = fp_mul(fp_sub_lazy(a, c), fp_from_u4(wlo[expo], whi[expo]));
+                slo[i0] = fp_lo(x0); shi[i0] = fp_hi(x0);
+                slo[i1] = fp_lo(x1); shi[i1] = fp_hi(x1);
+            }
+            __syncthreads();
+        }
+    }
+    if constexpr (B > 0) {
+#pragma unroll 2
+        for (int g = threadIdx.x; g < GROUPS; g += NT) {      // last stage: twiddle w^0
+            const int j = g % CC;
+            const int i0 = (2 * (g / CC)) * PITCH + j, i1 = i0 + PITCH;
+            const fp a = fp_from_u4(slo[i0], shi[i0]), c = fp_from_u4(slo[i1], shi[i1]);
+            const fp x0 = fp_add(a, c), x1 = fp_sub(a, c);
+            slo[i0] = fp_lo(x0); shi[i0] = fp_hi(x0);
+            slo[i1] = fp_lo(x1); shi[i1] = fp_hi(x1);
+        }
+        __syncthreads();
     }
 }
 
@@ -105,22 +142,17 @@ __device__ __forceinline__ unsigned long long ntt_digitrev_inv(const NttPassPara
     return o;
 }
 
-template <int B, int LOG_TILE>
-__global__ void __launch_bounds__((1 << LOG_TILE) / 8, LOG_TILE >= 11 ? 2 : 4) ntt_pass_kernel(const __grid_constant__ NttPassParams P) {
+#define NTT_MIN_CTAS(LOG_TILE, MAXQ) ((LOG_TILE) >= 11 ? ((MAXQ) >= 3 ? 2 : 3) : ((MAXQ) >= 3 ? 4 : ((MAXQ) == 2 ? 5 : 6)))   // MAXQ = 0, 1: 64 registers
+template <int B, int LOG_TILE, int MAXQ>
+__global__ void __launch_bounds__((1 << LOG_TILE) / 8, NTT_MIN_CTAS(LOG_TILE, MAXQ)) ntt_pass_kernel(const __grid_constant__ NttPassParams P) {
     constexpr int TILE = 1 << LOG_TILE, NT = TILE / 8, R = 1 << B, CC = TILE >> B, PITCH = CC + 1;
     extern __shared__ uint4 smem[];
     uint4 *slo = smem, *shi = smem + R * PITCH;
     uint4 *wlo = shi + R * PITCH, *whi = wlo + (R / 2 > 0 ? R / 2 : 1);
 
     const uint32_t log_cpp = P.log_n - B;                     // log2(columns per polynomial)
-    const bool gather = P.last && P.coset_store == NTT_STORE_GATHER;      // uniform over the grid
     unsigned long long blk_col0 = (unsigned long long)blockIdx.x * CC;
-    unsigned long long g_col = 0, g_gl0 = 0;                  // gather: the column and the first sub-transform of this CTA
-    if (gather) {             // CC / 8 adjacent sub-transforms x 8 cosets of one column (host guarantees 8 <= CC <= 8 * columns per polynomial)
-        const unsigned long long tiles = (1ull << log_cpp) / (CC / 8);
-        g_col = blockIdx.x / tiles;
-        g_gl0 = (blockIdx.x % tiles) * (CC / 8);
-    } else if (P.n_polys) {   // tile-major order (host guarantees CC divides the columns of one polynomial)
+    if (P.n_polys) {   // tile-major order (host guarantees CC divides the columns of one polynomial)
         const unsigned long long poly = blockIdx.x % P.n_polys, tile = blockIdx.x / P.n_polys;
         blk_col0 = (poly << log_cpp) + tile * CC;
     }
@@ -138,15 +170,7 @@ __global__ void __launch_bounds__((1 << LOG_TILE) / 8, LOG_TILE >= 11 ? 2 : 4) n
         int r, j;
         if (!P.last) { j = idx % CC; r = idx / CC; } else { r = idx % R; j = idx / R; }
         uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
-        if (gather) {
-            const uint32_t rr = j & 7;
-            if (rr) {         // coset rr of column g_col is polynomial g_col * 7 + rr - 1 of the batch
-                const unsigned long long e = (ntt_digitrev_inv(P, g_gl0 + (j >> 3)) << B) + r;
-                const uint4 *s = P.src + 2 * ((g_col * 7 + rr - 1) * P.src_stride + e);
-                lo = s[0];
-                hi = s[1];
-            }
-        } else {
+        {
             const unsigned long long g = blk_col0 + j;
             if (g < P.n_cols_total) {
                 const unsigned long long poly = g >> log_cpp, gl = g & ((1ull << log_cpp) - 1);
@@ -158,24 +182,11 @@ __global__ void __launch_bounds__((1 << LOG_TILE) / 8, LOG_TILE >= 11 ? 2 : 4) n
                     e = (ntt_digitrev_inv(P, gl) << B) + r;
                 }
                 if (!P.first || e < P.len_in) {
-                    if (P.first && P.coset_cnt) {
-                        // coefficient e of column poly / coset_cnt, scaled onto coset rr: c_e * W^(e rr)
-                        const unsigned long long col = poly / P.coset_cnt, rr = poly % P.coset_cnt + P.coset_r0;
-                        const uint4 *s = P.src + 2 * (col * P.src_stride + e);
-                        lo = s[0];
-                        hi = s[1];
-                        if (rr) {
-                            const unsigned long long nT = 1ull << P.tw_log_n;
-                            const unsigned long long ti = ((e * rr) << (P.tw_log_stride - P.coset_log)) & (nT - 1);
-                            fp v = fp_mul(fp_from_u4(lo, hi), fp_ldg_ro(P.tw, ti));
-                            lo = fp_lo(v);
-                            hi = fp_hi(v);
-                        }
-                    } else {
-                        const uint4 *s = P.src + 2 * (poly * P.src_stride + e);
-                        lo = s[0];
-                        hi = s[1];
-                    }
+                    // coset mode, first pass: coefficient e of column poly / coset_cnt (scaled onto its coset below)
+                    const unsigned long long sp = (P.first && P.coset_cnt) ? poly / P.coset_cnt : poly;
+                    const uint4 *s = P.src + 2 * (sp * P.src_stride + e);
+                    lo = s[0];
+                    hi = s[1];
                 }
             }
         }
@@ -183,9 +194,36 @@ __global__ void __launch_bounds__((1 << LOG_TILE) / 8, LOG_TILE >= 11 ? 2 : 4) n
         shi[r * PITCH + j] = hi;
     }
     __syncthreads();
+    if (P.first && P.coset_cnt) {
+        // scale onto the coset: c_e * W^(e rr) (a rolled loop with one product: keeps the unrolled load loop free of arithmetic)
+        const unsigned long long nT = 1ull << P.tw_log_n;
+#pragma unroll 1
+        for (int idx = threadIdx.x; idx < TILE; idx += NT) {
+            int r, j;
+            if (!P.last) { j = idx % CC; r = idx / CC; } else { r = idx % R; j = idx / R; }
+            const unsigned long long g = blk_col0 + j;
+            if (g >= P.n_cols_total) continue;
+            const unsigned long long poly = g >> log_cpp, gl = g & ((1ull << log_cpp) - 1);
+            const unsigned long long rr = poly % P.coset_cnt + P.coset_r0;
+            if (!rr) continue;
+            unsigned long long e;
+            if (!P.last) {
+                const unsigned long long o = gl >> P.log_inner, c = gl & ((1ull << P.log_inner) - 1);
+                e = (o << (B + P.log_inner)) + ((unsigned long long)r << P.log_inner) + c;
+            } else {
+                e = (ntt_digitrev_inv(P, gl) << B) + r;
+            }
+            const unsigned long long ti = ((e * rr) << (P.tw_log_stride - P.coset_log)) & (nT - 1);
+            fp v = fp_mul(fp_from_u4(slo[r * PITCH + j], shi[r * PITCH + j]), fp_ldg_ro(P.tw, ti));
+            slo[r * PITCH + j] = fp_lo(v);
+            shi[r * PITCH + j] = fp_hi(v);
+        }
+        __syncthreads();
+    }
 
     // ---- butterflies ----
-    ntt_rounds<B, B, LOG_TILE>(slo, shi, wlo, whi, gather);
+    if constexpr (MAXQ == 0) ntt_rounds_rolled<B, LOG_TILE>(slo, shi, wlo, whi);
+    else ntt_rounds<B, B, LOG_TILE, MAXQ>(slo, shi, wlo, whi);
 
     // ---- store tile (row r of the tile holds output k = bitrev_B(r)) ----
     fp ninv;
@@ -196,31 +234,22 @@ __global__ void __launch_bounds__((1 << LOG_TILE) / 8, LOG_TILE >= 11 ? 2 : 4) n
         const int j = idx % CC;
         const uint32_t kk = idx / CC;
         const uint32_t r = B ? (__brev(kk) >> (32 - B)) : 0;
-        if (gather) {         // lanes j = 0..7 write out[8 e .. 8 e + 7] of one output position e: 256 contiguous bytes
-            const uint32_t rr = j & 7;
-            const unsigned long long e = g_gl0 + (j >> 3) + ((unsigned long long)kk << P.log_outer);
-            fp v;
-            if (rr) v = fp_from_u4(slo[r * PITCH + j], shi[r * PITCH + j]);
-            else v = e < P.c0_len ? fp_ldg(P.c0_src, g_col * P.c0_stride + e) : fp_zero();
-            fp_stg(P.dst, g_col * P.dst_stride + (e << 3) + rr, fp_canon(v));
-            continue;
-        }
         const unsigned long long g = blk_col0 + j;
         if (g >= P.n_cols_total) continue;
         fp v = fp_from_u4(slo[r * PITCH + j], shi[r * PITCH + j]);
         const unsigned long long poly = g >> log_cpp, gl = g & ((1ull << log_cpp) - 1);
         unsigned long long e;
+        fp w = ninv;                          // one product per element: the inter-pass twiddle, or n^-1 at the end of an inverse
         if (!P.last) {
             const unsigned long long o = gl >> P.log_inner, c = gl & ((1ull << P.log_inner) - 1);
             e = (o << (B + P.log_inner)) + ((unsigned long long)kk << P.log_inner) + c;
             const unsigned long long ex = ((unsigned long long)kk * c) << P.log_outer;   // < n
-            fp w = fp_ldg_ro(P.tw, ntt_tw_index(P, ex));
-            v = fp_mul(v, w);
+            w = fp_ldg_ro(P.tw, ntt_tw_index(P, ex));
         } else {
             e = gl + ((unsigned long long)kk << P.log_outer);
-            if (P.inverse) v = fp_mul(v, ninv);
-            v = fp_canon(v);
         }
+        if (!P.last || P.inverse) v = fp_mul(v, w);
+        if (P.last) v = fp_canon(v);
         if (P.last && P.coset_store == NTT_STORE_INTERLEAVED) {
             const unsigned long long col = poly / P.coset_cnt, rr = poly % P.coset_cnt + P.coset_r0;
             fp_stg(P.dst, col * P.dst_stride + (e << P.coset_log) + rr, v);

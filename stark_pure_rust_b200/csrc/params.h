@@ -35,6 +35,7 @@ struct NttPassParams {
     uint32_t n_prev;               // last pass: widths of the earlier passes, in order
     uint32_t prev_bits[NTT_MAX_PASSES];
     uint32_t n_inv[8];             // Montgomery form of n^-1 (inverse transform, last pass)
+    uint32_t maxq;                 // radix 2^maxq of the register rounds (kernel variant: 1, 2 or 3)
     // coset mode (low-degree extension by 2^coset_log): the batch holds (column, coset) pairs, polynomial id =
     // column * coset_cnt + (coset - coset_r0) for cosets coset_r0 .. coset_r0 + coset_cnt - 1.  The first pass reads
     // coefficient j of `column` and scales it by W^(j * coset) (W = the extended domain's root, w = W^(2^coset_log)).
@@ -42,19 +43,11 @@ struct NttPassParams {
     //   NTT_STORE_PLAIN       polynomial-major like a plain transform: output k of (column, coset) at
     //                         dst[polynomial * dst_stride + k] -- the coset-major layout of the prover (ext.cu)
     //   NTT_STORE_INTERLEAVED natural order of the extended domain: element k * 2^coset_log + coset of `column`
-    //   NTT_STORE_GATHER      natural order as well, but one CTA holds the SAME tile of all 2^coset_log cosets of one
-    //                         column (tile columns = (sub-transform, coset) pairs, coset minor), so every output row is
-    //                         2^coset_log contiguous elements (256 B) instead of one 32-byte element per 256 B; the coset-0
-    //                         slots carry the input column itself (c0_src), which makes the separate copy kernel unnecessary.
-    //                         Needs coset_log == 3, coset_r0 == 1, coset_cnt == 7 and at least two passes.
     uint32_t coset_cnt, coset_r0, coset_log, coset_store;
     uint32_t coset_dst_cpd, coset_dst_r0;   // NTT_STORE_PLAIN: (column, coset) is stored as polynomial column * coset_dst_cpd + coset - coset_dst_r0
-    const uint4 *c0_src;           // NTT_STORE_GATHER: the LDE's input columns (coset 0)
-    unsigned long long c0_stride, c0_len;
 };
 #define NTT_STORE_PLAIN 0
 #define NTT_STORE_INTERLEAVED 1
-#define NTT_STORE_GATHER 2
 
 struct MerkleColsParams {
     const uint4 *cols[8];
@@ -99,6 +92,7 @@ struct MerkleBytesParams {
     uint4 *nodes;
     unsigned long long n;
     uint32_t leaf_bytes;
+    unsigned long long first, count;   // this launch hashes leaves [first, first + count) (chunks of a pipelined upload; first is a multiple of 1024)
 };
 
 // digest offset of level l (l = 0: leaf hashes) inside a tree's node array of 2n - 1 digests

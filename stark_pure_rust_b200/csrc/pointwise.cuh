@@ -32,6 +32,7 @@ struct PwConsts {
     uint32_t pw8[8][8];        // (g2^S)^(j mod 8)
     uint32_t r[3][8];          // accumulator challenges (utils.rs:272-290)
     uint32_t k[11][8];         // linear-combination challenges (prove.rs:274-283)
+    uint32_t kx[3][8][8];      // per coset r: k3 + k4 X_r, k5 + k6 X_r, k7 + k8 X_r with X_r = (g2^S)^r (the p, b2, b3 terms of l)
     uint32_t one[8];
     uint32_t x_last[8];        // xs[N - sk] (utils.rs:459)
 };
@@ -53,6 +54,12 @@ __global__ void pw_u64_to_fp_kernel(const unsigned long long *v, uint4 *out, uns
     a.l[0] = (uint32_t)x;
     a.l[1] = (uint32_t)(x >> 32);
     fp_stg(out, i, fp_to_mont(a));
+}
+
+// identity padding of the copy permutation beyond the original steps (prove.rs:55-56): perm[i] = i for os <= i < n
+__global__ void pw_perm_pad_kernel(unsigned long long *perm, unsigned long long os, unsigned long long n) {
+    const size_t i = os + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) perm[i] = i;
 }
 
 // accumulator-tree leaves (utils.rs:250-270): u64_LE(permuted_index[j]) || to_bytes_le(witness_trace[j]), 40 B
@@ -231,18 +238,98 @@ struct PwLParams {
 };
 __global__ void __launch_bounds__(128) pw_l_kernel(const __grid_constant__ PwLParams P, const __grid_constant__ PwConsts Cst) {
     PW_DECODE(P.v)
-    fp X = pw_const(Cst.pw8[r_]);
-    fp pj = fp_ldg(P.p, t), b2 = fp_ldg(P.b2, t), b3 = fp_ldg(P.b3, t);
+    // k3 p + k4 p X = (k3 + k4 X) p, and X takes one value per coset: 8 products per row instead of 14, same field element
     fp acc = fp_mul(fp_ldg(P.d1, t), pw_const(Cst.k[0]));
     acc = fp_add(acc, fp_mul(fp_ldg(P.d2, t), pw_const(Cst.k[1])));
     acc = fp_add(acc, fp_mul(fp_ldg(P.d3, t), pw_const(Cst.k[2])));
-    acc = fp_add(acc, fp_mul(pj, pw_const(Cst.k[3])));
-    acc = fp_add(acc, fp_mul(fp_mul(pj, pw_const(Cst.k[4])), X));
-    acc = fp_add(acc, fp_mul(b2, pw_const(Cst.k[5])));
-    acc = fp_add(acc, fp_mul(fp_mul(b2, pw_const(Cst.k[6])), X));
-    acc = fp_add(acc, fp_mul(b3, pw_const(Cst.k[7])));
-    acc = fp_add(acc, fp_mul(fp_mul(b3, pw_const(Cst.k[8])), X));
+    acc = fp_add(acc, fp_mul(fp_ldg(P.p, t), pw_const(Cst.kx[0][r_])));
+    acc = fp_add(acc, fp_mul(fp_ldg(P.b2, t), pw_const(Cst.kx[1][r_])));
+    acc = fp_add(acc, fp_mul(fp_ldg(P.b3, t), pw_const(Cst.kx[2][r_])));
     acc = fp_add(acc, fp_mul(fp_ldg(P.a, t), pw_const(Cst.k[9])));
     acc = fp_add(acc, fp_mul(fp_ldg(P.s, t), pw_const(Cst.k[10])));
     fp_stg(P.l, t, fp_canon(acc));
+}
+
+// ---- interpolation through n public points on the device (poly_utils.rs:409-439 lagrange_interp, :362-373 zpoly) ----------
+// The reference's O(n^2) scalar code; n = number of public wires in use (1062 for the bundled `bits` circuit, where the
+// threaded host version took 30 of the prover's 36 ms).  Same field elements (the interpolant is unique), computed as
+//     Z(X) = prod (X - x_i)                                       interp_zpoly_kernel (one CTA, coefficients in shared memory)
+//     s_i  = y_i / Z'(x_i),  Z'(x_i) = prod_{j != i} (x_i - x_j)  interp_denoms_kernel + the batch inverse + a product
+//     P[t] = sum_i s_i x_i^t                                      interp_powers_kernel + interp_powersum_kernel
+//     I[k] = sum_{m > k} Z[m] P[m - k - 1]                        interp_conv_kernel
+// because Z(X) / (X - x_i) = sum_k X^k sum_{m > k} Z[m] x_i^(m - k - 1).
+
+// Z's n + 1 coefficients, lowest first: n steps c <- c * (X - x_j), every thread owning a strided share of the coefficients
+__global__ void __launch_bounds__(1024) interp_zpoly_kernel(const uint4 *xs, uint32_t n, uint4 *zcoef) {
+    extern __shared__ uint4 zs[];                 // two buffers of n + 1 elements
+    uint4 *cur = zs, *nxt = zs + 2 * (n + 1);
+    for (uint32_t k = threadIdx.x; k <= n; k += blockDim.x) {
+        fp v = k == 0 ? fp_one() : fp_zero();
+        cur[2 * k] = fp_lo(v);
+        cur[2 * k + 1] = fp_hi(v);
+    }
+    __syncthreads();
+    for (uint32_t j = 0; j < n; j++) {            // degree j -> j + 1
+        const fp x = fp_ldg_ro(xs, j);
+        for (uint32_t k = threadIdx.x; k <= j + 1; k += blockDim.x) {
+            fp lower = k ? fp_from_u4(cur[2 * (k - 1)], cur[2 * (k - 1) + 1]) : fp_zero();
+            fp v = lower;
+            if (k <= j) v = fp_sub(lower, fp_mul(fp_from_u4(cur[2 * k], cur[2 * k + 1]), x));
+            nxt[2 * k] = fp_lo(v);
+            nxt[2 * k + 1] = fp_hi(v);
+        }
+        __syncthreads();
+        uint4 *t = cur; cur = nxt; nxt = t;
+    }
+    for (uint32_t k = threadIdx.x; k <= n; k += blockDim.x) fp_stg(zcoef, k, fp_canon(fp_from_u4(cur[2 * k], cur[2 * k + 1])));
+}
+// d[i] = prod_{j != i} (x_i - x_j)
+__global__ void __launch_bounds__(128) interp_denoms_kernel(const uint4 *xs, uint32_t n, uint4 *d) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const fp xi = fp_ldg_ro(xs, i);
+    fp acc = fp_one();
+    for (uint32_t j = 0; j < n; j++)
+        if (j != i) acc = fp_mul(fp_sub_lazy(xi, fp_ldg_ro(xs, j)), acc);
+    fp_stg(d, i, fp_canon(acc));
+}
+// tab[t * n + i] = s_i x_i^t, t < n
+__global__ void __launch_bounds__(128) interp_powers_kernel(const uint4 *xs, const uint4 *s, uint32_t n, uint4 *tab) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const fp x = fp_ldg_ro(xs, i);
+    fp v = fp_ldg(s, i);
+    for (uint32_t t = 0; t < n; t++) {
+        fp_stg(tab, (size_t)t * n + i, v);
+        v = fp_mul(v, x);
+    }
+}
+// P[t] = sum_i tab[t * n + i]: one CTA per t
+__global__ void __launch_bounds__(128) interp_powersum_kernel(const uint4 *tab, uint32_t n, uint4 *P) {
+    __shared__ uint4 red[256];
+    const uint32_t t = blockIdx.x;
+    fp acc = fp_zero();
+    for (uint32_t i = threadIdx.x; i < n; i += 128) acc = fp_add(acc, fp_ldg(tab, (size_t)t * n + i));
+    red[2 * threadIdx.x] = fp_lo(acc);
+    red[2 * threadIdx.x + 1] = fp_hi(acc);
+    __syncthreads();
+    for (uint32_t w = 64; w > 0; w >>= 1) {
+        if (threadIdx.x < w) {
+            fp a = fp_from_u4(red[2 * threadIdx.x], red[2 * threadIdx.x + 1]);
+            fp b = fp_from_u4(red[2 * (threadIdx.x + w)], red[2 * (threadIdx.x + w) + 1]);
+            a = fp_add(a, b);
+            red[2 * threadIdx.x] = fp_lo(a);
+            red[2 * threadIdx.x + 1] = fp_hi(a);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) fp_stg(P, t, fp_canon(fp_from_u4(red[0], red[1])));
+}
+// out[k] = sum_{m = k + 1}^{n} Z[m] P[m - k - 1], k < n
+__global__ void __launch_bounds__(128) interp_conv_kernel(const uint4 *z, const uint4 *P, uint32_t n, uint4 *out) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    fp acc = fp_zero();
+    for (uint32_t m = k + 1; m <= n; m++) acc = fp_add(acc, fp_mul(fp_ldg_ro(z, m), fp_ldg_ro(P, m - k - 1)));
+    fp_stg(out, k, fp_canon(acc));
 }

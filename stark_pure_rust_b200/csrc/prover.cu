@@ -124,6 +124,49 @@ static void host_lagrange(std::vector<hfp::el> &out, const std::vector<hfp::el> 
 
 static void put_const(uint32_t (&dst)[8], const hfp::el &v) { memcpy(dst, v.l, 32); }
 
+// lagrange_interp + zpoly (poly_utils.rs:409-439, :362-373) on the device: d_x = the n interpolation points (device),
+// ys on the host; returns the n coefficients of the interpolant and the n + 1 of the vanishing polynomial on the host.
+// Used from 32 points on (below that the scalar host code is faster than the launches); n is bounded by the shared memory
+// the coefficient buffers of interp_zpoly_kernel need.
+static const size_t INTERP_DEVICE_MIN = 32, INTERP_DEVICE_MAX = 3000;
+static int device_lagrange(sb_ctx *ctx, const uint4 *d_x, const std::vector<hfp::el> &ys, std::vector<hfp::el> &interp, std::vector<hfp::el> &zroot) {
+    const uint32_t n = (uint32_t)ys.size();
+    DevBuf z(ctx), s(ctx), y(ctx), tab(ctx), P(ctx), out(ctx);
+    TRY(z.alloc((size_t)(n + 1) * 32));
+    TRY(s.alloc((size_t)n * 32));
+    TRY(y.alloc((size_t)n * 32));
+    TRY(tab.alloc((size_t)n * n * 32));
+    TRY(P.alloc((size_t)n * 32));
+    TRY(out.alloc((size_t)n * 32));
+    CU(cudaMemcpyAsync(y.p, ys.data(), (size_t)n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    const size_t smem = (size_t)4 * (n + 1) * sizeof(uint4);
+    static bool attr_set = false;            // benign race: the attribute is idempotent
+    if (!attr_set) {
+        CU(cudaFuncSetAttribute(interp_zpoly_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)4 * (INTERP_DEVICE_MAX + 1) * sizeof(uint4))));
+        attr_set = true;
+    }
+    prof_begin(ctx, SB_KIND_OTHER);
+    interp_zpoly_kernel<<<1, 1024, smem, ctx->stream>>>(d_x, n, (uint4 *)z.p);
+    interp_denoms_kernel<<<nblk(n), 128, 0, ctx->stream>>>(d_x, n, (uint4 *)s.p);
+    prof_end(ctx);
+    ctx->launches += 2;
+    TRY(sb_batch_inverse_dev(ctx, (uint64_t *)s.p, n));
+    prof_begin(ctx, SB_KIND_OTHER);
+    pw_mul_kernel<<<nblk(n), 128, 0, ctx->stream>>>((const uint4 *)s.p, (const uint4 *)y.p, (uint4 *)s.p, n);
+    interp_powers_kernel<<<nblk(n), 128, 0, ctx->stream>>>(d_x, (const uint4 *)s.p, n, (uint4 *)tab.p);
+    interp_powersum_kernel<<<n, 128, 0, ctx->stream>>>((const uint4 *)tab.p, n, (uint4 *)P.p);
+    interp_conv_kernel<<<nblk(n), 128, 0, ctx->stream>>>((const uint4 *)z.p, (const uint4 *)P.p, n, (uint4 *)out.p);
+    prof_end(ctx);
+    ctx->launches += 4;
+    CU(cudaGetLastError());
+    interp.resize(n);
+    zroot.resize(n + 1);
+    CU(cudaMemcpyAsync(interp.data(), out.p, (size_t)n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(zroot.data(), z.p, (size_t)(n + 1) * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+
 // mk_r1cs_proof on the devices of `ctx` (one, or the several of sb_init_multi).  Every N-point column is coset-major and
 // sharded by cosets (sb_ext): pointwise kernels, leaf hashing and the first FRI fold run where the data is, the trees are
 // built as per-device subtrees with the top finished on the host, and only S-point coefficient vectors and 32-byte digests
@@ -220,22 +263,50 @@ extern "C" int sb_prove_r1cs(sb_ctx *ctx, const sb_trace *t, sb_stark_proof **ou
     }
     TRY(mark());
 
-    // ---- inputs: every column goes to the device that runs its inverse transform (:55-68, :105-113, :160-163) ----------
-    const uint64_t *srcs[6] = {t->coefficients, t->flag0, t->flag1, t->flag2, t->witness_trace, t->computational_trace};
-    for (int c = 0; c < 6; c++) {
-        sb_ctx *o = ctx->dev[E->owner[c]];
-        DevGuard dg(o);
-        DCU(cudaMemcpyAsync(E->input(c), srcs[c], os * 32, cudaMemcpyHostToDevice, o->stream));      // the tail stays zero (ext_create)
+    // ---- inputs: every column goes to the device that runs its inverse transform (:55-68, :105-113, :160-163), on that
+    // device's copy stream so that the uploads overlap the transforms of the columns that have already arrived ----------
+    static_assert(sizeof(size_t) == sizeof(unsigned long long), "permuted_indices are uploaded as 64-bit words");
+    cudaEvent_t up[6] = {0}, perm_up[SB_MAX_DEV] = {0};
+    struct EvGuard {
+        cudaEvent_t *a, *b;
+        ~EvGuard() {
+            for (int i = 0; i < 6; i++)
+                if (a[i]) cudaEventDestroy(a[i]);
+            for (int i = 0; i < SB_MAX_DEV; i++)
+                if (b[i]) cudaEventDestroy(b[i]);
+        }
+    } ev_guard{up, perm_up};
+    for (int d = 0; d < g; d++) {           // the copy streams start behind ext_create's allocations / memsets
+        sb_ctx *c = ctx->dev[d];
+        DevGuard dg(c);
+        if (!c->h2d_stream) DCU(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+        cudaEvent_t ready;
+        DCU(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+        DCU(cudaEventRecord(ready, c->stream));
+        DCU(cudaStreamWaitEvent(c->h2d_stream, ready, 0));
+        cudaEventDestroy(ready);
     }
-    std::vector<unsigned long long> perm(S);
-    for (size_t i = 0; i < os; i++) perm[i] = t->permuted_indices[i];
-    for (size_t i = os; i < S; i++) perm[i] = i;                                                    // :55-56
-    for (int d : {E->owner[PIDX_], dS}) {
+    for (int d : {E->owner[PIDX_], dS}) {   // the copy permutation: its padding (:55-56) is written on the device
         if (pd[d].perm) continue;
         sb_ctx *c = ctx->dev[d];
         DevGuard dg(c);
         DCU(cudaMallocAsync(&pd[d].perm, S * 8, c->stream));
-        DCU(cudaMemcpyAsync(pd[d].perm, perm.data(), S * 8, cudaMemcpyHostToDevice, c->stream));
+        DCU(cudaEventCreateWithFlags(&perm_up[d], cudaEventDisableTiming));
+        DCU(cudaEventRecord(perm_up[d], c->stream));
+        DCU(cudaStreamWaitEvent(c->h2d_stream, perm_up[d], 0));
+        DCU(cudaMemcpyAsync(pd[d].perm, t->permuted_indices, os * 8, cudaMemcpyHostToDevice, c->h2d_stream));
+        DCU(cudaEventRecord(perm_up[d], c->h2d_stream));
+        DCU(cudaStreamWaitEvent(c->stream, perm_up[d], 0));
+        if (S > os) pw_perm_pad_kernel<<<nblk(S - os), 128, 0, c->stream>>>((unsigned long long *)pd[d].perm, os, S);
+        c->launches++;
+    }
+    const uint64_t *srcs[6] = {t->coefficients, t->flag0, t->flag1, t->flag2, t->witness_trace, t->computational_trace};
+    for (int c = 0; c < 6; c++) {
+        sb_ctx *o = ctx->dev[E->owner[c]];
+        DevGuard dg(o);
+        DCU(cudaMemcpyAsync(E->input(c), srcs[c], os * 32, cudaMemcpyHostToDevice, o->h2d_stream));      // the tail stays zero (ext_create)
+        DCU(cudaEventCreateWithFlags(&up[c], cudaEventDisableTiming));
+        DCU(cudaEventRecord(up[c], o->h2d_stream));
     }
     {
         sb_ctx *c = ctx->dev[E->owner[IDX_]];
@@ -249,18 +320,35 @@ extern "C" int sb_prove_r1cs(sb_ctx *ctx, const sb_trace *t, sb_stark_proof **ou
         pw_u64_to_fp_kernel<<<nblk(S), 128, 0, c->stream>>>((const unsigned long long *)pd[E->owner[PIDX_]].perm, E->input(PIDX_), S);
         c->launches++;
     }
-    // :100-124, :160-167 the eight LDEs
-    TRY(ext_extend(E, 0, 8));
+    // :100-124, :160-167 the eight LDEs.  One device: the two index columns first (nothing to wait for), then pairs of columns
+    // as their uploads land; several devices: every owner waits for its own columns only.
+    auto wait_cols = [&](int c0, int c1) -> int {
+        for (int c = c0; c < c1; c++) {
+            sb_ctx *o = ctx->dev[E->owner[c]];
+            DevGuard dg(o);
+            DCU(cudaStreamWaitEvent(o->stream, up[c], 0));
+        }
+        return SB_OK;
+    };
+    if (g == 1 && S >= ((size_t)1 << 16)) {
+        TRY(ext_extend(E, IDX_, 2));
+        for (int c = 0; c < 6; c += 2) {
+            TRY(wait_cols(c, c + 2));
+            TRY(ext_extend(E, c, 2));
+        }
+    } else {
+        TRY(wait_cols(0, 6));
+        TRY(ext_extend(E, 0, 8));
+    }
     TRY(mark());
 
     // ---- constants of the pointwise stage ---------------------------------------------------------------
     PwConsts Cst;
     memset(&Cst, 0, sizeof Cst);
     {
-        hfp::el gs, x_last, pw = hfp::ONE;
-        DCU(cudaMemcpyAsync(&gs, (const uint8_t *)xs[0] + 32 * S, 32, cudaMemcpyDeviceToHost, ctx->stream));             // g2^S: primitive 8th root (:287-290)
-        DCU(cudaMemcpyAsync(&x_last, (const uint8_t *)xs[0] + 32 * (N - sk), 32, cudaMemcpyDeviceToHost, ctx->stream)); // utils.rs:459
-        DCU(cudaStreamSynchronize(ctx->stream));
+        // g2^S: primitive 8th root of unity (:287-290); xs[N - sk] = g2^-8 (utils.rs:459) -- host scalars, no round trip
+        const hfp::el gs = hfp::pow_u64(g2, S), x_last = hfp::inv(hfp::pow_u64(g2, sk));
+        hfp::el pw = hfp::ONE;
         for (int i = 0; i < 8; i++) {
             put_const(Cst.pw8[i], pw);
             hfp::el z = hfp::add(pw, hfp::neg(hfp::ONE));                   // z[j] = g2^(jS) - 1 (utils.rs:173-178)
@@ -353,7 +441,8 @@ extern "C" int sb_prove_r1cs(sb_ctx *ctx, const sb_trace *t, sb_stark_proof **ou
     {
         std::vector<hfp::el> xv(np), yv(np), interp, zroot;
         for (size_t i = 0; i < np; i++) yv[i] = hfp::from_limbs(t->public_wires + 4 * t->pfi_k[i]);   // utils.rs:421-435
-        if (np) {
+        const bool on_device = np >= INTERP_DEVICE_MIN && np <= INTERP_DEVICE_MAX;
+        if (np && on_device) {
             std::vector<unsigned long long> pos(np);
             for (size_t i = 0; i < np; i++) pos[i] = sk * t->pfi_w[i];
             DevBuf dpos(ctx), dx(ctx);
@@ -361,10 +450,11 @@ extern "C" int sb_prove_r1cs(sb_ctx *ctx, const sb_trace *t, sb_stark_proof **ou
             TRY(dx.alloc(np * 32));
             DCU(cudaMemcpyAsync(dpos.p, pos.data(), np * 8, cudaMemcpyHostToDevice, ctx->stream));
             ctx->launches += merkle_launch_gather_bytes(ctx->stream, (const uint8_t *)xs[0], 32, (const unsigned long long *)dpos.p, (uint32_t)np, (uint8_t *)dx.p);
-            DCU(cudaMemcpyAsync(xv.data(), dx.p, np * 32, cudaMemcpyDeviceToHost, ctx->stream));
-            DCU(cudaStreamSynchronize(ctx->stream));
+            TRY(device_lagrange(ctx, (const uint4 *)dx.p, yv, interp, zroot));
+        } else {
+            for (size_t i = 0; i < np; i++) xv[i] = hfp::pow_u64(g2, sk * t->pfi_w[i]);     // xs[sk w]: a handful of host scalars
         }
-        host_lagrange(interp, xv, yv, &zroot);
+        if (!on_device) host_lagrange(interp, xv, yv, &zroot);
         const bool horner = np + 1 <= 24;      // ~np products per point against the ~log2(S)/2 + 2 of a transform
         for (int d = 0; d < g; d++) {
             sb_ctx *c = ctx->dev[d];
@@ -437,6 +527,14 @@ extern "C" int sb_prove_r1cs(sb_ctx *ctx, const sb_trace *t, sb_stark_proof **ou
         b2s::hash_bytes(h, msg, 33);
         for (int b = 0; b < 32; b++) le[b] = h[31 - b];
         put_const(Cst.k[i], hfp::from_bytes_le32(le));
+    }
+    for (int r = 0; r < 8; r++) {         // X = (g2^S)^(j mod 8) in the p, b2, b3 terms (:287-322)
+        hfp::el X, kk[11];
+        memcpy(X.l, Cst.pw8[r], 32);
+        for (int i = 0; i < 11; i++) memcpy(kk[i].l, Cst.k[i], 32);
+        put_const(Cst.kx[0][r], hfp::add(kk[3], hfp::mul(kk[4], X)));
+        put_const(Cst.kx[1][r], hfp::add(kk[5], hfp::mul(kk[6], X)));
+        put_const(Cst.kx[2][r], hfp::add(kk[7], hfp::mul(kk[8], X)));
     }
     // :287-322 l
     for (int d = 0; d < g; d++) {

@@ -139,11 +139,13 @@ def test_fp_canon_half_codecs(ctx):
         assert g == (x - P if x >= P else x), "fp_canon(%x) = %x" % (x, g)
         assert h == ((x + P) >> 1 if x & 1 else x >> 1), "fp_half(%x) = %x" % (x, h)
         assert h < (3 * P + 1) // 2 + 1 and (2 * h - x) % P == 0
-    # from_mont: any a < 2^256 - p -> a R^-1 mod p, canonical
-    Y = in_range(edges() + limb_patterns(), R - P) + [rnd.randrange(R - P) for _ in range(20000)]
+    # from_mont (dedicated reduction): any a < 2^256 -> a R^-1 mod p, canonical
+    Y = in_range(edges() + limb_patterns(), R) + [rnd.randrange(R) for _ in range(20000)] + [R - 1 - d for d in range(8)]
     got = run(ctx, 6, Y, Y)
     for y, g in zip(Y, got):
         assert g == y * RINV % P, "fp_from_mont(%x) = %x" % (y, g)
+    # to_mont: any a < 2^256 - p -> a R mod p, canonical
+    Y = in_range(edges() + limb_patterns(), R - P) + [rnd.randrange(R - P) for _ in range(20000)]
     got = run(ctx, 7, Y, Y)
     for y, g in zip(Y, got):
         assert g == y * R % P, "fp_to_mont(%x) = %x" % (y, g)

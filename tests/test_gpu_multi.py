@@ -84,8 +84,8 @@ def test_ext_direct_fri_and_errors(mctx, oracle):
     log_s = 10
     N = 8 << log_s
     g2 = oracle.root_of_unity(log_s + 3)
-    col = np.zeros((1, 16, 4), dtype=np.uint64)
-    col[0] = random_elems(16, 31)
+    # a column of degree < 16: the S-point evaluations of 16 random coefficients
+    col = oracle.best_fft(random_elems(16, 31), oracle.root_of_unity(log_s), log_s).reshape(1, 1 << log_s, 4)
     e = sb.ext.ExtColumns(1, log_s, ctx=mctx)
     e.load(0, col)
     e.extend()

@@ -248,6 +248,44 @@ def gen_mul():
     return stmts
 
 
+def gen_redc():
+    """Montgomery reduction alone: r = a / 2^256 mod p (<= p) for any a < 2^256 -- gen_mul's rows without the a*b products
+    (E = a even-aligned, O = 0 on entry): 8 + 64 wide multiplies instead of mont_mul(a, 1)'s 8 + 128."""
+    stmts = []
+    st = Stmt()
+    m = st.temp("m")
+    mont_m(st, m, reg("E", 0))
+    mp_rows(st, "E", "O", m)
+    stmts.append(st)
+    for i in range(1, 8):
+        X, Y = ("O", "E") if i % 2 == 1 else ("E", "O")
+        st = Stmt()
+        m = st.temp("m")
+        st.add("add.cc.u32", reg(X, 0), reg(X, 0), reg(Y, 1))       # leftover word joins word 0
+        for j in range(8):                                          # Y' = Y >> 64 with the carry rippling through
+            src = reg(Y, j + 2) if j + 2 < 8 else imm(0)
+            st.add("addc.cc.u32" if j < 7 else "addc.u32", reg(Y, j), src, imm(0))
+        mont_m(st, m, reg(X, 0))
+        mp_rows(st, X, Y, m)
+        stmts.append(st)
+    st = Stmt()
+    for j in range(8):
+        op = "add.cc.u32" if j == 0 else ("addc.cc.u32" if j < 7 else "addc.u32")
+        src = reg("O", j + 1) if j < 7 else imm(0)
+        st.add(op, reg("E", j), reg("E", j), src)
+    stmts.append(st)
+    return stmts
+
+
+def run_redc(a):
+    env = {}
+    for j in range(8):
+        env[f"E{j}"] = limbs(a)[j]
+        env[f"O{j}"] = 0
+    emulate(REDC, env)
+    return sum(env[f"E{j}"] << (32 * j) for j in range(8))
+
+
 def run_mul(a, b):
     al, bl = limbs(a), limbs(b)
     env = {}
@@ -305,6 +343,7 @@ def gen_subk_borrow(KL):
 
 
 MUL = gen_mul()
+REDC = gen_redc()
 ADD = gen_add()
 ADD_P = gen_addk(PL)
 ADD_2P = gen_addk(P2L)
@@ -347,6 +386,11 @@ def selftest(iters=3000):
             continue
         got = run_mul(a, 1)
         assert got % P == a * Rinv % P and got <= P, hex(a)
+    # --- the dedicated reduction: any a < 2^256 ---
+    for a in edge + [rnd.randrange(R) for _ in range(iters)] + [R - 1 - rnd.randrange(1 << 40) for _ in range(50)]:
+        got = run_redc(a)
+        assert got % P == a * Rinv % P and got <= P, hex(a)
+        assert got == (a + ((a * ((-pow(P, -1, R)) % R)) % R) * P) >> 256
     # --- add / sub ---
     for _ in range(iters):
         a, b = rnd.randrange(2 * P), rnd.randrange(2 * P)
@@ -390,6 +434,13 @@ def generate():
     s += "        O[2 * k] = (uint32_t)o;      O[2 * k + 1] = (uint32_t)(o >> 32);\n"
     s += "    }\n"
     s += emit(MUL)
+    s += "#pragma unroll\n    for (int k = 0; k < 8; k++) r[k] = E[k];\n"
+    s += "}\n\n"
+    s += "// r = a/2^256 mod p, r <= p, for any a < 2^256 (Montgomery reduction without a product)\n"
+    s += "__device__ __forceinline__ void redc(uint32_t (&r)[8], const uint32_t (&a)[8]) {\n"
+    s += "    uint32_t E[8], O[8];\n"
+    s += "#pragma unroll\n    for (int k = 0; k < 8; k++) { E[k] = a[k]; O[k] = 0; }\n"
+    s += emit(REDC)
     s += "#pragma unroll\n    for (int k = 0; k < 8; k++) r[k] = E[k];\n"
     s += "}\n\n"
     def fn(sig, doc, prog):

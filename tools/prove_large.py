@@ -25,6 +25,8 @@ def main():
     ap.add_argument("--cpu", action="store_true")
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--dir", default="/tmp")
+    ap.add_argument("--devices", default=None, help="comma-separated device ordinals for ONE proof over several (logical) devices, e.g. 0,1,2,3 or 0,0")
+    ap.add_argument("--profile", action="store_true", help="print the per-kernel-family times of the last repetition (CUDA events around every launch)")
     a = ap.parse_args()
     prefix = os.path.join(a.dir, "syn_%d_%g_%d" % (a.constraints, a.avg_terms, a.seed))
     t0 = time.perf_counter()
@@ -32,13 +34,19 @@ def main():
     info = gen_r1cs.write_files(prefix, wit, cons, 2)
     print("generated", info, "in %.1f s" % (time.perf_counter() - t0), flush=True)
     import stark_pure_rust_b200 as sb
-    ctx = sb.default_context()
+    ctx = sb.Context(devices=[int(x) for x in a.devices.split(",")]) if a.devices else sb.default_context()
     out = prefix + ".proof.json"
     res = {"circuit": info}
     for r in range(a.reps):
+        if a.profile and r == a.reps - 1:
+            ctx.profile(True)
         t0 = time.perf_counter()
         ms = sb.prove.prove_with_file_path(prefix + ".r1cs", prefix + ".wtns", out, ctx=ctx)
         wall = (time.perf_counter() - t0) * 1e3
+        if a.profile and r == a.reps - 1:
+            kinds = ["ntt_pass", "merkle_leaves", "merkle_nodes", "fri_fold", "open", "other"]
+            print("kernel families (launches, ms summed over devices):", {k: ctx.profile_read(i) for i, k in enumerate(kinds)})
+            ctx.profile(False)
         import hashlib
         print("sha256", hashlib.sha256(open(out, "rb").read()).hexdigest())
         print("gpu rep %d: wall %.1f ms | LDE %.2f m_tree %.2f FRI %.2f rest %.2f | prove %.2f | front end %.2f | json+write %.2f | proof %d bytes" % (
