@@ -179,6 +179,28 @@ def pinned_array(ctx, shape, dtype):
     return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape), p
 
 
+def pcie_probe(ctx, barrier, nbytes=1 << 30, reps=3):
+    """host <-> device copy rates of this rank with every rank copying at the same time (pinned memory, the library's own
+    copy entry points): the ceiling of any host-buffer (e2e) path on this box.  Returns GB/s: h2d alone, d2h alone."""
+    lib = ctx.lib
+    h, hp = pinned_array(ctx, (nbytes,), np.uint8)
+    h[:] = 1
+    d = ctx.alloc(nbytes)
+    out = {}
+    for name, fn in (("h2d", lambda: ctx.check(lib.sb_h2d(ctx.h, C.c_void_p(d), C.c_void_p(hp.value), nbytes))),
+                     ("d2h", lambda: ctx.check(lib.sb_d2h(ctx.h, C.c_void_p(hp.value), C.c_void_p(d), nbytes)))):
+        fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        out[name] = nbytes * reps / (time.perf_counter() - t0) / 1e9
+        barrier()
+    ctx.free(d)
+    lib.sb_host_free_pinned(ctx.h, hp)
+    return out
+
+
 def gpu_step_ms(ctx, L, Cn, reps=5):
     """device-resident step (LDE + two trees + FRI) at domain 2^L, CUDA-event timed"""
     from stark_pure_rust_b200 import field
@@ -349,6 +371,7 @@ def run_gpu(args):
         e2e = {"ms": e2e_ms, "h2d": h2d, "d2h": d2h}
         for p in (p1, p2, p3):
             lib.sb_host_free_pinned(ctx.h, p)
+        e2e["pcie"] = pcie_probe(ctx, barrier)
 
     # max over ranks -------------------------------------------------------------------------------------------
     step_ms = ms / args.steps
@@ -359,6 +382,9 @@ def run_gpu(args):
         step_ms = float(t[0]);
         if e2e:
             e2e["ms"] = float(t[1])
+            t = torch.tensor([e2e["pcie"]["h2d"], e2e["pcie"]["d2h"]], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            e2e["pcie_all"] = {"h2d": float(t[0]), "d2h": float(t[1])}
     prove_multi = None
     if world > 1 and not args.no_prove:
         # BASELINE.json configs[3] at N > 1: one proof per GPU (replicas); aggregate = N proofs / slowest rank
@@ -493,10 +519,15 @@ def run_gpu(args):
         # the three reference-shaped calls are synchronous and each moves its whole argument / result across PCIe, so the copies of
         # one step cannot overlap each other beyond what happens inside a call: the floor is bytes / link rate
         link = 55e9
+        agg = e2e.get("pcie_all") or e2e["pcie"]
+        floor_ms = (world * e2e["h2d"] / (agg["h2d"] * 1e9) + world * e2e["d2h"] / (agg["d2h"] * 1e9)) * 1e3
         out["e2e"] = {"value": total_elems / (e2e["ms"] * 1e-3), "unit": "elems/s", "ms_per_step": e2e["ms"], "steps": args.steps,
                       "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]),
                       "pcie_gbs_achieved_both_directions": (e2e["h2d"] + e2e["d2h"]) / (e2e["ms"] * 1e-3) / 1e9,
                       "pcie_floor_ms_at_55gbs_per_direction_serialised": (e2e["h2d"] + e2e["d2h"]) / link * 1e3,
+                      "pcie_probe_gbs": {"h2d_all_ranks": agg["h2d"], "d2h_all_ranks": agg["d2h"], "rank0": e2e["pcie"],
+                                         "how": "1 GiB pinned copies through sb_h2d / sb_d2h, every rank copying at the same time"},
+                      "measured_floor_ms": floor_ms, "frac_of_measured_floor": floor_ms / e2e["ms"],
                       "note": "sb_lde_batch overlaps its upload / transform / download, sb_merkle_commit hashes chunk k while chunk k+1 uploads; what remains is PCIe "
                               "transfer time of the by-value Vec<Fp> signatures (best_fft returns the vector, MerkleProofInPlace::update takes the packed rows). "
                               "The resident pipeline behind sb_prove_r1cs / sb_ext_* moves 0.2 GB per 2^23 proof instead."}
@@ -594,7 +625,7 @@ def run_prove_extras(ctx, args, large_only=False, sync=None):
         tv = time.perf_counter()
         vms = sb.prove.verify_with_file_path(r1cs, wtns, os.path.join(tmp, "proof.json"), ctx=ctx)
         verify_s = time.perf_counter() - tv
-        return {"gpu_s": best[0], "gpu_verify_s": verify_s, "gpu_verify_ms": {"front_end_and_parse": vms[0], "verify": vms[1]}, "gpu_stage_ms": {"lde": best[1][0], "m_tree": best[1][1], "fri": best[1][2], "pointwise_and_rest": best[1][3],
+        return {"gpu_s": best[0], "gpu_verify_s": verify_s, "gpu_verify_ms": {"front_end_and_parse": vms[0], "verify": vms[1]}, "gpu_stage_ms": {"lde_and_pointwise": best[1][0], "m_tree": best[1][1], "fri": best[1][2], "l_tree_and_openings": best[1][3],
                                                    "device_total": best[1][4], "host_front_end": best[1][5], "json_write": best[1][6]},
                 "proof_bytes": os.path.getsize(os.path.join(tmp, "proof.json"))}
 
@@ -892,27 +923,41 @@ def run_multi_records(args, n_dev):
         e = sb.ext.ExtColumns(nc, log_s, ctx=ctx)
         e.load(0, h_cols)
 
+        stage = {"load": 0.0, "lde": 0.0, "merkle8": 0.0, "merkle1": 0.0, "fri": 0.0}
+
         def step(upload):
+            t = [time.perf_counter()]
             if upload:
                 e.load(0, h_cols)
+            t.append(time.perf_counter())
             e.extend()
+            t.append(time.perf_counter())
             rm, tm_ = e.commit(list(range(nc)))
+            t.append(time.perf_counter())
             rl, tl = e.commit([nc - 1])
+            t.append(time.perf_counter())
             text = e.fri_prove(nc - 1, N // 4, 8, tree=tl, as_json=True)
+            t.append(time.perf_counter())
             e.free_tree(tm_)
             e.free_tree(tl)
+            for k, name in enumerate(stage):
+                stage[name] += (t[k + 1] - t[k]) * 1e3
             return rm, rl, text
 
         rm, rl, text = step(False)
+        step(False)
         times = {}
         for name, upload in (("resident", False), ("e2e", True)):
             ctx.sync()
+            for k in stage:
+                stage[k] = 0.0
             l0 = ctx.launch_count()
             t0 = time.perf_counter()
             for _ in range(args.sharded_steps):
                 step(upload)
             times[name] = (time.perf_counter() - t0) * 1e3 / args.sharded_steps
             times[name + "_launches"] = (ctx.launch_count() - l0) // args.sharded_steps
+            times[name + "_stage_ms"] = {k: v / args.sharded_steps for k, v in stage.items()}
         res[g] = {"m_root": rm.hex(), "l_root": rl.hex(), "fri_json_sha256": sha(text.encode()), **times}
         e.close()
         lib.sb_host_free_pinned(ctx.h, hp)
@@ -925,6 +970,7 @@ def run_multi_records(args, n_dev):
         "elems_per_s": nc * N / (res[n_dev]["resident"] * 1e-3),
         "e2e_ms_per_step": res[n_dev]["e2e"], "e2e_ms_per_step_1gpu": res[1]["e2e"], "h2d_bytes_per_step": nc * S * 32,
         "gpu_launches_per_step": res[n_dev]["resident_launches"],
+        "stage_ms": res[n_dev]["resident_stage_ms"], "stage_ms_1gpu": res[1]["resident_stage_ms"],
         "parity": {"equal_to_1gpu": same, "m_root": res[n_dev]["m_root"], "l_root": res[n_dev]["l_root"], "fri_json_sha256": res[n_dev]["fri_json_sha256"],
                    "note": "domain 2^26 is beyond the reference sampler's 2^24 (sb_set_extended_domain): the parity target is the single-GPU natural-order path, itself oracle-checked up to 2^24"},
     }
@@ -945,7 +991,7 @@ def run_multi_records(args, n_dev):
             if best is None or ms[4] < best[1][4]:
                 best = (wall, ms)
         digest = sha(open(os.path.join(tmp, "proof.json"), "rb").read())
-        pres[g] = {"wall_s": best[0], "device_ms": best[1][4], "stage_ms": {"lde": best[1][0], "m_tree": best[1][1], "fri": best[1][2], "rest": best[1][3]},
+        pres[g] = {"wall_s": best[0], "device_ms": best[1][4], "stage_ms": {"lde_and_pointwise": best[1][0], "m_tree": best[1][1], "fri": best[1][2], "l_tree_and_openings": best[1][3]},
                    "host_front_end_ms": best[1][5], "json_ms": best[1][6], "proof_json_sha256": digest}
         assert digest == gold["proof_json_sha256"], "proof.json on %d GPU(s) differs from the oracle's golden hash" % g
     sb.prove.verify_with_file_path(os.path.join(tmp, "syn.r1cs"), os.path.join(tmp, "syn.wtns"), os.path.join(tmp, "proof.json"), ctx=ctxs[n_dev])

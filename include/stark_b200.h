@@ -220,8 +220,9 @@ typedef struct sb_stark_proof sb_stark_proof;
  * precision beyond the sampler's 2^24 or the field's two-adicity). */
 int sb_prove_r1cs(sb_ctx *ctx, const sb_trace *trace, sb_stark_proof **out);
 int sb_stark_proof_roots(const sb_stark_proof *p, uint8_t m_root[32], uint8_t l_root[32], uint8_t a_root[32]);
-/* Stage times of that proof (host clock, every device waited for at the stage boundaries): [0] inputs + LDEs, [1] m_tree
- * commit, [2] FRI, [3] the rest (pointwise stage, accumulator, l_tree, openings), [4] total (ms). */
+/* Stage times of that proof (host clock, every device waited for at the stage boundaries): [0] inputs, the nine LDEs, the
+ * accumulator chain and the pointwise stage (they overlap), [1] m_tree commit, [2] FRI, [3] l, l_tree and the openings,
+ * [4] total (ms). */
 int sb_stark_proof_stage_ms(const sb_stark_proof *p, double ms[5]);
 /* serde_json::to_string(&StarkProof) (utils.rs:122-130, run.rs:549): malloc'd, free with sb_free_string. */
 char *sb_stark_proof_json(const sb_stark_proof *p, size_t *len);
@@ -245,8 +246,8 @@ int sb_verify_files(sb_ctx *ctx, const char *r1cs_path, const char *wtns_path, c
 
 /* prove_with_file_path (r1cs-stark/src/run.rs:528-554): parse <r1cs> (circom2bellman_core/src/reader.rs:4-89) and
  * <wtns> (r1cs-stark/src/reader.rs:7-42), arrange the traces (run.rs:109-308, :390-419), prove on the device and
- * write the proof as compact JSON.  proof_path may be NULL.  stage_ms (may be NULL): [0] LDE [1] m_tree [2] FRI
- * [3] rest of the GPU pipeline [4] sb_prove_r1cs wall clock [5] host front end [6] JSON + file write. */
+ * write the proof as compact JSON.  proof_path may be NULL.  stage_ms (may be NULL): [0]..[3] as sb_stark_proof_stage_ms,
+ * [4] sb_prove_r1cs wall clock [5] host front end [6] JSON + file write. */
 int sb_prove_files(sb_ctx *ctx, const char *r1cs_path, const char *wtns_path, const char *proof_path, double stage_ms[7]);
 
 /* The host front end alone (run.rs:109-308, :390-419; circom2bellman_core/src/reader.rs:4-89; r1cs-stark/src/reader.rs:7-42):

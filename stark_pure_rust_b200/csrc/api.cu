@@ -96,6 +96,20 @@ extern "C" int sb_init_multi(const int *devices, int n_devices, sb_ctx **out) {
                     return SB_ERR_NO_DEVICE;
                 }
                 cudaGetLastError();
+                // the stream-ordered pool (cudaMallocAsync: every column, tree and scratch buffer) has its own access list:
+                // device i may read and write device j's pool
+                cudaMemPool_t pool;
+                cudaMemAccessDesc desc = {};
+                desc.location.type = cudaMemLocationTypeDevice;
+                desc.location.id = devices[i];
+                desc.flags = cudaMemAccessFlagsProtReadWrite;
+                if (cudaDeviceGetDefaultMemPool(&pool, devices[j]) != cudaSuccess || cudaMemPoolSetAccess(pool, &desc, 1) != cudaSuccess) {
+                    fail(root, SB_ERR_NO_DEVICE, "cannot open the memory pool of device %d to device %d: %s", devices[j], devices[i],
+                         cudaGetErrorString(cudaGetLastError()));
+                    fprintf(stderr, "stark_b200: %s\n", root->err);
+                    sb_destroy(root);
+                    return SB_ERR_NO_DEVICE;
+                }
             }
         *out = root;
         return SB_OK;
@@ -498,6 +512,7 @@ extern "C" int sb_ntt(sb_ctx *ctx, uint64_t *vals, size_t len_in, const uint64_t
 // arithmetic is exact), so it is copied.  This skips the three degenerate butterfly stages and one eighth of the rest.
 int lde_dev(sb_ctx *ctx, const uint4 *d_cols, size_t n_cols, size_t col_len, size_t col_stride,
                    const hfp::el &root_big, uint32_t log_s, uint32_t log_ext, uint4 *d_out) {
+    NvtxRange nvtx("lde_dev");
     if (log_s + log_ext > 28) return fail(ctx, SB_ERR_ARG, "extended domain 2^%u exceeds two-adicity 28", log_s + log_ext);
     const size_t S = (size_t)1 << log_s, N = S << log_ext;
     if (col_len > S) return fail(ctx, SB_ERR_ARG, "column of %zu elements does not fit 2^%u", col_len, log_s);
@@ -806,6 +821,7 @@ int commit_bytes_owned(sb_ctx *ctx, uint8_t *d_leaves, size_t leaf_bytes, size_t
 }
 
 int commit_cols(sb_ctx *ctx, const uint4 *const *d_cols, size_t n_cols, size_t n, sb_tree **tree) {
+    NvtxRange nvtx("commit_cols");
     if (n_cols < 1 || n_cols > 8) return fail(ctx, SB_ERR_ARG, "1..8 columns per leaf supported, got %zu", n_cols);
     sb_tree *t = nullptr;
     TRY(tree_new(ctx, n, 32 * n_cols, &t));
@@ -992,6 +1008,7 @@ extern "C" int sb_set_extended_domain(sb_ctx *ctx, int enable) {
 // ------------------------------------------------------------------------------------------------
 int fri_prove_dev(sb_ctx *ctx, const uint4 *d_vals, size_t n, const hfp::el &root, size_t max_deg_plus_1, uint32_t excl,
                          const sb_tree *values_tree, sb_fri_proof **out) {
+    NvtxRange nvtx("fri_prove_dev");
     if (!is_pow2(n)) return fail(ctx, SB_ERR_ARG, "FRI needs a power-of-two number of values, got %zu", n);
     const uint32_t log_n0 = ilog2(n);
     const uint4 *tw;

@@ -82,6 +82,7 @@ int ext_create(sb_ctx *root, size_t n_cols, size_t n_lde, uint32_t log_s, sb_ext
 // device, then each device's cosets.  Inputs are e->input(c) (S values, zero padded, canonical).  Asynchronous: the work is
 // queued on the devices' streams, ordered by events; the caller synchronises (sync_all) when it needs the host to see it.
 int ext_extend(sb_ext *e, size_t first, size_t count) {
+    NvtxRange nvtx("ext_extend: INTT + coefficient all-gather + coset transforms");
     sb_ctx *root = e->root, *ctx = root;
     if (first + count > e->n_lde) return fail(ctx, SB_ERR_ARG, "column range out of bounds");
     if (count == 0) return SB_OK;
@@ -125,47 +126,69 @@ int ext_extend(sb_ext *e, size_t first, size_t count) {
             CU(cudaEventRecord(done[o], c->stream));
         }
     }
-    // 2. every other device pulls the coefficients (peer copy on its own stream, behind the owner's event)
-    if (g > 1) {
-        for (int d = 0; d < g; d++) {
-            sb_ctx *c = root->dev[d];
-            DevGuard dg(c);
-            for (int o = 0; o < g; o++)
-                if (o != d && done[o]) CU(cudaStreamWaitEvent(c->stream, done[o], 0));
-            for (size_t col = first; col < first + count; col++) {
-                const int o = e->owner[col];
-                if (o == d) continue;
-                CU(cudaMemcpyAsync(e->coef[d] + 2 * col * S, e->coef[o] + 2 * col * S, S * 32, cudaMemcpyDefault, c->stream));
+    // 2. + 3. per device: the cosets of its own columns first, then -- in ring order, so that every source is read by one
+    // device at a time -- the columns of owner d+1, d+2, ...: their coefficients are pulled by peer copies on the device's
+    // copy stream (behind the owner's event) while the transforms of the previous group run on the compute stream.
+    auto transform = [&](int d, const std::vector<size_t> &cols) -> int {
+        // cosets of the given columns (a run with constant stride) on device d: S-point transforms of the coefficients scaled by W^(j r)
+        sb_ctx *c = root->dev[d];
+        size_t i = 0;
+        while (i < cols.size()) {
+            size_t j = i + 1, stride = j < cols.size() ? cols[j] - cols[i] : 1;
+            while (j < cols.size() && cols[j] - cols[j - 1] == stride) j++;
+            CosetSpec cs;
+            cs.log_ext = 3;
+            cs.store = NTT_STORE_PLAIN;
+            cs.dst_cpd = e->cpd * (uint32_t)stride;           // consecutive polynomials of the batch are `stride` columns apart
+            cs.dst_r0 = (uint32_t)d * e->cpd;
+            if (g == 1) {
+                // coset 0 is the input column itself (same field elements): a strided copy instead of a transform
+                cs.r0 = 1;
+                cs.cnt = 7;
+                CU(cudaMemcpy2DAsync(e->col(0, cols[i]), stride * 8 * S * 32, e->in[0] + 2 * cols[i] * S, stride * S * 32, S * 32, j - i,
+                                     cudaMemcpyDeviceToDevice, c->stream));
+            } else {
+                cs.r0 = (uint32_t)d * e->cpd;
+                cs.cnt = e->cpd;
             }
+            int rc = ntt_dev_tw(c, e->coef[d] + 2 * cols[i] * S, S, stride * S, e->col(d, cols[i]), S, j - i, e->log_s, 0, tw[d], tw_log_n[d],
+                                tw_stride[d] + 3, &cs);
+            if (rc != SB_OK) {
+                if (c != root) fail(ctx, rc, "%s", c->err);
+                return rc;
+            }
+            i = j;
         }
-        for (int o = 0; o < g; o++)
-            if (done[o]) cudaEventDestroy(done[o]);      // released once the recorded work has completed
-    }
-    // 3. each device's cosets of every column: S-point transforms of the coefficients scaled by W^(j r)
-    for (int d = 0; d < g; d++) {
+        return SB_OK;
+    };
+    std::vector<cudaEvent_t> pulled;
+    int rc = SB_OK;
+    for (int d = 0; d < g && rc == SB_OK; d++) {
         sb_ctx *c = root->dev[d];
         DevGuard dg(c);
-        CosetSpec cs;
-        cs.log_ext = 3;
-        cs.store = NTT_STORE_PLAIN;
-        cs.dst_cpd = e->cpd;
-        cs.dst_r0 = (uint32_t)d * e->cpd;
-        if (g == 1) {
-            // coset 0 is the input column itself (same field elements): a strided copy instead of a transform
-            cs.r0 = 1;
-            cs.cnt = 7;
-            CU(cudaMemcpy2DAsync(e->col(0, first), 8 * S * 32, e->in[0] + 2 * first * S, S * 32, S * 32, count, cudaMemcpyDeviceToDevice, c->stream));
-        } else {
-            cs.r0 = (uint32_t)d * e->cpd;
-            cs.cnt = e->cpd;
-        }
-        int rc = ntt_dev_tw(c, e->coef[d] + 2 * first * S, S, S, e->col(d, first), S, count, e->log_s, 0, tw[d], tw_log_n[d], tw_stride[d] + 3, &cs);
-        if (rc != SB_OK) {
-            if (c != root) fail(ctx, rc, "%s", c->err);
-            return rc;
+        if (g > 1 && !c->h2d_stream) CU(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < g && rc == SB_OK; k++) {
+            const int o = (d + k) % g;
+            std::vector<size_t> cols;
+            for (size_t col = first; col < first + count; col++)
+                if (e->owner[col] == o) cols.push_back(col);
+            if (cols.empty()) continue;
+            if (o != d) {
+                CU(cudaStreamWaitEvent(c->h2d_stream, done[o], 0));
+                for (size_t col : cols) CU(cudaMemcpyAsync(e->coef[d] + 2 * col * S, e->coef[o] + 2 * col * S, S * 32, cudaMemcpyDefault, c->h2d_stream));
+                cudaEvent_t ev;
+                CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                pulled.push_back(ev);
+                CU(cudaEventRecord(ev, c->h2d_stream));
+                CU(cudaStreamWaitEvent(c->stream, ev, 0));
+            }
+            rc = transform(d, cols);
         }
     }
-    return SB_OK;
+    for (int o = 0; o < g; o++)
+        if (done[o]) cudaEventDestroy(done[o]);      // released once the recorded work has completed
+    for (auto ev : pulled) cudaEventDestroy(ev);
+    return rc;
 }
 
 // levels above level 0 of a standard tree array of n_leaves leaf digests
@@ -181,15 +204,99 @@ static int nodes_build(sb_ctx *ctx, uint4 *nodes, size_t n_leaves) {
     return SB_OK;
 }
 
+// ---- trees whose levels are spread over the devices (TreeShards) -----------------------------------------------------
+// shards_begin allocates a device's low levels and subtree array on every device and makes every device's stream wait
+// for all of those allocations (peers store into them); the caller then launches its leaf kernels, records one event per
+// device, and shards_finish builds the subtrees, fetches their roots and finishes the top on the host.
+struct ShardGeom {
+    int g;
+    uint32_t log_s, cpd, lv;       // leaves = 8 << log_s; device d hashes cosets d * cpd .. of 2^log_s leaves each
+};
+static int shards_begin(sb_ctx *root, const ShardGeom &G, size_t leaf_bytes, int n_cols, sb_tree **out) {
+    sb_ctx *ctx = root;
+    const size_t S = (size_t)1 << G.log_s;
+    sb_tree *t = new sb_tree();
+    t->n = S << 3;
+    t->depth = G.log_s + 3;
+    t->leaf_bytes = leaf_bytes;
+    t->n_cols = n_cols;
+    t->stream = root->stream;
+    t->device = root->device;
+    TreeShards *sh = t->sh = new TreeShards();
+    sh->g = G.g;
+    sh->lv = G.lv;
+    sh->log_s = G.log_s;
+    sh->cpd = G.cpd;
+    const size_t low_digests = ext_low_off(G.log_s, G.cpd, G.lv);
+    int rc = SB_OK;
+    cudaEvent_t ready[SB_MAX_DEV] = {0};
+    for (int d = 0; d < G.g && rc == SB_OK; d++) {
+        sb_ctx *c = root->dev[d];
+        DevGuard dg(c);
+        sh->streams[d] = c->stream;
+        sh->devices[d] = c->device;
+        cudaError_t e1 = low_digests ? cudaMallocAsync((void **)&sh->low[d], low_digests * 32, c->stream) : cudaSuccess;
+        cudaError_t e2 = e1 == cudaSuccess ? cudaMallocAsync((void **)&sh->sub[d], (2 * S - 1) * 32, c->stream) : e1;
+        if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&ready[d], cudaEventDisableTiming);
+        if (e2 == cudaSuccess) e2 = cudaEventRecord(ready[d], c->stream);
+        if (e2 != cudaSuccess) rc = fail(ctx, e2 == cudaErrorMemoryAllocation ? SB_ERR_OOM : SB_ERR_CUDA, "device %d: tree allocation failed: %s", c->device, cudaGetErrorString(e2));
+    }
+    for (int d = 0; d < G.g && rc == SB_OK; d++) {
+        DevGuard dg(root->dev[d]);
+        for (int o = 0; o < G.g; o++)
+            if (o != d) cudaStreamWaitEvent(root->dev[d]->stream, ready[o], 0);
+    }
+    for (int d = 0; d < G.g; d++)
+        if (ready[d]) cudaEventDestroy(ready[d]);
+    if (rc != SB_OK) {
+        free_tree(t);
+        return rc;
+    }
+    *out = t;
+    return SB_OK;
+}
+// hashed[d]: recorded on device d's stream behind its leaf kernel (destroyed here)
+static int shards_finish(sb_ctx *root, sb_tree *t, cudaEvent_t *hashed) {
+    sb_ctx *ctx = root;
+    TreeShards *sh = t->sh;
+    const int g = sh->g;
+    const size_t S = (size_t)1 << sh->log_s;
+    std::vector<uint8_t> roots((size_t)g * 32);
+    int rc = SB_OK;
+    for (int d = 0; d < g && rc == SB_OK; d++) {        // a device waits for every device's leaf kernel (they all store into its level 0)
+        sb_ctx *c = root->dev[d];
+        DevGuard dg(c);
+        for (int o = 0; o < g; o++)
+            if (o != d && hashed[o]) cudaStreamWaitEvent(c->stream, hashed[o], 0);
+        rc = nodes_build(c, sh->sub[d], S);
+        if (rc != SB_OK && c != root) fail(ctx, rc, "%s", c->err);
+        if (rc == SB_OK && cudaMemcpyAsync(&roots[32 * d], (const uint8_t *)sh->sub[d] + (2 * S - 2) * 32, 32, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
+            rc = fail(ctx, SB_ERR_CUDA, "D2H subtree root: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    if (rc == SB_OK) rc = sync_all(root);
+    for (int d = 0; d < g; d++)
+        if (hashed[d]) cudaEventDestroy(hashed[d]);
+    if (rc != SB_OK) return rc;
+    // top of the tree on the host: g subtree roots -> root (merkle_proof_in_place.rs:78-98: parent = H(left || right))
+    sh->top.assign((size_t)(2 * g - 1) * 32, 0);
+    memcpy(sh->top.data(), roots.data(), (size_t)g * 32);
+    for (uint32_t l = 0; ((size_t)g >> l) > 1; l++) {
+        const size_t off = merkle_level_off((size_t)g, l), offn = merkle_level_off((size_t)g, l + 1);
+        for (size_t i = 0; i < ((size_t)g >> (l + 1)); i++) b2s::hash_bytes(&sh->top[(offn + i) * 32], &sh->top[(off + 2 * i) * 32], 64);
+    }
+    memcpy(t->root, &sh->top[(size_t)(2 * g - 2) * 32], 32);
+    return SB_OK;
+}
+
 // MerkleProofInPlace over the rows of the given columns (prove.rs:235-264 / :324-332): leaf 8 k + r =
 // to_bytes_le(col_0[r][k]) || ... .  Synchronous (the root is on the host when it returns).
 int ext_commit(const sb_ext *e, const size_t *col_ids, size_t n_ids, sb_tree **tree) {
+    NvtxRange nvtx("ext_commit: leaf hashing + subtrees + top");
     sb_ctx *root = e->root, *ctx = root;
     if (n_ids < 1 || n_ids > 8) return fail(ctx, SB_ERR_ARG, "1..8 columns per leaf supported, got %zu", n_ids);
     for (size_t i = 0; i < n_ids; i++)
         if (col_ids[i] >= e->n_cols) return fail(ctx, SB_ERR_ARG, "column %zu out of range", col_ids[i]);
     const int g = e->g;
-    const size_t S = e->S;
     ExtLeavesParams P;
     memset(&P, 0, sizeof P);
     P.nc = (uint32_t)n_ids;
@@ -213,46 +320,18 @@ int ext_commit(const sb_ext *e, const size_t *col_ids, size_t n_ids, sb_tree **t
         *tree = t;
         return SB_OK;
     }
-    sb_tree *t = new sb_tree();
-    t->n = e->N;
-    t->depth = e->log_s + 3;
-    t->leaf_bytes = 32 * n_ids;
-    t->n_cols = (int)n_ids;
-    t->stream = root->stream;
-    t->device = root->device;
-    TreeShards *sh = t->sh = new TreeShards();
-    sh->g = g;
-    sh->lv = e->lv;
-    sh->log_s = e->log_s;
-    sh->cpd = e->cpd;
-    const size_t low_digests = ext_low_off(e->log_s, e->cpd, e->lv);
+    sb_tree *t = nullptr;
+    const ShardGeom G{g, e->log_s, e->cpd, e->lv};
+    TRY(shards_begin(root, G, 32 * n_ids, (int)n_ids, &t));
+    TreeShards *sh = t->sh;
     cudaEvent_t hashed[SB_MAX_DEV] = {0};
     int rc = SB_OK;
     for (int d = 0; d < g && rc == SB_OK; d++) {
         sb_ctx *c = root->dev[d];
         DevGuard dg(c);
-        sh->streams[d] = c->stream;
-        sh->devices[d] = c->device;
-        for (size_t i = 0; i < n_ids; i++) sh->cols[d][i] = e->col(d, col_ids[i]);
-        cudaError_t e1 = low_digests ? cudaMallocAsync((void **)&sh->low[d], low_digests * 32, c->stream) : cudaSuccess;
-        cudaError_t e2 = e1 == cudaSuccess ? cudaMallocAsync((void **)&sh->sub[d], (2 * S - 1) * 32, c->stream) : e1;
-        if (e2 != cudaSuccess) rc = fail(ctx, SB_ERR_OOM, "device %d: tree allocation failed: %s", c->device, cudaGetErrorString(e2));
-    }
-    // every subtree array must exist before a peer stores into it
-    cudaEvent_t ready[SB_MAX_DEV] = {0};
-    for (int d = 0; d < g && rc == SB_OK; d++) {
-        DevGuard dg(root->dev[d]);
-        if (cudaEventCreateWithFlags(&ready[d], cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(ready[d], root->dev[d]->stream) != cudaSuccess)
-            rc = fail(ctx, SB_ERR_CUDA, "event: %s", cudaGetErrorString(cudaGetLastError()));
-    }
-    for (int d = 0; d < g && rc == SB_OK; d++) {
-        sb_ctx *c = root->dev[d];
-        DevGuard dg(c);
-        for (int o = 0; o < g; o++)
-            if (o != d) cudaStreamWaitEvent(c->stream, ready[o], 0);
         ExtLeavesParams Q = P;
         Q.d = (uint32_t)d;
-        for (size_t i = 0; i < n_ids; i++) Q.cols[i] = sh->cols[d][i];
+        for (size_t i = 0; i < n_ids; i++) Q.cols[i] = sh->cols[d][i] = e->col(d, col_ids[i]);
         Q.low = sh->low[d];
         for (int o = 0; o < g; o++) Q.sub[o] = sh->sub[o];
         {
@@ -262,35 +341,14 @@ int ext_commit(const sb_ext *e, const size_t *col_ids, size_t n_ids, sb_tree **t
         if (cudaEventCreateWithFlags(&hashed[d], cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(hashed[d], c->stream) != cudaSuccess)
             rc = fail(ctx, SB_ERR_CUDA, "event: %s", cudaGetErrorString(cudaGetLastError()));
     }
-    // subtrees: a device waits for every device's leaf kernel (they all store into its level 0), then reduces
-    std::vector<uint8_t> roots((size_t)g * 32);
-    for (int d = 0; d < g && rc == SB_OK; d++) {
-        sb_ctx *c = root->dev[d];
-        DevGuard dg(c);
-        for (int o = 0; o < g; o++)
-            if (o != d) cudaStreamWaitEvent(c->stream, hashed[o], 0);
-        rc = nodes_build(c, sh->sub[d], S);
-        if (rc != SB_OK && c != root) fail(ctx, rc, "%s", c->err);
-        if (rc == SB_OK && cudaMemcpyAsync(&roots[32 * d], (const uint8_t *)sh->sub[d] + (2 * S - 2) * 32, 32, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
-            rc = fail(ctx, SB_ERR_CUDA, "D2H subtree root: %s", cudaGetErrorString(cudaGetLastError()));
-    }
-    if (rc == SB_OK) rc = sync_all(root);
-    for (int d = 0; d < g; d++) {
-        if (ready[d]) cudaEventDestroy(ready[d]);
-        if (hashed[d]) cudaEventDestroy(hashed[d]);
-    }
+    if (rc == SB_OK) rc = shards_finish(root, t, hashed);
+    else
+        for (int d = 0; d < g; d++)
+            if (hashed[d]) cudaEventDestroy(hashed[d]);
     if (rc != SB_OK) {
         free_tree(t);
         return rc;
     }
-    // top of the tree on the host: g subtree roots -> root (merkle_proof_in_place.rs:78-98: parent = H(left || right))
-    sh->top.assign((size_t)(2 * g - 1) * 32, 0);
-    memcpy(sh->top.data(), roots.data(), (size_t)g * 32);
-    for (uint32_t l = 0; ((size_t)g >> l) > 1; l++) {
-        const size_t off = merkle_level_off((size_t)g, l), offn = merkle_level_off((size_t)g, l + 1);
-        for (size_t i = 0; i < ((size_t)g >> (l + 1)); i++) b2s::hash_bytes(&sh->top[(offn + i) * 32], &sh->top[(off + 2 * i) * 32], 64);
-    }
-    memcpy(t->root, &sh->top[(size_t)(2 * g - 2) * 32], 32);
     *tree = t;
     return SB_OK;
 }
@@ -311,122 +369,184 @@ int ext_to_natural(const sb_ext *e, size_t col, uint4 *d_out) {
     return SB_OK;
 }
 
-// prove_low_degree (fri/src/fri.rs:46-224) on one coset-major column.  Layer 0 (fri.rs:120-213) runs where the values
+// prove_low_degree (fri/src/fri.rs:46-224) on one coset-major column.  A layer (fri.rs:120-213) runs where its values
 // are: every device folds the rows of its cosets (the four values of a row share a coset: a quarter turn is S/4 steps of
-// 8), hashes the folded leaves and stores column + digests straight into the primary device's memory; the primary
-// finishes the column tree, the openings of the (sharded) values tree are gathered through peer pointers, and layers >= 1
-// run on the primary alone with the column tree already built.
+// 8) and hashes the folded leaves.  Row 8 k + r of the folded column is position 8 k + r of the next layer's domain, so
+// the column is coset-sharded exactly like its input: while a layer is large it stays on the devices (column next to the
+// data, its tree as per-device subtrees); the first small layer is written in natural order, with its leaf digests,
+// straight into the primary device's memory, and the remaining layers run there alone.  Openings of
+// sharded trees are gathered by the primary through peer pointers.
+static const uint32_t FRI_SHARD_MIN_LOG_S = 13;       // a layer stays sharded while every coset of the NEXT layer has >= 2^13 values
+
 int ext_fri_prove(const sb_ext *e, size_t col, const sb_tree *values_tree, size_t max_deg_plus_1, uint32_t excl, sb_fri_proof **out) {
+    NvtxRange nvtx("ext_fri_prove");
     sb_ctx *root = e->root, *ctx = root;
     if (col >= e->n_cols) return fail(ctx, SB_ERR_ARG, "column %zu out of range", col);
-    const size_t N = e->N, q = N / 4;
     const int g = e->g;
     if (max_deg_plus_1 <= FRI_MIN_DEG_DIRECT) {
         // fri.rs:88-112: the values themselves are the proof; gather them in natural order
         DevBuf nat(ctx);
-        TRY(nat.alloc(N * 32));
+        TRY(nat.alloc(e->N * 32));
         TRY(sync_all(root));
         TRY(ext_to_natural(e, col, (uint4 *)nat.p));
-        return fri_prove_dev(ctx, (const uint4 *)nat.p, N, e->g2, max_deg_plus_1, excl, nullptr, out);
+        return fri_prove_dev(ctx, (const uint4 *)nat.p, e->N, e->g2, max_deg_plus_1, excl, nullptr, out);
     }
-    if (q >= (1u << 24) && !(ctx->extended_domain && q <= (1u << 28))) return fail(ctx, SB_ERR_ARG, "FRI layer of %zu values unsupported", N);
-    sb_tree *own_tree = nullptr;
-    if (!values_tree) {
-        size_t id = col;
-        TRY(ext_commit(e, &id, 1, &own_tree));
-        values_tree = own_tree;
-    }
-    struct Guard {
-        sb_tree *a = nullptr, *b = nullptr;
-        void *col = nullptr;
-        cudaStream_t s;
-        ~Guard() {
-            free_tree(a);
-            free_tree(b);
-            if (col) cudaFreeAsync(col, s);
+    // everything this call owns: trees, per-device column buffers of the sharded layers, the natural-order column
+    struct Owned {
+        sb_ctx *root;
+        std::vector<sb_tree *> trees;
+        std::vector<std::pair<int, void *>> bufs;       // (device index, pointer)
+        sb_fri_proof *proof = nullptr;
+        ~Owned() {
+            for (auto t : trees) free_tree(t);
+            for (auto &b : bufs) {
+                DevGuard dg(root->dev[b.first]);
+                cudaFreeAsync(b.second, root->dev[b.first]->stream);
+            }
+            delete proof;
         }
-    } guard;
-    guard.a = own_tree;
-    guard.s = ctx->stream;
-    FriLayer L;
-    memcpy(L.values_root, values_tree->root, 32);
-    const hfp::el special_x = hfp::from_bytes_le32(values_tree->root);        // fri.rs:135
-    CU(cudaMallocAsync(&guard.col, q * 32, ctx->stream));
-    sb_tree *t2 = nullptr;
-    TRY(tree_new(ctx, q, 32, &t2));
-    guard.b = t2;
-    t2->n_cols = 1;
-    t2->cols[0] = (const uint4 *)guard.col;
-    cudaEvent_t ready = nullptr, folded[SB_MAX_DEV] = {0};
-    if (g > 1) {
-        CU(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
-        CU(cudaEventRecord(ready, ctx->stream));
+    } own;
+    own.root = root;
+    own.proof = new sb_fri_proof();
+    if (!values_tree) {
+        sb_tree *t = nullptr;
+        size_t id = col;
+        TRY(ext_commit(e, &id, 1, &t));
+        own.trees.push_back(t);
+        values_tree = t;
     }
-    int rc = SB_OK;
-    for (int d = 0; d < g && rc == SB_OK; d++) {
-        sb_ctx *c = root->dev[d];
-        DevGuard dg(c);
-        const uint4 *tw;
-        uint32_t tw_log_n, tw_stride;
-        rc = get_table(c, e->g2, e->log_s + 3, &tw, &tw_log_n, &tw_stride);
-        if (rc != SB_OK) {
-            if (c != root) fail(ctx, rc, "%s", c->err);
+    const uint4 *cur[SB_MAX_DEV];
+    for (int d = 0; d < g; d++) cur[d] = e->col(d, col);
+    uint32_t cur_log_s = e->log_s, layer = 0;
+    const sb_tree *cur_tree = values_tree;
+    size_t bound = max_deg_plus_1;
+    hfp::el w = e->g2;
+    while (true) {
+        const size_t n = (size_t)8 << cur_log_s, q = n / 4;
+        if (q >= (1u << 24) && !(ctx->extended_domain && q <= (1u << 28))) return fail(ctx, SB_ERR_ARG, "FRI layer of %zu values unsupported", n);
+        const bool next_sharded = g > 1 && cur_log_s >= FRI_SHARD_MIN_LOG_S + 2 && bound / 4 > FRI_MIN_DEG_DIRECT;
+        FriLayer L;
+        memcpy(L.values_root, cur_tree->root, 32);
+        const hfp::el special_x = hfp::from_bytes_le32(cur_tree->root);        // fri.rs:135
+        // destinations of the folded column and of its tree
+        sb_tree *t2 = nullptr;
+        void *col_nat = nullptr;
+        uint4 *nxt[SB_MAX_DEV] = {0};
+        cudaEvent_t ready = nullptr;
+        if (next_sharded) {
+            const ShardGeom G{g, cur_log_s - 2, e->cpd, e->lv};
+            TRY(shards_begin(root, G, 32, 1, &t2));
+            own.trees.push_back(t2);
+            for (int d = 0; d < g; d++) {
+                sb_ctx *c = root->dev[d];
+                DevGuard dg(c);
+                void *p = nullptr;
+                CU(cudaMallocAsync(&p, ((size_t)e->cpd << (cur_log_s - 2)) * 32, c->stream));
+                own.bufs.push_back({d, p});
+                nxt[d] = (uint4 *)p;
+                t2->sh->cols[d][0] = nxt[d];
+            }
+        } else {
+            CU(cudaMallocAsync(&col_nat, q * 32, ctx->stream));
+            own.bufs.push_back({0, col_nat});
+            TRY(tree_new(ctx, q, 32, &t2));
+            own.trees.push_back(t2);
+            t2->n_cols = 1;
+            t2->cols[0] = (const uint4 *)col_nat;
+            if (g > 1) {          // peers store into the primary's buffers
+                CU(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+                CU(cudaEventRecord(ready, ctx->stream));
+            }
+        }
+        cudaEvent_t folded[SB_MAX_DEV] = {0};
+        int rc = SB_OK;
+        for (int d = 0; d < g && rc == SB_OK; d++) {
+            sb_ctx *c = root->dev[d];
+            DevGuard dg(c);
+            const uint4 *tw;
+            uint32_t tw_log_n, tw_stride;
+            rc = get_table(c, e->g2, e->log_s + 3, &tw, &tw_log_n, &tw_stride);
+            if (rc != SB_OK) {
+                if (c != root) fail(ctx, rc, "%s", c->err);
+                break;
+            }
+            if (ready && d > 0) cudaStreamWaitEvent(c->stream, ready, 0);
+            FriFoldParams F;
+            memset(&F, 0, sizeof F);
+            F.vals = cur[d];
+            F.col = (uint4 *)col_nat;
+            F.col_local = nxt[d];
+            F.tw = tw;
+            F.n = n;
+            F.tw_log_n = tw_log_n;
+            F.tw_log_stride = tw_stride + 2 * layer;           // the layer's root is g2^(4^layer)
+            memcpy(F.special_x, special_x.l, 32);
+            F.log_s = cur_log_s; F.cpd = e->cpd; F.lv = e->lv; F.d = (uint32_t)d; F.g = (uint32_t)g;
+            if (next_sharded) {
+                F.low = t2->sh->low[d];
+                for (int o = 0; o < g; o++) F.sub[o] = t2->sh->sub[o];
+            }
+            {
+                sb_ctx *ctx = c;
+                KLAUNCH(SB_KIND_FRI_FOLD, merkle_launch_leaves_fold_ext(c->stream, F, next_sharded ? nullptr : t2->d_nodes));
+            }
+            if (g > 1 && (next_sharded || d > 0)) {
+                if (cudaEventCreateWithFlags(&folded[d], cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(folded[d], c->stream) != cudaSuccess)
+                    rc = fail(ctx, SB_ERR_CUDA, "event: %s", cudaGetErrorString(cudaGetLastError()));
+            }
+        }
+        if (ready) cudaEventDestroy(ready);
+        if (rc == SB_OK && next_sharded) {
+            rc = shards_finish(root, t2, folded);
+        } else {
+            for (int d = 1; d < g; d++)
+                if (folded[d]) {
+                    if (rc == SB_OK) cudaStreamWaitEvent(ctx->stream, folded[d], 0);
+                    cudaEventDestroy(folded[d]);
+                }
+            if (folded[0]) cudaEventDestroy(folded[0]);
+            if (rc == SB_OK) rc = merkle_finish(ctx, t2, e->lv, true);
+        }
+        if (rc != SB_OK) return rc;
+        memcpy(L.root2, t2->root, 32);
+        // fri.rs:181-204
+        uint32_t ys[FRI_QUERIES];
+        if (pseudorandom_indices(t2->root, 32, (uint32_t)q, FRI_QUERIES, excl, ys, ctx->extended_domain) != SB_OK)
+            return fail(ctx, SB_ERR_ARG, "sampler: column length %zu out of range", q);
+        std::vector<size_t> yi(FRI_QUERIES), pp(4 * FRI_QUERIES);
+        for (size_t i = 0; i < FRI_QUERIES; i++) {
+            yi[i] = ys[i];
+            for (size_t j = 0; j < 4; j++) pp[4 * i + j] = ys[i] + q * j;
+        }
+        L.n_column = FRI_QUERIES;
+        L.depth_column = t2->depth;
+        L.column_leaves.resize(FRI_QUERIES * 32);
+        L.column_nodes.resize(FRI_QUERIES * t2->depth * 32);
+        TRY(sb_merkle_open(ctx, t2, yi.data(), FRI_QUERIES, L.column_leaves.data(), L.column_nodes.data()));
+        L.n_poly = 4 * FRI_QUERIES;
+        L.depth_poly = cur_tree->depth;
+        L.poly_leaves.resize(L.n_poly * 32);
+        L.poly_nodes.resize(L.n_poly * cur_tree->depth * 32);
+        TRY(sb_merkle_open(ctx, cur_tree, pp.data(), L.n_poly, L.poly_leaves.data(), L.poly_nodes.data()));
+        own.proof->layers.push_back(std::move(L));
+        // fri.rs:215-223
+        w = hfp::sqr(hfp::sqr(w));
+        bound /= 4;
+        layer++;
+        if (!next_sharded) {
+            // the rest on the primary device: natural order, column tree already committed
+            sb_fri_proof *rest = nullptr;
+            TRY(fri_prove_dev(ctx, (const uint4 *)col_nat, q, w, bound, excl, t2, &rest));
+            for (auto &l : rest->layers) own.proof->layers.push_back(std::move(l));
+            delete rest;
             break;
         }
-        if (d > 0) cudaStreamWaitEvent(c->stream, ready, 0);
-        FriFoldParams F;
-        memset(&F, 0, sizeof F);
-        F.vals = e->col(d, col);
-        F.col = (uint4 *)guard.col;
-        F.tw = tw;
-        F.n = N;
-        F.tw_log_n = tw_log_n;
-        F.tw_log_stride = tw_stride;
-        memcpy(F.special_x, special_x.l, 32);
-        F.log_s = e->log_s; F.cpd = e->cpd; F.lv = e->lv; F.d = (uint32_t)d; F.g = (uint32_t)g;
-        {
-            sb_ctx *ctx = c;
-            KLAUNCH(SB_KIND_FRI_FOLD, merkle_launch_leaves_fold_ext(c->stream, F, t2->d_nodes));
-        }
-        if (d > 0) {
-            if (cudaEventCreateWithFlags(&folded[d], cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(folded[d], c->stream) != cudaSuccess)
-                rc = fail(ctx, SB_ERR_CUDA, "event: %s", cudaGetErrorString(cudaGetLastError()));
-        }
+        for (int d = 0; d < g; d++) cur[d] = nxt[d];
+        cur_log_s -= 2;
+        cur_tree = t2;
     }
-    for (int d = 1; d < g; d++)
-        if (folded[d]) {
-            cudaStreamWaitEvent(ctx->stream, folded[d], 0);
-            cudaEventDestroy(folded[d]);
-        }
-    if (ready) cudaEventDestroy(ready);
-    if (rc != SB_OK) return rc;
-    TRY(merkle_finish(ctx, t2, e->lv, true));
-    memcpy(L.root2, t2->root, 32);
-    // fri.rs:181-204
-    uint32_t ys[FRI_QUERIES];
-    if (pseudorandom_indices(t2->root, 32, (uint32_t)q, FRI_QUERIES, excl, ys, ctx->extended_domain) != SB_OK)
-        return fail(ctx, SB_ERR_ARG, "sampler: column length %zu out of range", q);
-    std::vector<size_t> yi(FRI_QUERIES), pp(4 * FRI_QUERIES);
-    for (size_t i = 0; i < FRI_QUERIES; i++) {
-        yi[i] = ys[i];
-        for (size_t j = 0; j < 4; j++) pp[4 * i + j] = ys[i] + q * j;
-    }
-    L.n_column = FRI_QUERIES;
-    L.depth_column = t2->depth;
-    L.column_leaves.resize(FRI_QUERIES * 32);
-    L.column_nodes.resize(FRI_QUERIES * t2->depth * 32);
-    TRY(sb_merkle_open(ctx, t2, yi.data(), FRI_QUERIES, L.column_leaves.data(), L.column_nodes.data()));
-    L.n_poly = 4 * FRI_QUERIES;
-    L.depth_poly = values_tree->depth;
-    L.poly_leaves.resize(L.n_poly * 32);
-    L.poly_nodes.resize(L.n_poly * values_tree->depth * 32);
-    TRY(sb_merkle_open(ctx, values_tree, pp.data(), L.n_poly, L.poly_leaves.data(), L.poly_nodes.data()));
-    // fri.rs:215-223: the rest on the primary device, natural order, column tree already committed
-    sb_fri_proof *rest = nullptr;
-    const hfp::el w4 = hfp::sqr(hfp::sqr(e->g2));
-    TRY(fri_prove_dev(ctx, (const uint4 *)guard.col, q, w4, max_deg_plus_1 / 4, excl, t2, &rest));
-    rest->layers.insert(rest->layers.begin(), std::move(L));
-    *out = rest;
+    *out = own.proof;
+    own.proof = nullptr;
     return SB_OK;
 }
 

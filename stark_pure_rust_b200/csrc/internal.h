@@ -2,6 +2,7 @@
 // Not part of the C ABI.
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -17,6 +18,28 @@
 #include "hostfp.h"
 #include "kernels.h"
 #include "params.h"
+
+// NVTX range over a stage (visible in Nsight Systems / ncu --nvtx): header-only NVTX v3, a no-op
+// without an attached tool
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
+
+// consecutive stages of one call: next() closes the previous range; the destructor closes the last one on every exit path
+struct NvtxStages {
+    bool open = false;
+    void next(const char *name) {
+        if (open) nvtxRangePop();
+        nvtxRangePushA(name);
+        open = true;
+    }
+    ~NvtxStages() {
+        if (open) nvtxRangePop();
+    }
+};
 
 struct TwTable {
     hfp::el root;

@@ -38,7 +38,7 @@ int main(int argc, char **argv) {
         sb_destroy(ctx);
         return 1;
     }
-    printf("Produced STARK proof: front end %.3f ms, GPU prove %.3f ms (LDE %.3f, m_tree %.3f, FRI %.3f, rest %.3f), JSON %.3f ms\n",
+    printf("Produced STARK proof: front end %.3f ms, GPU prove %.3f ms (LDE + pointwise %.3f, m_tree %.3f, FRI %.3f, l_tree + openings %.3f), JSON %.3f ms\n",
            ms[5], ms[4], ms[0], ms[1], ms[2], ms[3], ms[6]);
     // run_with_file_path (run.rs:592-626) verifies what it has just written
     double vms[2] = {0, 0};

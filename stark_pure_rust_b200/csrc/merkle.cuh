@@ -259,6 +259,19 @@ __device__ __forceinline__ void merkle_ext_reduce(uint32_t *sd, const ExtLeavesP
     }
 }
 
+// level-0 digest of leaf 8 k + r0 + i of this thread
+template <int LV>
+__device__ __forceinline__ void merkle_ext_store_leaf(const ExtLeavesParams &P, uint4 *single, size_t k, int i, const uint32_t (&h)[8]) {
+    if (single) {
+        digest_store(single, ((k * P.g + P.d) << LV) + i, h);
+    } else if (LV > 0) {
+        digest_store(P.low, k * P.cpd + i, h);
+    } else {
+        const size_t per = ((size_t)1 << P.log_s) / P.g, j = k / per;
+        digest_store(P.sub[j], (k - j * per) * P.g + P.d, h);
+    }
+}
+
 template <int LV>
 __global__ void __launch_bounds__(MERKLE_THREADS, 4) merkle_leaves_ext_kernel(const __grid_constant__ ExtLeavesParams P) {
     __shared__ uint32_t sd_all[MERKLE_SMEM_WORDS(LV)];
@@ -274,22 +287,15 @@ __global__ void __launch_bounds__(MERKLE_THREADS, 4) merkle_leaves_ext_kernel(co
         for (int c = 0; c < 8; c++) C.cols[c] = P.cols[c] + 2 * ((size_t)i << P.log_s);     // coset r0 + i of every column
         uint32_t h[8];
         merkle_leaf_from_cols(h, C, k);
-        const size_t leaf = ((k * P.g + P.d) << LV) + i;                                    // = 8 k + r0 + i
-        if (P.single) {
-            digest_store(P.single, leaf, h);
-        } else if (LV > 0) {
-            digest_store(P.low, k * P.cpd + i, h);
-        } else {
-            const size_t per = S / P.g, j = k / per;
-            digest_store(P.sub[j], (k - j * per) * P.g + P.d, h);
-        }
+        merkle_ext_store_leaf<LV>(P, P.single, k, i, h);
         sd_put(sd, i, h);
     }
     merkle_ext_reduce<LV>(sd, P, k, P.single, n_single);
 }
 
-// FRI layer over coset-major values: fold (fri.rs:141-164) + leaf hashing of the folded column, which is written in natural
-// order together with every level up to lv of its tree on the primary device (F.col / nodes may be peer memory).
+// FRI layer over coset-major values: fold (fri.rs:141-164) + leaf hashing of the folded column.  The column is written
+// coset-major next to the data (col_local: the next layer stays sharded) and / or in natural order on the primary device
+// (col: the next layer runs there alone); its tree goes to `nodes` (standard layout on the primary) or to the shards.
 template <int LV>
 __global__ void __launch_bounds__(MERKLE_THREADS, 4) merkle_leaves_fold_ext_kernel(const __grid_constant__ FriFoldParams F, uint4 *nodes) {
     __shared__ uint32_t sd_all[MERKLE_SMEM_WORDS(LV)];
@@ -305,6 +311,9 @@ __global__ void __launch_bounds__(MERKLE_THREADS, 4) merkle_leaves_fold_ext_kern
     ExtLeavesParams E;
     E.log_s = F.log_s - 2;
     E.cpd = F.cpd; E.lv = F.lv; E.d = F.d; E.g = F.g;
+    E.low = F.low;
+#pragma unroll
+    for (int o = 0; o < SB_MAX_DEV; o++) E.sub[o] = F.sub[o];
 #pragma unroll 1
     for (int i = 0; i < (1 << LV); i++) {
         const uint4 *v = F.vals + 2 * (((size_t)i << F.log_s) + k);
@@ -312,11 +321,12 @@ __global__ void __launch_bounds__(MERKLE_THREADS, 4) merkle_leaves_fold_ext_kern
         fp y0 = fp_from_u4(v[0], v[1]), y1 = fp_from_u4(v[2 * S4], v[2 * S4 + 1]), y2 = fp_from_u4(v[4 * S4], v[4 * S4 + 1]),
            y3 = fp_from_u4(v[6 * S4], v[6 * S4 + 1]);
         fp r = fri_fold_vals(F, row, y0, y1, y2, y3, sx, iota_inv);
-        fp_stg(F.col, row, r);
+        if (F.col) fp_stg(F.col, row, r);
+        if (F.col_local) fp_stg(F.col_local, ((size_t)i << (F.log_s - 2)) + k, r);
         fp c = fp_from_mont(r);
         uint32_t h[8];
         b2s::hash32(h, c.l);
-        digest_store(nodes, row, h);
+        merkle_ext_store_leaf<LV>(E, nodes, k, i, h);
         sd_put(sd, i, h);
     }
     merkle_ext_reduce<LV>(sd, E, k, nodes, q);

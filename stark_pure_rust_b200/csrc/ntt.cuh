@@ -22,6 +22,16 @@
 #include "fp.cuh"
 #include "params.h"
 
+// elements in flight per thread in the tile load / store loops (8 elements per thread and tile).  Measured on B200 (LDE
+// 2^21 -> 2^24 x 10, ntt_pass ms per step): load/store unroll 2/2 33.27, 4/2 33.77, 8/1 34.16, 8/2 34.69, 4/4 35.31, 8/4 36.75 --
+// less unrolling wins (the kernel is ~120 KB of SASS: instruction supply matters more than loads in flight).
+#ifndef NTT_LOAD_UNROLL
+#define NTT_LOAD_UNROLL 2
+#endif
+#ifndef NTT_STORE_UNROLL
+#define NTT_STORE_UNROLL 2
+#endif
+
 
 // table index of w^e (e < n) for the forward / inverse transform
 __device__ __forceinline__ size_t ntt_tw_index(const NttPassParams &P, unsigned long long e) {
@@ -29,6 +39,13 @@ __device__ __forceinline__ size_t ntt_tw_index(const NttPassParams &P, unsigned 
     unsigned long long i = e << P.tw_log_stride;
     return P.inverse ? ((nT - i) & (nT - 1)) : i;
 }
+
+// experiment switch: the butterfly product as a real function call instead of 12 inlined copies per radix-8 round
+#ifdef NTT_NOINLINE_MUL
+__device__ __noinline__ fp ntt_mul(fp a, fp b) { return fp_mul(a, b); }
+#else
+__device__ __forceinline__ fp ntt_mul(const fp &a, const fp &b) { return fp_mul(a, b); }
+#endif
 
 // one radix-2^Q register round over rows {base + e*2^S}; DIF, highest bit first.
 // x[e] in [0,2p).  wlo/whi: shared planes of W[i] = w^(i * n / 2^B), i < 2^(B-1).
@@ -48,7 +65,7 @@ __device__ __forceinline__ void ntt_round_regs(fp (&x)[1 << Q], uint32_t low, co
             } else {
                 uint32_t expo = (low | ((uint32_t)e_low << S)) << (B - 1 - t);
                 fp w = fp_from_u4(wlo[expo], whi[expo]);
-                x[e | (1 << tb)] = fp_mul(fp_sub_lazy(a, c), w);
+                x[e | (1 << tb)] = ntt_mul(fp_sub_lazy(a, c), w);
             }
         }
     }
@@ -165,7 +182,8 @@ __global__ void __launch_bounds__((1 << LOG_TILE) / 8, NTT_MIN_CTAS(LOG_TILE, MA
     }
 
     // ---- load tile ----
-#pragma unroll 4
+    constexpr int LOAD_UNROLL = NTT_LOAD_UNROLL, STORE_UNROLL = NTT_STORE_UNROLL;
+#pragma unroll LOAD_UNROLL
     for (int idx = threadIdx.x; idx < TILE; idx += NT) {
         int r, j;
         if (!P.last) { j = idx % CC; r = idx / CC; } else { r = idx % R; j = idx / R; }
@@ -229,7 +247,7 @@ __global__ void __launch_bounds__((1 << LOG_TILE) / 8, NTT_MIN_CTAS(LOG_TILE, MA
     fp ninv;
 #pragma unroll
     for (int i = 0; i < 8; i++) ninv.l[i] = P.n_inv[i];
-#pragma unroll 2
+#pragma unroll STORE_UNROLL
     for (int idx = threadIdx.x; idx < TILE; idx += NT) {
         const int j = idx % CC;
         const uint32_t kk = idx / CC;

@@ -49,6 +49,8 @@ struct NttPassParams {
 #define NTT_STORE_PLAIN 0
 #define NTT_STORE_INTERLEAVED 1
 
+#define SB_MAX_DEV 8
+
 struct MerkleColsParams {
     const uint4 *cols[8];
     uint4 *nodes;
@@ -56,8 +58,6 @@ struct MerkleColsParams {
     uint32_t nc;                   // columns per leaf, 1..8
     uint32_t coset_log_s;          // != 0 (openings only): coset-major columns, leaf i = element (i & 7) << coset_log_s | i >> 3
 };
-
-#define SB_MAX_DEV 8
 
 // Leaf hashing of coset-major columns on ONE device of a g-device context (merkle_leaves_ext_kernel): the device holds
 // cosets r0 .. r0 + cpd - 1 (r0 = d * cpd, cpd = 8 / g = 2^lv) of every column as arrays of S = 2^log_s values; leaf
@@ -108,8 +108,13 @@ struct FriFoldParams {
     uint32_t tw_log_n, tw_log_stride;   // layer root w = w_T^(2^tw_log_stride)
     uint32_t special_x[8];         // Montgomery
     // coset-major input (merkle_leaves_fold_ext_kernel): vals = this device's cosets r0 .. r0 + cpd - 1 of the layer's
-    // values, 2^log_s each (n = 8 * 2^log_s); row i = 8 k + r reads vals[(r - r0) * S + k + j S / 4], j < 4.  The folded
-    // column is written in natural order to `col` and its tree (standard layout, n / 4 leaves) to `nodes`, both on the
-    // primary device.
+    // values, 2^log_s each (n = 8 * 2^log_s); row i = 8 k + r reads vals[(r - r0) * S + k + j S / 4], j < 4.  Row i of the
+    // folded column is position 8 k + r of the next layer's domain, i.e. the same coset: col_local (this device's cosets of
+    // the column, S / 4 values each, when the next layer stays sharded) and / or col (natural order on the primary device,
+    // when the next layer runs there alone).  The column's tree goes to `nodes` (standard layout on the primary, kernel
+    // argument) or, when that is NULL, to low / sub like ExtLeavesParams.
+    uint4 *col_local;
+    uint4 *low;
+    uint4 *sub[SB_MAX_DEV];
     uint32_t log_s, cpd, lv, d, g;
 };

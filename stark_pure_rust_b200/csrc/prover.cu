@@ -263,6 +263,8 @@ extern "C" int sb_prove_r1cs(sb_ctx *ctx, const sb_trace *t, sb_stark_proof **ou
     }
     TRY(mark());
 
+    NvtxStages nvtx;
+    nvtx.next("sb_prove_r1cs: inputs + 8 LDEs");
     // ---- inputs: every column goes to the device that runs its inverse transform (:55-68, :105-113, :160-163), on that
     // device's copy stream so that the uploads overlap the transforms of the columns that have already arrived ----------
     static_assert(sizeof(size_t) == sizeof(unsigned long long), "permuted_indices are uploaded as 64-bit words");
@@ -299,6 +301,7 @@ extern "C" int sb_prove_r1cs(sb_ctx *ctx, const sb_trace *t, sb_stark_proof **ou
         DCU(cudaStreamWaitEvent(c->stream, perm_up[d], 0));
         if (S > os) pw_perm_pad_kernel<<<nblk(S - os), 128, 0, c->stream>>>((unsigned long long *)pd[d].perm, os, S);
         c->launches++;
+        DCU(cudaEventRecord(perm_up[d], c->stream));          // from here on: "permutation complete on device d"
     }
     const uint64_t *srcs[6] = {t->coefficients, t->flag0, t->flag1, t->flag2, t->witness_trace, t->computational_trace};
     for (int c = 0; c < 6; c++) {
@@ -320,8 +323,8 @@ extern "C" int sb_prove_r1cs(sb_ctx *ctx, const sb_trace *t, sb_stark_proof **ou
         pw_u64_to_fp_kernel<<<nblk(S), 128, 0, c->stream>>>((const unsigned long long *)pd[E->owner[PIDX_]].perm, E->input(PIDX_), S);
         c->launches++;
     }
-    // :100-124, :160-167 the eight LDEs.  One device: the two index columns first (nothing to wait for), then pairs of columns
-    // as their uploads land; several devices: every owner waits for its own columns only.
+    // :100-124, :160-167 the eight LDEs: the two index columns first (nothing to wait for), then pairs of columns as their
+    // uploads land (every owner waits for its own columns only)
     auto wait_cols = [&](int c0, int c1) -> int {
         for (int c = c0; c < c1; c++) {
             sb_ctx *o = ctx->dev[E->owner[c]];
@@ -330,7 +333,7 @@ extern "C" int sb_prove_r1cs(sb_ctx *ctx, const sb_trace *t, sb_stark_proof **ou
         }
         return SB_OK;
     };
-    if (g == 1 && S >= ((size_t)1 << 16)) {
+    if (S >= ((size_t)1 << 16)) {
         TRY(ext_extend(E, IDX_, 2));
         for (int c = 0; c < 6; c += 2) {
             TRY(wait_cols(c, c + 2));
@@ -340,8 +343,6 @@ extern "C" int sb_prove_r1cs(sb_ctx *ctx, const sb_trace *t, sb_stark_proof **ou
         TRY(wait_cols(0, 6));
         TRY(ext_extend(E, 0, 8));
     }
-    TRY(mark());
-
     // ---- constants of the pointwise stage ---------------------------------------------------------------
     PwConsts Cst;
     memset(&Cst, 0, sizeof Cst);
@@ -379,11 +380,16 @@ extern "C" int sb_prove_r1cs(sb_ctx *ctx, const sb_trace *t, sb_stark_proof **ou
         c->launches++;
     }
 
-    // :171 a_root (utils.rs:250-270): S leaves of 40 bytes, on the device that holds the witness column
+    nvtx.next("sb_prove_r1cs: a_tree + accumulator + LDE(A)");
+    // :171-184 a_root, the challenges r and the accumulator: an S-point, latency-bound chain (tree, two prefix-product scans,
+    // batch inverse) on the device that holds the witness column.  (Tried: running it on a side stream next to the eight LDEs.
+    // The stream-ordered pool then serves two streams and its cross-stream reuse rules made the prover slower and erratic --
+    // 60-180 ms per 2^23 proof against a steady 29 ms -- so the chain stays on the device's main stream.)
     sb_tree *a_tree = nullptr;
     {
         sb_ctx *c = ctx->dev[dS];
         DevGuard dg(c);
+        // :171 a_root (utils.rs:250-270): S leaves of 40 bytes
         DCU(cudaMallocAsync(&pd[dS].aleaves, S * 40, c->stream));
         pw_a_leaves_kernel<<<nblk(S), 128, 0, c->stream>>>((const unsigned long long *)pd[dS].perm, E->input(S_), (uint32_t *)pd[dS].aleaves, S);
         c->launches++;
@@ -393,9 +399,7 @@ extern "C" int sb_prove_r1cs(sb_ctx *ctx, const sb_trace *t, sb_stark_proof **ou
         if (rc != SB_OK) return sub_err(c, rc);
         trees.push_back(a_tree);
         memcpy(proof->a_root, a_tree->root, 32);
-    }
-    // :172 r = get_random_ff_values(a_root, precision, 3, 0) (utils.rs:272-290)
-    {
+        // :172 r = get_random_ff_values(a_root, precision, 3, 0) (utils.rs:272-290)
         uint32_t idx[24];
         if (sb_pseudorandom_indices(proof->a_root, 32, (uint32_t)N, 24, 0, idx) != SB_OK) return fail(ctx, SB_ERR_ARG, "sampler rejected precision %zu", N);
         for (int i = 0; i < 3; i++) {
@@ -406,25 +410,19 @@ extern "C" int sb_prove_r1cs(sb_ctx *ctx, const sb_trace *t, sb_stark_proof **ou
             }
             put_const(Cst.r[i], hfp::from_bytes_le32(b));
         }
-    }
-    // :175-184 accumulator (utils.rs:293-339) and its LDE
-    {
-        sb_ctx *c = ctx->dev[dS];
-        DevGuard dg(c);
+        // :175-184 accumulator (utils.rs:293-339)
         DCU(cudaMallocAsync(&pd[dS].amini, 2 * S * 32, c->stream));
         uint4 *nmr = (uint4 *)pd[dS].amini, *dnm = nmr + 2 * S;
         pw_acc_terms_kernel<<<nblk(S), 128, 0, c->stream>>>((const unsigned long long *)pd[dS].perm, E->input(S_), nmr, dnm, S, Cst);
         c->launches++;
-        int rc = prefix_product(c, nmr, nmr, S);
+        rc = prefix_product(c, nmr, nmr, S);
         if (rc == SB_OK) rc = prefix_product(c, dnm, dnm, S);
         if (rc == SB_OK) rc = sb_batch_inverse_dev(c, (uint64_t *)dnm, S);
         if (rc != SB_OK) return sub_err(c, rc);
         pw_mul_kernel<<<nblk(S), 128, 0, c->stream>>>(nmr, dnm, E->input(A_), S);
         c->launches++;
     }
-    TRY(mark());
     TRY(ext_extend(E, A_, 1));
-    TRY(mark());
     // :192-214 d3
     for (int d = 0; d < g; d++) {
         sb_ctx *c = ctx->dev[d];
@@ -509,6 +507,7 @@ extern "C" int sb_prove_r1cs(sb_ctx *ctx, const sb_trace *t, sb_stark_proof **ou
             return fail(ctx, SB_ERR_ARG, bad == 1 ? "invalid D1/D2/D3: the witness does not satisfy the constraints (utils.rs:379-418)"
                                                   : (bad == 2 ? "invalid B2: public wires do not match the trace (utils.rs:489)" : "invalid B3 (utils.rs:514)"));
     }
+    nvtx.next("sb_prove_r1cs: m_tree");
     // :235-264 m_tree over p a s d1 d2 d3 b2 b3
     sb_tree *m_tree = nullptr;
     {
@@ -518,6 +517,7 @@ extern "C" int sb_prove_r1cs(sb_ctx *ctx, const sb_trace *t, sb_stark_proof **ou
         memcpy(proof->m_root, m_tree->root, 32);
     }
     TRY(mark());
+    nvtx.next("sb_prove_r1cs: l + l_tree + openings");
     // :274-283 k[i] = int_BE(blake(m_root || i)) mod p
     put_const(Cst.k[0], hfp::ONE);
     for (int i = 1; i < 11; i++) {
@@ -575,16 +575,17 @@ extern "C" int sb_prove_r1cs(sb_ctx *ctx, const sb_trace *t, sb_stark_proof **ou
         TRY(sb_merkle_open(ctx, m_tree, aug.data(), aug.size(), proof->main_leaves.data(), proof->main_nodes.data()));
     }
     TRY(mark());
+    nvtx.next("sb_prove_r1cs: FRI");
     // :367 FRI on l with the committed l_tree
     TRY(ext_fri_prove(E, L_, l_tree, N / 4, (uint32_t)sk, &proof->fri));
     TRY(mark());
-    // marks: 0 start, 1 inputs + eight LDEs, 2 a_tree + accumulator, 3 LDE of A, 4 pointwise stage checked, 5 m_tree, 6 l + l_tree +
-    // openings, 7 FRI (host clock; every device has been waited for at each mark)
-    proof->stage_ms[0] = (tm[1] - tm[0]) + (tm[3] - tm[2]);
-    proof->stage_ms[1] = tm[5] - tm[4];
-    proof->stage_ms[2] = tm[7] - tm[6];
-    proof->stage_ms[4] = tm[7] - tm[0];
-    proof->stage_ms[3] = proof->stage_ms[4] - proof->stage_ms[0] - proof->stage_ms[1] - proof->stage_ms[2];
+    // marks: 0 start, 1 pointwise stage checked (inputs, nine LDEs, accumulator chain, quotients), 2 m_tree, 3 l + l_tree +
+    // openings, 4 FRI (host clock; every device has been waited for at each mark)
+    proof->stage_ms[0] = tm[1] - tm[0];
+    proof->stage_ms[1] = tm[2] - tm[1];
+    proof->stage_ms[2] = tm[4] - tm[3];
+    proof->stage_ms[4] = tm[4] - tm[0];
+    proof->stage_ms[3] = tm[3] - tm[2];
     cleanup.ok = true;
     *out = proof;
     return SB_OK;

@@ -73,7 +73,7 @@ def _ext_chain(ctx, oracle, log_s, n_cols, col_len, seed):
     e.close()
 
 
-@pytest.mark.parametrize("log_s,n_cols,col_len", [(10, 3, 1024), (11, 9, 2000), (13, 8, 6684), (5, 2, 32), (3, 1, 8)])
+@pytest.mark.parametrize("log_s,n_cols,col_len", [(10, 3, 1024), (11, 9, 2000), (13, 8, 6684), (5, 2, 32), (3, 1, 8), (17, 2, 100000)])
 def test_ext_chain_matches_oracle(mctx, oracle, log_s, n_cols, col_len):
     _ext_chain(mctx, oracle, log_s, n_cols, col_len, 9000 + log_s + n_cols)
 
@@ -148,6 +148,7 @@ def test_ext_chain_real_gpus(oracle, g):
     try:
         _ext_chain(ctx, oracle, 13, 9, 6684, 77)
         _ext_chain(ctx, oracle, 10, 8, 1024, 78)
+        _ext_chain(ctx, oracle, 17, 2, 1 << 17, 79)        # three FRI layers stay sharded
     finally:
         ctx.close()
 

@@ -49,7 +49,7 @@ def main():
             ctx.profile(False)
         import hashlib
         print("sha256", hashlib.sha256(open(out, "rb").read()).hexdigest())
-        print("gpu rep %d: wall %.1f ms | LDE %.2f m_tree %.2f FRI %.2f rest %.2f | prove %.2f | front end %.2f | json+write %.2f | proof %d bytes" % (
+        print("gpu rep %d: wall %.1f ms | LDE+pointwise %.2f m_tree %.2f FRI %.2f l_tree+openings %.2f | prove %.2f | front end %.2f | json+write %.2f | proof %d bytes" % (
             r, wall, ms[0], ms[1], ms[2], ms[3], ms[4], ms[5], ms[6], os.path.getsize(out)), flush=True)
         res["gpu"] = {"wall_ms": wall, "stage_ms": ms}
     if a.cpu:
