@@ -382,16 +382,6 @@ static int plan_bits(uint32_t log_n, uint32_t *bits) {
 
 // cs != NULL: the coset transforms of a low-degree extension (see NttPassParams); the transform's root is then
 // W^(2^log_ext) and the table must be the extended domain's (tw of W).
-// kernel variant (radix of the register rounds); SB_NTT_MAXQ overrides the default for experiments
-static uint32_t ntt_maxq() {
-    static const uint32_t v = []() {
-        const char *e = getenv("SB_NTT_MAXQ");
-        const int q = e ? atoi(e) : 3;
-        return (uint32_t)(q >= 0 && q <= 3 ? q : 3);
-    }();
-    return v;
-}
-
 int ntt_dev_tw(sb_ctx *ctx, const uint4 *d_src, size_t len_in, size_t src_stride, uint4 *d_dst, size_t dst_stride,
                size_t n_polys, uint32_t log_n, int inverse, const uint4 *tw, uint32_t tw_log_n, uint32_t log_stride,
                const CosetSpec *cs) {
@@ -444,7 +434,6 @@ int ntt_dev_tw(sb_ctx *ctx, const uint4 *d_src, size_t len_in, size_t src_stride
         P.n_prev = (uint32_t)p;
         for (int i = 0; i < p; i++) P.prev_bits[i] = bits[i];
         memcpy(P.n_inv, ninv.l, 32);
-        P.maxq = ntt_maxq();
         if (bits[p] > 8) return fail(ctx, SB_ERR_ARG, "internal: pass width %u", bits[p]);
         KLAUNCH(SB_KIND_NTT_PASS, ntt_launch_pass(ctx->stream, bits[p], P));
         log_outer += bits[p];

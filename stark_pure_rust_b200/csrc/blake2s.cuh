@@ -39,6 +39,10 @@ B2S_HD void init(uint32_t (&h)[8]) {
     h[4] = B2S_IV4; h[5] = B2S_IV5; h[6] = B2S_IV6; h[7] = B2S_IV7;
 }
 
+// Pipe balance on the device: 10 of the 12 operations of a G run on the ALU pipe (LOP3 / SHF / PRMT / IADD3), the compiler
+// issues the two two-input adds as IMAD on the FMA pipe.  (Tried: moving one / both three-input adds over as well, written as
+// multiply-adds by gridDim.z so that ptxas cannot fold them back into IADD3 -- ALU 9 / 8, FMA 4 / 6 operations per G.  Slower on
+// B200: the 8-column tree of 2^24 leaves 5.12 -> 5.51 / 5.66 ms, the 1-column tree 1.78 -> 1.91 / 1.96 ms.)
 #define B2S_G(a, b, c, d, x, y)            \
     a = a + b + (x); d = rotr(d ^ a, 16);  \
     c = c + d;       b = rotr(b ^ c, 12);  \

@@ -24,12 +24,13 @@
 
 // elements in flight per thread in the tile load / store loops (8 elements per thread and tile).  Measured on B200 (LDE
 // 2^21 -> 2^24 x 10, ntt_pass ms per step): load/store unroll 2/2 33.27, 4/2 33.77, 8/1 34.16, 8/2 34.69, 4/4 35.31, 8/4 36.75 --
-// less unrolling wins (the kernel is ~120 KB of SASS: instruction supply matters more than loads in flight).
+// 2/1 32.88, 1/2 32.89, 1/1 32.72 -- less unrolling wins (the kernel is ~110 KB of SASS: instruction supply matters more than
+// loads in flight).
 #ifndef NTT_LOAD_UNROLL
-#define NTT_LOAD_UNROLL 2
+#define NTT_LOAD_UNROLL 1
 #endif
 #ifndef NTT_STORE_UNROLL
-#define NTT_STORE_UNROLL 2
+#define NTT_STORE_UNROLL 1
 #endif
 
 
@@ -39,13 +40,6 @@ __device__ __forceinline__ size_t ntt_tw_index(const NttPassParams &P, unsigned 
     unsigned long long i = e << P.tw_log_stride;
     return P.inverse ? ((nT - i) & (nT - 1)) : i;
 }
-
-// experiment switch: the butterfly product as a real function call instead of 12 inlined copies per radix-8 round
-#ifdef NTT_NOINLINE_MUL
-__device__ __noinline__ fp ntt_mul(fp a, fp b) { return fp_mul(a, b); }
-#else
-__device__ __forceinline__ fp ntt_mul(const fp &a, const fp &b) { return fp_mul(a, b); }
-#endif
 
 // one radix-2^Q register round over rows {base + e*2^S}; DIF, highest bit first.
 // x[e] in [0,2p).  wlo/whi: shared planes of W[i] = w^(i * n / 2^B), i < 2^(B-1).
@@ -65,12 +59,16 @@ __device__ __forceinline__ void ntt_round_regs(fp (&x)[1 << Q], uint32_t low, co
             } else {
                 uint32_t expo = (low | ((uint32_t)e_low << S)) << (B - 1 - t);
                 fp w = fp_from_u4(wlo[expo], whi[expo]);
-                x[e | (1 << tb)] = ntt_mul(fp_sub_lazy(a, c), w);
+                x[e | (1 << tb)] = fp_mul(fp_sub_lazy(a, c), w);
             }
         }
     }
 }
 
+// (Tried: the S > 0 radix-8 round as one rolled loop over its three stages with a constant-geometry register renumbering -- 4
+// inlined products instead of 12, 64 KB of SASS instead of 91 KB -- and the product as a real function call (47 KB).  Both
+// slower on B200: 34.9 ms of ntt_pass per step against 32.7: the moves / spills / call overhead cost more than the smaller
+// instruction footprint gains.)
 template <int B, int S, int Q, int LOG_TILE>
 __device__ __forceinline__ void ntt_round(uint4 *slo, uint4 *shi, const uint4 *wlo, const uint4 *whi) {
     constexpr int TILE = 1 << LOG_TILE, NT = TILE / 8, CC = TILE >> B, PITCH = CC + 1;
@@ -97,53 +95,17 @@ __device__ __forceinline__ void ntt_round(uint4 *slo, uint4 *shi, const uint4 *w
     }
 }
 
-// all rounds of a 2^B sub-transform: first round takes B mod MAXQ bits (if any), the rest MAXQ each (radix 2^MAXQ in
-// registers between shared-memory round trips).  MAXQ = 3 has the fewest round trips but inlines 12 Montgomery products per
-// round (the whole kernel: 133 KB of SASS, at the size of the instruction cache); MAXQ = 2 / 1 trade round trips for code
-// size and registers (more resident CTAs).
-template <int B, int HI, int LOG_TILE, int MAXQ>
+// all rounds of a 2^B sub-transform: first round takes B mod 3 bits (if any), the rest 3 each (radix 8 in registers between
+// shared-memory round trips).  Measured alternatives on B200 (LDE 2^21 -> 2^24 x 10, ms of ntt_pass per step): radix 8 33.8,
+// radix 4 34.0 (96 registers, 5 CTAs per SM), radix 2 35.9, radix 2 rolled into one loop 36.5 (64 registers, 6 CTAs per SM):
+// fewer shared-memory round trips beat more resident warps.
+template <int B, int HI, int LOG_TILE>
 __device__ __forceinline__ void ntt_rounds(uint4 *slo, uint4 *shi, const uint4 *wlo, const uint4 *whi) {
     if constexpr (HI > 0) {
-        constexpr int Q = (HI % MAXQ) ? (HI % MAXQ) : MAXQ;
+        constexpr int Q = (HI % 3) ? (HI % 3) : 3;
         ntt_round<B, HI - Q, Q, LOG_TILE>(slo, shi, wlo, whi);
         __syncthreads();
-        ntt_rounds<B, HI - Q, LOG_TILE, MAXQ>(slo, shi, wlo, whi);
-    }
-}
-
-// MAXQ = 0: radix-2 stages rolled into ONE loop with the stage as a run-time value (a single inlined product for all stages
-// with non-trivial twiddles, ~30 KB of SASS for the whole kernel, 64 registers); B shared-memory round trips per tile.
-template <int B, int LOG_TILE>
-__device__ __forceinline__ void ntt_rounds_rolled(uint4 *slo, uint4 *shi, const uint4 *wlo, const uint4 *whi) {
-    constexpr int TILE = 1 << LOG_TILE, NT = TILE / 8, CC = TILE >> B, PITCH = CC + 1, GROUPS = TILE / 2;
-    if constexpr (B > 1) {
-#pragma unroll 1
-        for (int S = B - 1; S >= 1; S--) {
-#pragma unroll 2
-            for (int g = threadIdx.x; g < GROUPS; g += NT) {
-                const int j = g % CC;
-                const uint32_t rb = g / CC, low = rb & ((1u << S) - 1), high = rb >> S;
-                const int i0 = ((high << (S + 1)) | low) * PITCH + j, i1 = i0 + (PITCH << S);
-                const fp a = fp_from_u4(slo[i0], shi[i0]), c = fp_from_u4(slo[i1], shi[i1]);
-                const uint32_t expo = low << (B - 1 - S);
-                const fp x0 = fp_add(a, c), x1 = fp_mul(fp_sub_lazy(a, c), fp_from_u4(wlo[expo], whi[expo]));
-                slo[i0] = fp_lo(x0); shi[i0] = fp_hi(x0);
-                slo[i1] = fp_lo(x1); shi[i1] = fp_hi(x1);
-            }
-            __syncthreads();
-        }
-    }
-    if constexpr (B > 0) {
-#pragma unroll 2
-        for (int g = threadIdx.x; g < GROUPS; g += NT) {      // last stage: twiddle w^0
-            const int j = g % CC;
-            const int i0 = (2 * (g / CC)) * PITCH + j, i1 = i0 + PITCH;
-            const fp a = fp_from_u4(slo[i0], shi[i0]), c = fp_from_u4(slo[i1], shi[i1]);
-            const fp x0 = fp_add(a, c), x1 = fp_sub(a, c);
-            slo[i0] = fp_lo(x0); shi[i0] = fp_hi(x0);
-            slo[i1] = fp_lo(x1); shi[i1] = fp_hi(x1);
-        }
-        __syncthreads();
+        ntt_rounds<B, HI - Q, LOG_TILE>(slo, shi, wlo, whi);
     }
 }
 
@@ -159,9 +121,8 @@ __device__ __forceinline__ unsigned long long ntt_digitrev_inv(const NttPassPara
     return o;
 }
 
-#define NTT_MIN_CTAS(LOG_TILE, MAXQ) ((LOG_TILE) >= 11 ? ((MAXQ) >= 3 ? 2 : 3) : ((MAXQ) >= 3 ? 4 : ((MAXQ) == 2 ? 5 : 6)))   // MAXQ = 0, 1: 64 registers
-template <int B, int LOG_TILE, int MAXQ>
-__global__ void __launch_bounds__((1 << LOG_TILE) / 8, NTT_MIN_CTAS(LOG_TILE, MAXQ)) ntt_pass_kernel(const __grid_constant__ NttPassParams P) {
+template <int B, int LOG_TILE>
+__global__ void __launch_bounds__((1 << LOG_TILE) / 8, LOG_TILE >= 11 ? 2 : 4) ntt_pass_kernel(const __grid_constant__ NttPassParams P) {
     constexpr int TILE = 1 << LOG_TILE, NT = TILE / 8, R = 1 << B, CC = TILE >> B, PITCH = CC + 1;
     extern __shared__ uint4 smem[];
     uint4 *slo = smem, *shi = smem + R * PITCH;
@@ -240,8 +201,7 @@ __global__ void __launch_bounds__((1 << LOG_TILE) / 8, NTT_MIN_CTAS(LOG_TILE, MA
     }
 
     // ---- butterflies ----
-    if constexpr (MAXQ == 0) ntt_rounds_rolled<B, LOG_TILE>(slo, shi, wlo, whi);
-    else ntt_rounds<B, B, LOG_TILE, MAXQ>(slo, shi, wlo, whi);
+    ntt_rounds<B, B, LOG_TILE>(slo, shi, wlo, whi);
 
     // ---- store tile (row r of the tile holds output k = bitrev_B(r)) ----
     fp ninv;

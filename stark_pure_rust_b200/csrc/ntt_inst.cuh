@@ -8,22 +8,14 @@ static size_t ntt_smem_bytes() {
     constexpr int R = 1 << B, CC = (1 << NTT_LOG_TILE_FOR(B)) >> B, PITCH = CC + 1;
     return (size_t)(2 * R * PITCH + 2 * (R / 2 > 0 ? R / 2 : 1)) * sizeof(uint4);
 }
-// radix of the register rounds (NttPassParams::maxq, chosen by the host: api.cu ntt_maxq())
 template <int B>
 static cudaError_t ntt_set_attr_one() {
-    cudaError_t e = cudaFuncSetAttribute(ntt_pass_kernel<B, NTT_LOG_TILE_FOR(B), 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes<B>());
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(ntt_pass_kernel<B, NTT_LOG_TILE_FOR(B), 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes<B>());
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(ntt_pass_kernel<B, NTT_LOG_TILE_FOR(B), 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes<B>());
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(ntt_pass_kernel<B, NTT_LOG_TILE_FOR(B), 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes<B>());
-    return e;
+    return cudaFuncSetAttribute(ntt_pass_kernel<B, NTT_LOG_TILE_FOR(B)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes<B>());
 }
 template <int B>
 static int ntt_launch_one(cudaStream_t stream, const NttPassParams &P) {
     constexpr int TILE = 1 << NTT_LOG_TILE_FOR(B), CC = TILE >> B;
     unsigned long long grid = (P.n_cols_total + CC - 1) / CC;
-    if (P.maxq == 0) ntt_pass_kernel<B, NTT_LOG_TILE_FOR(B), 0><<<(unsigned)grid, TILE / 8, ntt_smem_bytes<B>(), stream>>>(P);
-    else if (P.maxq == 1) ntt_pass_kernel<B, NTT_LOG_TILE_FOR(B), 1><<<(unsigned)grid, TILE / 8, ntt_smem_bytes<B>(), stream>>>(P);
-    else if (P.maxq == 2) ntt_pass_kernel<B, NTT_LOG_TILE_FOR(B), 2><<<(unsigned)grid, TILE / 8, ntt_smem_bytes<B>(), stream>>>(P);
-    else ntt_pass_kernel<B, NTT_LOG_TILE_FOR(B), 3><<<(unsigned)grid, TILE / 8, ntt_smem_bytes<B>(), stream>>>(P);
+    ntt_pass_kernel<B, NTT_LOG_TILE_FOR(B)><<<(unsigned)grid, TILE / 8, ntt_smem_bytes<B>(), stream>>>(P);
     return 1;
 }

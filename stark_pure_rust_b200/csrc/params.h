@@ -35,7 +35,6 @@ struct NttPassParams {
     uint32_t n_prev;               // last pass: widths of the earlier passes, in order
     uint32_t prev_bits[NTT_MAX_PASSES];
     uint32_t n_inv[8];             // Montgomery form of n^-1 (inverse transform, last pass)
-    uint32_t maxq;                 // radix 2^maxq of the register rounds (kernel variant: 1, 2 or 3)
     // coset mode (low-degree extension by 2^coset_log): the batch holds (column, coset) pairs, polynomial id =
     // column * coset_cnt + (coset - coset_r0) for cosets coset_r0 .. coset_r0 + coset_cnt - 1.  The first pass reads
     // coefficient j of `column` and scales it by W^(j * coset) (W = the extended domain's root, w = W^(2^coset_log)).
