@@ -654,6 +654,8 @@ void free_tree(sb_tree *t) {
             DevGuard g(t->sh->devices[d]);
             if (t->sh->low[d]) cudaFreeAsync(t->sh->low[d], t->sh->streams[d]);
             if (t->sh->sub[d]) cudaFreeAsync(t->sh->sub[d], t->sh->streams[d]);
+            if (t->sh->stage[d]) cudaFreeAsync(t->sh->stage[d], t->sh->streams[d]);
+            if (t->sh->recv[d]) cudaFreeAsync(t->sh->recv[d], t->sh->streams[d]);
         }
         delete t->sh;
     }

@@ -235,11 +235,30 @@ static int shards_begin(sb_ctx *root, const ShardGeom &G, size_t leaf_bytes, int
         DevGuard dg(c);
         sh->streams[d] = c->stream;
         sh->devices[d] = c->device;
-        cudaError_t e1 = low_digests ? cudaMallocAsync((void **)&sh->low[d], low_digests * 32, c->stream) : cudaSuccess;
-        cudaError_t e2 = e1 == cudaSuccess ? cudaMallocAsync((void **)&sh->sub[d], (2 * S - 1) * 32, c->stream) : e1;
-        if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&ready[d], cudaEventDisableTiming);
+        struct { uint4 **p; size_t bytes; const char *what; } want[4] = {{&sh->low[d], low_digests * 32, "low levels"}, {&sh->sub[d], (2 * S - 1) * 32, "subtree"},
+                                                                        {&sh->stage[d], S * 32, "digest staging"}, {&sh->recv[d], S * 32, "digest receive"}};
+        for (auto &w : want) {
+            if (!w.bytes) continue;
+            cudaError_t e = cudaMallocAsync((void **)w.p, w.bytes, c->stream);
+            if (e == cudaErrorMemoryAllocation) {          // let pending frees of other streams land, then try once more
+                cudaGetLastError();
+                cudaDeviceSynchronize();
+                e = cudaMallocAsync((void **)w.p, w.bytes, c->stream);
+            }
+            if (e != cudaSuccess) {
+                *w.p = nullptr;
+                size_t fr = 0, tot = 0;
+                cudaMemGetInfo(&fr, &tot);
+                rc = fail(ctx, e == cudaErrorMemoryAllocation ? SB_ERR_OOM : SB_ERR_CUDA, "device %d: cudaMallocAsync(%s, %zu bytes) failed: %s (free %zu of %zu MiB)", c->device,
+                          w.what, w.bytes, cudaGetErrorString(e), fr >> 20, tot >> 20);
+                cudaGetLastError();
+                break;
+            }
+        }
+        if (rc != SB_OK) break;
+        cudaError_t e2 = cudaEventCreateWithFlags(&ready[d], cudaEventDisableTiming);
         if (e2 == cudaSuccess) e2 = cudaEventRecord(ready[d], c->stream);
-        if (e2 != cudaSuccess) rc = fail(ctx, e2 == cudaErrorMemoryAllocation ? SB_ERR_OOM : SB_ERR_CUDA, "device %d: tree allocation failed: %s", c->device, cudaGetErrorString(e2));
+        if (e2 != cudaSuccess) rc = fail(ctx, SB_ERR_CUDA, "device %d: event: %s", c->device, cudaGetErrorString(e2));
     }
     for (int d = 0; d < G.g && rc == SB_OK; d++) {
         DevGuard dg(root->dev[d]);
@@ -255,29 +274,52 @@ static int shards_begin(sb_ctx *root, const ShardGeom &G, size_t leaf_bytes, int
     *out = t;
     return SB_OK;
 }
-// hashed[d]: recorded on device d's stream behind its leaf kernel (destroyed here)
-static int shards_finish(sb_ctx *root, sb_tree *t, cudaEvent_t *hashed) {
+// Called after every device has queued its leaf kernel (which leaves the level-lv digests in stage[d]).  Every device pushes the
+// k-range of each node-range owner to that owner with one contiguous copy (peer DMA at full NVLink rate), every owner interleaves
+// the g sources into level 0 of its subtree and reduces it; the subtree roots go to the host.
+static int shards_finish(sb_ctx *root, sb_tree *t) {
     sb_ctx *ctx = root;
     TreeShards *sh = t->sh;
     const int g = sh->g;
-    const size_t S = (size_t)1 << sh->log_s;
+    const size_t S = (size_t)1 << sh->log_s, per = S / g;
     std::vector<uint8_t> roots((size_t)g * 32);
+    cudaEvent_t pushed[SB_MAX_DEV] = {0};
     int rc = SB_OK;
-    for (int d = 0; d < g && rc == SB_OK; d++) {        // a device waits for every device's leaf kernel (they all store into its level 0)
+    for (int d = 0; d < g && rc == SB_OK; d++) {
+        sb_ctx *c = root->dev[d];
+        DevGuard dg(c);
+        for (int k = 0; k < g && rc == SB_OK; k++) {        // ring order: every owner receives from one source at a time
+            const int j = (d + k) % g;
+            if (cudaMemcpyAsync(sh->recv[j] + 2 * ((size_t)d * per), sh->stage[d] + 2 * ((size_t)j * per), per * 32, cudaMemcpyDefault, c->stream) != cudaSuccess)
+                rc = fail(ctx, SB_ERR_CUDA, "digest exchange %d -> %d: %s", d, j, cudaGetErrorString(cudaGetLastError()));
+        }
+        if (rc == SB_OK && (cudaEventCreateWithFlags(&pushed[d], cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(pushed[d], c->stream) != cudaSuccess))
+            rc = fail(ctx, SB_ERR_CUDA, "event: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    for (int d = 0; d < g && rc == SB_OK; d++) {
         sb_ctx *c = root->dev[d];
         DevGuard dg(c);
         for (int o = 0; o < g; o++)
-            if (o != d && hashed[o]) cudaStreamWaitEvent(c->stream, hashed[o], 0);
+            if (o != d) cudaStreamWaitEvent(c->stream, pushed[o], 0);
+        {
+            sb_ctx *ctx = c;
+            KLAUNCH(SB_KIND_MERKLE_NODES, merkle_launch_interleave(c->stream, sh->recv[d], sh->sub[d], per, (uint32_t)g));
+        }
         rc = nodes_build(c, sh->sub[d], S);
         if (rc != SB_OK && c != root) fail(ctx, rc, "%s", c->err);
         if (rc == SB_OK && cudaMemcpyAsync(&roots[32 * d], (const uint8_t *)sh->sub[d] + (2 * S - 2) * 32, 32, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
             rc = fail(ctx, SB_ERR_CUDA, "D2H subtree root: %s", cudaGetErrorString(cudaGetLastError()));
     }
     if (rc == SB_OK) rc = sync_all(root);
-    for (int d = 0; d < g; d++)
-        if (hashed[d]) cudaEventDestroy(hashed[d]);
+    for (int d = 0; d < g; d++) {
+        if (pushed[d]) cudaEventDestroy(pushed[d]);
+        DevGuard dg(root->dev[d]);                    // the staging buffers are only needed while the tree is built
+        if (sh->stage[d]) cudaFreeAsync(sh->stage[d], root->dev[d]->stream);
+        if (sh->recv[d]) cudaFreeAsync(sh->recv[d], root->dev[d]->stream);
+        sh->stage[d] = sh->recv[d] = nullptr;
+    }
     if (rc != SB_OK) return rc;
-    // top of the tree on the host: g subtree roots -> root (merkle_proof_in_place.rs:78-98: parent = H(left || right))
+    // top of the tree on the host    // top of the tree on the host: g subtree roots -> root (merkle_proof_in_place.rs:78-98: parent = H(left || right))
     sh->top.assign((size_t)(2 * g - 1) * 32, 0);
     memcpy(sh->top.data(), roots.data(), (size_t)g * 32);
     for (uint32_t l = 0; ((size_t)g >> l) > 1; l++) {
@@ -324,27 +366,19 @@ int ext_commit(const sb_ext *e, const size_t *col_ids, size_t n_ids, sb_tree **t
     const ShardGeom G{g, e->log_s, e->cpd, e->lv};
     TRY(shards_begin(root, G, 32 * n_ids, (int)n_ids, &t));
     TreeShards *sh = t->sh;
-    cudaEvent_t hashed[SB_MAX_DEV] = {0};
     int rc = SB_OK;
-    for (int d = 0; d < g && rc == SB_OK; d++) {
+    for (int d = 0; d < g; d++) {
         sb_ctx *c = root->dev[d];
         DevGuard dg(c);
         ExtLeavesParams Q = P;
         Q.d = (uint32_t)d;
         for (size_t i = 0; i < n_ids; i++) Q.cols[i] = sh->cols[d][i] = e->col(d, col_ids[i]);
         Q.low = sh->low[d];
-        for (int o = 0; o < g; o++) Q.sub[o] = sh->sub[o];
-        {
-            sb_ctx *ctx = c;       // launch accounting on the device that runs the kernel
-            KLAUNCH(SB_KIND_MERKLE_LEAVES, merkle_launch_leaves_ext(c->stream, Q));
-        }
-        if (cudaEventCreateWithFlags(&hashed[d], cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(hashed[d], c->stream) != cudaSuccess)
-            rc = fail(ctx, SB_ERR_CUDA, "event: %s", cudaGetErrorString(cudaGetLastError()));
+        Q.stage = sh->stage[d];
+        sb_ctx *ctx = c;       // launch accounting on the device that runs the kernel
+        KLAUNCH(SB_KIND_MERKLE_LEAVES, merkle_launch_leaves_ext(c->stream, Q));
     }
-    if (rc == SB_OK) rc = shards_finish(root, t, hashed);
-    else
-        for (int d = 0; d < g; d++)
-            if (hashed[d]) cudaEventDestroy(hashed[d]);
+    rc = shards_finish(root, t);
     if (rc != SB_OK) {
         free_tree(t);
         return rc;
@@ -376,7 +410,10 @@ int ext_to_natural(const sb_ext *e, size_t col, uint4 *d_out) {
 // data, its tree as per-device subtrees); the first small layer is written in natural order, with its leaf digests,
 // straight into the primary device's memory, and the remaining layers run there alone.  Openings of
 // sharded trees are gathered by the primary through peer pointers.
-static const uint32_t FRI_SHARD_MIN_LOG_S = 13;       // a layer stays sharded while every coset of the NEXT layer has >= 2^13 values
+static const uint32_t FRI_SHARD_MIN_LOG_S = 19;       // a layer stays sharded while every coset of the NEXT layer has >= 2^19 values
+// (i.e. the next layer holds >= 2^22 values: below that a layer is a few hundred microseconds on one GPU and the per-device launches and
+// synchronisations of a sharded layer cost more than they save -- measured: FRI of a 2^23 proof 2.4 ms with layer 0 alone sharded, 4.4 ms
+// on 8 GPUs with three sharded layers)
 
 int ext_fri_prove(const sb_ext *e, size_t col, const sb_tree *values_tree, size_t max_deg_plus_1, uint32_t excl, sb_fri_proof **out) {
     NvtxRange nvtx("ext_fri_prove");
@@ -422,43 +459,44 @@ int ext_fri_prove(const sb_ext *e, size_t col, const sb_tree *values_tree, size_
     size_t bound = max_deg_plus_1;
     hfp::el w = e->g2;
     while (true) {
-        const size_t n = (size_t)8 << cur_log_s, q = n / 4;
+        const size_t n = (size_t)8 << cur_log_s, q = n / 4, S4 = (size_t)1 << (cur_log_s - 2);
         if (q >= (1u << 24) && !(ctx->extended_domain && q <= (1u << 28))) return fail(ctx, SB_ERR_ARG, "FRI layer of %zu values unsupported", n);
         const bool next_sharded = g > 1 && cur_log_s >= FRI_SHARD_MIN_LOG_S + 2 && bound / 4 > FRI_MIN_DEG_DIRECT;
         FriLayer L;
         memcpy(L.values_root, cur_tree->root, 32);
         const hfp::el special_x = hfp::from_bytes_le32(cur_tree->root);        // fri.rs:135
-        // destinations of the folded column and of its tree
+        // where the folded column and its tree go:
+        //   next_sharded     column next to the data (coset-major), tree as per-device subtrees (fused fold + leaf hashing)
+        //   g == 1           natural-order column + standard tree on the device (fused fold + leaf hashing)
+        //   otherwise        the devices fold into local coset arrays, the primary pulls them with one contiguous peer copy per
+        //                    device, reorders to natural order and hashes the (small) column itself
         sb_tree *t2 = nullptr;
         void *col_nat = nullptr;
         uint4 *nxt[SB_MAX_DEV] = {0};
-        cudaEvent_t ready = nullptr;
         if (next_sharded) {
             const ShardGeom G{g, cur_log_s - 2, e->cpd, e->lv};
             TRY(shards_begin(root, G, 32, 1, &t2));
             own.trees.push_back(t2);
+        } else {
+            CU(cudaMallocAsync(&col_nat, q * 32, ctx->stream));
+            own.bufs.push_back({0, col_nat});
+        }
+        if (g > 1) {
             for (int d = 0; d < g; d++) {
                 sb_ctx *c = root->dev[d];
                 DevGuard dg(c);
                 void *p = nullptr;
-                CU(cudaMallocAsync(&p, ((size_t)e->cpd << (cur_log_s - 2)) * 32, c->stream));
+                CU(cudaMallocAsync(&p, ((size_t)e->cpd * S4) * 32, c->stream));
                 own.bufs.push_back({d, p});
                 nxt[d] = (uint4 *)p;
-                t2->sh->cols[d][0] = nxt[d];
+                if (next_sharded) t2->sh->cols[d][0] = nxt[d];
             }
         } else {
-            CU(cudaMallocAsync(&col_nat, q * 32, ctx->stream));
-            own.bufs.push_back({0, col_nat});
             TRY(tree_new(ctx, q, 32, &t2));
             own.trees.push_back(t2);
             t2->n_cols = 1;
             t2->cols[0] = (const uint4 *)col_nat;
-            if (g > 1) {          // peers store into the primary's buffers
-                CU(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
-                CU(cudaEventRecord(ready, ctx->stream));
-            }
         }
-        cudaEvent_t folded[SB_MAX_DEV] = {0};
         int rc = SB_OK;
         for (int d = 0; d < g && rc == SB_OK; d++) {
             sb_ctx *c = root->dev[d];
@@ -470,44 +508,65 @@ int ext_fri_prove(const sb_ext *e, size_t col, const sb_tree *values_tree, size_
                 if (c != root) fail(ctx, rc, "%s", c->err);
                 break;
             }
-            if (ready && d > 0) cudaStreamWaitEvent(c->stream, ready, 0);
             FriFoldParams F;
             memset(&F, 0, sizeof F);
             F.vals = cur[d];
-            F.col = (uint4 *)col_nat;
-            F.col_local = nxt[d];
             F.tw = tw;
             F.n = n;
             F.tw_log_n = tw_log_n;
             F.tw_log_stride = tw_stride + 2 * layer;           // the layer's root is g2^(4^layer)
             memcpy(F.special_x, special_x.l, 32);
             F.log_s = cur_log_s; F.cpd = e->cpd; F.lv = e->lv; F.d = (uint32_t)d; F.g = (uint32_t)g;
+            F.col_local = nxt[d];
+            sb_ctx *ctx = c;
             if (next_sharded) {
                 F.low = t2->sh->low[d];
-                for (int o = 0; o < g; o++) F.sub[o] = t2->sh->sub[o];
+                F.stage = t2->sh->stage[d];
+                KLAUNCH(SB_KIND_FRI_FOLD, merkle_launch_leaves_fold_ext(c->stream, F, nullptr));
+            } else if (g == 1) {
+                F.col = (uint4 *)col_nat;
+                KLAUNCH(SB_KIND_FRI_FOLD, merkle_launch_leaves_fold_ext(c->stream, F, t2->d_nodes));
+            } else {
+                KLAUNCH(SB_KIND_FRI_FOLD, fri_launch_fold_ext(c->stream, F));
             }
-            {
-                sb_ctx *ctx = c;
-                KLAUNCH(SB_KIND_FRI_FOLD, merkle_launch_leaves_fold_ext(c->stream, F, next_sharded ? nullptr : t2->d_nodes));
-            }
-            if (g > 1 && (next_sharded || d > 0)) {
-                if (cudaEventCreateWithFlags(&folded[d], cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(folded[d], c->stream) != cudaSuccess)
-                    rc = fail(ctx, SB_ERR_CUDA, "event: %s", cudaGetErrorString(cudaGetLastError()));
-            }
-        }
-        if (ready) cudaEventDestroy(ready);
-        if (rc == SB_OK && next_sharded) {
-            rc = shards_finish(root, t2, folded);
-        } else {
-            for (int d = 1; d < g; d++)
-                if (folded[d]) {
-                    if (rc == SB_OK) cudaStreamWaitEvent(ctx->stream, folded[d], 0);
-                    cudaEventDestroy(folded[d]);
-                }
-            if (folded[0]) cudaEventDestroy(folded[0]);
-            if (rc == SB_OK) rc = merkle_finish(ctx, t2, e->lv, true);
         }
         if (rc != SB_OK) return rc;
+        if (next_sharded) {
+            TRY(shards_finish(root, t2));
+        } else if (g == 1) {
+            TRY(merkle_finish(ctx, t2, e->lv, true));
+        } else {
+            // gather: coset arrays -> one coset-major buffer on the primary -> natural order -> standard tree
+            DevBuf cm(ctx);
+            TRY(cm.alloc(q * 32));
+            cudaEvent_t ready, folded[SB_MAX_DEV] = {0};
+            CU(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+            CU(cudaEventRecord(ready, ctx->stream));
+            for (int d = 0; d < g && rc == SB_OK; d++) {
+                sb_ctx *c = root->dev[d];
+                DevGuard dg(c);
+                if (d > 0) cudaStreamWaitEvent(c->stream, ready, 0);
+                if (cudaMemcpyAsync((uint4 *)cm.p + 2 * ((size_t)d * e->cpd * S4), nxt[d], (size_t)e->cpd * S4 * 32, cudaMemcpyDefault, c->stream) != cudaSuccess)
+                    rc = fail(ctx, SB_ERR_CUDA, "column gather from device %d: %s", d, cudaGetErrorString(cudaGetLastError()));
+                if (d > 0 && rc == SB_OK && (cudaEventCreateWithFlags(&folded[d], cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(folded[d], c->stream) != cudaSuccess))
+                    rc = fail(ctx, SB_ERR_CUDA, "event: %s", cudaGetErrorString(cudaGetLastError()));
+            }
+            cudaEventDestroy(ready);
+            for (int d = 1; d < g; d++)
+                if (folded[d]) {
+                    cudaStreamWaitEvent(ctx->stream, folded[d], 0);
+                    cudaEventDestroy(folded[d]);
+                }
+            if (rc != SB_OK) return rc;
+            ExtOpenParams P;
+            memset(&P, 0, sizeof P);
+            P.cols[0][0] = (const uint4 *)cm.p;
+            P.nc = 1; P.log_s = cur_log_s - 2; P.cpd = 8; P.lv = 3; P.g = 1;
+            KLAUNCH(SB_KIND_OTHER, ext_launch_to_natural(ctx->stream, P, (uint4 *)col_nat));
+            const uint4 *cols1[1] = {(const uint4 *)col_nat};
+            TRY(commit_cols(ctx, cols1, 1, q, &t2));
+            own.trees.push_back(t2);
+        }
         memcpy(L.root2, t2->root, 32);
         // fri.rs:181-204
         uint32_t ys[FRI_QUERIES];

@@ -207,6 +207,8 @@ struct TreeShards {
     uint32_t lv = 0, log_s = 0, cpd = 8;
     uint4 *low[SB_MAX_DEV] = {0};          // per device: levels 0 .. lv-1 of its own leaves (NULL when lv == 0)
     uint4 *sub[SB_MAX_DEV] = {0};          // per device: 2S - 1 digests, standard layout over its S level-lv digests
+    uint4 *stage[SB_MAX_DEV] = {0};        // build only: the level-lv digests a device produced (S, by step k)
+    uint4 *recv[SB_MAX_DEV] = {0};         // build only: the digests of a device's node range, by source device (g x S/g)
     const uint4 *cols[SB_MAX_DEV][8] = {{0}};   // per device: (column, coset 0, k = 0) of the committed columns
     cudaStream_t streams[SB_MAX_DEV] = {0};
     int devices[SB_MAX_DEV] = {0};

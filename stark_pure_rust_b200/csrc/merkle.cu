@@ -88,6 +88,15 @@ int merkle_launch_open_ext(cudaStream_t s, const ExtOpenParams &P, const unsigne
     }
     return n;
 }
+int merkle_launch_interleave(cudaStream_t s, const uint4 *recv, uint4 *sub0, unsigned long long per, uint32_t g) {
+    merkle_interleave_kernel<<<(unsigned)((per * g + 255) / 256), 256, 0, s>>>(recv, sub0, per, g);
+    return 1;
+}
+int fri_launch_fold_ext(cudaStream_t s, const FriFoldParams &F) {
+    const size_t total = (size_t)F.cpd << (F.log_s - 2);
+    fri_fold_ext_kernel<<<blocks128(total), 128, 0, s>>>(F);
+    return 1;
+}
 int ext_launch_to_natural(cudaStream_t s, const ExtOpenParams &P, uint4 *out) {
     ext_to_natural_kernel<<<(unsigned)((((size_t)8 << P.log_s) + 255) / 256), 256, 0, s>>>(P, out);
     return 1;

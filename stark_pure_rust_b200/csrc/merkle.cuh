@@ -231,7 +231,6 @@ __global__ void __launch_bounds__(MERKLE_THREADS, 4) merkle_nodes_kernel(uint4 *
 template <int LV>
 __device__ __forceinline__ void merkle_ext_reduce(uint32_t *sd, const ExtLeavesParams &P, size_t k, uint4 *single, size_t n_single) {
     // digests 0 .. 2^LV - 1 of this thread sit in its smem slots; they are nodes (k cpd g + d cpd + i) of level 0 (cpd = 2^LV)
-    const size_t S = (size_t)1 << P.log_s;
     const size_t first0 = (k * P.g + P.d) << LV;                  // level-0 index of this thread's first leaf
 #pragma unroll 1
     for (int s = 0; s < LV; s++) {
@@ -251,9 +250,8 @@ __device__ __forceinline__ void merkle_ext_reduce(uint32_t *sd, const ExtLeavesP
                 digest_store(single, merkle_level_off(n_single, l) + (first0 >> l) + i, o);
             } else if (l < (uint32_t)LV) {
                 digest_store(P.low, ext_low_off(P.log_s, P.cpd, l) + k * (P.cpd >> l) + i, o);
-            } else {                                              // l == LV: node k g + d of level lv -> its range owner
-                const size_t per = S / P.g, j = k / per;
-                digest_store(P.sub[j], (k - j * per) * P.g + P.d, o);
+            } else {                                              // l == LV: node k g + d of level lv, staged for its range owner
+                digest_store(P.stage, k, o);
             }
         }
     }
@@ -267,8 +265,7 @@ __device__ __forceinline__ void merkle_ext_store_leaf(const ExtLeavesParams &P, 
     } else if (LV > 0) {
         digest_store(P.low, k * P.cpd + i, h);
     } else {
-        const size_t per = ((size_t)1 << P.log_s) / P.g, j = k / per;
-        digest_store(P.sub[j], (k - j * per) * P.g + P.d, h);
+        digest_store(P.stage, k, h);
     }
 }
 
@@ -312,8 +309,7 @@ __global__ void __launch_bounds__(MERKLE_THREADS, 4) merkle_leaves_fold_ext_kern
     E.log_s = F.log_s - 2;
     E.cpd = F.cpd; E.lv = F.lv; E.d = F.d; E.g = F.g;
     E.low = F.low;
-#pragma unroll
-    for (int o = 0; o < SB_MAX_DEV; o++) E.sub[o] = F.sub[o];
+    E.stage = F.stage;
 #pragma unroll 1
     for (int i = 0; i < (1 << LV); i++) {
         const uint4 *v = F.vals + 2 * (((size_t)i << F.log_s) + k);
@@ -330,6 +326,32 @@ __global__ void __launch_bounds__(MERKLE_THREADS, 4) merkle_leaves_fold_ext_kern
         sd_put(sd, i, h);
     }
     merkle_ext_reduce<LV>(sd, E, k, nodes, q);
+}
+
+// level 0 of a device's subtree from the staged digests of the g sources: sub0[k' g + d] = recv[d * per + k']
+__global__ void merkle_interleave_kernel(const uint4 *recv, uint4 *sub0, unsigned long long per, uint32_t g) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= per * g) return;
+    const size_t d = t / per, k = t - d * per, o = k * g + d;
+    sub0[2 * o] = recv[2 * t];
+    sub0[2 * o + 1] = recv[2 * t + 1];
+}
+// fold alone on coset-major values (the layer after it runs on the primary device, which hashes the gathered column itself)
+__global__ void __launch_bounds__(128) fri_fold_ext_kernel(const __grid_constant__ FriFoldParams F) {
+    const size_t S = (size_t)1 << F.log_s, S4 = S >> 2, q = F.n >> 2;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)F.cpd * S4) return;
+    const size_t i = t / S4, k = t - i * S4;
+    fp sx;
+#pragma unroll
+    for (int w = 0; w < 8; w++) sx.l[w] = F.special_x[w];
+    const unsigned long long nT = 1ull << F.tw_log_n;
+    const fp iota_inv = fp_ldg_ro(F.tw, (nT - ((unsigned long long)q << F.tw_log_stride)) & (nT - 1));
+    const uint4 *v = F.vals + 2 * ((i << F.log_s) + k);
+    const size_t row = (k << 3) + (size_t)F.d * F.cpd + i;
+    fp y0 = fp_from_u4(v[0], v[1]), y1 = fp_from_u4(v[2 * S4], v[2 * S4 + 1]), y2 = fp_from_u4(v[4 * S4], v[4 * S4 + 1]),
+       y3 = fp_from_u4(v[6 * S4], v[6 * S4 + 1]);
+    fp_stg(F.col_local, t, fri_fold_vals(F, row, y0, y1, y2, y3, sx, iota_inv));
 }
 
 // sibling digests of the levels held in the shards (levels 0 .. lv + log_s - 1), leaf level first:

@@ -78,6 +78,32 @@ def test_ext_chain_matches_oracle(mctx, oracle, log_s, n_cols, col_len):
     _ext_chain(mctx, oracle, log_s, n_cols, col_len, 9000 + log_s + n_cols)
 
 
+def test_ext_chain_2_24_golden(mctx):
+    """the headline size on g devices: 8-column LDE 2^21 -> 2^24, both trees and the FRI proof against the oracle's digests
+    (tests/golden/vectors_large.json).  At this size the first FRI layer stays sharded (column next to the data, column tree as
+    per-device subtrees with the staged digest exchange); the second one is gathered to the primary device."""
+    import stark_pure_rust_b200 as sb
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "vectors_large.json")))
+    log_s, nc = gold["log_s"], gold["n_cols"]
+    S, N = 1 << log_s, 8 << log_s
+    e = sb.ext.ExtColumns(nc, log_s, ctx=mctx)
+    e.load(0, random_elems(nc * S, gold["lde"]["seed"]).reshape(nc, S, 4))
+    e.extend()
+    assert hashlib.sha256(e.read(nc - 1).tobytes()).hexdigest() == gold["lde"]["col_sha256"][nc - 1]
+    root8, t8 = e.commit(list(range(nc)))
+    assert root8.hex() == gold["merkle8"]["root"]
+    proofs = e.open(t8, gold["merkle8"]["open"])
+    assert hashlib.sha256(b"".join(p.leaf for p in proofs)).hexdigest() == gold["merkle8"]["leaves_sha256"]
+    assert hashlib.sha256(b"".join(b"".join(p.nodes) for p in proofs)).hexdigest() == gold["merkle8"]["nodes_sha256"]
+    e.free_tree(t8)
+    root1, t1 = e.commit([nc - 1])
+    assert root1.hex() == gold["merkle1"]["root"]
+    text = e.fri_prove(nc - 1, N // 4, 8, tree=t1, as_json=True)
+    e.free_tree(t1)
+    e.close()
+    assert len(text) == gold["fri"]["json_len"] and hashlib.sha256(text.encode()).hexdigest() == gold["fri"]["json_sha256"]
+
+
 def test_ext_direct_fri_and_errors(mctx, oracle):
     """max_deg_plus_1 <= 16: the proof is the values themselves (fri.rs:88-112), gathered in natural order"""
     import stark_pure_rust_b200 as sb
