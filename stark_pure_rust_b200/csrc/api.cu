@@ -127,6 +127,11 @@ extern "C" void sb_destroy(sb_ctx *ctx) {
     }
     DevGuard g(ctx);
     cudaStreamSynchronize(ctx->stream);
+    for (auto &b : ctx->blk_free) cudaFreeAsync(b.p, ctx->stream);
+    for (auto &b : ctx->blk_live) cudaFreeAsync(b.p, ctx->stream);      // leaked by the caller (trees / columns never freed)
+    ctx->blk_free.clear();
+    ctx->blk_live.clear();
+    cudaStreamSynchronize(ctx->stream);
     for (auto &t : ctx->tables) cudaFree(t.d);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
@@ -651,17 +656,24 @@ void free_tree(sb_tree *t) {
     if (!t) return;
     if (t->sh) {
         for (int d = 0; d < t->sh->g; d++) {
-            DevGuard g(t->sh->devices[d]);
-            if (t->sh->low[d]) cudaFreeAsync(t->sh->low[d], t->sh->streams[d]);
-            if (t->sh->sub[d]) cudaFreeAsync(t->sh->sub[d], t->sh->streams[d]);
-            if (t->sh->stage[d]) cudaFreeAsync(t->sh->stage[d], t->sh->streams[d]);
-            if (t->sh->recv[d]) cudaFreeAsync(t->sh->recv[d], t->sh->streams[d]);
+            if (!t->sh->ctxs[d]) continue;
+            DevGuard g(t->sh->ctxs[d]);
+            blk_release(t->sh->ctxs[d], t->sh->low[d]);
+            blk_release(t->sh->ctxs[d], t->sh->sub[d]);
+            blk_release(t->sh->ctxs[d], t->sh->stage[d]);
+            blk_release(t->sh->ctxs[d], t->sh->recv[d]);
         }
         delete t->sh;
     }
     DevGuard g(t->device);
-    if (t->d_nodes) cudaFreeAsync(t->d_nodes, t->stream);
-    if (t->d_leaves) cudaFreeAsync(t->d_leaves, t->stream);
+    if (t->d_nodes) {
+        if (t->owner) blk_release(t->owner, t->d_nodes);
+        else cudaFreeAsync(t->d_nodes, t->stream);
+    }
+    if (t->d_leaves) {
+        if (t->owner) blk_release(t->owner, t->d_leaves);      // falls back to cudaFreeAsync for blocks the cache does not know
+        else cudaFreeAsync(t->d_leaves, t->stream);
+    }
     delete t;
 }
 
@@ -722,10 +734,11 @@ int tree_new(sb_ctx *ctx, size_t n, size_t leaf_bytes, sb_tree **out) {
     t->leaf_bytes = leaf_bytes;
     t->stream = ctx->stream;
     t->device = ctx->device;
-    cudaError_t e = cudaMallocAsync(&t->d_nodes, (2 * n - 1) * 32, ctx->stream);
-    if (e != cudaSuccess) {
+    t->owner = ctx;
+    int rc = blk_alloc(ctx, (2 * n - 1) * 32, (void **)&t->d_nodes);
+    if (rc != SB_OK) {
         delete t;
-        return fail(ctx, SB_ERR_OOM, "cudaMallocAsync(tree levels): %s", cudaGetErrorString(e));
+        return rc;
     }
     *out = t;
     return SB_OK;
@@ -738,10 +751,13 @@ extern "C" int sb_merkle_commit(sb_ctx *ctx, const void *leaves, size_t leaf_byt
     if (leaf_bytes >= ((size_t)1 << 31)) return fail(ctx, SB_ERR_ARG, "leaf too long");
     sb_tree *t = nullptr;
     TRY(tree_new(ctx, n, leaf_bytes, &t));
-    cudaError_t e = cudaMallocAsync(&t->d_leaves, n * leaf_bytes ? n * leaf_bytes : 16, ctx->stream);
-    if (e != cudaSuccess) {
-        free_tree(t);
-        return fail(ctx, SB_ERR_OOM, "cudaMalloc(leaves): %s", cudaGetErrorString(e));
+    cudaError_t e = cudaSuccess;
+    {
+        int rc0 = blk_alloc(ctx, n * leaf_bytes, (void **)&t->d_leaves);
+        if (rc0 != SB_OK) {
+            free_tree(t);
+            return rc0;
+        }
     }
     int rc = SB_OK;
     const size_t total = n * leaf_bytes;
@@ -942,7 +958,7 @@ extern "C" int sb_tree_root(const sb_tree *t, uint8_t root[32]) {
 }
 extern "C" void sb_tree_free(sb_ctx *ctx, sb_tree *t) {
     DevGuard g(ctx);
-    if (t && ctx && t->device == ctx->device) t->stream = ctx->stream;   // the context's stream may have been replaced since the tree was built (sb_set_stream)
+    if (t && ctx && t->device == ctx->device && !t->owner) t->stream = ctx->stream;   // the context's stream may have been replaced since the tree was built (sb_set_stream)
     free_tree(t);      // stream-ordered: work already queued on the stream finishes first
 }
 
@@ -1011,7 +1027,7 @@ int fri_prove_dev(sb_ctx *ctx, const uint4 *d_vals, size_t n, const hfp::el &roo
     std::vector<void *> owned_cols;
     auto cleanup = [&]() {
         for (auto t : owned_trees) free_tree(t);
-        for (auto p : owned_cols) cudaFreeAsync(p, ctx->stream);
+        for (auto p : owned_cols) blk_release(ctx, p);
     };
     int rc = SB_OK;
     const uint4 *cur = d_vals;
@@ -1049,8 +1065,7 @@ int fri_prove_dev(sb_ctx *ctx, const uint4 *d_vals, size_t n, const hfp::el &roo
         // fri.rs:141-164
         const size_t q = cur_n / 4;
         void *d_col = nullptr;
-        cudaError_t e = cudaMallocAsync(&d_col, q * 32, ctx->stream);
-        if (e != cudaSuccess) { rc = fail(ctx, SB_ERR_OOM, "cudaMallocAsync(column): %s", cudaGetErrorString(e)); break; }
+        if ((rc = blk_alloc(ctx, q * 32, &d_col)) != SB_OK) break;
         owned_cols.push_back(d_col);
         FriFoldParams P;
         P.vals = cur;

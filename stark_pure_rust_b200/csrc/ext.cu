@@ -28,9 +28,9 @@ void ext_free(sb_ext *e) {
     for (int d = 0; d < e->g; d++) {
         sb_ctx *c = e->root->dev[d];
         DevGuard g(c);
-        if (e->buf[d]) cudaFreeAsync(e->buf[d], c->stream);
-        if (e->coef[d]) cudaFreeAsync(e->coef[d], c->stream);
-        if (e->in[d]) cudaFreeAsync(e->in[d], c->stream);
+        blk_release(c, e->buf[d]);
+        blk_release(c, e->coef[d]);
+        blk_release(c, e->in[d]);
     }
     delete e;
 }
@@ -65,13 +65,15 @@ int ext_create(sb_ctx *root, size_t n_cols, size_t n_lde, uint32_t log_s, sb_ext
         sb_ctx *c = root->dev[d];
         DevGuard g(c);
         const size_t nb = n_cols * e->cpd * e->S * 32, nc = e->n_lde * e->S * 32;
-        cudaError_t e1 = cudaMallocAsync((void **)&e->buf[d], nb ? nb : 16, c->stream);
-        cudaError_t e2 = e1 == cudaSuccess ? cudaMallocAsync((void **)&e->coef[d], nc ? nc : 16, c->stream) : e1;
-        cudaError_t e3 = e2 == cudaSuccess ? cudaMallocAsync((void **)&e->in[d], nc ? nc : 16, c->stream) : e2;
-        if (e3 == cudaSuccess) e3 = cudaMemsetAsync(e->in[d], 0, nc ? nc : 16, c->stream);      // zero padding of short columns
-        if (e3 != cudaSuccess) {
+        int rc = blk_alloc(c, nb, (void **)&e->buf[d]);
+        if (rc == SB_OK) rc = blk_alloc(c, nc, (void **)&e->coef[d]);
+        if (rc == SB_OK) rc = blk_alloc(c, nc, (void **)&e->in[d]);
+        if (rc == SB_OK && cudaMemsetAsync(e->in[d], 0, nc ? nc : 16, c->stream) != cudaSuccess)      // zero padding of short columns
+            rc = fail(c, SB_ERR_CUDA, "memset: %s", cudaGetErrorString(cudaGetLastError()));
+        if (rc != SB_OK) {
+            if (c != root) fail(ctx, rc, "%s", c->err);
             ext_free(e);
-            return fail(ctx, SB_ERR_OOM, "device %d: allocation of the extended columns failed: %s", c->device, cudaGetErrorString(e3));
+            return rc;
         }
     }
     *out = e;
@@ -222,6 +224,7 @@ static int shards_begin(sb_ctx *root, const ShardGeom &G, size_t leaf_bytes, int
     t->n_cols = n_cols;
     t->stream = root->stream;
     t->device = root->device;
+    t->owner = root;
     TreeShards *sh = t->sh = new TreeShards();
     sh->g = G.g;
     sh->lv = G.lv;
@@ -233,25 +236,14 @@ static int shards_begin(sb_ctx *root, const ShardGeom &G, size_t leaf_bytes, int
     for (int d = 0; d < G.g && rc == SB_OK; d++) {
         sb_ctx *c = root->dev[d];
         DevGuard dg(c);
-        sh->streams[d] = c->stream;
-        sh->devices[d] = c->device;
+        sh->ctxs[d] = c;
         struct { uint4 **p; size_t bytes; const char *what; } want[4] = {{&sh->low[d], low_digests * 32, "low levels"}, {&sh->sub[d], (2 * S - 1) * 32, "subtree"},
                                                                         {&sh->stage[d], S * 32, "digest staging"}, {&sh->recv[d], S * 32, "digest receive"}};
         for (auto &w : want) {
             if (!w.bytes) continue;
-            cudaError_t e = cudaMallocAsync((void **)w.p, w.bytes, c->stream);
-            if (e == cudaErrorMemoryAllocation) {          // let pending frees of other streams land, then try once more
-                cudaGetLastError();
-                cudaDeviceSynchronize();
-                e = cudaMallocAsync((void **)w.p, w.bytes, c->stream);
-            }
-            if (e != cudaSuccess) {
-                *w.p = nullptr;
-                size_t fr = 0, tot = 0;
-                cudaMemGetInfo(&fr, &tot);
-                rc = fail(ctx, e == cudaErrorMemoryAllocation ? SB_ERR_OOM : SB_ERR_CUDA, "device %d: cudaMallocAsync(%s, %zu bytes) failed: %s (free %zu of %zu MiB)", c->device,
-                          w.what, w.bytes, cudaGetErrorString(e), fr >> 20, tot >> 20);
-                cudaGetLastError();
+            rc = blk_alloc(c, w.bytes, (void **)w.p);
+            if (rc != SB_OK) {
+                fail(ctx, rc, "%s (%s)", c->err, w.what);
                 break;
             }
         }
@@ -314,8 +306,8 @@ static int shards_finish(sb_ctx *root, sb_tree *t) {
     for (int d = 0; d < g; d++) {
         if (pushed[d]) cudaEventDestroy(pushed[d]);
         DevGuard dg(root->dev[d]);                    // the staging buffers are only needed while the tree is built
-        if (sh->stage[d]) cudaFreeAsync(sh->stage[d], root->dev[d]->stream);
-        if (sh->recv[d]) cudaFreeAsync(sh->recv[d], root->dev[d]->stream);
+        blk_release(root->dev[d], sh->stage[d]);
+        blk_release(root->dev[d], sh->recv[d]);
         sh->stage[d] = sh->recv[d] = nullptr;
     }
     if (rc != SB_OK) return rc;
@@ -438,7 +430,7 @@ int ext_fri_prove(const sb_ext *e, size_t col, const sb_tree *values_tree, size_
             for (auto t : trees) free_tree(t);
             for (auto &b : bufs) {
                 DevGuard dg(root->dev[b.first]);
-                cudaFreeAsync(b.second, root->dev[b.first]->stream);
+                blk_release(root->dev[b.first], b.second);
             }
             delete proof;
         }
@@ -478,7 +470,7 @@ int ext_fri_prove(const sb_ext *e, size_t col, const sb_tree *values_tree, size_
             TRY(shards_begin(root, G, 32, 1, &t2));
             own.trees.push_back(t2);
         } else {
-            CU(cudaMallocAsync(&col_nat, q * 32, ctx->stream));
+            TRY(blk_alloc(ctx, q * 32, &col_nat));
             own.bufs.push_back({0, col_nat});
         }
         if (g > 1) {
@@ -486,7 +478,7 @@ int ext_fri_prove(const sb_ext *e, size_t col, const sb_tree *values_tree, size_
                 sb_ctx *c = root->dev[d];
                 DevGuard dg(c);
                 void *p = nullptr;
-                CU(cudaMallocAsync(&p, ((size_t)e->cpd * S4) * 32, c->stream));
+                if (blk_alloc(c, ((size_t)e->cpd * S4) * 32, &p) != SB_OK) return fail(ctx, SB_ERR_OOM, "%s", c->err);
                 own.bufs.push_back({d, p});
                 nxt[d] = (uint4 *)p;
                 if (next_sharded) t2->sh->cols[d][0] = nxt[d];
@@ -537,7 +529,7 @@ int ext_fri_prove(const sb_ext *e, size_t col, const sb_tree *values_tree, size_
             TRY(merkle_finish(ctx, t2, e->lv, true));
         } else {
             // gather: coset arrays -> one coset-major buffer on the primary -> natural order -> standard tree
-            DevBuf cm(ctx);
+            DevBuf cm(ctx);                    // (block cache: peer-mapped pool memory is expensive to hand out)
             TRY(cm.alloc(q * 32));
             cudaEvent_t ready, folded[SB_MAX_DEV] = {0};
             CU(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));

@@ -71,6 +71,14 @@ struct sb_ctx {
     std::vector<cudaEvent_t> prof_pool;
     double prof_ms[SB_KIND_COUNT] = {0};
     uint64_t prof_n[SB_KIND_COUNT] = {0};
+    // Block cache for the large per-call arrays of the resident pipeline (extended columns, sharded trees, FRI layers).  Sizes repeat
+    // from proof to proof, so a freed block is kept and handed out again instead of going back to the stream-ordered pool: with
+    // peer access enabled, allocating / freeing pool memory cost ~0.1 ms per call and device on an 8-GPU context (measured: a
+    // sharded tree of 2^26 leaves spent 7 of its 9 ms there).  All users enqueue on the device's one compute stream, so reuse is
+    // stream-ordered like the pool's.
+    struct Block { void *p; size_t bytes; };
+    std::vector<Block> blk_free, blk_live;
+    size_t blk_free_bytes = 0;
     // multi-device contexts (sb_init_multi): the primary context is dev[0] and owns one sub-context per further device;
     // every sub-context is a full context (own stream, table cache, profile counters) whose `primary` points back.
     // Plain sb_init contexts have dev = {this}.  Two entries may name the same physical GPU (logical devices: the
@@ -178,26 +186,6 @@ static int guarded(sb_ctx *ctx, F &&body) {
         if (rc_ != SB_OK) return rc_; \
     } while (0)
 
-struct DevBuf {   // stream-ordered scratch
-    sb_ctx *ctx;
-    void *p = nullptr;
-    explicit DevBuf(sb_ctx *c) : ctx(c) {}
-    int alloc(size_t bytes) {
-        cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 16, ctx->stream);
-        if (e != cudaSuccess) {
-            p = nullptr;
-            return fail(ctx, e == cudaErrorMemoryAllocation ? SB_ERR_OOM : SB_ERR_CUDA, "cudaMallocAsync(%zu): %s", bytes,
-                        cudaGetErrorString(e));
-        }
-        return SB_OK;
-    }
-    ~DevBuf() {
-        if (p) cudaFreeAsync(p, ctx->stream);
-    }
-    DevBuf(const DevBuf &) = delete;
-    DevBuf &operator=(const DevBuf &) = delete;
-};
-
 // Tree over coset-major columns spread over g devices (ext.cu): device d hashes the leaves of its cosets and keeps the
 // lv = log2(cosets per device) lowest levels of those; the level-lv digests are written straight into the memory of the
 // device that owns their node range, which builds the subtree over its S level-lv digests; the top log2 g levels are
@@ -210,9 +198,90 @@ struct TreeShards {
     uint4 *stage[SB_MAX_DEV] = {0};        // build only: the level-lv digests a device produced (S, by step k)
     uint4 *recv[SB_MAX_DEV] = {0};         // build only: the digests of a device's node range, by source device (g x S/g)
     const uint4 *cols[SB_MAX_DEV][8] = {{0}};   // per device: (column, coset 0, k = 0) of the committed columns
-    cudaStream_t streams[SB_MAX_DEV] = {0};
-    int devices[SB_MAX_DEV] = {0};
+    sb_ctx *ctxs[SB_MAX_DEV] = {0};        // the devices' contexts (block cache, stream, ordinal)
     std::vector<uint8_t> top;              // host: (2g - 1) digests over the subtree roots, standard layout
+};
+
+// cached device blocks (see sb_ctx::blk_free): blk_alloc never returns a block more than twice the requested size
+static int blk_alloc(sb_ctx *ctx, size_t bytes, void **out) {
+    if (!bytes) bytes = 16;
+    size_t best = (size_t)-1;
+    for (size_t i = 0; i < ctx->blk_free.size(); i++)
+        if (ctx->blk_free[i].bytes >= bytes && ctx->blk_free[i].bytes <= 2 * bytes && (best == (size_t)-1 || ctx->blk_free[i].bytes < ctx->blk_free[best].bytes)) best = i;
+    if (best != (size_t)-1) {
+        sb_ctx::Block b = ctx->blk_free[best];
+        ctx->blk_free.erase(ctx->blk_free.begin() + best);
+        ctx->blk_free_bytes -= b.bytes;
+        ctx->blk_live.push_back(b);
+        *out = b.p;
+        return SB_OK;
+    }
+    void *p = nullptr;
+    cudaError_t e = cudaMallocAsync(&p, bytes, ctx->stream);
+    if (e == cudaErrorMemoryAllocation) {          // give the cache back, let pending frees land, try once more
+        cudaGetLastError();
+        for (auto &b : ctx->blk_free) cudaFreeAsync(b.p, ctx->stream);
+        ctx->blk_free.clear();
+        ctx->blk_free_bytes = 0;
+        cudaDeviceSynchronize();
+        e = cudaMallocAsync(&p, bytes, ctx->stream);
+    }
+    if (e != cudaSuccess) {
+        size_t fr = 0, tot = 0;
+        cudaMemGetInfo(&fr, &tot);
+        cudaGetLastError();
+        *out = nullptr;
+        return fail(ctx, e == cudaErrorMemoryAllocation ? SB_ERR_OOM : SB_ERR_CUDA, "device %d: cudaMallocAsync(%zu bytes) failed: %s (free %zu of %zu MiB)", ctx->device, bytes,
+                    cudaGetErrorString(e), fr >> 20, tot >> 20);
+    }
+    ctx->blk_live.push_back({p, bytes});
+    *out = p;
+    return SB_OK;
+}
+static void blk_release(sb_ctx *ctx, void *p) {
+    if (!p) return;
+    for (size_t i = 0; i < ctx->blk_live.size(); i++)
+        if (ctx->blk_live[i].p == p) {
+            sb_ctx::Block b = ctx->blk_live[i];
+            ctx->blk_live.erase(ctx->blk_live.begin() + i);
+            ctx->blk_free.push_back(b);
+            ctx->blk_free_bytes += b.bytes;
+            // soft cap: keep at most 48 GiB parked; the oldest blocks go back to the pool
+            while (ctx->blk_free_bytes > ((size_t)48 << 30) && !ctx->blk_free.empty()) {
+                cudaFreeAsync(ctx->blk_free.front().p, ctx->stream);
+                ctx->blk_free_bytes -= ctx->blk_free.front().bytes;
+                ctx->blk_free.erase(ctx->blk_free.begin());
+            }
+            return;
+        }
+    cudaFreeAsync(p, ctx->stream);       // not one of ours
+}
+
+struct DevBuf {   // stream-ordered scratch: the block cache from 1 MiB on, the pool below
+    sb_ctx *ctx;
+    void *p = nullptr;
+    bool cached = false;
+    explicit DevBuf(sb_ctx *c) : ctx(c) {}
+    int alloc(size_t bytes) {
+        if (bytes >= ((size_t)1 << 20)) {
+            cached = true;
+            return blk_alloc(ctx, bytes, &p);
+        }
+        cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 16, ctx->stream);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return fail(ctx, e == cudaErrorMemoryAllocation ? SB_ERR_OOM : SB_ERR_CUDA, "cudaMallocAsync(%zu): %s", bytes,
+                        cudaGetErrorString(e));
+        }
+        return SB_OK;
+    }
+    ~DevBuf() {
+        if (!p) return;
+        if (cached) blk_release(ctx, p);
+        else cudaFreeAsync(p, ctx->stream);
+    }
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
 };
 
 struct sb_tree {
@@ -227,6 +296,7 @@ struct sb_tree {
     uint8_t root[32] = {0};
     cudaStream_t stream = nullptr; // allocations are stream-ordered (pool) on the owning context's stream
     int device = 0;
+    sb_ctx *owner = nullptr;       // context whose block cache d_nodes came from
     TreeShards *sh = nullptr;      // != NULL: the levels live in the shards (d_nodes == NULL)
 };
 
