@@ -134,6 +134,7 @@ extern "C" void sb_destroy(sb_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (auto &t : ctx->tables) cudaFree(t.d);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->pinned2) cudaFreeHost(ctx->pinned2);
     if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
     if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     prof_collect(ctx);
@@ -150,23 +151,54 @@ extern "C" void sb_destroy(sb_ctx *ctx) {
 
 void *pinned_arena(sb_ctx *ctx, size_t bytes) {
     if (bytes <= ctx->pinned_bytes) return ctx->pinned;
-    cudaStreamSynchronize(ctx->stream);            // an upload from the old arena may still be in flight
-    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    // uploads from the old arena ran on the devices' copy streams as well: wait for everything before it goes away (syncing the
+    // compute stream alone left a pending "invalid argument" behind the next cudaMallocHost and a crash later on)
+    for (sb_ctx *c : ctx->dev) {
+        DevGuard g(c);
+        cudaDeviceSynchronize();
+    }
+    static const bool verbose = getenv("SB_DEBUG_ERRORS") != nullptr;
+    if (ctx->pinned) {
+        const cudaError_t e = cudaFreeHost(ctx->pinned);
+        if (verbose) fprintf(stderr, "stark_b200: pinned_arena: cudaFreeHost(%p) -> %s\n", ctx->pinned, cudaGetErrorString(e));
+        cudaGetLastError();
+    }
     ctx->pinned = nullptr;
     ctx->pinned_bytes = 0;
     const size_t want = bytes + bytes / 8;
-    if (cudaMallocHost(&ctx->pinned, want) != cudaSuccess) {
+    const cudaError_t e = cudaMallocHost(&ctx->pinned, want);
+    if (verbose) fprintf(stderr, "stark_b200: pinned_arena: cudaMallocHost(%zu) -> %s, %p, pending: %s\n", want, cudaGetErrorString(e), ctx->pinned, cudaGetErrorString(cudaPeekAtLastError()));
+    if (e != cudaSuccess) {
         cudaGetLastError();
+        ctx->pinned = nullptr;
         return nullptr;
     }
     ctx->pinned_bytes = want;
     return ctx->pinned;
 }
 
+void *pinned_scratch(sb_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->pinned2_bytes) return ctx->pinned2;
+    for (sb_ctx *c : ctx->dev) {                                       // an upload from the old buffer may still be in flight
+        DevGuard g(c);
+        cudaDeviceSynchronize();
+    }
+    if (ctx->pinned2) cudaFreeHost(ctx->pinned2);
+    ctx->pinned2 = nullptr;
+    ctx->pinned2_bytes = 0;
+    const size_t want = bytes < ((size_t)1 << 16) ? ((size_t)1 << 16) : 2 * bytes;
+    if (cudaMallocHost(&ctx->pinned2, want) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    ctx->pinned2_bytes = want;
+    return ctx->pinned2;
+}
+
 extern "C" const char *sb_last_error(const sb_ctx *ctx) { return ctx ? ctx->err : "no context"; }
 
 extern "C" int sb_set_stream(sb_ctx *ctx, void *s) {
-    return guarded(ctx, [&]() -> int {
+    return guarded(ctx, __func__, [&]() -> int {
     if (!ctx) return SB_ERR_ARG;
     CU(cudaStreamSynchronize(ctx->stream));
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -176,7 +208,7 @@ extern "C" int sb_set_stream(sb_ctx *ctx, void *s) {
     });
 }
 extern "C" int sb_sync(sb_ctx *ctx) {
-    return guarded(ctx, [&]() -> int {
+    return guarded(ctx, __func__, [&]() -> int {
     if (!ctx) return SB_ERR_ARG;
     CU(cudaStreamSynchronize(ctx->stream));
     for (size_t i = 1; i < ctx->dev.size(); i++) CU(cudaStreamSynchronize(ctx->dev[i]->stream));
@@ -184,14 +216,14 @@ extern "C" int sb_sync(sb_ctx *ctx) {
     });
 }
 extern "C" int sb_timer_start(sb_ctx *ctx) {
-    return guarded(ctx, [&]() -> int {
+    return guarded(ctx, __func__, [&]() -> int {
     if (!ctx) return SB_ERR_ARG;
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
     return SB_OK;
     });
 }
 extern "C" int sb_timer_stop(sb_ctx *ctx, float *ms) {
-    return guarded(ctx, [&]() -> int {
+    return guarded(ctx, __func__, [&]() -> int {
     if (!ctx || !ms) return SB_ERR_ARG;
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
     CU(cudaEventSynchronize(ctx->ev1));
@@ -206,7 +238,7 @@ extern "C" uint64_t sb_launch_count(const sb_ctx *ctx) {
     return n;
 }
 extern "C" int sb_profile(sb_ctx *ctx, int enable) {
-    return guarded(ctx, [&]() -> int {
+    return guarded(ctx, __func__, [&]() -> int {
     if (!ctx) return SB_ERR_ARG;
     for (sb_ctx *c : ctx->dev) {
         DevGuard g(c);
@@ -219,7 +251,7 @@ extern "C" int sb_profile(sb_ctx *ctx, int enable) {
 }
 // multi-device contexts: launches and milliseconds are summed over the devices
 extern "C" int sb_profile_read(sb_ctx *ctx, int kind, uint64_t *launches, double *total_ms) {
-    return guarded(ctx, [&]() -> int {
+    return guarded(ctx, __func__, [&]() -> int {
     if (!ctx || kind < 0 || kind >= SB_KIND_COUNT) return SB_ERR_ARG;
     uint64_t n = 0;
     double ms = 0;
@@ -237,7 +269,7 @@ extern "C" int sb_profile_read(sb_ctx *ctx, int kind, uint64_t *launches, double
 }
 
 extern "C" int sb_dev_alloc(sb_ctx *ctx, size_t bytes, void **p) {
-    return guarded(ctx, [&]() -> int {
+    return guarded(ctx, __func__, [&]() -> int {
     if (!ctx || !p) return SB_ERR_ARG;
     CU(cudaSetDevice(ctx->device));
     CU(cudaMalloc(p, bytes ? bytes : 16));
@@ -245,7 +277,7 @@ extern "C" int sb_dev_alloc(sb_ctx *ctx, size_t bytes, void **p) {
     });
 }
 extern "C" int sb_dev_free(sb_ctx *ctx, void *p) {
-    return guarded(ctx, [&]() -> int {
+    return guarded(ctx, __func__, [&]() -> int {
     if (!ctx) return SB_ERR_ARG;
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaFree(p));
@@ -253,7 +285,7 @@ extern "C" int sb_dev_free(sb_ctx *ctx, void *p) {
     });
 }
 extern "C" int sb_h2d(sb_ctx *ctx, void *d, const void *s, size_t bytes) {
-    return guarded(ctx, [&]() -> int {
+    return guarded(ctx, __func__, [&]() -> int {
     if (!ctx) return SB_ERR_ARG;
     CU(cudaMemcpyAsync(d, s, bytes, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -261,7 +293,7 @@ extern "C" int sb_h2d(sb_ctx *ctx, void *d, const void *s, size_t bytes) {
     });
 }
 extern "C" int sb_d2h(sb_ctx *ctx, void *d, const void *s, size_t bytes) {
-    return guarded(ctx, [&]() -> int {
+    return guarded(ctx, __func__, [&]() -> int {
     if (!ctx) return SB_ERR_ARG;
     CU(cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -269,14 +301,14 @@ extern "C" int sb_d2h(sb_ctx *ctx, void *d, const void *s, size_t bytes) {
     });
 }
 extern "C" int sb_host_alloc_pinned(sb_ctx *ctx, size_t bytes, void **p) {
-    return guarded(ctx, [&]() -> int {
+    return guarded(ctx, __func__, [&]() -> int {
     if (!ctx || !p) return SB_ERR_ARG;
     CU(cudaMallocHost(p, bytes ? bytes : 16));
     return SB_OK;
     });
 }
 extern "C" int sb_host_free_pinned(sb_ctx *ctx, void *p) {
-    return guarded(ctx, [&]() -> int {
+    return guarded(ctx, __func__, [&]() -> int {
     if (!ctx) return SB_ERR_ARG;
     CU(cudaFreeHost(p));
     return SB_OK;
@@ -288,6 +320,7 @@ extern "C" int sb_host_free_pinned(sb_ctx *ctx, void *p) {
 // ------------------------------------------------------------------------------------------------
 static int powers_into(sb_ctx *ctx, const hfp::el &root, size_t n, uint4 *d_out) {
     if (n == 0) return SB_OK;
+    dbg_check("powers_into entry");
     size_t seed = n < 1024 ? n : 1024;
     KLAUNCH(SB_KIND_OTHER, powers_launch_seed(ctx->stream, d_out, seed, to_dev_fp(root)));
     hfp::el wc = hfp::pow_u64(root, 1024);
@@ -343,6 +376,7 @@ int get_table(sb_ctx *ctx, const hfp::el &w, uint32_t log_n, const uint4 **tw, u
             ctx->tables.erase(ctx->tables.begin() + lru);
         }
     }
+    dbg_check("get_table before cudaMalloc");
     TwTable t;
     t.root = w;
     t.log_n = log_n;
@@ -460,7 +494,7 @@ int ntt_dev(sb_ctx *ctx, const uint4 *d_src, size_t len_in, size_t src_stride, u
 
 extern "C" int sb_ntt_dev(sb_ctx *ctx, const uint64_t *d_src, size_t len_in, size_t src_stride, uint64_t *d_dst,
                           size_t dst_stride, size_t n_polys, const uint64_t root[4], uint32_t log_n, int inverse) {
-    return guarded(ctx, [&]() -> int {
+    return guarded(ctx, __func__, [&]() -> int {
     if (!ctx || !d_src || !d_dst || !root) return SB_ERR_ARG;
     if (d_src == d_dst) return fail(ctx, SB_ERR_ARG, "sb_ntt_dev is out of place");
     return ntt_dev(ctx, (const uint4 *)d_src, len_in, src_stride, (uint4 *)d_dst, dst_stride, n_polys, hfp::from_limbs(root),
@@ -471,7 +505,7 @@ extern "C" int sb_ntt_dev(sb_ctx *ctx, const uint64_t *d_src, size_t len_in, siz
 // four-step twiddle step of a transform split over several GPUs (sharded.py::distributed_ntt)
 extern "C" int sb_twiddle_mul_dev(sb_ctx *ctx, uint64_t *d_vals, size_t rows, size_t cols, size_t row0, const uint64_t root[4],
                                   uint32_t log_n, int inverse) {
-    return guarded(ctx, [&]() -> int {
+    return guarded(ctx, __func__, [&]() -> int {
     if (!ctx || !d_vals || !root) return SB_ERR_ARG;
     if (log_n > 28) return fail(ctx, SB_ERR_ARG, "log_n %u exceeds the field's two-adicity 28", log_n);
     const uint4 *tw;
@@ -484,7 +518,7 @@ extern "C" int sb_twiddle_mul_dev(sb_ctx *ctx, uint64_t *d_vals, size_t rows, si
 }
 
 extern "C" int sb_ntt(sb_ctx *ctx, uint64_t *vals, size_t len_in, const uint64_t root[4], uint32_t log_n, int inverse) {
-    return guarded(ctx, [&]() -> int {
+    return guarded(ctx, __func__, [&]() -> int {
     if (!ctx || !vals || !root) return SB_ERR_ARG;
     if (log_n > 28) return fail(ctx, SB_ERR_ARG, "log_n %u exceeds the field's two-adicity 28", log_n);
     const size_t n = (size_t)1 << log_n;
@@ -540,7 +574,7 @@ int lde_dev(sb_ctx *ctx, const uint4 *d_cols, size_t n_cols, size_t col_len, siz
 
 extern "C" int sb_lde_batch_dev(sb_ctx *ctx, const uint64_t *d_cols, size_t n_cols, size_t col_len, size_t col_stride,
                                 const uint64_t root_big[4], uint32_t log_s, uint32_t log_ext, uint64_t *d_out) {
-    return guarded(ctx, [&]() -> int {
+    return guarded(ctx, __func__, [&]() -> int {
     if (!ctx || !d_cols || !d_out || !root_big) return SB_ERR_ARG;
     return lde_dev(ctx, (const uint4 *)d_cols, n_cols, col_len, col_stride, hfp::from_limbs(root_big), log_s, log_ext,
                    (uint4 *)d_out);
@@ -549,7 +583,7 @@ extern "C" int sb_lde_batch_dev(sb_ctx *ctx, const uint64_t *d_cols, size_t n_co
 
 extern "C" int sb_lde_batch(sb_ctx *ctx, const uint64_t *cols, size_t n_cols, size_t col_len, const uint64_t root_big[4],
                             uint32_t log_s, uint32_t log_ext, uint64_t *out) {
-    return guarded(ctx, [&]() -> int {
+    return guarded(ctx, __func__, [&]() -> int {
     if (!ctx || !cols || !out || !root_big) return SB_ERR_ARG;
     if (log_s + log_ext > 28) return fail(ctx, SB_ERR_ARG, "extended domain 2^%u exceeds two-adicity 28", log_s + log_ext);
     const size_t N = (size_t)1 << (log_s + log_ext);
@@ -608,13 +642,13 @@ extern "C" int sb_lde_batch(sb_ctx *ctx, const uint64_t *cols, size_t n_cols, si
 }
 
 extern "C" int sb_powers_dev(sb_ctx *ctx, const uint64_t root[4], size_t n, uint64_t *d_out) {
-    return guarded(ctx, [&]() -> int {
+    return guarded(ctx, __func__, [&]() -> int {
     if (!ctx || !root || !d_out) return SB_ERR_ARG;
     return powers_into(ctx, hfp::from_limbs(root), n, (uint4 *)d_out);
     });
 }
 extern "C" int sb_powers(sb_ctx *ctx, const uint64_t root[4], size_t n, uint64_t *out) {
-    return guarded(ctx, [&]() -> int {
+    return guarded(ctx, __func__, [&]() -> int {
     if (!ctx || !root || !out) return SB_ERR_ARG;
     DevBuf b(ctx);
     TRY(b.alloc(n * 32));
@@ -626,7 +660,7 @@ extern "C" int sb_powers(sb_ctx *ctx, const uint64_t root[4], size_t n, uint64_t
 }
 
 extern "C" int sb_batch_inverse_dev(sb_ctx *ctx, uint64_t *d_vals, size_t n) {
-    return guarded(ctx, [&]() -> int {
+    return guarded(ctx, __func__, [&]() -> int {
     if (!ctx || !d_vals) return SB_ERR_ARG;
     if (n == 0) return SB_OK;
     DevBuf scratch(ctx);
@@ -637,7 +671,7 @@ extern "C" int sb_batch_inverse_dev(sb_ctx *ctx, uint64_t *d_vals, size_t n) {
     });
 }
 extern "C" int sb_batch_inverse(sb_ctx *ctx, uint64_t *vals, size_t n) {
-    return guarded(ctx, [&]() -> int {
+    return guarded(ctx, __func__, [&]() -> int {
     if (!ctx || !vals) return SB_ERR_ARG;
     DevBuf b(ctx);
     TRY(b.alloc(n * 32));
@@ -745,7 +779,7 @@ int tree_new(sb_ctx *ctx, size_t n, size_t leaf_bytes, sb_tree **out) {
 }
 
 extern "C" int sb_merkle_commit(sb_ctx *ctx, const void *leaves, size_t leaf_bytes, size_t n, uint8_t root[32], sb_tree **tree) {
-    return guarded(ctx, [&]() -> int {
+    return guarded(ctx, __func__, [&]() -> int {
     if (!ctx || !tree) return SB_ERR_ARG;
     if (!leaves && n * leaf_bytes) return fail(ctx, SB_ERR_ARG, "leaves is NULL");
     if (leaf_bytes >= ((size_t)1 << 31)) return fail(ctx, SB_ERR_ARG, "leaf too long");
@@ -861,7 +895,7 @@ static int commit_fold(sb_ctx *ctx, const FriFoldParams &F, sb_tree **tree) {
 
 extern "C" int sb_merkle_commit_cols_dev(sb_ctx *ctx, const uint64_t *const *d_cols, size_t n_cols, size_t n, uint8_t root[32],
                                          sb_tree **tree) {
-    return guarded(ctx, [&]() -> int {
+    return guarded(ctx, __func__, [&]() -> int {
     if (!ctx || !d_cols || !tree) return SB_ERR_ARG;
     TRY(commit_cols(ctx, (const uint4 *const *)d_cols, n_cols, n, tree));
     if (root) memcpy(root, (*tree)->root, 32);
@@ -870,7 +904,7 @@ extern "C" int sb_merkle_commit_cols_dev(sb_ctx *ctx, const uint64_t *const *d_c
 }
 
 extern "C" int sb_merkle_open(sb_ctx *ctx, const sb_tree *t, const size_t *idx, size_t n_idx, uint8_t *leaves_out, uint8_t *nodes_out) {
-    return guarded(ctx, [&]() -> int {
+    return guarded(ctx, __func__, [&]() -> int {
     if (!ctx || !t || (!idx && n_idx)) return SB_ERR_ARG;
     if (n_idx == 0) return SB_OK;
     if (n_idx > ((size_t)1 << 24)) return fail(ctx, SB_ERR_ARG, "too many openings");
@@ -1122,7 +1156,7 @@ int fri_prove_dev(sb_ctx *ctx, const uint4 *d_vals, size_t n, const hfp::el &roo
 // subtrees live on several GPUs and only needs the column from this GPU
 extern "C" int sb_fri_fold_dev(sb_ctx *ctx, const uint64_t *d_vals, size_t n, const uint64_t root[4], const uint8_t values_root[32],
                                uint64_t *d_col) {
-    return guarded(ctx, [&]() -> int {
+    return guarded(ctx, __func__, [&]() -> int {
     if (!ctx || !d_vals || !root || !values_root || !d_col) return SB_ERR_ARG;
     if (!is_pow2(n) || n < 4) return fail(ctx, SB_ERR_ARG, "FRI fold needs a power-of-two number of values >= 4, got %zu", n);
     const uint4 *tw;
@@ -1145,7 +1179,7 @@ extern "C" int sb_fri_fold_dev(sb_ctx *ctx, const uint64_t *d_vals, size_t n, co
 
 extern "C" int sb_fri_prove_dev(sb_ctx *ctx, const uint64_t *d_vals, size_t n, const uint64_t root[4], size_t max_deg_plus_1,
                                 uint32_t excl, const sb_tree *values_tree, sb_fri_proof **out) {
-    return guarded(ctx, [&]() -> int {
+    return guarded(ctx, __func__, [&]() -> int {
     if (!ctx || !d_vals || !root || !out) return SB_ERR_ARG;
     if (values_tree && (values_tree->n != n || values_tree->leaf_bytes != 32)) return fail(ctx, SB_ERR_ARG, "values_tree does not match the values");
     return fri_prove_dev(ctx, (const uint4 *)d_vals, n, hfp::from_limbs(root), max_deg_plus_1, excl, values_tree, out);
@@ -1154,7 +1188,7 @@ extern "C" int sb_fri_prove_dev(sb_ctx *ctx, const uint64_t *d_vals, size_t n, c
 
 extern "C" int sb_fri_prove(sb_ctx *ctx, const uint64_t *vals, size_t n, const uint64_t root[4], size_t max_deg_plus_1, uint32_t excl,
                             sb_fri_proof **out) {
-    return guarded(ctx, [&]() -> int {
+    return guarded(ctx, __func__, [&]() -> int {
     if (!ctx || !vals || !root || !out) return SB_ERR_ARG;
     void *d = nullptr;
     CU(cudaMallocAsync(&d, n * 32 ? n * 32 : 16, ctx->stream));
@@ -1280,7 +1314,7 @@ extern "C" void sb_fri_proof_free(sb_fri_proof *p) { delete p; }
 
 // element-wise field op on raw 256-bit limbs (no range checks): unit-test hook for the device field library
 extern "C" int sb_fp_vec_op(sb_ctx *ctx, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n) {
-    return guarded(ctx, [&]() -> int {
+    return guarded(ctx, __func__, [&]() -> int {
     if (!ctx || !a || !b || !out) return SB_ERR_ARG;
     DevBuf da(ctx), db(ctx), dout(ctx);
     TRY(da.alloc(n * 32));
@@ -1299,7 +1333,7 @@ extern "C" int sb_fp_vec_op(sb_ctx *ctx, int op, const uint64_t *a, const uint64
 // Measured issue-rate ceilings for bench.py's integer roofline: a register-only kernel of independent chains, timed with
 // CUDA events on the context's stream (best of 5).  which = 0: Montgomery products per second, 1: IMAD.WIDE.U32 per second.
 extern "C" int sb_pipe_peak(sb_ctx *ctx, int which, double *ops_per_s) {
-    return guarded(ctx, [&]() -> int {
+    return guarded(ctx, __func__, [&]() -> int {
     if (!ctx || !ops_per_s || which < 0 || which > 1) return SB_ERR_ARG;
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, ctx->device));

@@ -269,8 +269,9 @@ const char *build_trace(sb_ctx *ctx, const R1cs &r, const std::vector<hfp::el> &
 // proof_path may be NULL (timing only).  stage_ms (may be NULL): [0] LDE [1] m_tree [2] FRI [3] rest [4] GPU total,
 // [5] host front end (parse + trace arrangement), [6] JSON serialisation + write.
 extern "C" int sb_prove_files(sb_ctx *ctx, const char *r1cs_path, const char *wtns_path, const char *proof_path, double stage_ms[7]) {
-    return guarded(ctx, [&]() -> int {
+    return guarded(ctx, __func__, [&]() -> int {
     if (!ctx || !r1cs_path || !wtns_path) return SB_ERR_ARG;
+    dbg_check("sb_prove_files entry");
     auto now = []() {
         struct timespec ts;
         clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -288,9 +289,11 @@ extern "C" int sb_prove_files(sb_ctx *ctx, const char *r1cs_path, const char *wt
     e = read_witness(wb, witness);
     if (e) return fail(ctx, SB_ERR_ARG, "%s: %s", wtns_path, e);
     if (witness.empty() || !hfp::eq(witness[0], hfp::ONE)) return fail(ctx, SB_ERR_ARG, "witness[0] must be 1 (run.rs:358)");
+    dbg_check("sb_prove_files before build_trace");
     Trace t;
     e = build_trace(ctx, r, witness, t);
     if (e) return fail(ctx, SB_ERR_ARG, "%s", e);
+    dbg_check("sb_prove_files after build_trace");
     sb_trace st;
     st.original_steps = t.os;
     st.witness_trace = (const uint64_t *)t.wit;
@@ -307,6 +310,7 @@ extern "C" int sb_prove_files(sb_ctx *ctx, const char *r1cs_path, const char *wt
     st.pfi_w = t.pfi_w.data();
     const double t1 = now();
     sb_stark_proof *proof = nullptr;
+    dbg_check("sb_prove_files after the front end");
     TRY(sb_prove_r1cs(ctx, &st, &proof));
     const double t2 = now();
     int rc = SB_OK;
@@ -332,7 +336,7 @@ extern "C" int sb_prove_files(sb_ctx *ctx, const char *r1cs_path, const char *wt
 
 // verify_with_file_path (run.rs:556-590): the public wires are the head of the witness file (run.rs:582-585)
 extern "C" int sb_verify_files(sb_ctx *ctx, const char *r1cs_path, const char *wtns_path, const char *proof_path, double verify_ms[2]) {
-    return guarded(ctx, [&]() -> int {
+    return guarded(ctx, __func__, [&]() -> int {
     if (!ctx || !r1cs_path || !wtns_path || !proof_path) return SB_ERR_ARG;
     auto now = []() {
         struct timespec ts;
@@ -390,7 +394,7 @@ struct sb_host_trace {
     sb_trace view;
 };
 extern "C" int sb_trace_from_files(const char *r1cs_path, const char *wtns_path, sb_host_trace **out, const sb_trace **view) {
-    return guarded((sb_ctx *)nullptr, [&]() -> int {
+    return guarded((sb_ctx *)nullptr, __func__, [&]() -> int {
     if (!r1cs_path || !wtns_path || !out || !view) return SB_ERR_ARG;
     std::vector<uint8_t> rb, wb;
     if (!slurp(r1cs_path, rb) || !slurp(wtns_path, wb)) return SB_ERR_ARG;

@@ -64,6 +64,8 @@ struct sb_ctx {
     // pinned host staging arena (front end -> sb_prove_r1cs uploads); grows on demand, freed in sb_destroy
     void *pinned = nullptr;
     size_t pinned_bytes = 0;
+    void *pinned2 = nullptr;          // small pinned scratch for host scalars / coefficient vectors sent to several devices
+    size_t pinned2_bytes = 0;
     // optional per-kernel-family timing (sb_profile): CUDA events around every launch
     bool prof = false;
     struct ProfRec { int kind; cudaEvent_t a, b; };
@@ -167,17 +169,37 @@ struct DevGuard {
     DevGuard &operator=(const DevGuard &) = delete;
 };
 template <class F>
-static int guarded(sb_ctx *ctx, F &&body) {
+static int guarded(sb_ctx *ctx, const char *entry, F &&body) {
     DevGuard g(ctx);
+    int rc;
     try {
-        return body();
+        rc = body();
     } catch (const std::bad_alloc &) {
-        return fail(ctx, SB_ERR_OOM, "host allocation failed");
+        rc = fail(ctx, SB_ERR_OOM, "host allocation failed");
     } catch (const std::exception &e) {
-        return fail(ctx, SB_ERR_ARG, "exception: %s", e.what());
+        rc = fail(ctx, SB_ERR_ARG, "exception: %s", e.what());
     } catch (...) {
-        return fail(ctx, SB_ERR_ARG, "unknown exception");
+        rc = fail(ctx, SB_ERR_ARG, "unknown exception");
     }
+    // A CUDA call whose status was dropped leaves its error pending and the NEXT entry point reports it against the wrong call:
+    // surface it here (SB_DEBUG_ERRORS=1 names the entry point on stderr) and do not let it leak out of a successful call.
+    if (ctx) {
+        const cudaError_t pending = cudaGetLastError();
+        if (pending != cudaSuccess) {
+            static const bool verbose = getenv("SB_DEBUG_ERRORS") != nullptr;
+            if (verbose) fprintf(stderr, "stark_b200: %s left a pending CUDA error: %s (rc %d)\n", entry, cudaGetErrorString(pending), rc);
+            if (rc == SB_OK) rc = fail(ctx, SB_ERR_CUDA, "%s: a CUDA call failed: %s", entry, cudaGetErrorString(pending));
+        }
+    }
+    return rc;
+}
+
+// SB_DEBUG_ERRORS=1: report (and clear) a pending CUDA error at a named point
+static inline void dbg_check(const char *where) {
+    static const bool verbose = getenv("SB_DEBUG_ERRORS") != nullptr;
+    if (!verbose) return;
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) fprintf(stderr, "stark_b200: pending CUDA error at %s: %s\n", where, cudaGetErrorString(e));
 }
 
 #define TRY(expr)                \
@@ -333,6 +355,7 @@ int pseudorandom_indices(const uint8_t *seed, size_t seed_len, uint32_t modulus,
                          bool extended);
 // returns a pinned host buffer of at least `bytes` owned by the context (contents are scratch), NULL on failure
 void *pinned_arena(sb_ctx *ctx, size_t bytes);
+void *pinned_scratch(sb_ctx *ctx, size_t bytes);
 // dense: the caller indexes the table directly (the prover's `xs`), so a strided view of a larger cached table will not do
 int get_table(sb_ctx *ctx, const hfp::el &w, uint32_t log_n, const uint4 **tw, uint32_t *tw_log_n, uint32_t *log_stride,
               bool dense = false);

@@ -31,7 +31,7 @@ int merkle_launch_leaves_ext(cudaStream_t stream, const ExtLeavesParams &P);
 int merkle_launch_leaves_fold_ext(cudaStream_t stream, const FriFoldParams &F, uint4 *nodes);
 int merkle_launch_open_ext(cudaStream_t stream, const ExtOpenParams &P, const unsigned long long *idx, uint32_t n_idx, uint4 *nodes_out,
                            uint4 *leaves_out);
-int merkle_launch_interleave(cudaStream_t stream, const uint4 *recv, uint4 *sub0, unsigned long long per, uint32_t g);
+int merkle_launch_gather_reduce(cudaStream_t stream, const uint4 *recv, uint4 *sub, unsigned long long per, uint32_t g);
 int fri_launch_fold_ext(cudaStream_t stream, const FriFoldParams &F);
 int ext_launch_to_natural(cudaStream_t stream, const ExtOpenParams &P, uint4 *out);
 int merkle_launch_gather_bytes(cudaStream_t stream, const uint8_t *leaves, size_t leaf_bytes,

@@ -88,8 +88,14 @@ int merkle_launch_open_ext(cudaStream_t s, const ExtOpenParams &P, const unsigne
     }
     return n;
 }
-int merkle_launch_interleave(cudaStream_t s, const uint4 *recv, uint4 *sub0, unsigned long long per, uint32_t g) {
-    merkle_interleave_kernel<<<(unsigned)((per * g + 255) / 256), 256, 0, s>>>(recv, sub0, per, g);
+// levels 0 .. log2 g of a subtree from the digests staged by source device; g = 2, 4 or 8
+int merkle_launch_gather_reduce(cudaStream_t s, const uint4 *recv, uint4 *sub, unsigned long long per, uint32_t g) {
+    const unsigned b = blocks128(per);
+    switch (g) {
+        case 2: merkle_gather_reduce_kernel<1><<<b, 128, 0, s>>>(recv, sub, per); break;
+        case 4: merkle_gather_reduce_kernel<2><<<b, 128, 0, s>>>(recv, sub, per); break;
+        default: merkle_gather_reduce_kernel<3><<<b, 128, 0, s>>>(recv, sub, per); break;
+    }
     return 1;
 }
 int fri_launch_fold_ext(cudaStream_t s, const FriFoldParams &F) {

@@ -328,13 +328,24 @@ __global__ void __launch_bounds__(MERKLE_THREADS, 4) merkle_leaves_fold_ext_kern
     merkle_ext_reduce<LV>(sd, E, k, nodes, q);
 }
 
-// level 0 of a device's subtree from the staged digests of the g sources: sub0[k' g + d] = recv[d * per + k']
-__global__ void merkle_interleave_kernel(const uint4 *recv, uint4 *sub0, unsigned long long per, uint32_t g) {
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= per * g) return;
-    const size_t d = t / per, k = t - d * per, o = k * g + d;
-    sub0[2 * o] = recv[2 * t];
-    sub0[2 * o + 1] = recv[2 * t + 1];
+// Level 0 .. log2 g of a device's subtree from the staged digests of the g sources: thread k reads the g digests of step k
+// (recv[d * per + k], coalesced over k for every d), stores them as nodes k g .. k g + g - 1 of level 0 (g contiguous digests
+// per thread) and reduces them log2 g levels.  (First version: a separate interleave pass whose 32-byte writes of one 128-byte
+// line came from threads far apart in the grid -- 2.5 ms for 2^23 digests; L2 evicted the partial lines.)
+template <int LG>
+__global__ void __launch_bounds__(MERKLE_THREADS, 4) merkle_gather_reduce_kernel(const uint4 *recv, uint4 *sub, unsigned long long per) {
+    __shared__ uint32_t sd_all[MERKLE_SMEM_WORDS(LG)];
+    uint32_t *sd = sd_all + threadIdx.x;
+    const size_t k = (size_t)blockIdx.x * MERKLE_THREADS + threadIdx.x;
+    if (k >= per) return;
+#pragma unroll
+    for (int d = 0; d < (1 << LG); d++) {
+        uint32_t h[8];
+        digest_load(h, recv, (size_t)d * per + k);
+        digest_store(sub, (k << LG) + d, h);
+        sd_put(sd, d, h);
+    }
+    merkle_reduce_smem<LG>(sd, sub, per << LG, 0, k << LG);
 }
 // fold alone on coset-major values (the layer after it runs on the primary device, which hashes the gathered column itself)
 __global__ void __launch_bounds__(128) fri_fold_ext_kernel(const __grid_constant__ FriFoldParams F) {

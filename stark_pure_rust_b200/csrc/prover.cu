@@ -172,7 +172,7 @@ static int device_lagrange(sb_ctx *ctx, const uint4 *d_x, const std::vector<hfp:
 // built as per-device subtrees with the top finished on the host, and only S-point coefficient vectors and 32-byte digests
 // cross NVLink.  The S-point accumulator chain (prefix products) runs on the device that holds the witness column.
 extern "C" int sb_prove_r1cs(sb_ctx *ctx, const sb_trace *t, sb_stark_proof **out) {
-    return guarded(ctx, [&]() -> int {
+    return guarded(ctx, __func__, [&]() -> int {
     if (!ctx || !t || !out) return SB_ERR_ARG;
     const size_t os = t->original_steps;
     if (os == 0 || os % 3 != 0) return fail(ctx, SB_ERR_ARG, "original_steps %zu must be a positive multiple of 3", os);   // :33
@@ -197,7 +197,9 @@ extern "C" int sb_prove_r1cs(sb_ctx *ctx, const sb_trace *t, sb_stark_proof **ou
     // columns: nine low-degree extensions (prove.rs:100-124, :160-167, :183-184), six quotient / combination columns, I2
     enum { K_ = 0, F0_, F1_, F2_, S_, P_, IDX_, PIDX_, A_, D1_, D2_, D3_, B2_, B3_, L_, I2_, N_COLS };
     sb_ext *E = nullptr;
+    dbg_check("sb_prove_r1cs entry");
     TRY(ext_create(ctx, N_COLS, A_ + 1, log_steps, &E));
+    dbg_check("after ext_create");
     const int g = E->g;
     const uint32_t cpd = E->cpd;
     const int dS = E->owner[S_];               // the device with the witness column runs the accumulator chain
@@ -454,13 +456,18 @@ extern "C" int sb_prove_r1cs(sb_ctx *ctx, const sb_trace *t, sb_stark_proof **ou
         }
         if (!on_device) host_lagrange(interp, xv, yv, &zroot);
         const bool horner = np + 1 <= 24;      // ~np products per point against the ~log2(S)/2 + 2 of a transform
+        // the 2 np + 1 coefficients go to every device from pinned memory (a pageable source would make each upload wait for
+        // its device's stream and run the devices one after the other)
+        hfp::el *hcoef = (hfp::el *)pinned_scratch(ctx, (2 * np + 1) * 32);
+        if (!hcoef) return fail(ctx, SB_ERR_OOM, "pinned scratch");
+        if (np) memcpy(hcoef, interp.data(), np * 32);
+        memcpy(hcoef + np, zroot.data(), (np + 1) * 32);
         for (int d = 0; d < g; d++) {
             sb_ctx *c = ctx->dev[d];
             DevGuard dg(c);
             DCU(cudaMallocAsync(&pd[d].coef, (2 * np + 1) * 32, c->stream));
             uint4 *ci = (uint4 *)pd[d].coef, *cz = ci + 2 * np;
-            if (np) DCU(cudaMemcpyAsync(ci, interp.data(), np * 32, cudaMemcpyHostToDevice, c->stream));
-            DCU(cudaMemcpyAsync(cz, zroot.data(), (np + 1) * 32, cudaMemcpyHostToDevice, c->stream));
+            DCU(cudaMemcpyAsync(ci, hcoef, (2 * np + 1) * 32, cudaMemcpyHostToDevice, c->stream));
             uint4 *zb2 = E->col(d, B2_), *zb3 = E->col(d, B3_);          // adjacent columns: one batch inverse over both
             if (horner) {
                 if (np) {
@@ -768,7 +775,7 @@ int fri_verify_host(sb_ctx *ctx, const sb_fri_proof *pr, const uint8_t values_ro
 }  // namespace
 
 extern "C" int sb_verify_r1cs(sb_ctx *ctx, const sb_trace *t, const sb_stark_proof *proof) {
-    return guarded(ctx, [&]() -> int {
+    return guarded(ctx, __func__, [&]() -> int {
     if (!ctx || !t || !proof) return SB_ERR_ARG;
     const size_t os = t->original_steps;
     if (os == 0 || os % 3 != 0) return fail(ctx, SB_ERR_ARG, "original_steps %zu must be a positive multiple of 3", os);   // verify.rs:27
@@ -1075,7 +1082,7 @@ static void parse_fri_layers(JsonIn &j, sb_fri_proof *fri) {
 }
 
 extern "C" int sb_stark_proof_from_json(const char *text, size_t len, sb_stark_proof **out) {
-    return guarded((sb_ctx *)nullptr, [&]() -> int {
+    return guarded((sb_ctx *)nullptr, __func__, [&]() -> int {
     if (!text || !out) return SB_ERR_ARG;
     JsonIn j{text, text + len};
     sb_stark_proof *p = new sb_stark_proof();
@@ -1117,7 +1124,7 @@ extern "C" int sb_stark_proof_from_json(const char *text, size_t len, sb_stark_p
 // (then the sampler keeps the reference's 2^24 limit and no error text is recorded).
 extern "C" int sb_fri_verify_json(sb_ctx *ctx, const char *text, size_t len, const uint8_t merkle_root[32], const uint64_t root_of_unity[4],
                                   size_t n, size_t max_deg_plus_1, uint32_t exclude_multiples_of) {
-    return guarded(ctx, [&]() -> int {
+    return guarded(ctx, __func__, [&]() -> int {
     if (!text || !merkle_root || !root_of_unity) return SB_ERR_ARG;
     JsonIn j{text, text + len};
     sb_fri_proof fri;
