@@ -554,13 +554,18 @@ def independent_pipe_probe(sm_mhz):
     try:
         txt = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout
         open(os.path.join(ROOT, "profiles", "pipe_bench_r02.txt"), "w").write(txt)
-        best = 0.0
+        best, best_line = 0.0, None
         for line in txt.splitlines():
             if line.startswith("mad.lo.cc+madc.hi.cc pair") or line.startswith("IMAD.WIDE.U32") or line.startswith("mul.wide.u32"):
-                best = max(best, float(line.split("warps/SM")[1].split()[1]))
+                # "<name> warps/SM <w> <rate> slots/clk/SM ( ... ) <ms> ms clk <MHz> MHz": the rate is per clock at the clock of THAT run
+                rate = float(line.split("warps/SM")[1].split()[1])
+                mhz = float(line.split("clk")[-1].split()[0])
+                if rate * mhz > best:
+                    best, best_line = rate * mhz, (rate, mhz, line.split("warps/SM")[0].strip())
         # one Montgomery product = 128 IMAD.WIDE.U32 (64 for a*b, 64 for m*p)
-        return {"imad_wide_lanes_per_clk_per_sm": best, "products_per_s": best * 148 * sm_mhz * 1e6 / 128.0,
-                "source": "tools/pipe_bench.cu (stand-alone), best IMAD.WIDE-class rate over 16 / 32 warps per SM"}
+        return {"imad_wide_lanes_per_clk_per_sm": best_line[0], "sm_mhz_during_probe": best_line[1], "instruction": best_line[2],
+                "products_per_s": best * 1e6 * 148 / 128.0,
+                "source": "tools/pipe_bench.cu (stand-alone), best IMAD.WIDE-class issue rate x its own clock over 16 / 32 warps per SM"}
     except Exception as ex:      # noqa: BLE001
         return {"error": repr(ex)}
 

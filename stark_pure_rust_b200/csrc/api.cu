@@ -903,83 +903,113 @@ extern "C" int sb_merkle_commit_cols_dev(sb_ctx *ctx, const uint64_t *const *d_c
     });
 }
 
+// gen_proofs for several (tree, index list) pairs with ONE device round trip: every gather kernel is queued, the results of all
+// requests come back in one copy into pinned staging memory, one synchronisation.  (A FRI layer needs the openings of two trees and
+// the prover those of m_tree and l_tree; one call each used to cost a synchronisation -- and the copy into the caller's pageable
+// memory a second, implicit one.)  The staging buffer is the context's pinned scratch: no other user may have a transfer in flight.
+int merkle_open_many(sb_ctx *ctx, const OpenReq *reqs, int n_req) {
+    struct Lay { size_t idx_off, nodes_off, leaves_off, nodes_bytes, leaves_bytes; uint32_t dlow; };
+    std::vector<Lay> lay(n_req);
+    size_t total = 0;
+    for (int r = 0; r < n_req; r++) {
+        const OpenReq &R = reqs[r];
+        if (!R.t || (!R.idx && R.n_idx)) return SB_ERR_ARG;
+        if (R.n_idx > ((size_t)1 << 24)) return fail(ctx, SB_ERR_ARG, "too many openings");
+        for (size_t i = 0; i < R.n_idx; i++)
+            if (R.idx[i] >= R.t->n) return fail(ctx, SB_ERR_ARG, "leaf index %zu out of range (width %zu)", R.idx[i], R.t->n);
+        Lay &L = lay[r];
+        L.dlow = R.t->sh ? R.t->sh->lv + R.t->sh->log_s : R.t->depth;          // levels that live on the device(s)
+        L.nodes_bytes = R.nodes_out ? R.n_idx * L.dlow * 32 : 0;
+        L.leaves_bytes = R.leaves_out ? R.n_idx * R.t->leaf_bytes : 0;
+        L.idx_off = total;
+        total += (R.n_idx * 8 + 31) & ~(size_t)31;
+    }
+    const size_t out_off = total;
+    for (int r = 0; r < n_req; r++) {
+        lay[r].nodes_off = total;
+        total += (lay[r].nodes_bytes + 31) & ~(size_t)31;
+        lay[r].leaves_off = total;
+        total += (lay[r].leaves_bytes + 31) & ~(size_t)31;
+    }
+    if (total == 0 || total == out_off) return SB_OK;
+    uint8_t *host = (uint8_t *)pinned_scratch(ctx, total);
+    if (!host) return fail(ctx, SB_ERR_OOM, "pinned staging for the openings");
+    DevBuf dev(ctx);
+    TRY(dev.alloc(total));
+    uint8_t *d = (uint8_t *)dev.p;
+    for (int r = 0; r < n_req; r++) {
+        unsigned long long *h = (unsigned long long *)(host + lay[r].idx_off);
+        for (size_t i = 0; i < reqs[r].n_idx; i++) h[i] = reqs[r].idx[i];
+    }
+    CU(cudaMemcpyAsync(d, host, out_off, cudaMemcpyHostToDevice, ctx->stream));
+    for (int r = 0; r < n_req; r++) {
+        const OpenReq &R = reqs[r];
+        const Lay &L = lay[r];
+        const sb_tree *t = R.t;
+        if (!R.n_idx) continue;
+        const unsigned long long *d_idx = (const unsigned long long *)(d + L.idx_off);
+        uint4 *d_nodes = L.nodes_bytes ? (uint4 *)(d + L.nodes_off) : nullptr, *d_leaves = L.leaves_bytes ? (uint4 *)(d + L.leaves_off) : nullptr;
+        if (t->sh) {
+            // sharded tree: one gather kernel on this (the primary) device reads the shards through peer pointers; the top
+            // log2 g levels are appended from the host copy
+            const TreeShards &sh = *t->sh;
+            ExtOpenParams P;
+            memset(&P, 0, sizeof P);
+            for (int dd = 0; dd < sh.g; dd++) {
+                P.low[dd] = sh.low[dd];
+                P.sub[dd] = sh.sub[dd];
+                for (int c = 0; c < 8; c++) P.cols[dd][c] = sh.cols[dd][c];
+            }
+            P.nc = (uint32_t)t->n_cols; P.log_s = sh.log_s; P.cpd = sh.cpd; P.lv = sh.lv; P.g = (uint32_t)sh.g;
+            if (d_nodes || d_leaves) KLAUNCH(SB_KIND_OPEN, merkle_launch_open_ext(ctx->stream, P, d_idx, (uint32_t)R.n_idx, d_nodes, d_leaves));
+            continue;
+        }
+        if (d_nodes) KLAUNCH(SB_KIND_OPEN, merkle_launch_open(ctx->stream, t->d_nodes, t->n, t->depth, d_idx, (uint32_t)R.n_idx, d_nodes));
+        if (d_leaves) {
+            if (t->n_cols) {
+                MerkleColsParams P;
+                for (int k = 0; k < 8; k++) P.cols[k] = t->cols[k];
+                P.nodes = nullptr;
+                P.n = t->n;
+                P.nc = (uint32_t)t->n_cols;
+                P.coset_log_s = t->coset_log_s;
+                KLAUNCH(SB_KIND_OPEN, merkle_launch_open_leaves_cols(ctx->stream, P, d_idx, (uint32_t)R.n_idx, d_leaves));
+            } else {
+                KLAUNCH(SB_KIND_OPEN, merkle_launch_gather_bytes(ctx->stream, t->d_leaves, t->leaf_bytes, d_idx, (uint32_t)R.n_idx, (uint8_t *)d_leaves));
+            }
+        }
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(host + out_off, d + out_off, total - out_off, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int r = 0; r < n_req; r++) {
+        const OpenReq &R = reqs[r];
+        const Lay &L = lay[r];
+        if (L.leaves_bytes) memcpy(R.leaves_out, host + L.leaves_off, L.leaves_bytes);
+        if (!R.nodes_out) continue;
+        if (!R.t->sh) {
+            if (L.nodes_bytes) memcpy(R.nodes_out, host + L.nodes_off, L.nodes_bytes);
+            continue;
+        }
+        const TreeShards &sh = *R.t->sh;
+        for (size_t q = 0; q < R.n_idx; q++) {
+            uint8_t *o = R.nodes_out + q * R.t->depth * 32;
+            if (L.dlow) memcpy(o, host + L.nodes_off + q * L.dlow * 32, L.dlow * 32);
+            for (uint32_t l = L.dlow; l < R.t->depth; l++) {
+                const size_t m = (R.idx[q] >> l) ^ 1;
+                memcpy(o + l * 32, sh.top.data() + (merkle_level_off((size_t)sh.g, l - L.dlow) + m) * 32, 32);
+            }
+        }
+    }
+    return SB_OK;
+}
+
 extern "C" int sb_merkle_open(sb_ctx *ctx, const sb_tree *t, const size_t *idx, size_t n_idx, uint8_t *leaves_out, uint8_t *nodes_out) {
     return guarded(ctx, __func__, [&]() -> int {
     if (!ctx || !t || (!idx && n_idx)) return SB_ERR_ARG;
     if (n_idx == 0) return SB_OK;
-    if (n_idx > ((size_t)1 << 24)) return fail(ctx, SB_ERR_ARG, "too many openings");
-    std::vector<unsigned long long> h(n_idx);
-    for (size_t i = 0; i < n_idx; i++) {
-        if (idx[i] >= t->n) return fail(ctx, SB_ERR_ARG, "leaf index %zu out of range (width %zu)", idx[i], t->n);
-        h[i] = idx[i];
-    }
-    DevBuf d_idx(ctx), d_nodes(ctx), d_leaves(ctx);
-    TRY(d_idx.alloc(n_idx * 8));
-    CU(cudaMemcpyAsync(d_idx.p, h.data(), n_idx * 8, cudaMemcpyHostToDevice, ctx->stream));
-    if (t->sh) {
-        // sharded tree: one gather kernel on this (the primary) device reads the shards through peer pointers; the top
-        // log2 g levels are appended from the host copy
-        const TreeShards &sh = *t->sh;
-        const uint32_t dlow = sh.lv + sh.log_s;
-        ExtOpenParams P;
-        memset(&P, 0, sizeof P);
-        for (int d = 0; d < sh.g; d++) {
-            P.low[d] = sh.low[d];
-            P.sub[d] = sh.sub[d];
-            for (int c = 0; c < 8; c++) P.cols[d][c] = sh.cols[d][c];
-        }
-        P.nc = (uint32_t)t->n_cols; P.log_s = sh.log_s; P.cpd = sh.cpd; P.lv = sh.lv; P.g = (uint32_t)sh.g;
-        std::vector<uint8_t> low_nodes;
-        if (nodes_out && dlow) TRY(d_nodes.alloc(n_idx * dlow * 32));
-        if (leaves_out) TRY(d_leaves.alloc(n_idx * t->leaf_bytes));
-        KLAUNCH(SB_KIND_OPEN, merkle_launch_open_ext(ctx->stream, P, (const unsigned long long *)d_idx.p, (uint32_t)n_idx,
-                                                     nodes_out && dlow ? (uint4 *)d_nodes.p : nullptr, leaves_out ? (uint4 *)d_leaves.p : nullptr));
-        if (nodes_out && dlow) {
-            low_nodes.resize(n_idx * dlow * 32);
-            CU(cudaMemcpyAsync(low_nodes.data(), d_nodes.p, low_nodes.size(), cudaMemcpyDeviceToHost, ctx->stream));
-        }
-        if (leaves_out) CU(cudaMemcpyAsync(leaves_out, d_leaves.p, n_idx * t->leaf_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaGetLastError());
-        CU(cudaStreamSynchronize(ctx->stream));
-        if (nodes_out) {
-            for (size_t q = 0; q < n_idx; q++) {
-                uint8_t *o = nodes_out + q * t->depth * 32;
-                if (dlow) memcpy(o, low_nodes.data() + q * dlow * 32, dlow * 32);
-                for (uint32_t l = dlow; l < t->depth; l++) {
-                    const size_t m = (idx[q] >> l) ^ 1;
-                    memcpy(o + l * 32, sh.top.data() + (merkle_level_off((size_t)sh.g, l - dlow) + m) * 32, 32);
-                }
-            }
-        }
-        return SB_OK;
-    }
-    if (nodes_out && t->depth) {
-        TRY(d_nodes.alloc(n_idx * t->depth * 32));
-        const size_t tot = n_idx * t->depth;
-        KLAUNCH(SB_KIND_OPEN, merkle_launch_open(ctx->stream, t->d_nodes, t->n, t->depth, (const unsigned long long *)d_idx.p,
-                                            (uint32_t)n_idx, (uint4 *)d_nodes.p));
-        CU(cudaMemcpyAsync(nodes_out, d_nodes.p, tot * 32, cudaMemcpyDeviceToHost, ctx->stream));
-    }
-    if (leaves_out && t->leaf_bytes) {
-        TRY(d_leaves.alloc(n_idx * t->leaf_bytes));
-        if (t->n_cols) {
-            MerkleColsParams P;
-            for (int k = 0; k < 8; k++) P.cols[k] = t->cols[k];
-            P.nodes = nullptr;
-            P.n = t->n;
-            P.nc = (uint32_t)t->n_cols;
-            P.coset_log_s = t->coset_log_s;
-            KLAUNCH(SB_KIND_OPEN, merkle_launch_open_leaves_cols(ctx->stream, P, (const unsigned long long *)d_idx.p, (uint32_t)n_idx,
-                                                            (uint4 *)d_leaves.p));
-        } else {
-            KLAUNCH(SB_KIND_OPEN, merkle_launch_gather_bytes(ctx->stream, t->d_leaves, t->leaf_bytes, (const unsigned long long *)d_idx.p,
-                                                        (uint32_t)n_idx, (uint8_t *)d_leaves.p));
-        }
-        CU(cudaMemcpyAsync(leaves_out, d_leaves.p, n_idx * t->leaf_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    }
-    CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(ctx->stream));
-    return SB_OK;
+    const OpenReq req{t, idx, n_idx, t->leaf_bytes ? leaves_out : nullptr, t->depth ? nodes_out : nullptr};
+    return merkle_open_many(ctx, &req, 1);
     });
 }
 
@@ -1129,12 +1159,15 @@ int fri_prove_dev(sb_ctx *ctx, const uint4 *d_vals, size_t n, const hfp::el &roo
         L.depth_column = t2->depth;
         L.column_leaves.resize(FRI_QUERIES * 32);
         L.column_nodes.resize(FRI_QUERIES * t2->depth * 32);
-        if ((rc = sb_merkle_open(ctx, t2, yi.data(), FRI_QUERIES, L.column_leaves.data(), L.column_nodes.data())) != SB_OK) break;
         L.n_poly = 4 * FRI_QUERIES;
         L.depth_poly = cur_tree->depth;
         L.poly_leaves.resize(L.n_poly * 32);
         L.poly_nodes.resize(L.n_poly * cur_tree->depth * 32);
-        if ((rc = sb_merkle_open(ctx, cur_tree, pp.data(), L.n_poly, L.poly_leaves.data(), L.poly_nodes.data())) != SB_OK) break;
+        {
+            const OpenReq reqs[2] = {{t2, yi.data(), FRI_QUERIES, L.column_leaves.data(), L.column_nodes.data()},
+                                     {cur_tree, pp.data(), L.n_poly, L.poly_leaves.data(), L.poly_nodes.data()}};
+            if ((rc = merkle_open_many(ctx, reqs, 2)) != SB_OK) break;
+        }
         proof->layers.push_back(std::move(L));
         // fri.rs:215-223
         cur = (const uint4 *)d_col;

@@ -616,12 +616,15 @@ int ext_fri_prove(const sb_ext *e, size_t col, const sb_tree *values_tree, size_
         L.depth_column = t2->depth;
         L.column_leaves.resize(FRI_QUERIES * 32);
         L.column_nodes.resize(FRI_QUERIES * t2->depth * 32);
-        TRY(sb_merkle_open(ctx, t2, yi.data(), FRI_QUERIES, L.column_leaves.data(), L.column_nodes.data()));
         L.n_poly = 4 * FRI_QUERIES;
         L.depth_poly = cur_tree->depth;
         L.poly_leaves.resize(L.n_poly * 32);
         L.poly_nodes.resize(L.n_poly * cur_tree->depth * 32);
-        TRY(sb_merkle_open(ctx, cur_tree, pp.data(), L.n_poly, L.poly_leaves.data(), L.poly_nodes.data()));
+        {
+            const OpenReq reqs[2] = {{t2, yi.data(), FRI_QUERIES, L.column_leaves.data(), L.column_nodes.data()},
+                                     {cur_tree, pp.data(), L.n_poly, L.poly_leaves.data(), L.poly_nodes.data()}};
+            TRY(merkle_open_many(ctx, reqs, 2));
+        }
         own.proof->layers.push_back(std::move(L));
         // fri.rs:215-223
         w = hfp::sqr(hfp::sqr(w));

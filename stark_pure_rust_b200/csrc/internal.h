@@ -405,6 +405,13 @@ int ext_fri_prove(const sb_ext *e, size_t col, const sb_tree *values_tree, size_
 int ext_to_natural(const sb_ext *e, size_t col, uint4 *d_out);
 int sync_all(sb_ctx *root);
 
+struct OpenReq {
+    const sb_tree *t;
+    const size_t *idx;
+    size_t n_idx;
+    uint8_t *leaves_out, *nodes_out;      // either may be NULL
+};
+int merkle_open_many(sb_ctx *ctx, const OpenReq *reqs, int n_req);
 void json_bytes(std::string &s, const uint8_t *b, size_t n);
 void json_branches(std::string &s, const uint8_t *leaves, size_t leaf_bytes, const uint8_t *nodes, size_t depth, size_t count);
 void fri_proof_json_into(std::string &s, const sb_fri_proof *p);

@@ -576,10 +576,11 @@ extern "C" int sb_prove_r1cs(sb_ctx *ctx, const sb_trace *t, sb_stark_proof **ou
         }
         proof->lc_leaves.resize(positions.size() * 32);
         proof->lc_nodes.resize(positions.size() * log_prec * 32);
-        TRY(sb_merkle_open(ctx, l_tree, positions.data(), positions.size(), proof->lc_leaves.data(), proof->lc_nodes.data()));
         proof->main_leaves.resize(aug.size() * 256);
         proof->main_nodes.resize(aug.size() * log_prec * 32);
-        TRY(sb_merkle_open(ctx, m_tree, aug.data(), aug.size(), proof->main_leaves.data(), proof->main_nodes.data()));
+        const OpenReq reqs[2] = {{l_tree, positions.data(), positions.size(), proof->lc_leaves.data(), proof->lc_nodes.data()},
+                                 {m_tree, aug.data(), aug.size(), proof->main_leaves.data(), proof->main_nodes.data()}};
+        TRY(merkle_open_many(ctx, reqs, 2));
     }
     TRY(mark());
     nvtx.next("sb_prove_r1cs: FRI");
