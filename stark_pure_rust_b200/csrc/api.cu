@@ -1309,27 +1309,29 @@ void json_branches(std::string &s, const uint8_t *leaves, size_t leaf_bytes, con
     }
     s.push_back(']');
 }
+void fri_layer_json_into(std::string &s, const FriLayer &L) {
+    if (L.is_last) {
+        s += "{\"Last\":{\"last\":[";
+        for (size_t k = 0; k < L.last.size() / 32; k++) {
+            if (k) s.push_back(',');
+            json_bytes(s, L.last.data() + 32 * k, 32);
+        }
+        s += "]}}";
+    } else {
+        s += "{\"Middle\":{\"root2\":";
+        json_bytes(s, L.root2, 32);
+        s += ",\"column_branches\":";
+        json_branches(s, L.column_leaves.data(), 32, L.column_nodes.data(), L.depth_column, L.n_column);
+        s += ",\"poly_branches\":";
+        json_branches(s, L.poly_leaves.data(), 32, L.poly_nodes.data(), L.depth_poly, L.n_poly);
+        s += "}}";
+    }
+}
 void fri_proof_json_into(std::string &s, const sb_fri_proof *p) {
     s.push_back('[');
     for (size_t i = 0; i < p->layers.size(); i++) {
-        const FriLayer &L = p->layers[i];
         if (i) s.push_back(',');
-        if (L.is_last) {
-            s += "{\"Last\":{\"last\":[";
-            for (size_t k = 0; k < L.last.size() / 32; k++) {
-                if (k) s.push_back(',');
-                json_bytes(s, L.last.data() + 32 * k, 32);
-            }
-            s += "]}}";
-        } else {
-            s += "{\"Middle\":{\"root2\":";
-            json_bytes(s, L.root2, 32);
-            s += ",\"column_branches\":";
-            json_branches(s, L.column_leaves.data(), 32, L.column_nodes.data(), L.depth_column, L.n_column);
-            s += ",\"poly_branches\":";
-            json_branches(s, L.poly_leaves.data(), 32, L.poly_nodes.data(), L.depth_poly, L.n_poly);
-            s += "}}";
-        }
+        fri_layer_json_into(s, p->layers[i]);
     }
     s.push_back(']');
 }

@@ -616,26 +616,72 @@ extern "C" int sb_stark_proof_stage_ms(const sb_stark_proof *p, double ms[5]) {
 // serde_json::to_string(&StarkProof) (utils.rs:122-130 field order; run.rs:549 compact)
 extern "C" char *sb_stark_proof_json(const sb_stark_proof *p, size_t *len) {
     if (!p) return nullptr;
-    std::string s;
-    s.reserve((size_t)3 << 20);
-    s += "{\"m_root\":";
-    json_bytes(s, p->m_root, 32);
-    s += ",\"l_root\":";
-    json_bytes(s, p->l_root, 32);
-    s += ",\"a_root\":";
-    json_bytes(s, p->a_root, 32);
-    s += ",\"main_branches\":";
-    json_branches(s, p->main_leaves.data(), 256, p->main_nodes.data(), p->depth, p->main_leaves.size() / 256);
-    s += ",\"linear_comb_branches\":";
-    json_branches(s, p->lc_leaves.data(), 32, p->lc_nodes.data(), p->depth, p->lc_leaves.size() / 32);
-    s += ",\"fri_proof\":";
-    fri_proof_json_into(s, p->fri);
-    s += "}";
-    char *r = (char *)malloc(s.size() + 1);
-    if (!r) return nullptr;
-    memcpy(r, s.c_str(), s.size() + 1);
-    if (len) *len = s.size();
-    return r;
+    try {
+        // The proof is megabytes of decimal byte arrays: the three big sections (main branches, linear-combination branches, FRI
+        // layers) are formatted on their own host threads and concatenated (JSON was 1.2 of poseidon3_test's 5 ms, 3.5 of the 2^23
+        // circuit's 54 ms when written by one thread).
+        std::string head, main_b, lc_b, fri_b;
+        head += "{\"m_root\":";
+        json_bytes(head, p->m_root, 32);
+        head += ",\"l_root\":";
+        json_bytes(head, p->l_root, 32);
+        head += ",\"a_root\":";
+        json_bytes(head, p->a_root, 32);
+        head += ",\"main_branches\":";
+        auto do_main = [&]() {
+            main_b.reserve(p->main_leaves.size() * 4 + p->main_nodes.size() * 4 + 4096);
+            json_branches(main_b, p->main_leaves.data(), 256, p->main_nodes.data(), p->depth, p->main_leaves.size() / 256);
+        };
+        auto do_lc = [&]() {
+            lc_b.reserve(p->lc_leaves.size() * 4 + p->lc_nodes.size() * 4 + 4096);
+            json_branches(lc_b, p->lc_leaves.data(), 32, p->lc_nodes.data(), p->depth, p->lc_leaves.size() / 32);
+        };
+        const size_t n_layers = p->fri ? p->fri->layers.size() : 0;
+        std::vector<std::string> layer_s(n_layers);
+        auto do_layer = [&](size_t i) {
+            layer_s[i].reserve((size_t)1 << 19);
+            fri_layer_json_into(layer_s[i], p->fri->layers[i]);
+        };
+        if (p->main_nodes.size() >= ((size_t)1 << 16)) {
+            std::vector<std::thread> th;
+            th.emplace_back(do_main);
+            th.emplace_back(do_lc);
+            for (size_t i = 1; i < n_layers; i++) th.emplace_back(do_layer, i);
+            if (n_layers) do_layer(0);
+            for (auto &t : th) t.join();
+        } else {
+            do_main();
+            do_lc();
+            for (size_t i = 0; i < n_layers; i++) do_layer(i);
+        }
+        fri_b.push_back('[');
+        for (size_t i = 0; i < n_layers; i++) {
+            if (i) fri_b.push_back(',');
+            fri_b += layer_s[i];
+        }
+        fri_b.push_back(']');
+        static const char k_lc[] = ",\"linear_comb_branches\":", k_fri[] = ",\"fri_proof\":";
+        const size_t total = head.size() + main_b.size() + (sizeof k_lc - 1) + lc_b.size() + (sizeof k_fri - 1) + fri_b.size() + 1;
+        char *r = (char *)malloc(total + 1);
+        if (!r) return nullptr;
+        char *w = r;
+        auto put = [&](const char *src, size_t n) {
+            memcpy(w, src, n);
+            w += n;
+        };
+        put(head.data(), head.size());
+        put(main_b.data(), main_b.size());
+        put(k_lc, sizeof k_lc - 1);
+        put(lc_b.data(), lc_b.size());
+        put(k_fri, sizeof k_fri - 1);
+        put(fri_b.data(), fri_b.size());
+        put("}", 1);
+        *w = 0;
+        if (len) *len = total;
+        return r;
+    } catch (...) {
+        return nullptr;
+    }
 }
 extern "C" void sb_stark_proof_free(sb_stark_proof *p) { delete p; }
 
