@@ -158,21 +158,25 @@ struct Trace {
     hfp::el *wit = nullptr, *comp = nullptr, *coef = nullptr, *f0 = nullptr, *f1 = nullptr, *f2 = nullptr;
     std::vector<hfp::el> pub, heap;
     size_t *perm = nullptr;                     // original_steps entries, in the arena (or perm_heap)
+    std::vector<unsigned long long> last_rows;  // last row of every constraint (the flag vectors in compressed form)
+    size_t a = 0;
     std::vector<size_t> perm_heap, pfi_k, pfi_w;
 };
 
 // run.rs:109-281, :283-308, :390-419
 // with_witness = false (verifier, run.rs:454-526): only the public part is built -- coefficients, flags, permutation,
 // public wires and their first uses; `witness` then only needs the public wires
-const char *build_trace(sb_ctx *ctx, const R1cs &r, const std::vector<hfp::el> &witness, Trace &t, bool with_witness = true) {
+// flags_on_device: the three flag vectors are not materialised (sb_prove_files: the prover generates them from last_rows)
+const char *build_trace(sb_ctx *ctx, const R1cs &r, const std::vector<hfp::el> &witness, Trace &t, bool with_witness = true, bool flags_on_device = false) {
     const size_t n_wires = r.n_wires, nc = r.n_constraints;
     if ((with_witness && witness.size() < n_wires) || n_wires == 0) return "witness shorter than the circuit's wire count";
     const size_t a = r.row_off[nc], os = 3 * a;
     if (a == 0) return "circuit has no constraint rows";
     hfp::el *arena;
     if (ctx) {
-        arena = (hfp::el *)pinned_arena(ctx, 6 * os * sizeof(hfp::el) + os * sizeof(size_t));
-        if (arena) t.perm = (size_t *)(arena + 6 * os);
+        const size_t n_vec = flags_on_device ? 3 : 6;
+        arena = (hfp::el *)pinned_arena(ctx, n_vec * os * sizeof(hfp::el) + os * sizeof(size_t));
+        if (arena) t.perm = (size_t *)(arena + n_vec * os);
     } else {                      // host-only use (sb_trace_from_files): ordinary memory owned by the Trace
         t.heap.resize(6 * os);
         arena = t.heap.data();
@@ -181,7 +185,13 @@ const char *build_trace(sb_ctx *ctx, const R1cs &r, const std::vector<hfp::el> &
     }
     if (!arena) return "cannot allocate the pinned staging arena";
     t.os = os;
-    t.coef = arena; t.f0 = arena + os; t.f1 = arena + 2 * os; t.f2 = arena + 3 * os; t.wit = arena + 4 * os; t.comp = arena + 5 * os;
+    t.a = a;
+    if (flags_on_device && ctx) {
+        t.coef = arena; t.wit = arena + os; t.comp = arena + 2 * os;
+    } else {
+        flags_on_device = false;
+        t.coef = arena; t.f0 = arena + os; t.f1 = arena + 2 * os; t.f2 = arena + 3 * os; t.wit = arena + 4 * os; t.comp = arena + 5 * os;
+    }
     std::vector<uint32_t> wire_at(os);
     std::atomic<int> bad(0);
     // rows of constraint c sit at row_off[c] .. in each third k (A, B, C); threads take ranges of constraints
@@ -219,18 +229,21 @@ const char *build_trace(sb_ctx *ctx, const R1cs &r, const std::vector<hfp::el> &
     });
     if (bad.load()) return "wire id out of range";
     // calc_flags, run.rs:283-308
-    parallel_for(os, 1 << 16, [&](size_t lo, size_t hi) {
-        for (size_t i = lo; i < hi; i++) {
-            t.f0[i] = hfp::ONE;
-            t.f1[i] = hfp::ONE;
-            t.f2[i] = hfp::ZERO;
+    for (size_t c = 0; c < nc; c++)
+        if (r.row_off[c + 1] != r.row_off[c]) t.last_rows.push_back(r.row_off[c + 1] - 1);     // (every well-formed constraint has a term)
+    if (!flags_on_device) {
+        parallel_for(os, 1 << 16, [&](size_t lo, size_t hi) {
+            for (size_t i = lo; i < hi; i++) {
+                t.f0[i] = hfp::ONE;
+                t.f1[i] = hfp::ONE;
+                t.f2[i] = hfp::ZERO;
+            }
+        });
+        for (unsigned long long l : t.last_rows) {
+            const size_t k = (l + 1) % a;
+            t.f1[k] = t.f1[k + a] = t.f1[k + 2 * a] = hfp::ZERO;
+            t.f2[l] = hfp::ONE;
         }
-    });
-    for (size_t c = 0; c < nc; c++) {
-        if (r.row_off[c + 1] == r.row_off[c]) continue;     // cannot happen for well-formed circuits (every constraint has a term)
-        const size_t l = r.row_off[c + 1] - 1, k = (l + 1) % a;
-        t.f1[k] = t.f1[k + a] = t.f1[k + 2 * a] = hfp::ZERO;
-        t.f2[l] = hfp::ONE;
     }
     // copy permutation, run.rs:390-401: the uses of a wire in (constraint, factor, row) order form a cycle,
     // perm[first use] = last use, perm[use j] = use j-1
@@ -291,7 +304,7 @@ extern "C" int sb_prove_files(sb_ctx *ctx, const char *r1cs_path, const char *wt
     if (witness.empty() || !hfp::eq(witness[0], hfp::ONE)) return fail(ctx, SB_ERR_ARG, "witness[0] must be 1 (run.rs:358)");
     dbg_check("sb_prove_files before build_trace");
     Trace t;
-    e = build_trace(ctx, r, witness, t);
+    e = build_trace(ctx, r, witness, t, true, true);
     if (e) return fail(ctx, SB_ERR_ARG, "%s", e);
     dbg_check("sb_prove_files after build_trace");
     sb_trace st;
@@ -311,7 +324,8 @@ extern "C" int sb_prove_files(sb_ctx *ctx, const char *r1cs_path, const char *wt
     const double t1 = now();
     sb_stark_proof *proof = nullptr;
     dbg_check("sb_prove_files after the front end");
-    TRY(sb_prove_r1cs(ctx, &st, &proof));
+    const FlagSpec flags{t.last_rows.data(), t.last_rows.size(), t.a};
+    TRY(prove_r1cs_impl(ctx, &st, t.f0 ? nullptr : &flags, &proof));
     const double t2 = now();
     int rc = SB_OK;
     if (proof_path) {

@@ -405,6 +405,16 @@ int ext_fri_prove(const sb_ext *e, size_t col, const sb_tree *values_tree, size_
 int ext_to_natural(const sb_ext *e, size_t col, uint4 *d_out);
 int sync_all(sb_ctx *root);
 
+// calc_flags (run.rs:283-308) in compressed form: the three flag vectors are all-one / all-one / all-zero except at one position per
+// constraint (its last row l, and (l + 1) mod a in each third), so sb_prove_files hands the prover the list of those rows and the
+// vectors are generated on the device instead of being written (92 MB at 955 086 steps) and uploaded
+struct FlagSpec {
+    const unsigned long long *last_rows;   // l = last row of every constraint that has rows
+    size_t n_last;
+    size_t a;                              // rows of one third (original_steps / 3)
+};
+int prove_r1cs_impl(sb_ctx *ctx, const sb_trace *t, const FlagSpec *flags, sb_stark_proof **out);
+
 struct OpenReq {
     const sb_tree *t;
     const size_t *idx;

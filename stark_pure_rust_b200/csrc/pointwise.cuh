@@ -56,6 +56,26 @@ __global__ void pw_u64_to_fp_kernel(const unsigned long long *v, uint4 *out, uns
     fp_stg(out, i, fp_to_mont(a));
 }
 
+// flag vectors generated on the device (FlagSpec, internal.h; run.rs:283-308): out[i] = value
+__global__ void pw_fill_kernel(uint4 *out, unsigned long long n, const fp value) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) fp_stg(out, i, value);
+}
+// f1[k] = f1[k + a] = f1[k + 2a] = 0 with k = (l + 1) mod a, f2[l] = 1 for the last row l of every constraint (either may be NULL)
+__global__ void pw_flags_scatter_kernel(const unsigned long long *last_rows, unsigned long long n_last, unsigned long long a, uint4 *f1, uint4 *f2,
+                                        const fp one) {
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_last) return;
+    const unsigned long long l = last_rows[c], k = (l + 1) % a;
+    if (f1) {
+        const fp z = fp_zero();
+        fp_stg(f1, k, z);
+        fp_stg(f1, k + a, z);
+        fp_stg(f1, k + 2 * a, z);
+    }
+    if (f2) fp_stg(f2, l, one);
+}
+
 // identity padding of the copy permutation beyond the original steps (prove.rs:55-56): perm[i] = i for os <= i < n
 __global__ void pw_perm_pad_kernel(unsigned long long *perm, unsigned long long os, unsigned long long n) {
     const size_t i = os + (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -172,12 +172,21 @@ static int device_lagrange(sb_ctx *ctx, const uint4 *d_x, const std::vector<hfp:
 // built as per-device subtrees with the top finished on the host, and only S-point coefficient vectors and 32-byte digests
 // cross NVLink.  The S-point accumulator chain (prefix products) runs on the device that holds the witness column.
 extern "C" int sb_prove_r1cs(sb_ctx *ctx, const sb_trace *t, sb_stark_proof **out) {
-    return guarded(ctx, __func__, [&]() -> int {
+    return prove_r1cs_impl(ctx, t, nullptr, out);
+}
+// flags != NULL: t->flag0 .. flag2 are not read, the flag columns are generated on the device from the constraints' last rows
+int prove_r1cs_impl(sb_ctx *ctx, const sb_trace *t, const FlagSpec *flags, sb_stark_proof **out) {
+    return guarded(ctx, "sb_prove_r1cs", [&]() -> int {
     if (!ctx || !t || !out) return SB_ERR_ARG;
     const size_t os = t->original_steps;
     if (os == 0 || os % 3 != 0) return fail(ctx, SB_ERR_ARG, "original_steps %zu must be a positive multiple of 3", os);   // :33
-    if (!t->witness_trace || !t->computational_trace || !t->coefficients || !t->flag0 || !t->flag1 || !t->flag2 || !t->permuted_indices)
+    if (!t->witness_trace || !t->computational_trace || !t->coefficients || !t->permuted_indices || (!flags && (!t->flag0 || !t->flag1 || !t->flag2)))
         return fail(ctx, SB_ERR_ARG, "missing trace array");
+    if (flags) {
+        if (flags->a * 3 != os || (flags->n_last && !flags->last_rows)) return fail(ctx, SB_ERR_ARG, "flag description does not match the trace");
+        for (size_t i = 0; i < flags->n_last; i++)
+            if (flags->last_rows[i] >= flags->a) return fail(ctx, SB_ERR_ARG, "constraint row out of range");
+    }
     // :37-53 sizes
     const uint32_t log_steps = log2_ceil_quirk(os - 1);
     const size_t S = (size_t)1 << log_steps;
@@ -290,6 +299,32 @@ extern "C" int sb_prove_r1cs(sb_ctx *ctx, const sb_trace *t, sb_stark_proof **ou
         DCU(cudaStreamWaitEvent(c->h2d_stream, ready, 0));
         cudaEventDestroy(ready);
     }
+    if (flags) {
+        // run.rs:283-308 on the devices that extend the flag columns: f0 = 1, f1 = 1 except after a constraint's last row, f2 = 1 only there.
+        // Issued BEFORE the column uploads: the copy engine serves its queue in order, and the small upload of the row list on the
+        // main stream would otherwise wait behind all of them (measured: +3.5 ms on the 2^23 proof).
+        fp one;
+        memcpy(one.l, hfp::ONE.l, 32);
+        unsigned long long *h_rows = (unsigned long long *)pinned_scratch(ctx, flags->n_last * 8 + 8);
+        if (!h_rows) return fail(ctx, SB_ERR_OOM, "pinned scratch");
+        memcpy(h_rows, flags->last_rows, flags->n_last * 8);
+        for (int col : {F0_, F1_, F2_}) {
+            sb_ctx *c = ctx->dev[E->owner[col]];
+            DevGuard dg(c);
+            if (col != F2_) {
+                pw_fill_kernel<<<nblk(os), 128, 0, c->stream>>>(E->input(col), os, one);
+                c->launches++;
+            }
+            if (col != F0_ && flags->n_last) {
+                DevBuf rows(c);
+                TRY(rows.alloc(flags->n_last * 8));
+                DCU(cudaMemcpyAsync(rows.p, h_rows, flags->n_last * 8, cudaMemcpyHostToDevice, c->stream));
+                pw_flags_scatter_kernel<<<nblk(flags->n_last), 128, 0, c->stream>>>((const unsigned long long *)rows.p, flags->n_last, flags->a,
+                                                                                   col == F1_ ? E->input(F1_) : nullptr, col == F2_ ? E->input(F2_) : nullptr, one);
+                c->launches++;
+            }
+        }
+    }
     for (int d : {E->owner[PIDX_], dS}) {   // the copy permutation: its padding (:55-56) is written on the device
         if (pd[d].perm) continue;
         sb_ctx *c = ctx->dev[d];
@@ -305,8 +340,10 @@ extern "C" int sb_prove_r1cs(sb_ctx *ctx, const sb_trace *t, sb_stark_proof **ou
         c->launches++;
         DCU(cudaEventRecord(perm_up[d], c->stream));          // from here on: "permutation complete on device d"
     }
-    const uint64_t *srcs[6] = {t->coefficients, t->flag0, t->flag1, t->flag2, t->witness_trace, t->computational_trace};
+    const uint64_t *srcs[6] = {t->coefficients, flags ? nullptr : t->flag0, flags ? nullptr : t->flag1, flags ? nullptr : t->flag2, t->witness_trace,
+                               t->computational_trace};
     for (int c = 0; c < 6; c++) {
+        if (!srcs[c]) continue;
         sb_ctx *o = ctx->dev[E->owner[c]];
         DevGuard dg(o);
         DCU(cudaMemcpyAsync(E->input(c), srcs[c], os * 32, cudaMemcpyHostToDevice, o->h2d_stream));      // the tail stays zero (ext_create)
@@ -329,6 +366,7 @@ extern "C" int sb_prove_r1cs(sb_ctx *ctx, const sb_trace *t, sb_stark_proof **ou
     // uploads land (every owner waits for its own columns only)
     auto wait_cols = [&](int c0, int c1) -> int {
         for (int c = c0; c < c1; c++) {
+            if (!up[c]) continue;                     // generated on the device
             sb_ctx *o = ctx->dev[E->owner[c]];
             DevGuard dg(o);
             DCU(cudaStreamWaitEvent(o->stream, up[c], 0));
