@@ -273,6 +273,18 @@ int sb_pseudorandom_indices_ctx(const sb_ctx *ctx, const uint8_t *seed, size_t s
 /* blake (fri/src/utils.rs:5-10) */
 void sb_blake2s(const uint8_t *msg, size_t len, uint8_t out[32]);
 
+/* ---- the alternative digest -------------------------------------------------------------------
+ * `PoseidonDigest` (commitment/src/poseidon.rs:10-63): neptune 5.1.0 Poseidon, arity 2, Strength::Standard,
+ * HashMode::Correct over the BLS12-381 scalar field.  A message is 1..64 bytes, zero-padded to 32-byte chunks, every chunk a
+ * canonical little-endian scalar; anything else makes the reference panic (:33, :48) and returns SB_ERR_ARG here. */
+/* PoseidonDigest::hash of n messages of msg_bytes each, on the device; out = n x 32 bytes */
+int sb_poseidon_hash(sb_ctx *ctx, const void *msgs, size_t msg_bytes, size_t n, uint8_t *out);
+/* the same digest of one message on the host (Proof::validate with H = PoseidonDigest, merkle_tree.rs:25-43) */
+int sb_poseidon_hash_host(const uint8_t *msg, size_t len, uint8_t out[32]);
+/* ParallelMerkleTree<Vec<u8>, PoseidonDigest>::update + get_root (commitment/src/pallarel_merkle_tree.rs:219-253): the tree of
+ * sb_merkle_commit with the other digest; sb_merkle_open / sb_tree_* / sb_tree_free apply to it unchanged */
+int sb_merkle_commit_poseidon(sb_ctx *ctx, const void *leaves, size_t leaf_bytes, size_t n, uint8_t root[32], sb_tree **tree);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,6 +12,7 @@
  *       (commitment/src/pallarel_merkle_tree.rs:133-216,
  *        commitment/src/merkle_proof_in_place.rs:209-261),
  *       field byte codecs (ff_utils/src/fp.rs:28-68), parsers (r1cs-stark/src/reader.rs:45-89).
+ *       the Poseidon digest and its tree (commitment/src/poseidon.rs:66-106, pallarel_merkle_tree.rs:219-253).
  *   PARITY UNPINNED by the reference    : F_p products, NTT outputs, FRI columns/roots and
  *       proof.json have no golden vectors in the reference and the Rust code cannot be built
  *       here (no cargo/rustc).  They are anchored instead by (i) uniqueness of exact field
@@ -22,6 +23,7 @@
  * Third-party arithmetic restated here (not under /root/reference):
  *   ff / ff_derive 0.10.0  (Cargo.lock:448-449,496-497) — Montgomery F_p, R = 2^256, 4 x u64 limbs
  *   blake2 0.9.1           (Cargo.lock:103-104)         — Blake2s-256, RFC 7693
+ *   neptune 5.1.0, blstrs 0.4.1 (commitment/Cargo.toml:10,13) — Poseidon arity 2 over the BLS12-381 scalar field (poseidon.c)
  *   num-bigint 0.4.0, serde_json 1.0.66                 — byte<->integer and compact JSON
  */
 #ifndef STARK_ORACLE_H
@@ -99,6 +101,15 @@ void orc_merkle_gen_proofs(const uint8_t *leaves, size_t leaf_bytes, size_t n,
 /* merkle_tree.rs:25-43: returns 1 when the branch hashes to root */
 int orc_merkle_validate(const uint8_t root[32], size_t index, const uint8_t *leaf, size_t leaf_bytes,
                         const uint8_t *nodes, size_t depth);
+
+/* ---- the alternative digest (commitment/src/poseidon.rs:30-63; neptune 5.1.0 arity 2 over the BLS12-381 scalar field,
+ * restated in poseidon.c; pinned by the KATs of poseidon.rs:66-106 and pallarel_merkle_tree.rs:235-246) ------------------ */
+/* 0, or -1 where the reference panics: len == 0, len > 64, or a 32-byte chunk that is not a canonical scalar */
+int orc_poseidon_hash(uint8_t out[32], const uint8_t *msg, size_t len);
+int orc_poseidon_merkle_gen_proofs(const uint8_t *leaves, size_t leaf_bytes, size_t n, const size_t *indices, size_t n_idx,
+                                   uint8_t root[32], uint8_t *nodes_out);
+int orc_poseidon_merkle_validate(const uint8_t root[32], size_t index, const uint8_t *leaf, size_t leaf_bytes,
+                                 const uint8_t *nodes, size_t depth);
 
 /* ---- growable byte buffer used for JSON output ------------------------------------------- */
 typedef struct { char *p; size_t len, cap; } orc_buf;

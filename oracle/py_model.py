@@ -457,3 +457,65 @@ if __name__ == "__main__":
     if len(sys.argv) > 3:
         open(sys.argv[3], "w").write(js)
     print(hashlib.sha256(js.encode()).hexdigest(), len(js))
+
+
+# ---- the alternative digest: neptune 5.1.0 Poseidon, arity 2, over the BLS12-381 scalar field ----------------------------
+# (commitment/src/poseidon.rs:30-63; second, independent restatement next to oracle/poseidon.c -- big-int arithmetic)
+BLS_R = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+
+
+def _grain_bits(field, sbox, n_bits, t, rf, rp):
+    st = []
+    for v, w in ((field, 2), (sbox, 4), (n_bits, 12), (t, 12), (rf, 10), (rp, 10), ((1 << 30) - 1, 30)):
+        st += [(v >> i) & 1 for i in range(w - 1, -1, -1)]
+
+    def step():
+        b = st[62] ^ st[51] ^ st[38] ^ st[23] ^ st[13] ^ st[0]
+        st.pop(0)
+        st.append(b)
+        return b
+    for _ in range(160):
+        step()
+    while True:
+        a, b = step(), step()
+        if a:
+            yield b
+
+
+_POSEIDON = {}
+
+
+def poseidon_params(arity=2, rf=8, rp=55):
+    if arity not in _POSEIDON:
+        t = arity + 1
+        bits = _grain_bits(1, 1, 255, t, rf, rp)
+        rc = []
+        while len(rc) < t * (rf + rp):
+            v = 0
+            for _ in range(255):
+                v = (v << 1) | next(bits)
+            if v < BLS_R:
+                rc.append(v)
+        mds = [[pow(i + t + j, -1, BLS_R) for j in range(t)] for i in range(t)]
+        _POSEIDON[arity] = (rc, mds)
+    return _POSEIDON[arity]
+
+
+def poseidon_digest(msg, rf=8, rp=55):
+    """PoseidonDigest::hash: 1..64 bytes -> 32 bytes"""
+    if not 0 < len(msg) <= 64:
+        raise ValueError("message length")
+    pad = bytes(msg) + bytes((-len(msg)) % 32)
+    ins = [int.from_bytes(pad[i:i + 32], "little") for i in range(0, len(pad), 32)]
+    if any(x >= BLS_R for x in ins):
+        raise ValueError("chunk is not a canonical scalar")
+    rc, mds = poseidon_params(2, rf, rp)
+    st = [3] + ins + [0] * (2 - len(ins))
+    for r in range(rf + rp):
+        st = [(st[i] + rc[3 * r + i]) % BLS_R for i in range(3)]
+        if r < rf // 2 or r >= rf // 2 + rp:
+            st = [pow(x, 5, BLS_R) for x in st]
+        else:
+            st[0] = pow(st[0], 5, BLS_R)
+        st = [sum(st[i] * mds[i][j] for i in range(3)) % BLS_R for j in range(3)]
+    return st[1].to_bytes(32, "little")

@@ -79,6 +79,9 @@ def load():
         "sb_batch_inverse": (i32, [vp, vp, sz]),
         "sb_batch_inverse_dev": (i32, [vp, vp, sz]),
         "sb_merkle_commit": (i32, [vp, vp, sz, sz, vp, C.POINTER(vp)]),
+        "sb_merkle_commit_poseidon": (i32, [vp, vp, sz, sz, vp, C.POINTER(vp)]),
+        "sb_poseidon_hash": (i32, [vp, vp, sz, sz, vp]),
+        "sb_poseidon_hash_host": (i32, [vp, sz, vp]),
         "sb_merkle_commit_cols_dev": (i32, [vp, C.POINTER(vp), sz, sz, vp, C.POINTER(vp)]),
         "sb_merkle_open": (i32, [vp, vp, szp, sz, vp, vp]),
         "sb_tree_width": (sz, [vp]),

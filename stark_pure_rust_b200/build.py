@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libstark_b200.so")
 CLI = os.path.join(HERE, "r1cs-stark")
-SOURCES = ["api.cu", "ntt.cu", "ntt_b05.cu", "ntt_b6.cu", "ntt_b7.cu", "ntt_b8.cu", "merkle.cu", "fri.cu", "prover.cu", "frontend.cu", "ext.cu"]
+SOURCES = ["api.cu", "ntt.cu", "ntt_b05.cu", "ntt_b6.cu", "ntt_b7.cu", "ntt_b8.cu", "merkle.cu", "poseidon.cu", "fri.cu", "prover.cu", "frontend.cu", "ext.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ARCH + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-O3,-Wall", "-c"] + os.environ.get("SB_NVCC_EXTRA", "").split()

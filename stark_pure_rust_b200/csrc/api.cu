@@ -135,6 +135,7 @@ extern "C" void sb_destroy(sb_ctx *ctx) {
     for (auto &t : ctx->tables) cudaFree(t.d);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->pinned2) cudaFreeHost(ctx->pinned2);
+    if (ctx->poseidon_consts) cudaFree(ctx->poseidon_consts);
     if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
     if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     prof_collect(ctx);

@@ -66,6 +66,7 @@ struct sb_ctx {
     size_t pinned_bytes = 0;
     void *pinned2 = nullptr;          // small pinned scratch for host scalars / coefficient vectors sent to several devices
     size_t pinned2_bytes = 0;
+    uint32_t *poseidon_consts = nullptr;   // device copy of the Poseidon parameters (poseidon.cu), made on first use
     // optional per-kernel-family timing (sb_profile): CUDA events around every launch
     bool prof = false;
     struct ProfRec { int kind; cudaEvent_t a, b; };

@@ -1,4 +1,5 @@
-"""Mirror of packages/commitment/src/{merkle_tree.rs, merkle_proof_in_place.rs} with H = BlakeDigest."""
+"""Mirror of packages/commitment/src/{merkle_tree.rs, merkle_proof_in_place.rs, pallarel_merkle_tree.rs}: H = BlakeDigest
+(the digest the binary fixes, r1cs-stark/src/main.rs:9) or H = PoseidonDigest (commitment/src/poseidon.rs) per tree."""
 import ctypes as C
 from dataclasses import dataclass
 from typing import List
@@ -15,18 +16,42 @@ class Proof:
     leaf: bytes
     nodes: List[bytes]
 
-    def validate(self, root, index):
-        """merkle_tree.rs:25-43"""
-        h = utils.blake(self.leaf)
+    def validate(self, root, index, digest="blake"):
+        """merkle_tree.rs:25-43 (generic in the digest H)"""
+        H = _digest(digest)
+        h = H(self.leaf)
         for node in self.nodes:
-            h = utils.blake(node + h) if index & 1 else utils.blake(h + node)
+            h = H(node + h) if index & 1 else H(h + node)
             index >>= 1
         return h == bytes(root)
 
 
-def verify_multi_branch(root, indices, proofs):
+def _digest(name):
+    if name == "blake":
+        return utils.blake
+    if name == "poseidon":
+        return utils.poseidon
+    raise ValueError("digest must be 'blake' or 'poseidon'")
+
+
+def verify_multi_branch(root, indices, proofs, digest="blake"):
     """merkle_tree.rs:46-58"""
-    return all(p.validate(root, i) for i, p in zip(indices, proofs))
+    return all(p.validate(root, i, digest) for i, p in zip(indices, proofs))
+
+
+def poseidon_hash_many(messages, ctx=None):
+    """PoseidonDigest::hash (poseidon.rs:30-63) of equally long messages, one device thread per message"""
+    ctx = ctx or default_context()
+    msgs = [bytes(m) for m in messages]
+    if not msgs:
+        return []
+    lb = len(msgs[0])
+    assert all(len(m) == lb for m in msgs), "messages must have equal length"
+    flat = np.frombuffer(b"".join(msgs), dtype=np.uint8)
+    out = np.empty(32 * len(msgs), dtype=np.uint8)
+    ctx.check(ctx.lib.sb_poseidon_hash(ctx.h, _ptr(flat) if flat.size else None, lb, len(msgs), _ptr(out)))
+    o = out.tobytes()
+    return [o[32 * i:32 * i + 32] for i in range(len(msgs))]
 
 
 class MerkleProofInPlace:
@@ -34,8 +59,10 @@ class MerkleProofInPlace:
     is built once on the first gen_proofs/get_root after update() and kept in HBM; later gen_proofs
     calls are gathers (the reference rebuilds it every time, :106-206)."""
 
-    def __init__(self, ctx=None):
+    def __init__(self, ctx=None, digest="blake"):
         self.ctx = ctx or default_context()
+        _digest(digest)
+        self.digest = digest
         self._leaves = None
         self._tree = None
         self._root = b""            # H::default(), :19
@@ -63,7 +90,8 @@ class MerkleProofInPlace:
         flat = np.frombuffer(b"".join(leaves), dtype=np.uint8)
         root = np.empty(32, dtype=np.uint8)
         t = C.c_void_p()
-        self.ctx.check(self.ctx.lib.sb_merkle_commit(self.ctx.h, _ptr(flat) if flat.size else None, lb, n, _ptr(root), C.byref(t)))
+        commit = self.ctx.lib.sb_merkle_commit if self.digest == "blake" else self.ctx.lib.sb_merkle_commit_poseidon
+        self.ctx.check(commit(self.ctx.h, _ptr(flat) if flat.size else None, lb, n, _ptr(root), C.byref(t)))
         self._tree = t
         self._root = root.tobytes()
 
@@ -93,3 +121,8 @@ class MerkleProofInPlace:
             self._free()
         except Exception:
             pass
+
+
+class ParallelMerkleTree(MerkleProofInPlace):
+    """pallarel_merkle_tree.rs:13-131: same leaves, nodes, root and proofs as MerkleProofInPlace (the reference's two
+    builders differ only in how the CPU work is chunked)"""

@@ -16,6 +16,18 @@ def blake(message):
     return out.tobytes()
 
 
+def poseidon(message):
+    """commitment/src/poseidon.rs:30-63 `PoseidonDigest::hash` (host side; the batched device version is
+    `merkle.poseidon_hash_many`).  ValueError where the reference panics: empty or > 64 bytes, or a 32-byte chunk
+    that is not a canonical BLS12-381 scalar."""
+    lib = load()
+    m = np.frombuffer(bytes(message), dtype=np.uint8)
+    out = np.empty(32, dtype=np.uint8)
+    if lib.sb_poseidon_hash_host(_ptr(m) if m.size else None, m.size, _ptr(out)) != 0:
+        raise ValueError("PoseidonDigest::hash: message must be 1..64 bytes of canonical 32-byte scalars")
+    return out.tobytes()
+
+
 def get_pseudorandom_indices(seed, modulus, count, exclude_multiples_of=0, ctx=None):
     """utils.rs:82-109.  With a context whose extended domain is enabled (sb_set_extended_domain) moduli >= 2^24
     are accepted; the reference asserts modulus < 2^24 (utils.rs:88)."""

@@ -73,6 +73,12 @@ def lib():
         L.orc_merkle_gen_proofs.argtypes = [vp, sz, sz, vp, sz, vp, vp]
         L.orc_merkle_validate.argtypes = [vp, sz, vp, sz, vp, sz]
         L.orc_merkle_validate.restype = C.c_int
+        L.orc_poseidon_hash.argtypes = [vp, vp, sz]
+        L.orc_poseidon_hash.restype = C.c_int
+        L.orc_poseidon_merkle_gen_proofs.argtypes = [vp, sz, sz, vp, sz, vp, vp]
+        L.orc_poseidon_merkle_gen_proofs.restype = C.c_int
+        L.orc_poseidon_merkle_validate.argtypes = [vp, sz, vp, sz, vp, sz]
+        L.orc_poseidon_merkle_validate.restype = C.c_int
         L.orc_prove_low_degree.argtypes = [C.POINTER(FriProof), vp, sz, vp, sz, u32]
         L.orc_verify_low_degree_proof.argtypes = [vp, vp, C.POINTER(FriProof), sz, u32]
         L.orc_verify_low_degree_proof.restype = C.c_int
@@ -156,6 +162,34 @@ def merkle_gen_proofs(leaves_flat, leaf_bytes, n, indices):
     nodes = np.zeros((max(idx.size, 1), max(depth, 1), 32), dtype=np.uint8)
     lib().orc_merkle_gen_proofs(_p(lv), leaf_bytes, n, _p(idx) if idx.size else None, idx.size, _p(root), _p(nodes) if idx.size else None)
     return root.tobytes(), nodes[: idx.size, :depth].copy()
+
+
+def poseidon(msg):
+    """poseidon.rs:30-63; raises ValueError where the reference panics"""
+    m = np.frombuffer(bytes(msg), dtype=np.uint8).copy()
+    out = np.zeros(32, dtype=np.uint8)
+    if lib().orc_poseidon_hash(_p(out), _p(m) if m.size else None, m.size):
+        raise ValueError("message cannot be hashed (length 0 or > 64, or a chunk is not a canonical scalar)")
+    return out.tobytes()
+
+
+def poseidon_merkle_gen_proofs(leaves_flat, leaf_bytes, n, indices):
+    """ParallelMerkleTree<_, PoseidonDigest>: (root bytes, nodes array (n_idx, depth, 32))"""
+    lv = np.frombuffer(bytes(leaves_flat), dtype=np.uint8).copy()
+    idx = np.asarray(list(indices), dtype=np.uint64)
+    depth = (n - 1).bit_length()
+    root = np.zeros(32, dtype=np.uint8)
+    nodes = np.zeros((max(idx.size, 1), max(depth, 1), 32), dtype=np.uint8)
+    if lib().orc_poseidon_merkle_gen_proofs(_p(lv), leaf_bytes, n, _p(idx), idx.size, _p(root), _p(nodes)):
+        raise ValueError("a leaf cannot be hashed")
+    return root.tobytes(), nodes[: idx.size, :depth].copy()
+
+
+def poseidon_merkle_validate(root, index, leaf, nodes):
+    lf = np.frombuffer(bytes(leaf), dtype=np.uint8).copy()
+    nd = np.ascontiguousarray(nodes, dtype=np.uint8).reshape(-1, 32)
+    r = np.frombuffer(bytes(root), dtype=np.uint8).copy()
+    return bool(lib().orc_poseidon_merkle_validate(_p(r), index, _p(lf), lf.size, _p(nd) if nd.size else None, nd.shape[0]))
 
 
 def fp_to_bytes_le(vals):

@@ -110,6 +110,34 @@ def test_oracle_proof_golden(oracle, name, tmp_path):
     assert os.path.getsize(out) == GOLD["proofs"][name]["proof_json_bytes"]
 
 
+def test_oracle_poseidon_kats(oracle):
+    """the alternative digest against every vector the reference holds for it, in both restatements"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import py_model as pm
+    k = GOLD["reference_kats"]["poseidon"]
+    for n, want in k["digest"].items():
+        msg = bytes(range(int(n))) + bytes(64 - int(n))
+        assert oracle.poseidon(msg).hex() == want and pm.poseidon_digest(msg).hex() == want
+    root, nodes = oracle.poseidon_merkle_gen_proofs(bytes.fromhex("7fffffff") * 4096, 4, 4096, [2, 7, 13])
+    assert root.hex() == k["merkle4096"]["root"]
+    assert nodes[0][0].tobytes().hex() == k["merkle4096"]["first_node_of_2"]
+    for j, i in enumerate([2, 7, 13]):                       # verify_multi_branch, pallarel_merkle_tree.rs:248
+        assert oracle.poseidon_merkle_validate(root, i, bytes.fromhex("7fffffff"), nodes[j])
+    assert not oracle.poseidon_merkle_validate(root, 3, bytes.fromhex("7ffffffe"), nodes[0])
+    rng = np.random.default_rng(11)
+    for ln in (1, 4, 31, 32, 33, 40, 64):                    # the two restatements on random messages of every shape
+        m = bytearray(rng.integers(0, 256, ln, dtype=np.uint8).tobytes())
+        for top in (31, 63):
+            if top < ln:
+                m[top] &= 0x3f                               # keep every chunk below the modulus
+        assert oracle.poseidon(bytes(m)) == pm.poseidon_digest(bytes(m))
+    r_le = pm.BLS_R.to_bytes(32, "little")
+    for bad in (b"", bytes(65), r_le, bytes(32) + r_le, b"\xff" * 32):   # where the reference panics (poseidon.rs:33, :48)
+        with pytest.raises(ValueError):
+            oracle.poseidon(bad)
+    assert oracle.poseidon((pm.BLS_R - 1).to_bytes(32, "little")) == pm.poseidon_digest((pm.BLS_R - 1).to_bytes(32, "little"))
+
+
 def test_oracle_matches_python_model(oracle):
     """the second, independent restatement (oracle/py_model.py) on a small case of every stage"""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -148,6 +176,34 @@ def test_host_blake_and_sampler_match_reference_kats():
         assert sb.utils.blake(m) == hashlib.blake2s(m).digest()
     assert sb.utils.get_pseudorandom_indices(d, 7, 5, 0) == k["sampler"]["hello world,7,5,0"]
     assert sb.utils.get_pseudorandom_indices(sb.utils.blake(b"hello another world"), 7, 20, 0) == k["sampler"]["hello another world,7,20,0"]
+
+
+def test_host_poseidon_matches_reference_kats_and_oracle(oracle):
+    """the product's host digest (Proof::validate with H = PoseidonDigest): poseidon.rs:66-106, pallarel_merkle_tree.rs:235-246"""
+    import stark_pure_rust_b200 as sb
+    k = GOLD["reference_kats"]["poseidon"]
+    for n, want in k["digest"].items():
+        assert sb.utils.poseidon(bytes(range(int(n))) + bytes(64 - int(n))).hex() == want
+    h = sb.utils.poseidon(bytes.fromhex("7fffffff"))
+    assert h.hex() == k["merkle4096"]["first_node_of_2"]
+    for _ in range(12):
+        h = sb.utils.poseidon(h + h)
+    assert h.hex() == k["merkle4096"]["root"]
+    rng = np.random.default_rng(5)
+    for ln in list(range(1, 65)):
+        m = bytearray(rng.integers(0, 256, ln, dtype=np.uint8).tobytes())
+        for top in (31, 63):
+            if top < ln:
+                m[top] &= 0x3f
+        assert sb.utils.poseidon(bytes(m)) == oracle.poseidon(bytes(m))
+    r_le = bytes.fromhex("01000000fffffffffe5bfeff02a4bd5305d8a10908d83933487d9d2953a7ed73")
+    assert sb.utils.poseidon((int.from_bytes(r_le, "little") - 1).to_bytes(32, "little")) == oracle.poseidon((int.from_bytes(r_le, "little") - 1).to_bytes(32, "little"))
+    for bad in (b"", bytes(65), r_le, bytes(32) + r_le, b"\xff" * 64):
+        with pytest.raises(ValueError):
+            sb.utils.poseidon(bad)
+    root, nodes = oracle.poseidon_merkle_gen_proofs(bytes(range(64)) * 2, 16, 8, [5])
+    pr = sb.merkle.Proof(bytes(range(64))[16:32], [nodes[0][l].tobytes() for l in range(3)])
+    assert pr.validate(root, 5, "poseidon") and not pr.validate(root, 4, "poseidon") and not pr.validate(root, 5)
 
 
 def test_host_sampler_matches_oracle(oracle):

@@ -2,11 +2,12 @@
 against the CPU oracle on the same seeded inputs.  Bit-exact everywhere (integer / byte work)."""
 import ctypes as C
 import hashlib
+import os
 
 import numpy as np
 import pytest
 
-from conftest import P, random_elems
+from conftest import P, ROOT, random_elems
 
 pytestmark = pytest.mark.gpu
 
@@ -185,6 +186,88 @@ def test_merkle_in_place_reference_test(ctx, oracle):
     root, nodes = oracle.merkle_gen_proofs(b"".join(leaves), 4, 16, idx)
     assert t.get_root() == root
     assert [b"".join(p.nodes) for p in prs] == [nodes[q].tobytes() for q in range(len(idx))]
+
+
+# ---- the alternative digest (commitment/src/poseidon.rs) ------------------------------------------------
+def test_poseidon_reference_kats(ctx):
+    """poseidon.rs:66-106 and pallarel_merkle_tree.rs:219-253 on the device"""
+    import json
+    import stark_pure_rust_b200 as sb
+    k = json.load(open(os.path.join(ROOT, "tests", "golden", "vectors.json")))["reference_kats"]["poseidon"]
+    msgs = [bytes(range(int(n))) + bytes(64 - int(n)) for n in k["digest"]]
+    assert [d.hex() for d in sb.merkle.poseidon_hash_many(msgs, ctx)] == list(k["digest"].values())
+    t = sb.merkle.ParallelMerkleTree(ctx, digest="poseidon")
+    t.update([bytes.fromhex("7fffffff")] * 4096)
+    prs = t.gen_proofs([2, 7, 13])
+    assert t.get_root().hex() == k["merkle4096"]["root"]
+    assert prs[0].leaf == bytes.fromhex("7fffffff")
+    assert prs[0].nodes[0].hex() == k["merkle4096"]["first_node_of_2"]
+    assert sb.merkle.verify_multi_branch(t.get_root(), [2, 7, 13], prs, "poseidon")
+    assert not sb.merkle.verify_multi_branch(t.get_root(), [2, 7, 13], prs)             # not a Blake tree
+
+
+def _canonical_messages(rng, n, ln):
+    a = rng.integers(0, 256, size=(n, ln), dtype=np.uint8)
+    for top in (31, 63):
+        if top < ln:
+            a[:, top] &= 0x3f                     # every 32-byte chunk below the BLS12-381 scalar modulus
+    return a
+
+
+@pytest.mark.parametrize("ln", [1, 3, 4, 31, 32, 33, 36, 40, 63, 64])
+def test_poseidon_hash_matches_oracle(ctx, oracle, ln):
+    import stark_pure_rust_b200 as sb
+    rng = np.random.default_rng(700 + ln)
+    a = _canonical_messages(rng, 300, ln)
+    r = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+    if ln >= 32:                                  # the largest scalar, zero, and limbs of all ones below the top
+        a[0, :32] = np.frombuffer((r - 1).to_bytes(32, "little"), dtype=np.uint8)
+        a[1, :32] = 0
+        a[2, :31] = 0xff
+    if ln == 64:
+        a[3, 32:] = np.frombuffer((r - 1).to_bytes(32, "little"), dtype=np.uint8)
+        a[4, 32:63] = 0xff
+    got = sb.merkle.poseidon_hash_many([row.tobytes() for row in a], ctx)
+    assert got == [oracle.poseidon(row.tobytes()) for row in a]
+    assert got[:8] == [sb.utils.poseidon(row.tobytes()) for row in a[:8]]
+
+
+def test_poseidon_rejects_what_the_reference_panics_on(ctx):
+    import stark_pure_rust_b200 as sb
+    r_le = (0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001).to_bytes(32, "little")
+    for bad in ([bytes(65)], [b""], [bytes(32), r_le], [bytes(32) + r_le], [b"\xff" * 64], [bytes(31) + b"\x80"]):
+        with pytest.raises(sb.StarkB200Error):    # poseidon.rs:33 assert, :48 unwrap
+            sb.merkle.poseidon_hash_many(bad, ctx)
+    t = sb.merkle.MerkleProofInPlace(ctx, digest="poseidon")
+    t.update([bytes(32), r_le])
+    with pytest.raises(sb.StarkB200Error):
+        t.gen_proofs([0])
+    t.update([bytes(66)] * 4)
+    with pytest.raises(sb.StarkB200Error):
+        t.gen_proofs([0])
+    t.update([b"abcd"] * 12)
+    with pytest.raises(sb.StarkB200Error):
+        t.gen_proofs([0])
+    assert sb.merkle.poseidon_hash_many([], ctx) == []
+
+
+@pytest.mark.parametrize("n,leaf_bytes", [(1, 32), (2, 4), (8, 64), (16, 40), (256, 33), (1024, 32), (1 << 13, 64), (1 << 15, 32)])
+def test_poseidon_merkle_matches_oracle(ctx, oracle, n, leaf_bytes):
+    """ParallelMerkleTree<Vec<u8>, PoseidonDigest>: root, caller-order / duplicate openings, branch checks"""
+    import stark_pure_rust_b200 as sb
+    rng = np.random.default_rng(n * 77 + leaf_bytes)
+    flat = _canonical_messages(rng, n, leaf_bytes).tobytes()
+    idx = [int(x) for x in rng.integers(0, n, size=9)] + [0, n - 1, n // 2, n // 2]
+    t = sb.merkle.MerkleProofInPlace(ctx, digest="poseidon")
+    t.update([flat[i * leaf_bytes:(i + 1) * leaf_bytes] for i in range(n)])
+    prs = t.gen_proofs(idx)
+    root, nodes = oracle.poseidon_merkle_gen_proofs(flat, leaf_bytes, n, idx)
+    assert t.get_root() == root and t.width() == n
+    for q, i in enumerate(idx):
+        assert prs[q].leaf == flat[i * leaf_bytes:(i + 1) * leaf_bytes]
+        assert b"".join(prs[q].nodes) == nodes[q].tobytes()
+        assert oracle.poseidon_merkle_validate(root, i, prs[q].leaf, nodes[q])
+    assert sb.merkle.verify_multi_branch(root, idx[:3], prs[:3], "poseidon")
 
 
 def test_merkle_not_power_of_two(ctx):
