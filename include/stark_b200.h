@@ -109,6 +109,14 @@ int sb_ntt(sb_ctx *ctx, uint64_t *vals, size_t len_in, const uint64_t root[4], u
  * dst_stride (elements), d_dst must not alias d_src. */
 int sb_ntt_dev(sb_ctx *ctx, const uint64_t *d_src, size_t len_in, size_t src_stride, uint64_t *d_dst,
                size_t dst_stride, size_t n_polys, const uint64_t root[4], uint32_t log_n, int inverse);
+/* ONE best_fft / inv_best_fft (fft.rs:327-379) spread over the g = 2, 4 or 8 devices of an sb_init_multi context
+ * (SURVEY.md 8e(5)): device d holds elements [d n/g, (d+1) n/g) of the vector in d_slabs[d] (natural order, memory of that
+ * device, e.g. from sb_dev_alloc_on) on entry and the same range of the result on return; 2^20 <= n <= 2^28.  The exchanges of
+ * the four-step formulation happen inside the pass kernels' loads and stores over peer memory (no transposes, no staging
+ * copies).  sb_ntt on host vectors takes this path by itself on a multi-device context from 2^20 points on. */
+int sb_ntt_multi_dev(sb_ctx *ctx, uint64_t *const *d_slabs, const uint64_t root[4], uint32_t log_n, int inverse);
+/* device memory on device dev_index of the context (0 .. sb_device_count - 1); free with sb_dev_free */
+int sb_dev_alloc_on(sb_ctx *ctx, int dev_index, size_t bytes, void **d_ptr);
 /* Twiddle step of a 2^log_n-point transform split four-step style over several GPUs (stark_pure_rust_b200/sharded.py,
  * SURVEY.md 8e(5)): d_vals[r * cols + c] *= root^((row0 + r) * c) (inverse: root^-1), canonical result. */
 int sb_twiddle_mul_dev(sb_ctx *ctx, uint64_t *d_vals, size_t rows, size_t cols, size_t row0, const uint64_t root[4],

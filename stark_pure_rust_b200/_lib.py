@@ -79,6 +79,8 @@ def load():
         "sb_batch_inverse": (i32, [vp, vp, sz]),
         "sb_batch_inverse_dev": (i32, [vp, vp, sz]),
         "sb_merkle_commit": (i32, [vp, vp, sz, sz, vp, C.POINTER(vp)]),
+        "sb_ntt_multi_dev": (i32, [vp, C.POINTER(vp), vp, u32, i32]),
+        "sb_dev_alloc_on": (i32, [vp, i32, sz, C.POINTER(vp)]),
         "sb_merkle_commit_poseidon": (i32, [vp, vp, sz, sz, vp, C.POINTER(vp)]),
         "sb_poseidon_hash": (i32, [vp, vp, sz, sz, vp]),
         "sb_poseidon_hash_host": (i32, [vp, sz, vp]),

@@ -503,6 +503,147 @@ extern "C" int sb_ntt_dev(sb_ctx *ctx, const uint64_t *d_src, size_t len_in, siz
     });
 }
 
+// ---- ONE transform over the devices of a multi-device context -----------------------------------------------
+// Device d holds elements [d n/g, (d+1) n/g) of the vector in slabs[d] (natural order) on entry and the same range of the result
+// on return.  The passes are those of the single-device transform on the virtual array "element e lives on device
+// e >> log2(n/g)"; what a four-step formulation does as three separate all-to-all exchanges with transposes in between happens
+// inside the pass kernels' own loads and stores over peer memory (ntt_pass_kernel<.., DIST>):
+//   pass 0        every device takes a contiguous share of the tiles; a tile's rows are spread over all devices -> remote reads
+//                 (exchange 1), and its outputs k1 belong to the device that owns the k1 range -> remote writes (exchange 2)
+//   passes 1..m-2 work inside one k1 range: local, in place
+//   last pass     device d takes the tiles whose inputs it holds; outputs go to their natural-order owner -> remote writes (3)
+// always in runs of CC x 32 contiguous bytes (256-512 B).  Cross-device barriers (events) sit before pass 0, after it and at the end.
+static const uint32_t NTT_MULTI_MIN_LOG_N = 20;
+
+static int cross_barrier(sb_ctx *ctx) {
+    const int g = ctx->n_dev();
+    cudaEvent_t ev[SB_MAX_DEV] = {0};
+    int rc = SB_OK;
+    for (int d = 0; d < g && rc == SB_OK; d++) {
+        DevGuard dg(ctx->dev[d]);
+        if (cudaEventCreateWithFlags(&ev[d], cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(ev[d], ctx->dev[d]->stream) != cudaSuccess)
+            rc = fail(ctx, SB_ERR_CUDA, "barrier event on device %d: %s", d, cudaGetErrorString(cudaGetLastError()));
+    }
+    for (int d = 0; d < g && rc == SB_OK; d++) {
+        DevGuard dg(ctx->dev[d]);
+        for (int o = 0; o < g; o++)
+            if (o != d && cudaStreamWaitEvent(ctx->dev[d]->stream, ev[o], 0) != cudaSuccess)
+                rc = fail(ctx, SB_ERR_CUDA, "barrier wait on device %d: %s", d, cudaGetErrorString(cudaGetLastError()));
+    }
+    for (int d = 0; d < g; d++)
+        if (ev[d]) cudaEventDestroy(ev[d]);           // released once the waits have passed
+    return rc;
+}
+
+static int launch_pass_on(sb_ctx *ctx, uint32_t bits, const NttPassParams &P) {
+    KLAUNCH(SB_KIND_NTT_PASS, ntt_launch_pass(ctx->stream, bits, P));
+    CU(cudaGetLastError());
+    return SB_OK;
+}
+
+int ntt_multi(sb_ctx *ctx, uint4 *const *slabs, const hfp::el &root, uint32_t log_n, int inverse) {
+    NvtxRange nvtx("ntt_multi");
+    const int g = ctx->n_dev();
+    const uint32_t lg = ilog2((size_t)g);
+    if (g < 2 || (1 << lg) != g) return fail(ctx, SB_ERR_ARG, "a transform over several devices needs 2, 4 or 8 of them, got %d", g);
+    if (log_n < NTT_MULTI_MIN_LOG_N || log_n > 28) return fail(ctx, SB_ERR_ARG, "transforms over several devices: 2^%u .. 2^28 points, got 2^%u", NTT_MULTI_MIN_LOG_N, log_n);
+    const size_t n = (size_t)1 << log_n;
+    uint32_t bits[NTT_MAX_PASSES];
+    const int m = plan_bits(log_n, bits);
+    auto log_cc = [&](int p) { return (uint32_t)NTT_LOG_TILE_FOR(bits[p]) - bits[p]; };
+    for (int p = 0; p < m; p++)
+        if (bits[p] < 6 || bits[p] > 8) return fail(ctx, SB_ERR_ARG, "internal: pass width %u has no multi-device kernel", bits[p]);
+    if (m < 2 || bits[0] < lg + log_cc(m - 1)) return fail(ctx, SB_ERR_ARG, "internal: pass plan of 2^%u does not split over %d devices", log_n, g);
+    const uint4 *tw[SB_MAX_DEV];
+    uint4 *work[SB_MAX_DEV] = {0};
+    uint32_t tw_log_n = 0, log_stride = 0;
+    struct Release {
+        sb_ctx *ctx;
+        uint4 **w;
+        ~Release() {
+            for (int d = 0; d < ctx->n_dev(); d++)
+                if (w[d]) {
+                    DevGuard dg(ctx->dev[d]);
+                    blk_release(ctx->dev[d], w[d]);       // stream ordered: the device's queued passes still own the block
+                }
+        }
+    } release{ctx, work};
+    for (int d = 0; d < g; d++) {
+        sb_ctx *c = ctx->dev[d];
+        DevGuard dg(c);
+        int rc = get_table(c, root, log_n, &tw[d], &tw_log_n, &log_stride);
+        if (rc == SB_OK) rc = blk_alloc(c, (n >> lg) * 32, (void **)&work[d]);
+        if (rc != SB_OK) {
+            if (c != ctx) fail(ctx, rc, "%s", c->err);
+            return rc;
+        }
+    }
+    const hfp::el ninv = hfp::inv(hfp::from_u64((uint64_t)n));
+    TRY(cross_barrier(ctx));                       // every slab is complete before a peer reads it
+    uint32_t log_outer = 0;
+    for (int p = 0; p < m; p++) {
+        const bool first = p == 0, last = p == m - 1;
+        const uint32_t log_tiles = log_n - bits[p] - log_cc(p);
+        for (int d = 0; d < g; d++) {
+            sb_ctx *c = ctx->dev[d];
+            DevGuard dg(c);
+            NttPassParams P;
+            memset(&P, 0, sizeof P);
+            for (int o = 0; o < g; o++) {
+                P.src_tab[o] = first ? slabs[o] : work[o];
+                P.dst_tab[o] = last ? slabs[o] : work[o];
+            }
+            P.tw = tw[d];
+            P.len_in = n;
+            P.n_cols_total = (unsigned long long)n >> bits[p];
+            P.log_n = log_n;
+            P.log_outer = log_outer;
+            P.log_inner = log_n - log_outer - bits[p];
+            P.first = first;
+            P.last = last;
+            P.inverse = inverse ? 1 : 0;
+            P.tw_log_n = tw_log_n;
+            P.tw_log_stride = log_stride;
+            P.n_prev = (uint32_t)p;
+            for (int i = 0; i < p; i++) P.prev_bits[i] = bits[i];
+            memcpy(P.n_inv, ninv.l, 32);
+            P.dist_log_slab = log_n - lg;
+            P.dist_log_g = lg;
+            P.dist_dev = (uint32_t)d;
+            // last pass: the inputs of output column gl sit at digitrev_inv(gl), whose top digit is gl's low bits[0] bits -- the
+            // owner is bits [bits[0] - lg, bits[0]) of gl; earlier passes: the owner is the top of the tile index
+            P.dist_blk_lo = last ? bits[0] - lg - log_cc(p) : log_tiles - lg;
+            int rc = launch_pass_on(c, bits[p], P);
+            if (rc != SB_OK) {
+                if (c != ctx) fail(ctx, rc, "%s", c->err);
+                return rc;
+            }
+        }
+        if (first || last) TRY(cross_barrier(ctx));
+        log_outer += bits[p];
+    }
+    return SB_OK;
+}
+
+extern "C" int sb_ntt_multi_dev(sb_ctx *ctx, uint64_t *const *d_slabs, const uint64_t root[4], uint32_t log_n, int inverse) {
+    return guarded(ctx, __func__, [&]() -> int {
+    if (!ctx || !d_slabs || !root) return SB_ERR_ARG;
+    for (int d = 0; d < ctx->n_dev(); d++)
+        if (!d_slabs[d]) return fail(ctx, SB_ERR_ARG, "slab %d is NULL", d);
+    return ntt_multi(ctx, (uint4 *const *)d_slabs, hfp::from_limbs(root), log_n, inverse);
+    });
+}
+
+extern "C" int sb_dev_alloc_on(sb_ctx *ctx, int dev_index, size_t bytes, void **p) {
+    return guarded(ctx, __func__, [&]() -> int {
+    if (!ctx || !p) return SB_ERR_ARG;
+    if (dev_index < 0 || dev_index >= ctx->n_dev()) return fail(ctx, SB_ERR_ARG, "device index %d outside the context's %d devices", dev_index, ctx->n_dev());
+    DevGuard dg(ctx->dev[dev_index]);
+    CU(cudaMalloc(p, bytes ? bytes : 16));
+    return SB_OK;
+    });
+}
+
 // four-step twiddle step of a transform split over several GPUs (sharded.py::distributed_ntt)
 extern "C" int sb_twiddle_mul_dev(sb_ctx *ctx, uint64_t *d_vals, size_t rows, size_t cols, size_t row0, const uint64_t root[4],
                                   uint32_t log_n, int inverse) {
@@ -524,6 +665,44 @@ extern "C" int sb_ntt(sb_ctx *ctx, uint64_t *vals, size_t len_in, const uint64_t
     if (log_n > 28) return fail(ctx, SB_ERR_ARG, "log_n %u exceeds the field's two-adicity 28", log_n);
     const size_t n = (size_t)1 << log_n;
     if (len_in > n) return fail(ctx, SB_ERR_ARG, "vector of %zu elements does not fit a 2^%u transform", len_in, log_n);
+    if (ctx->n_dev() > 1 && log_n >= NTT_MULTI_MIN_LOG_N) {
+        // several devices: slab d of the vector goes to device d (the uploads and downloads of the slabs run on the devices'
+        // own PCIe links side by side when `vals` is pinned), one transform over all of them (ntt_multi)
+        const int g = ctx->n_dev();
+        const size_t slab = n / g;
+        uint4 *slabs[SB_MAX_DEV] = {0};
+        struct Release {
+            sb_ctx *ctx;
+            uint4 **s;
+            ~Release() {
+                for (int d = 0; d < ctx->n_dev(); d++)
+                    if (s[d]) {
+                        DevGuard dg(ctx->dev[d]);
+                        blk_release(ctx->dev[d], s[d]);
+                    }
+            }
+        } release{ctx, slabs};
+        for (int d = 0; d < g; d++) {
+            sb_ctx *c = ctx->dev[d];
+            DevGuard dg(c);
+            int rc = blk_alloc(c, slab * 32, (void **)&slabs[d]);
+            if (rc != SB_OK) return c != ctx ? fail(ctx, rc, "%s", c->err) : rc;
+            const size_t lo = (size_t)d * slab, have = len_in > lo ? std::min(len_in - lo, slab) : 0;
+            if (have) CU(cudaMemcpyAsync(slabs[d], vals + 4 * lo, have * 32, cudaMemcpyHostToDevice, c->stream));
+            if (have < slab) CU(cudaMemsetAsync((uint8_t *)slabs[d] + have * 32, 0, (slab - have) * 32, c->stream));   // fft.rs:335-338
+        }
+        TRY(ntt_multi(ctx, slabs, hfp::from_limbs(root), log_n, inverse));
+        for (int d = 0; d < g; d++) {
+            sb_ctx *c = ctx->dev[d];
+            DevGuard dg(c);
+            CU(cudaMemcpyAsync(vals + 4 * (size_t)d * slab, slabs[d], slab * 32, cudaMemcpyDeviceToHost, c->stream));
+        }
+        for (int d = 0; d < g; d++) {
+            DevGuard dg(ctx->dev[d]);
+            CU(cudaStreamSynchronize(ctx->dev[d]->stream));
+        }
+        return SB_OK;
+    }
     DevBuf a(ctx), b(ctx);
     TRY(a.alloc((len_in ? len_in : 1) * 32));
     TRY(b.alloc(n * 32));

@@ -121,7 +121,11 @@ __device__ __forceinline__ unsigned long long ntt_digitrev_inv(const NttPassPara
     return o;
 }
 
-template <int B, int LOG_TILE>
+// DIST: one transform over several devices (see NttPassParams::src_tab): the tile index comes from the device's share of the
+// tiles, loads and stores go through the slab tables -- remote reads in the first pass (the exchange "rows -> columns" of a
+// four-step transform), remote writes in the first and in the last pass (the exchanges "-> k1 slabs" and "-> natural order"),
+// always in runs of CC x 32 contiguous bytes.  Plain single-vector transforms only (no batch, no cosets, no zero padding).
+template <int B, int LOG_TILE, bool DIST = false>
 __global__ void __launch_bounds__((1 << LOG_TILE) / 8, LOG_TILE >= 11 ? 2 : 4) ntt_pass_kernel(const __grid_constant__ NttPassParams P) {
     constexpr int TILE = 1 << LOG_TILE, NT = TILE / 8, R = 1 << B, CC = TILE >> B, PITCH = CC + 1;
     extern __shared__ uint4 smem[];
@@ -130,7 +134,10 @@ __global__ void __launch_bounds__((1 << LOG_TILE) / 8, LOG_TILE >= 11 ? 2 : 4) n
 
     const uint32_t log_cpp = P.log_n - B;                     // log2(columns per polynomial)
     unsigned long long blk_col0 = (unsigned long long)blockIdx.x * CC;
-    if (P.n_polys) {   // tile-major order (host guarantees CC divides the columns of one polynomial)
+    if constexpr (DIST) {
+        const unsigned long long i = blockIdx.x, lo = P.dist_blk_lo;
+        blk_col0 = ((((i >> lo) << P.dist_log_g) | P.dist_dev) << lo | (i & ((1ull << lo) - 1))) * CC;
+    } else if (P.n_polys) {   // tile-major order (host guarantees CC divides the columns of one polynomial)
         const unsigned long long poly = blockIdx.x % P.n_polys, tile = blockIdx.x / P.n_polys;
         blk_col0 = (poly << log_cpp) + tile * CC;
     }
@@ -163,7 +170,8 @@ __global__ void __launch_bounds__((1 << LOG_TILE) / 8, LOG_TILE >= 11 ? 2 : 4) n
                 if (!P.first || e < P.len_in) {
                     // coset mode, first pass: coefficient e of column poly / coset_cnt (scaled onto its coset below)
                     const unsigned long long sp = (P.first && P.coset_cnt) ? poly / P.coset_cnt : poly;
-                    const uint4 *s = P.src + 2 * (sp * P.src_stride + e);
+                    const uint4 *s = DIST ? P.src_tab[e >> P.dist_log_slab] + 2 * (e & ((1ull << P.dist_log_slab) - 1))
+                                          : P.src + 2 * (sp * P.src_stride + e);
                     lo = s[0];
                     hi = s[1];
                 }
@@ -228,7 +236,9 @@ __global__ void __launch_bounds__((1 << LOG_TILE) / 8, LOG_TILE >= 11 ? 2 : 4) n
         }
         if (!P.last || P.inverse) v = fp_mul(v, w);
         if (P.last) v = fp_canon(v);
-        if (P.last && P.coset_store == NTT_STORE_INTERLEAVED) {
+        if constexpr (DIST) {
+            fp_stg(P.dst_tab[e >> P.dist_log_slab], e & ((1ull << P.dist_log_slab) - 1), v);
+        } else if (P.last && P.coset_store == NTT_STORE_INTERLEAVED) {
             const unsigned long long col = poly / P.coset_cnt, rr = poly % P.coset_cnt + P.coset_r0;
             fp_stg(P.dst, col * P.dst_stride + (e << P.coset_log) + rr, v);
         } else {

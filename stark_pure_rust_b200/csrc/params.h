@@ -44,6 +44,13 @@ struct NttPassParams {
     //   NTT_STORE_INTERLEAVED natural order of the extended domain: element k * 2^coset_log + coset of `column`
     uint32_t coset_cnt, coset_r0, coset_log, coset_store;
     uint32_t coset_dst_cpd, coset_dst_r0;   // NTT_STORE_PLAIN: (column, coset) is stored as polynomial column * coset_dst_cpd + coset - coset_dst_r0
+    // ONE transform spread over 2^dist_log_g devices (ntt_pass_kernel<.., DIST = true>, ntt_multi in api.cu): the vector lives in
+    // natural-order slabs of 2^dist_log_slab elements, element e on device e >> dist_log_slab; src_tab / dst_tab hold every
+    // device's slab (peer pointers).  This launch runs on device dist_dev and takes the tiles whose index carries dist_dev in
+    // the bits [dist_blk_lo, dist_blk_lo + dist_log_g): CTA i works on tile ((i >> lo) << (lo + log_g)) | dev << lo | (i & (2^lo - 1)).
+    const uint4 *src_tab[8];
+    uint4 *dst_tab[8];
+    uint32_t dist_log_slab, dist_log_g, dist_dev, dist_blk_lo;
 };
 #define NTT_STORE_PLAIN 0
 #define NTT_STORE_INTERLEAVED 1

@@ -179,6 +179,80 @@ def test_ext_chain_real_gpus(oracle, g):
         ctx.close()
 
 
+# ---- ONE transform over several devices (sb_ntt on a multi-device context, sb_ntt_multi_dev) ----------
+def _ntt_multi_checks(ctx, ctx1, oracle, log_ns):
+    """best_fft / inv_best_fft through the multi-device context against the single-device result (and the oracle at 2^20)"""
+    import stark_pure_rust_b200 as sb
+    for log_n in log_ns:
+        n = 1 << log_n
+        w = oracle.root_of_unity(log_n)
+        v = random_elems(n, 40 + log_n)
+        got = sb.fft.best_fft(v, w, log_n, ctx=ctx)
+        want = sb.fft.best_fft(v, w, log_n, ctx=ctx1)
+        assert np.array_equal(got, want), "forward 2^%d" % log_n
+        if log_n == 20:
+            assert np.array_equal(want, oracle.best_fft(v, w, log_n))
+        back = sb.fft.inv_best_fft(got, w, log_n, ctx=ctx)
+        assert np.array_equal(back, v), "round trip 2^%d" % log_n
+        short = v[: n // 2 + 12345]                                     # zero padding, fft.rs:335-338
+        assert np.array_equal(sb.fft.best_fft(short, w, log_n, ctx=ctx), sb.fft.best_fft(short, w, log_n, ctx=ctx1))
+        assert np.array_equal(sb.fft.best_fft(v[:3], w, log_n, ctx=ctx), sb.fft.best_fft(v[:3], w, log_n, ctx=ctx1))
+
+
+def test_ntt_multi_logical(mctx, ctx, oracle):
+    g = mctx.lib.sb_device_count(mctx.h)
+    _ntt_multi_checks(mctx, ctx, oracle, [20, 21, 22] if g > 1 else [20])
+
+
+def test_ntt_multi_dev_slabs(oracle, ctx):
+    """sb_ntt_multi_dev on slabs the caller placed (sb_dev_alloc_on), and its argument checks"""
+    import stark_pure_rust_b200 as sb
+    from stark_pure_rust_b200._lib import _ptr
+    g, log_n = 4, 20
+    n = 1 << log_n
+    m = sb.Context(devices=[0] * g)
+    try:
+        w = oracle.root_of_unity(log_n)
+        v = random_elems(n, 7)
+        slabs = (C.c_void_p * g)()
+        for d in range(g):
+            p = C.c_void_p()
+            m.check(m.lib.sb_dev_alloc_on(m.h, d, (n // g) * 32, C.byref(p)))
+            slabs[d] = p
+            part = np.ascontiguousarray(v[d * (n // g):(d + 1) * (n // g)])
+            m.check(m.lib.sb_h2d(m.h, p, _ptr(part), part.nbytes))
+        root = np.ascontiguousarray(w, dtype=np.uint64).reshape(4)
+        m.check(m.lib.sb_ntt_multi_dev(m.h, slabs, _ptr(root), log_n, 0))
+        out = np.empty_like(v)
+        for d in range(g):
+            part = np.empty((n // g, 4), dtype=np.uint64)
+            m.check(m.lib.sb_d2h(m.h, _ptr(part), slabs[d], part.nbytes))
+            out[d * (n // g):(d + 1) * (n // g)] = part
+        assert np.array_equal(out, sb.fft.best_fft(v, w, log_n, ctx=ctx))
+        with pytest.raises(sb.StarkB200Error):
+            m.check(m.lib.sb_ntt_multi_dev(m.h, slabs, _ptr(root), 19, 0))          # below the multi-device range
+        with pytest.raises(sb.StarkB200Error):
+            m.check(m.lib.sb_ntt_multi_dev(ctx.h, slabs, _ptr(root), log_n, 0))     # single-device context
+        with pytest.raises(sb.StarkB200Error):
+            m.check(m.lib.sb_dev_alloc_on(m.h, g, 32, C.byref(C.c_void_p())))
+        for d in range(g):
+            m.lib.sb_dev_free(m.h, slabs[d])
+    finally:
+        m.close()
+
+
+@pytest.mark.parametrize("g", [2, 4, 8])
+def test_ntt_multi_real_gpus(g, ctx, oracle):
+    if n_gpus() < g:
+        pytest.skip("needs %d GPUs" % g)
+    import stark_pure_rust_b200 as sb
+    m = sb.Context(devices=list(range(g)))
+    try:
+        _ntt_multi_checks(m, ctx, oracle, [20, 23])
+    finally:
+        m.close()
+
+
 @pytest.mark.parametrize("g", [2, 4, 8])
 def test_prove_real_gpus(g, tmp_path):
     if n_gpus() < g:
