@@ -980,6 +980,9 @@ def run_multi_records(args, n_dev):
                    "note": "domain 2^26 is beyond the reference sampler's 2^24 (sb_set_extended_domain): the parity target is the single-GPU natural-order path, itself oracle-checked up to 2^24"},
     }
 
+    # ---- ONE transform over n_dev GPUs (sb_ntt_multi_dev: no transposes, exchanges inside the pass kernels) ----
+    out["ntt_multi"] = ntt_multi_record(args, ctxs, n_dev)
+
     # ---- one proof over n_dev GPUs -------------------------------------------------------------------------------------
     import gen_r1cs
     tmp = tempfile.mkdtemp(prefix="sb_bench_multi_")
@@ -1013,6 +1016,74 @@ def run_multi_records(args, n_dev):
     for c in ctxs.values():
         c.close()
     return out
+
+
+def ntt_multi_record(args, ctxs, n_dev):
+    """best_fft of ONE 2^L-point vector resident in natural-order slabs on n_dev GPUs against the same transform on one GPU;
+    parity asserted in-run (slab digests against the single-GPU result)."""
+    import hashlib
+    from stark_pure_rust_b200 import field
+    L = min(args.sharded_log_n, 26)
+    n = 1 << L
+    rootL = np.ascontiguousarray(field.mont_scalar(field.root_of_unity(L)))
+    base = random_elems(1 << 20, 0x77)
+    host = np.tile(base, (n >> 20, 1))
+    host[:: 4097, 0] ^= np.arange(host[:: 4097].shape[0], dtype=np.uint64)            # not periodic
+    res = {}
+    for g, ctx in ctxs.items():
+        lib = ctx.lib
+        slab = n // g
+        ptrs = (C.c_void_p * g)()
+        for d in range(g):
+            p = C.c_void_p()
+            ctx.check(lib.sb_dev_alloc_on(ctx.h, d, slab * 32, C.byref(p)))
+            ptrs[d] = p
+        out_ptr = C.c_void_p()
+        if g == 1:
+            ctx.check(lib.sb_dev_alloc(ctx.h, n * 32, C.byref(out_ptr)))
+
+        def upload():
+            for d in range(g):
+                part = host[d * slab:(d + 1) * slab]
+                ctx.check(lib.sb_h2d(ctx.h, ptrs[d], part.ctypes.data_as(C.c_void_p), part.nbytes))
+
+        def run():
+            if g == 1:
+                ctx.check(lib.sb_ntt_dev(ctx.h, ptrs[0], n, n, out_ptr, n, 1, rootL.ctypes.data_as(C.c_void_p), L, 0))
+            else:
+                ctx.check(lib.sb_ntt_multi_dev(ctx.h, ptrs, rootL.ctypes.data_as(C.c_void_p), L, 0))
+
+        upload()
+        run()                                                            # builds the tables
+        digests = []
+        for d in range(g):
+            for q in range(n_dev // g):                                  # digests per n_dev-th of the vector, whatever g is
+                cnt = n // n_dev
+                part = np.empty((cnt, 4), dtype=np.uint64)
+                src = (out_ptr.value if g == 1 else ptrs[d]) + q * cnt * 32
+                ctx.check(lib.sb_d2h(ctx.h, part.ctypes.data_as(C.c_void_p), C.c_void_p(src), part.nbytes))
+                digests.append(hashlib.sha256(part.tobytes()).hexdigest())
+        best = None
+        for _ in range(max(3, args.sharded_steps)):
+            if g > 1:
+                upload()                                                 # the transform is in place
+            ctx.sync()
+            ctx.check(lib.sb_timer_start(ctx.h))
+            run()
+            ms = C.c_float()
+            ctx.check(lib.sb_timer_stop(ctx.h, C.byref(ms)))
+            best = ms.value if best is None else min(best, ms.value)
+        res[g] = {"ms": best, "digests": digests}
+        for d in range(g):
+            lib.sb_dev_free(ctx.h, ptrs[d])
+        if g == 1:
+            lib.sb_dev_free(ctx.h, out_ptr)
+    same = res[1]["digests"] == res[n_dev]["digests"]
+    assert same, "transform over %d GPUs differs from the single-GPU result" % n_dev
+    return {"workload": "ONE best_fft of 2^%d points, natural-order slabs resident on %d GPUs (sb_ntt_multi_dev)" % (L, n_dev), "scaling": "strong",
+            "n_gpus": n_dev, "ms": res[n_dev]["ms"], "ms_1gpu": res[1]["ms"], "speedup_vs_1gpu": res[1]["ms"] / res[n_dev]["ms"],
+            "elems_per_s": n / (res[n_dev]["ms"] * 1e-3), "nvlink_bytes_per_gpu": 3 * (n_dev - 1) * (n // n_dev // n_dev) * 32,
+            "parity": {"equal_to_1gpu": same, "sha256_of_first_slab": res[n_dev]["digests"][0]}}
 
 
 def ntt_plan(log_n, maxb=8):
