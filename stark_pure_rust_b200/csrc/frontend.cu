@@ -174,8 +174,10 @@ const char *build_trace(sb_ctx *ctx, const R1cs &r, const std::vector<hfp::el> &
     if (a == 0) return "circuit has no constraint rows";
     hfp::el *arena;
     if (ctx) {
+        // always sized for six vectors: the verifier (which materialises the flag vectors) then reuses the prover's arena
+        // instead of re-allocating ~200 MB of pinned memory (~100 ms) on the first verification after a proof
         const size_t n_vec = flags_on_device ? 3 : 6;
-        arena = (hfp::el *)pinned_arena(ctx, n_vec * os * sizeof(hfp::el) + os * sizeof(size_t));
+        arena = (hfp::el *)pinned_arena(ctx, 6 * os * sizeof(hfp::el) + os * sizeof(size_t));
         if (arena) t.perm = (size_t *)(arena + n_vec * os);
     } else {                      // host-only use (sb_trace_from_files): ordinary memory owned by the Trace
         t.heap.resize(6 * os);

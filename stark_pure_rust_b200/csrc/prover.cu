@@ -971,7 +971,12 @@ extern "C" int sb_verify_r1cs(sb_ctx *ctx, const sb_trace *t, const sb_stark_pro
     }
     const hfp::el x_last = xv[V + np];
     std::vector<hfp::el> interp2;                                              // calc_i2_polynomial once (verify.rs:152), Horner per position
-    host_lagrange(interp2, pub_x, pub_y);
+    if (np >= INTERP_DEVICE_MIN && np <= INTERP_DEVICE_MAX) {                  // many public wires (`bits`: 1062): O(np^2) on the device, like the prover
+        std::vector<hfp::el> zroot;
+        VTRY(device_lagrange(ctx, (const uint4 *)((const uint8_t *)dgath.p + (n_ev + V) * 32), pub_y, interp2, zroot));
+    } else {
+        host_lagrange(interp2, pub_x, pub_y);
+    }
     hfp::el r[3], k[11];
     {
         uint32_t idx[24];
