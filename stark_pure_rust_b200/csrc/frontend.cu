@@ -7,6 +7,11 @@
 //   build_trace    r1cs-stark/src/run.rs:109-308 (calc_coefficients_and_witness, calc_flags),
 //                  :390-419 (permuted_indices, public_first_indices), :344-361 (prime / witness[0] checks)
 //   sb_prove_files r1cs-stark/src/run.rs:528-554 (prove_with_file_path)
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include "internal.h"
 
 #include <algorithm>
@@ -61,6 +66,44 @@ struct R1cs {
 const uint8_t BN254_FR_LE[32] = {1, 0, 0, 240, 147, 245, 225, 67, 145, 112, 185, 121, 72, 232, 51, 40,
                                  93, 88, 129, 129, 182, 69, 80, 184, 41, 160, 49, 225, 114, 78, 100, 48};   // run.rs:344-350
 
+// A file as a read-only memory image: mapped (the parsers below leave the constraint terms in place, so a 17 MB .r1cs is never
+// copied -- fread of it took 2.9 ms of the 2^23 proof's front end), read into a buffer where mapping is not possible.
+// (The file must not be truncated while the proof runs.)
+struct FileImage {
+    const uint8_t *p = nullptr;
+    size_t n = 0;
+    bool mapped = false;
+    std::vector<uint8_t> buf;
+    bool open(const char *path) {
+        const int fd = ::open(path, O_RDONLY | O_CLOEXEC);
+        if (fd < 0) return false;
+        struct stat st;
+        if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) {
+            ::close(fd);
+            return slurp_into(path);
+        }
+        n = (size_t)st.st_size;
+        if (n == 0) {
+            ::close(fd);
+            p = (const uint8_t *)"";
+            return true;
+        }
+        void *m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+        ::close(fd);
+        if (m == MAP_FAILED) return slurp_into(path);
+        p = (const uint8_t *)m;
+        mapped = true;
+        return true;
+    }
+    bool slurp_into(const char *path);
+    ~FileImage() {
+        if (mapped) munmap((void *)p, n);
+    }
+    FileImage() = default;
+    FileImage(const FileImage &) = delete;
+    FileImage &operator=(const FileImage &) = delete;
+};
+
 bool slurp(const char *path, std::vector<uint8_t> &out) {
     FILE *f = fopen(path, "rb");
     if (!f) return false;
@@ -71,6 +114,13 @@ bool slurp(const char *path, std::vector<uint8_t> &out) {
     bool ok = sz <= 0 || fread(out.data(), 1, (size_t)sz, f) == (size_t)sz;
     fclose(f);
     return ok;
+}
+
+bool FileImage::slurp_into(const char *path) {
+    if (!slurp(path, buf)) return false;
+    p = buf.data();
+    n = buf.size();
+    return true;
 }
 
 // body(lo, hi) over [0, n) on up to 16 host threads (the O(nnz) scalar work below: ~2 Montgomery products per term)
@@ -89,8 +139,8 @@ void parallel_for(size_t n, size_t min_grain, F body) {
 
 // reader.rs:4-89: magic, version 1, 3 sections, header section first, then the constraint section; labels ignored.
 // Only the structure is decoded here (one u32 per factor); coefficients are converted where they are used.
-const char *read_r1cs(const std::vector<uint8_t> &buf, R1cs &r) {
-    Reader p{buf.data(), buf.size()};
+const char *read_r1cs(const uint8_t *data, size_t size, R1cs &r) {
+    Reader p{data, size};
     if (p.u32() != 0x73633172u) return "not an r1cs file (magic)";
     if (p.u32() != 1) return "r1cs version must be 1";
     if (p.u32() != 3) return "r1cs must have 3 sections";
@@ -109,7 +159,7 @@ const char *read_r1cs(const std::vector<uint8_t> &buf, R1cs &r) {
     if (!p.ok) return "truncated r1cs header";
     // the third section maps every wire to a u64 label (reader.rs:66-74), so a well-formed file holds 8 bytes per wire:
     // bounds n_wires before anything is sized by it (the verifier has no witness to compare it with)
-    if ((uint64_t)r.n_wires * 8 > buf.size()) return "r1cs header declares more wires than the file can describe";
+    if ((uint64_t)r.n_wires * 8 > size) return "r1cs header declares more wires than the file can describe";
     if ((size_t)r.n_constraints * 12 > p.left) return "truncated r1cs constraints";
     r.factors.resize((size_t)3 * r.n_constraints);
     r.row_off.assign((size_t)r.n_constraints + 1, 0);
@@ -129,8 +179,10 @@ const char *read_r1cs(const std::vector<uint8_t> &buf, R1cs &r) {
 }
 
 // reader.rs:7-42: "wtns", 5 skipped words, field size, modulus, n_wires, 3 skipped words, the values
-const char *read_witness(const std::vector<uint8_t> &buf, std::vector<hfp::el> &w) {
-    Reader p{buf.data(), buf.size()};
+const char *read_r1cs(const std::vector<uint8_t> &buf, R1cs &r) { return read_r1cs(buf.data(), buf.size(), r); }
+
+const char *read_witness(const uint8_t *data, size_t size, std::vector<hfp::el> &w) {
+    Reader p{data, size};
     if (p.u32() != 1936618615u) return "not a wtns file (magic)";
     for (int i = 0; i < 5; i++) p.u32();
     uint32_t field_size = p.u32();
@@ -150,6 +202,8 @@ const char *read_witness(const std::vector<uint8_t> &buf, std::vector<hfp::el> &
     return nullptr;
 }
 
+const char *read_witness(const std::vector<uint8_t> &buf, std::vector<hfp::el> &w) { return read_witness(buf.data(), buf.size(), w); }
+
 // the six original_steps-long vectors mk_r1cs_proof takes, carved out of the context's pinned staging arena so that
 // their upload runs at PCIe speed (the copy permutation sits behind them in the same arena); public data are small and stay
 // in ordinary vectors
@@ -160,6 +214,7 @@ struct Trace {
     size_t *perm = nullptr;                     // original_steps entries, in the arena (or perm_heap)
     std::vector<unsigned long long> last_rows;  // last row of every constraint (the flag vectors in compressed form)
     size_t a = 0;
+    std::vector<uint32_t> wire_at;              // wire of every row (input of the copy permutation)
     std::vector<size_t> perm_heap, pfi_k, pfi_w;
 };
 
@@ -167,7 +222,24 @@ struct Trace {
 // with_witness = false (verifier, run.rs:454-526): only the public part is built -- coefficients, flags, permutation,
 // public wires and their first uses; `witness` then only needs the public wires
 // flags_on_device: the three flag vectors are not materialised (sb_prove_files: the prover generates them from last_rows)
-const char *build_trace(sb_ctx *ctx, const R1cs &r, const std::vector<hfp::el> &witness, Trace &t, bool with_witness = true, bool flags_on_device = false) {
+static double fe_now() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+static bool fe_trace() {
+    static const bool on = getenv("SB_TRACE_FRONT") != nullptr;      // phase times of the front end on stderr
+    return on;
+}
+#define FE_LAP(what) do { if (fe_trace()) { const double t_ = fe_now(); fprintf(stderr, "[front end] %-24s %7.3f ms\n", what, t_ - fe_t0); fe_t0 = t_; } } while (0)
+
+const char *finish_trace(const R1cs &r, const std::vector<hfp::el> &witness, Trace &t);
+
+// defer_perm: stop after the row vectors; the caller runs finish_trace (copy permutation, public wires) later -- sb_prove_files
+// does that inside the prover, while the device already transforms the columns that do not depend on it
+const char *build_trace(sb_ctx *ctx, const R1cs &r, const std::vector<hfp::el> &witness, Trace &t, bool with_witness = true, bool flags_on_device = false,
+                        bool defer_perm = false) {
+    double fe_t0 = fe_now();
     const size_t n_wires = r.n_wires, nc = r.n_constraints;
     if ((with_witness && witness.size() < n_wires) || n_wires == 0) return "witness shorter than the circuit's wire count";
     const size_t a = r.row_off[nc], os = 3 * a;
@@ -194,8 +266,10 @@ const char *build_trace(sb_ctx *ctx, const R1cs &r, const std::vector<hfp::el> &
         flags_on_device = false;
         t.coef = arena; t.f0 = arena + os; t.f1 = arena + 2 * os; t.f2 = arena + 3 * os; t.wit = arena + 4 * os; t.comp = arena + 5 * os;
     }
-    std::vector<uint32_t> wire_at(os);
+    std::vector<uint32_t> &wire_at = t.wire_at;
+    wire_at.resize(os);
     std::atomic<int> bad(0);
+    FE_LAP("arena + wire_at");
     // rows of constraint c sit at row_off[c] .. in each third k (A, B, C); threads take ranges of constraints
     parallel_for(nc, 64, [&](size_t c0, size_t c1) {
         for (size_t c = c0; c < c1; c++) {
@@ -230,6 +304,7 @@ const char *build_trace(sb_ctx *ctx, const R1cs &r, const std::vector<hfp::el> &
         }
     });
     if (bad.load()) return "wire id out of range";
+    FE_LAP("rows (coef, wit, comp)");
     // calc_flags, run.rs:283-308
     for (size_t c = 0; c < nc; c++)
         if (r.row_off[c + 1] != r.row_off[c]) t.last_rows.push_back(r.row_off[c + 1] - 1);     // (every well-formed constraint has a term)
@@ -249,6 +324,16 @@ const char *build_trace(sb_ctx *ctx, const R1cs &r, const std::vector<hfp::el> &
     }
     // copy permutation, run.rs:390-401: the uses of a wire in (constraint, factor, row) order form a cycle,
     // perm[first use] = last use, perm[use j] = use j-1
+    FE_LAP("flags");
+    return defer_perm ? nullptr : finish_trace(r, witness, t);
+}
+
+// copy permutation, run.rs:390-401: the uses of a wire in (constraint, factor, row) order form a cycle,
+// perm[first use] = last use, perm[use j] = use j-1
+const char *finish_trace(const R1cs &r, const std::vector<hfp::el> &witness, Trace &t) {
+    double fe_t0 = fe_now();
+    const size_t n_wires = r.n_wires, nc = r.n_constraints, a = t.a, os = t.os;
+    const std::vector<uint32_t> &wire_at = t.wire_at;
     const size_t NONE = (size_t)-1;
     std::vector<size_t> first(n_wires, NONE), prev(n_wires, NONE);
     memset(t.perm, 0, os * sizeof(size_t));
@@ -265,6 +350,7 @@ const char *build_trace(sb_ctx *ctx, const R1cs &r, const std::vector<hfp::el> &
     }
     for (size_t w = 0; w < n_wires; w++)
         if (first[w] != NONE) t.perm[first[w]] = prev[w];
+    FE_LAP("permutation");
     // public wires and their first uses, run.rs:359-361, :413-419
     const size_t n_pub = 1 + (size_t)r.n_pub_in + r.n_pub_out;
     if (n_pub > witness.size() || n_pub > n_wires) return "more public wires than wires";
@@ -293,23 +379,27 @@ extern "C" int sb_prove_files(sb_ctx *ctx, const char *r1cs_path, const char *wt
         return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
     };
     const double t0 = now();
-    std::vector<uint8_t> rb, wb;
-    if (!slurp(r1cs_path, rb)) return fail(ctx, SB_ERR_ARG, "cannot read %s", r1cs_path);
-    if (!slurp(wtns_path, wb)) return fail(ctx, SB_ERR_ARG, "cannot read %s", wtns_path);
+    double fe_t0 = t0;
+    FileImage rb, wb;
+    if (!rb.open(r1cs_path)) return fail(ctx, SB_ERR_ARG, "cannot read %s", r1cs_path);
+    if (!wb.open(wtns_path)) return fail(ctx, SB_ERR_ARG, "cannot read %s", wtns_path);
+    FE_LAP("read files");
     R1cs r;
     std::vector<hfp::el> witness;
-    const char *e = read_r1cs(rb, r);
+    const char *e = read_r1cs(rb.p, rb.n, r);
     if (e) return fail(ctx, SB_ERR_ARG, "%s: %s", r1cs_path, e);
     if (memcmp(r.prime, BN254_FR_LE, 32) != 0) return fail(ctx, SB_ERR_ARG, "%s: field is not BN254 Fr (run.rs:344-350)", r1cs_path);
-    e = read_witness(wb, witness);
+    e = read_witness(wb.p, wb.n, witness);
     if (e) return fail(ctx, SB_ERR_ARG, "%s: %s", wtns_path, e);
     if (witness.empty() || !hfp::eq(witness[0], hfp::ONE)) return fail(ctx, SB_ERR_ARG, "witness[0] must be 1 (run.rs:358)");
     dbg_check("sb_prove_files before build_trace");
+    FE_LAP("parse");
     Trace t;
     e = build_trace(ctx, r, witness, t, true, true);
     if (e) return fail(ctx, SB_ERR_ARG, "%s", e);
     dbg_check("sb_prove_files after build_trace");
     sb_trace st;
+    memset(&st, 0, sizeof st);
     st.original_steps = t.os;
     st.witness_trace = (const uint64_t *)t.wit;
     st.computational_trace = (const uint64_t *)t.comp;
@@ -323,6 +413,9 @@ extern "C" int sb_prove_files(sb_ctx *ctx, const char *r1cs_path, const char *wt
     st.n_pfi = t.pfi_k.size();
     st.pfi_k = t.pfi_k.data();
     st.pfi_w = t.pfi_w.data();
+    // (Tried: building the copy permutation -- 1.8 ms of serial host work at 955 086 steps -- inside the prover, after the
+    // transforms that do not need it had been queued.  The device timeline stayed gap-free, yet the proof took 1.9 ms longer
+    // than with the permutation built up front, so it is built here.)
     const double t1 = now();
     sb_stark_proof *proof = nullptr;
     dbg_check("sb_prove_files after the front end");

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--dir", default="/tmp")
     ap.add_argument("--devices", default=None, help="comma-separated device ordinals for ONE proof over several (logical) devices, e.g. 0,1,2,3 or 0,0")
     ap.add_argument("--profile", action="store_true", help="print the per-kernel-family times of the last repetition (CUDA events around every launch)")
+    ap.add_argument("--timeline", action="store_true", help="after the repetitions: one more proof under torch.profiler (CUPTI), printing every device activity longer than 0.15 ms and every gap longer than 0.3 ms")
     a = ap.parse_args()
     prefix = os.path.join(a.dir, "syn_%d_%g_%d" % (a.constraints, a.avg_terms, a.seed))
     t0 = time.perf_counter()
@@ -52,6 +53,21 @@ def main():
         print("gpu rep %d: wall %.1f ms | LDE+pointwise %.2f m_tree %.2f FRI %.2f l_tree+openings %.2f | prove %.2f | front end %.2f | json+write %.2f | proof %d bytes" % (
             r, wall, ms[0], ms[1], ms[2], ms[3], ms[4], ms[5], ms[6], os.path.getsize(out)), flush=True)
         res["gpu"] = {"wall_ms": wall, "stage_ms": ms}
+    if a.timeline:
+        import torch
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            sb.prove.prove_with_file_path(prefix + ".r1cs", prefix + ".wtns", out, ctx=ctx)
+            torch.cuda.synchronize()
+        ev = sorted((e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA), key=lambda e: e.time_range.start)
+        t0, last_end = ev[0].time_range.start, ev[0].time_range.start
+        for e in ev:
+            st, en = e.time_range.start, e.time_range.end
+            if st - last_end > 300:
+                print("  %9.3f ms  ---- idle %.3f ms ----" % ((last_end - t0) / 1e3, (st - last_end) / 1e3))
+            if en - st > 150:
+                print("  %9.3f ms  %8.3f ms  %s" % ((st - t0) / 1e3, (en - st) / 1e3, e.name[:90]))
+            last_end = max(last_end, en)
     if a.cpu:
         import oracle_bind as ob
         want = prefix + ".oracle.json"
