@@ -5,11 +5,14 @@
 //
 // One thread computes one digest.  The field is NOT the prover's field: r = 0x73eda753...00000001 has 255 bits, so 4r > 2^256 and
 // the lazy [0, 2p) ranges of fp_gen.cuh do not carry over; elements here are 8 x u32 limbs in Montgomery form (R = 2^256), always
-// fully reduced.  r = 1 mod 2^32, hence -r^-1 mod 2^32 = 0xffffffff and the Montgomery factor of a row is just -t[0].
+// fully reduced; the product is the generated carry-chain code of tools/gen_fp_bls.py (r = 1 mod 2^32, so the Montgomery factor
+// of a row is just the negated low word).
 // The 189 round constants and the 9 matrix entries (Montgomery form, made on the host: poseidon.cu) are staged in shared memory;
 // every thread reads the same word at the same time (broadcast).
 #pragma once
 #include <stdint.h>
+
+#include "fp_bls_gen.cuh"
 
 #define POS_T 3
 #define POS_RF 8
@@ -24,18 +27,12 @@ __device__ __constant__ uint32_t MOD[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu
 
 // t - r if t >= r (t < 2r)
 __device__ __forceinline__ void reduce_once(uint32_t (&t)[8]) {
-    uint32_t d[8];
-    uint64_t bw = 0;
+    uint32_t d[8], bw = 0;
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const uint64_t x = (uint64_t)t[i] - MOD[i] - bw;
-        d[i] = (uint32_t)x;
-        bw = (x >> 63) & 1;
-    }
-    if (!bw) {
+    for (int i = 0; i < 8; i++) d[i] = t[i];
+    blsgen::sub_r_bw_ip(d, bw);
 #pragma unroll
-        for (int i = 0; i < 8; i++) t[i] = d[i];
-    }
+    for (int i = 0; i < 8; i++) t[i] = bw ? t[i] : d[i];
 }
 __device__ __forceinline__ bool is_canonical(const uint32_t (&a)[8]) {
     for (int i = 7; i >= 0; i--) {
@@ -45,47 +42,27 @@ __device__ __forceinline__ bool is_canonical(const uint32_t (&a)[8]) {
     return false;
 }
 __device__ __forceinline__ void add(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t *b) {
-    uint64_t c = 0;
+    uint32_t bb[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        c += (uint64_t)a[i] + b[i];
-        r[i] = (uint32_t)c;
-        c >>= 32;
+        bb[i] = b[i];
+        r[i] = a[i];
     }
-    reduce_once(r);                 // a + b < 2r < 2^256: no carry out
+    blsgen::add_ip(r, bb);          // a + b < 2r < 2^256: no carry out
+    reduce_once(r);
 }
-// Montgomery product a b / 2^256 mod r, operands and result < r (CIOS, one row of b per step)
+// Montgomery product a b / 2^256 mod r, operands and result < r: the generated IMAD.WIDE carry chains (fp_bls_gen.cuh, the
+// same statement lists as the prover's field) and one conditional subtraction.  (First version: a CIOS loop in plain C with
+// 64-bit accumulators -- 2.7e7 digests/s on B200; the chains: see DESIGN.md 4.8.)
 __device__ __forceinline__ void mul(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t *b) {
-    uint32_t t[9];
-#pragma unroll
-    for (int i = 0; i < 9; i++) t[i] = 0;
+    uint32_t aa[8], bb[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        const uint32_t bi = b[i];
-        uint64_t c = 0;
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            c += (uint64_t)a[j] * bi + t[j];
-            t[j] = (uint32_t)c;
-            c >>= 32;
-        }
-        c += t[8];
-        const uint32_t t8 = (uint32_t)c, t9 = (uint32_t)(c >> 32);
-        const uint32_t m = 0u - t[0];
-        c = ((uint64_t)m * MOD[0] + t[0]) >> 32;
-#pragma unroll
-        for (int j = 1; j < 8; j++) {
-            c += (uint64_t)m * MOD[j] + t[j];
-            t[j - 1] = (uint32_t)c;
-            c >>= 32;
-        }
-        c += t8;
-        t[7] = (uint32_t)c;
-        t[8] = t9 + (uint32_t)(c >> 32);
+        aa[i] = a[i];
+        bb[i] = b[i];
     }
-#pragma unroll
-    for (int i = 0; i < 8; i++) r[i] = t[i];
-    reduce_once(r);                 // a b < r^2 => the sum is < 2r and t[8] == 0
+    blsgen::mont_mul(r, aa, bb);    // < 2r
+    reduce_once(r);
 }
 __device__ __forceinline__ void sbox(uint32_t (&x)[8]) {
     uint32_t x2[8], x4[8];

@@ -247,8 +247,9 @@ def test_no_cpu_fallback():
 
 
 def test_generated_field_code_is_current_and_emulator_passes():
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_fp.py"), "--check"], capture_output=True, text=True)
-    assert r.returncode == 0, r.stdout + r.stderr
+    for gen in ("gen_fp.py", "gen_fp_bls.py"):         # the prover's field, the Poseidon digest's field
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", gen), "--check"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
 
 
 def test_ntt_plan_model():
