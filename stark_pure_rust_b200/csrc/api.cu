@@ -929,14 +929,14 @@ int merkle_finish(sb_ctx *ctx, sb_tree *t, uint32_t level, bool fetch_root) {
 
 // hashes the leaves and every level; leaves the root in t->root.
 // fold != NULL: the leaves are produced by the FRI fold of *fold (fused kernel), which also writes the column t->cols[0].
-static int merkle_build(sb_ctx *ctx, sb_tree *t, const FriFoldParams *fold = nullptr) {
+static int merkle_build(sb_ctx *ctx, sb_tree *t, const FriFoldParams *fold = nullptr, bool fetch_root = true) {
     uint32_t level = t->depth < 3 ? t->depth : 3;
     if (fold) {
         KLAUNCH(SB_KIND_FRI_FOLD, merkle_launch_leaves_fold(ctx->stream, level, *fold, t->d_nodes));
     } else {
         launch_leaves(ctx, t, level);
     }
-    return merkle_finish(ctx, t, level, true);
+    return merkle_finish(ctx, t, level, fetch_root);
 }
 
 int tree_new(sb_ctx *ctx, size_t n, size_t leaf_bytes, sb_tree **out) {
@@ -1058,13 +1058,14 @@ int commit_cols(sb_ctx *ctx, const uint4 *const *d_cols, size_t n_cols, size_t n
 }
 
 // FRI: column = fold(values) and the tree over the column in one pass over the data (fri.rs:141-172)
-static int commit_fold(sb_ctx *ctx, const FriFoldParams &F, sb_tree **tree) {
+// fetch_root = false: everything is only queued; the root stays in the node array until the caller reads it
+static int commit_fold(sb_ctx *ctx, const FriFoldParams &F, sb_tree **tree, bool fetch_root = true) {
     const size_t q = F.n >> 2;
     sb_tree *t = nullptr;
     TRY(tree_new(ctx, q, 32, &t));
     t->n_cols = 1;
     t->cols[0] = F.col;
-    int rc = merkle_build(ctx, t, &F);
+    int rc = merkle_build(ctx, t, &F, fetch_root);
     if (rc != SB_OK) {
         free_tree(t);
         return rc;
@@ -1273,25 +1274,37 @@ int fri_prove_dev(sb_ctx *ctx, const uint4 *d_vals, size_t n, const hfp::el &roo
         for (auto t : owned_trees) free_tree(t);
         for (auto p : owned_cols) blk_release(ctx, p);
     };
+    // All layers are queued back to back: from the second layer on the fold kernel derives special_x from the previous column
+    // tree's root where it lies in device memory (FriFoldParams::special_root), so the host does not wait for a root between
+    // layers; the roots come back in one pinned buffer, then the host samples every layer's positions and all openings of all
+    // layers are one round trip (merkle_open_many).  Before: two host round trips per layer (root, openings).
     int rc = SB_OK;
     const uint4 *cur = d_vals;
     const sb_tree *cur_tree = values_tree;
     size_t cur_n = n, bound = max_deg_plus_1;
     uint32_t cur_stride = log_stride;
-
+    struct Mid {
+        const sb_tree *poly_tree;      // tree over the layer's values
+        sb_tree *col_tree;             // tree over the folded column (root fetched late)
+        size_t q;
+    };
+    std::vector<Mid> mids;
+    FriLayer last;
+    DevBuf last_bytes(ctx);
+    size_t max_layers = 2;
+    for (size_t b = max_deg_plus_1; b > FRI_MIN_DEG_DIRECT; b /= 4) max_layers++;
+    uint8_t *h_roots = (uint8_t *)pinned_scratch(ctx, 32 * max_layers);
+    if (!h_roots) {
+        delete proof;
+        return fail(ctx, SB_ERR_OOM, "pinned scratch for the FRI roots");
+    }
     while (true) {
-        FriLayer L;
         if (bound <= FRI_MIN_DEG_DIRECT) {
             // fri.rs:88-112: the remaining values go into the proof verbatim (to_bytes_le each)
-            L.is_last = true;
-            L.last.resize(cur_n * 32);
-            DevBuf tmp(ctx);
-            if ((rc = tmp.alloc(cur_n * 32)) != SB_OK) break;
-            KLAUNCH(SB_KIND_OTHER, fp_launch_to_bytes(ctx->stream, cur, (uint4 *)tmp.p, cur_n));
-            cudaError_t e = cudaMemcpyAsync(L.last.data(), tmp.p, cur_n * 32, cudaMemcpyDeviceToHost, ctx->stream);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-            if (e != cudaSuccess) { rc = fail(ctx, SB_ERR_CUDA, "FRI last layer: %s", cudaGetErrorString(e)); break; }
-            proof->layers.push_back(std::move(L));
+            last.is_last = true;
+            last.last.resize(cur_n * 32);
+            if ((rc = last_bytes.alloc(cur_n * 32)) != SB_OK) break;
+            KLAUNCH(SB_KIND_OTHER, fp_launch_to_bytes(ctx->stream, cur, (uint4 *)last_bytes.p, cur_n));
             break;
         }
         if (cur_n < 4 || (cur_n / 4 >= (1u << 24) && !(ctx->extended_domain && cur_n / 4 <= (1u << 28)))) { rc = fail(ctx, SB_ERR_ARG, "FRI layer of %zu values unsupported", cur_n); break; }
@@ -1303,58 +1316,80 @@ int fri_prove_dev(sb_ctx *ctx, const uint4 *d_vals, size_t n, const hfp::el &roo
             owned_trees.push_back(t);
             cur_tree = t;
         }
-        memcpy(L.values_root, cur_tree->root, 32);
-        // fri.rs:135
-        hfp::el special_x = hfp::from_bytes_le32(cur_tree->root);
         // fri.rs:141-164
         const size_t q = cur_n / 4;
         void *d_col = nullptr;
         if ((rc = blk_alloc(ctx, q * 32, &d_col)) != SB_OK) break;
         owned_cols.push_back(d_col);
         FriFoldParams P;
+        memset(&P, 0, sizeof P);
         P.vals = cur;
         P.col = (uint4 *)d_col;
         P.tw = tw;
         P.n = cur_n;
         P.tw_log_n = tw_log_n;
         P.tw_log_stride = cur_stride;
-        memcpy(P.special_x, special_x.l, 32);
+        if (mids.empty()) {
+            const hfp::el special_x = hfp::from_bytes_le32(cur_tree->root);      // fri.rs:135: the first tree's root is on the host
+            memcpy(P.special_x, special_x.l, 32);
+        } else {
+            P.special_root = cur_tree->d_nodes + 2 * (2 * cur_n - 2);            // previous layer's column tree (this function built it)
+        }
         // fri.rs:141-172: fold and commit the column in one kernel
         sb_tree *t2 = nullptr;
-        if ((rc = commit_fold(ctx, P, &t2)) != SB_OK) break;
+        if ((rc = commit_fold(ctx, P, &t2, false)) != SB_OK) break;
         owned_trees.push_back(t2);
-        memcpy(L.root2, t2->root, 32);
-        // fri.rs:181-190
-        uint32_t ys[FRI_QUERIES];
-        if (pseudorandom_indices(t2->root, 32, (uint32_t)q, FRI_QUERIES, excl, ys, ctx->extended_domain) != SB_OK) {
-            rc = fail(ctx, SB_ERR_ARG, "sampler: column length %zu out of range", q);
-            break;
-        }
-        std::vector<size_t> yi(FRI_QUERIES), pp(4 * FRI_QUERIES);
-        for (size_t i = 0; i < FRI_QUERIES; i++) {
-            yi[i] = ys[i];
-            for (size_t j = 0; j < 4; j++) pp[4 * i + j] = ys[i] + q * j;     // fri.rs:193-204
-        }
-        L.n_column = FRI_QUERIES;
-        L.depth_column = t2->depth;
-        L.column_leaves.resize(FRI_QUERIES * 32);
-        L.column_nodes.resize(FRI_QUERIES * t2->depth * 32);
-        L.n_poly = 4 * FRI_QUERIES;
-        L.depth_poly = cur_tree->depth;
-        L.poly_leaves.resize(L.n_poly * 32);
-        L.poly_nodes.resize(L.n_poly * cur_tree->depth * 32);
-        {
-            const OpenReq reqs[2] = {{t2, yi.data(), FRI_QUERIES, L.column_leaves.data(), L.column_nodes.data()},
-                                     {cur_tree, pp.data(), L.n_poly, L.poly_leaves.data(), L.poly_nodes.data()}};
-            if ((rc = merkle_open_many(ctx, reqs, 2)) != SB_OK) break;
-        }
-        proof->layers.push_back(std::move(L));
+        cudaError_t e = cudaMemcpyAsync(h_roots + 32 * mids.size(), (const uint8_t *)t2->d_nodes + (2 * q - 2) * 32, 32, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e != cudaSuccess) { rc = fail(ctx, SB_ERR_CUDA, "FRI root: %s", cudaGetErrorString(e)); break; }
+        mids.push_back(Mid{cur_tree, t2, q});
         // fri.rs:215-223
         cur = (const uint4 *)d_col;
         cur_tree = t2;
         cur_n = q;
         bound /= 4;
         cur_stride += 2;
+    }
+    if (rc == SB_OK) {
+        cudaError_t e = last.is_last ? cudaMemcpyAsync(last.last.data(), last_bytes.p, last.last.size(), cudaMemcpyDeviceToHost, ctx->stream) : cudaSuccess;
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = fail(ctx, SB_ERR_CUDA, "FRI layers: %s", cudaGetErrorString(e));
+    }
+    if (rc == SB_OK) {
+        // fri.rs:181-204 for every layer, then all openings at once
+        proof->layers.resize(mids.size());
+        std::vector<std::vector<size_t>> idx(2 * mids.size());
+        std::vector<OpenReq> reqs;
+        for (size_t k = 0; k < mids.size() && rc == SB_OK; k++) {
+            const Mid &M = mids[k];
+            memcpy(M.col_tree->root, h_roots + 32 * k, 32);
+            FriLayer &L = proof->layers[k];
+            memcpy(L.values_root, M.poly_tree->root, 32);
+            memcpy(L.root2, M.col_tree->root, 32);
+            uint32_t ys[FRI_QUERIES];
+            if (pseudorandom_indices(M.col_tree->root, 32, (uint32_t)M.q, FRI_QUERIES, excl, ys, ctx->extended_domain) != SB_OK) {
+                rc = fail(ctx, SB_ERR_ARG, "sampler: column length %zu out of range", M.q);
+                break;
+            }
+            std::vector<size_t> &yi = idx[2 * k], &pp = idx[2 * k + 1];
+            yi.resize(FRI_QUERIES);
+            pp.resize(4 * FRI_QUERIES);
+            for (size_t i = 0; i < FRI_QUERIES; i++) {
+                yi[i] = ys[i];
+                for (size_t j = 0; j < 4; j++) pp[4 * i + j] = ys[i] + M.q * j;     // fri.rs:193-204
+            }
+            L.n_column = FRI_QUERIES;
+            L.depth_column = M.col_tree->depth;
+            L.column_leaves.resize(FRI_QUERIES * 32);
+            L.column_nodes.resize(FRI_QUERIES * M.col_tree->depth * 32);
+            L.n_poly = 4 * FRI_QUERIES;
+            L.depth_poly = M.poly_tree->depth;
+            L.poly_leaves.resize(L.n_poly * 32);
+            L.poly_nodes.resize(L.n_poly * M.poly_tree->depth * 32);
+            reqs.push_back(OpenReq{M.col_tree, yi.data(), FRI_QUERIES, L.column_leaves.data(), L.column_nodes.data()});
+            reqs.push_back(OpenReq{M.poly_tree, pp.data(), L.n_poly, L.poly_leaves.data(), L.poly_nodes.data()});
+        }
+        if (rc == SB_OK && !reqs.empty()) rc = merkle_open_many(ctx, reqs.data(), (int)reqs.size());
+        if (rc == SB_OK && last.is_last) proof->layers.push_back(std::move(last));
     }
     cleanup();
     if (rc != SB_OK) {
@@ -1377,6 +1412,7 @@ extern "C" int sb_fri_fold_dev(sb_ctx *ctx, const uint64_t *d_vals, size_t n, co
     TRY(get_table(ctx, hfp::from_limbs(root), ilog2(n), &tw, &tw_log_n, &log_stride));
     hfp::el special_x = hfp::from_bytes_le32(values_root);      // fri.rs:135
     FriFoldParams P;
+    memset(&P, 0, sizeof P);
     P.vals = (const uint4 *)d_vals;
     P.col = (uint4 *)d_col;
     P.tw = tw;

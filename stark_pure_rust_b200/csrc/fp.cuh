@@ -150,6 +150,15 @@ __device__ __forceinline__ fp fp_to_mont(const fp &a) {
     for (int i = 0; i < 8; i++) r2.l[i] = k[i];
     return fp_canon(fp_mul(a, r2));
 }
+// 32 little-endian bytes (any value < 2^256 ~ 5.3 p) -> field element: int_LE mod p in Montgomery form (fp.rs:70-77 from_bytes_le)
+__device__ __forceinline__ fp fp_from_le256(const uint4 *d) {
+    const uint4 lo = d[0], hi = d[1];
+    fp v;
+    v.l[0] = lo.x; v.l[1] = lo.y; v.l[2] = lo.z; v.l[3] = lo.w;
+    v.l[4] = hi.x; v.l[5] = hi.y; v.l[6] = hi.z; v.l[7] = hi.w;
+    v = fp_reduce_2p(fp_reduce_2p(v));      // < 2p after two conditional subtractions of 2p (5.3 p -> 3.3 p -> < 2p)
+    return fp_to_mont(fp_canon(v));
+}
 __device__ __forceinline__ bool fp_is_zero_canon(const fp &a) {
     uint32_t o = 0;
 #pragma unroll

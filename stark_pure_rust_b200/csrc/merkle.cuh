@@ -133,8 +133,12 @@ __global__ void __launch_bounds__(MERKLE_THREADS, 4) merkle_leaves_fold_kernel(c
     const size_t q = F.n >> 2;
     const size_t base = ((size_t)blockIdx.x * MERKLE_THREADS) << LV;
     fp sx;
+    if (F.special_root) {
+        sx = fp_from_le256(F.special_root);
+    } else {
 #pragma unroll
-    for (int k = 0; k < 8; k++) sx.l[k] = F.special_x[k];
+        for (int k = 0; k < 8; k++) sx.l[k] = F.special_x[k];
+    }
     const unsigned long long nT = 1ull << F.tw_log_n;
     const fp iota_inv = fp_ldg_ro(F.tw, (nT - ((unsigned long long)q << F.tw_log_stride)) & (nT - 1));
 #pragma unroll 1

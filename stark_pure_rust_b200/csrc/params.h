@@ -117,6 +117,9 @@ struct FriFoldParams {
     unsigned long long n;
     uint32_t tw_log_n, tw_log_stride;   // layer root w = w_T^(2^tw_log_stride)
     uint32_t special_x[8];         // Montgomery
+    const uint4 *special_root;     // != NULL: special_x is derived on the device from this 32-byte digest (int_LE mod p, fri.rs:135)
+                                   // -- the root of the previous layer's column tree, still in its node array: the host never
+                                   // waits for it between layers (merkle_leaves_fold_kernel only)
     // coset-major input (merkle_leaves_fold_ext_kernel): vals = this device's cosets r0 .. r0 + cpd - 1 of the layer's
     // values, 2^log_s each (n = 8 * 2^log_s); row i = 8 k + r reads vals[(r - r0) * S + k + j S / 4], j < 4.  Row i of the
     // folded column is position 8 k + r of the next layer's domain, i.e. the same coset: col_local (this device's cosets of
