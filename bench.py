@@ -627,9 +627,13 @@ def run_prove_extras(ctx, args, large_only=False, sync=None):
             wall = time.perf_counter() - t0
             if best is None or wall < best[0]:
                 best = (wall, ms)
-        tv = time.perf_counter()
-        vms = sb.prove.verify_with_file_path(r1cs, wtns, os.path.join(tmp, "proof.json"), ctx=ctx)
-        verify_s = time.perf_counter() - tv
+        verify_s, vms = None, None
+        for _ in range(2):             # like the proof: best of the repetitions (the first call sizes the context's device buffers)
+            tv = time.perf_counter()
+            ms = sb.prove.verify_with_file_path(r1cs, wtns, os.path.join(tmp, "proof.json"), ctx=ctx)
+            dt = time.perf_counter() - tv
+            if verify_s is None or dt < verify_s:
+                verify_s, vms = dt, ms
         return {"gpu_s": best[0], "gpu_verify_s": verify_s, "gpu_verify_ms": {"front_end_and_parse": vms[0], "verify": vms[1]}, "gpu_stage_ms": {"lde_and_pointwise": best[1][0], "m_tree": best[1][1], "fri": best[1][2], "l_tree_and_openings": best[1][3],
                                                    "device_total": best[1][4], "host_front_end": best[1][5], "json_write": best[1][6]},
                 "proof_bytes": os.path.getsize(os.path.join(tmp, "proof.json"))}
