@@ -91,8 +91,76 @@ def gpu_ntt_model(v, w, bits):
         outer *= n_p
     return out
 
+# ---- ONE transform over g devices (ntt_multi in csrc/api.cu, ntt_pass_kernel<.., DIST>) --------------------------------
+def plan_bits(log_n, maxb=8):
+    m = (log_n + maxb - 1) // maxb
+    base, rem = divmod(log_n, m)
+    return [base + (1 if i < rem else 0) for i in range(m)]
+
+def log_tile_for(b):
+    return 11 if b >= 8 else 10
+
+def digitrev_inv(d, prev_bits):
+    """ntt_digitrev_inv of ntt.cuh: block index of the inputs of output column d in the last pass"""
+    o = 0
+    for b in prev_bits:
+        o = (o << b) | (d & ((1 << b) - 1)); d >>= b
+    return o
+
+def check_distributed_plan(log_n, g):
+    """index model of the tile -> device assignment: every tile of every pass is taken by exactly one device, the loads of
+    the passes after the first and the stores of the passes before the last stay inside the device's own slab"""
+    lg = g.bit_length() - 1
+    n, bits = 1 << log_n, plan_bits(log_n)
+    m = len(bits)
+    slab = log_n - lg
+    log_cc = [log_tile_for(b) - b for b in bits]
+    assert m >= 2 and all(6 <= b <= 8 for b in bits) and bits[0] >= lg + log_cc[-1], (log_n, g, bits)
+    log_outer = 0
+    remote = {"load": 0, "store": 0}
+    for p, b in enumerate(bits):
+        first, last = p == 0, p == m - 1
+        log_inner = log_n - log_outer - b
+        log_tiles = log_n - b - log_cc[p]
+        lo = bits[0] - lg - log_cc[p] if last else log_tiles - lg
+        seen = set()
+        for d in range(g):
+            for i in range(0, 1 << (log_tiles - lg), max(1, (1 << (log_tiles - lg)) // 97)):      # a sample of the device's CTAs
+                tile = (((i >> lo) << lg | d) << lo) | (i & ((1 << lo) - 1))
+                assert tile < (1 << log_tiles) and tile not in seen
+                seen.add(tile)
+                for j in (0, (1 << log_cc[p]) - 1):
+                    gl = (tile << log_cc[p]) + j
+                    for r in (0, (1 << b) - 1):
+                        if not last:
+                            o, c = gl >> log_inner, gl & ((1 << log_inner) - 1)
+                            e_load = (o << (b + log_inner)) + (r << log_inner) + c
+                            e_store = e_load                          # in place (row kk instead of r: same index set)
+                        else:
+                            e_load = (digitrev_inv(gl, bits[:-1]) << b) + r
+                            e_store = gl + (r << log_outer)
+                        assert e_load < n and e_store < n
+                        if first:
+                            remote["load"] += (e_load >> slab) != d
+                        else:
+                            assert (e_load >> slab) == d, ("load not local", log_n, g, p, tile)
+                        if not first and not last:
+                            assert (e_store >> slab) == d, ("store not local", log_n, g, p, tile)
+                        else:
+                            remote["store"] += (e_store >> slab) != d
+        # the bijection i -> tile covers all tiles of the pass: each (hi, lo) pair once per device
+        assert (1 << (log_tiles - lg)) * g == 1 << log_tiles
+        log_outer += b
+    assert remote["load"] and remote["store"]              # the exchanges are there (first-pass loads, first / last pass stores)
+    return bits
+
+
 if __name__ == "__main__":
     random.seed(1)
+    for log_n in range(20, 29):
+        for g in (2, 4, 8):
+            check_distributed_plan(log_n, g)
+    print("ok distributed plans 2^20..2^28 over 2, 4, 8 devices")
     for bits in [[3], [4], [5], [1], [2], [3, 3], [4, 3], [5, 4], [3, 4, 3], [6, 5], [3, 3, 3, 3], [7, 3], [2, 3]]:
         k = sum(bits); n = 1 << k
         w = root_of_unity(k)
