@@ -556,7 +556,7 @@ int ntt_multi(sb_ctx *ctx, uint4 *const *slabs, const hfp::el &root, uint32_t lo
     if (m < 2 || bits[0] < lg + log_cc(m - 1)) return fail(ctx, SB_ERR_ARG, "internal: pass plan of 2^%u does not split over %d devices", log_n, g);
     const uint4 *tw[SB_MAX_DEV];
     uint4 *work[SB_MAX_DEV] = {0};
-    uint32_t tw_log_n = 0, log_stride = 0;
+    uint32_t tw_log_n[SB_MAX_DEV] = {0}, log_stride[SB_MAX_DEV] = {0};   // per device: a device may serve the root from a larger cached table
     struct Release {
         sb_ctx *ctx;
         uint4 **w;
@@ -571,7 +571,7 @@ int ntt_multi(sb_ctx *ctx, uint4 *const *slabs, const hfp::el &root, uint32_t lo
     for (int d = 0; d < g; d++) {
         sb_ctx *c = ctx->dev[d];
         DevGuard dg(c);
-        int rc = get_table(c, root, log_n, &tw[d], &tw_log_n, &log_stride);
+        int rc = get_table(c, root, log_n, &tw[d], &tw_log_n[d], &log_stride[d]);
         if (rc == SB_OK) rc = blk_alloc(c, (n >> lg) * 32, (void **)&work[d]);
         if (rc != SB_OK) {
             if (c != ctx) fail(ctx, rc, "%s", c->err);
@@ -602,8 +602,8 @@ int ntt_multi(sb_ctx *ctx, uint4 *const *slabs, const hfp::el &root, uint32_t lo
             P.first = first;
             P.last = last;
             P.inverse = inverse ? 1 : 0;
-            P.tw_log_n = tw_log_n;
-            P.tw_log_stride = log_stride;
+            P.tw_log_n = tw_log_n[d];
+            P.tw_log_stride = log_stride[d];
             P.n_prev = (uint32_t)p;
             for (int i = 0; i < p; i++) P.prev_bits[i] = bits[i];
             memcpy(P.n_inv, ninv.l, 32);

@@ -204,6 +204,23 @@ def test_ntt_multi_logical(mctx, ctx, oracle):
     _ntt_multi_checks(mctx, ctx, oracle, [20, 21, 22] if g > 1 else [20])
 
 
+def test_ntt_multi_with_a_larger_table_cached_on_one_device(oracle, ctx):
+    """the primary serves the root from a strided view of a larger table it already holds, the other devices build the
+    small table: every device must index its own table geometry"""
+    import stark_pure_rust_b200 as sb
+    m = sb.Context(devices=[0] * 4)
+    try:
+        w23 = oracle.root_of_unity(23)
+        cols = random_elems(2 * (1 << 20), 5).reshape(2, 1 << 20, 4)
+        sb.fft.lde_batch(cols, w23, 20, 3, ctx=m)                       # primary only: caches the 2^23 table of w23 there
+        w20 = oracle.root_of_unity(20)                                  # = w23^8
+        v = random_elems(1 << 20, 6)
+        assert np.array_equal(sb.fft.best_fft(v, w20, 20, ctx=m), sb.fft.best_fft(v, w20, 20, ctx=ctx))
+        assert np.array_equal(sb.fft.inv_best_fft(v, w20, 20, ctx=m), sb.fft.inv_best_fft(v, w20, 20, ctx=ctx))
+    finally:
+        m.close()
+
+
 def test_ntt_multi_dev_slabs(oracle, ctx):
     """sb_ntt_multi_dev on slabs the caller placed (sb_dev_alloc_on), and its argument checks"""
     import stark_pure_rust_b200 as sb
