@@ -1480,34 +1480,63 @@ extern "C" int sb_fri_layer_root(const sb_fri_proof *p, size_t i, uint8_t root[3
     return SB_OK;
 }
 
-void json_bytes(std::string &s, const uint8_t *b, size_t n) {
-    // serde_json prints a Vec<u8> / BlakeDigest(Vec<u8>) as an array of decimal integers.  Written straight into the
-    // string's buffer (at most 4 characters per byte): the proof is megabytes of these.
-    struct Tab {
-        char tab[256][4];
-        uint8_t len[256];
-        Tab() {
-            for (int v = 0; v < 256; v++) {
-                char t[8];
-                len[v] = (uint8_t)snprintf(t, sizeof t, "%d,", v);
-                memcpy(tab[v], t, 4);
-            }
+// serde_json prints a Vec<u8> / BlakeDigest(Vec<u8>) as an array of decimal integers; the proof is megabytes of these.
+// One 8-byte table entry per byte value: up to three digits and the comma, and the length in the last byte.
+namespace {
+struct ByteTab {
+    uint64_t e[256];
+    ByteTab() {
+        for (int v = 0; v < 256; v++) {
+            char t[8] = {0};
+            const int len = snprintf(t, sizeof t, "%d,", v);
+            t[7] = (char)len;
+            memcpy(&e[v], t, 8);
         }
-    };
-    static const Tab T;            // C++11 magic static: initialised once, thread-safe
-    const auto &tab = T.tab;
-    const auto &len = T.len;
-    const size_t at = s.size();
-    s.resize(at + 4 * n + 2);
-    char *w = &s[at];
+    }
+};
+const ByteTab &byte_tab() {
+    static const ByteTab T;        // C++11 magic static: initialised once, thread-safe
+    return T;
+}
+}  // namespace
+// writes "[b0,b1,...]" at w (at most 4 n + 2 characters, the caller provides 4 more of slack); returns the end
+char *json_bytes_raw(char *w, const uint8_t *b, size_t n) {
+    const uint64_t *tab = byte_tab().e;
     *w++ = '[';
     for (size_t i = 0; i < n; i++) {
-        memcpy(w, tab[b[i]], 4);
-        w += len[b[i]];
+        const uint64_t t = tab[b[i]];
+        memcpy(w, &t, 4);          // (little endian: the low four bytes are the characters)
+        w += t >> 56;
     }
-    if (n) w--;                   // the last element's comma
+    if (n) w--;                    // the last element's comma
     *w++ = ']';
+    return w;
+}
+void json_bytes(std::string &s, const uint8_t *b, size_t n) {
+    const size_t at = s.size();
+    s.resize(at + 4 * n + 6);
+    char *w = json_bytes_raw(&s[at], b, n);
     s.resize((size_t)(w - &s[0]));
+}
+// branches q0 .. q1 - 1 of a Proof{leaf,nodes} array (merkle_tree.rs:14-18), comma separated, without the enclosing brackets
+char *json_branches_raw(char *w, const uint8_t *leaves, size_t leaf_bytes, const uint8_t *nodes, size_t depth, size_t q0, size_t q1) {
+    for (size_t q = q0; q < q1; q++) {
+        if (q != q0) *w++ = ',';
+        memcpy(w, "{\"leaf\":", 8);
+        w = json_bytes_raw(w + 8, leaves + q * leaf_bytes, leaf_bytes);
+        memcpy(w, ",\"nodes\":[", 10);
+        w += 10;
+        for (size_t l = 0; l < depth; l++) {
+            if (l) *w++ = ',';
+            w = json_bytes_raw(w, nodes + (q * depth + l) * 32, 32);
+        }
+        *w++ = ']';
+        *w++ = '}';
+    }
+    return w;
+}
+size_t json_branches_bound(size_t leaf_bytes, size_t depth, size_t count) {
+    return count * (8 + 4 * leaf_bytes + 2 + 10 + depth * (4 * 32 + 3) + 3) + 8;
 }
 // Proof{leaf,nodes} (merkle_tree.rs:14-18)
 void json_branches(std::string &s, const uint8_t *leaves, size_t leaf_bytes, const uint8_t *nodes, size_t depth, size_t count) {

@@ -424,6 +424,9 @@ struct OpenReq {
 };
 int merkle_open_many(sb_ctx *ctx, const OpenReq *reqs, int n_req);
 void json_bytes(std::string &s, const uint8_t *b, size_t n);
+char *json_bytes_raw(char *w, const uint8_t *b, size_t n);
+char *json_branches_raw(char *w, const uint8_t *leaves, size_t leaf_bytes, const uint8_t *nodes, size_t depth, size_t q0, size_t q1);
+size_t json_branches_bound(size_t leaf_bytes, size_t depth, size_t count);
 void json_branches(std::string &s, const uint8_t *leaves, size_t leaf_bytes, const uint8_t *nodes, size_t depth, size_t count);
 void fri_proof_json_into(std::string &s, const sb_fri_proof *p);
 void fri_layer_json_into(std::string &s, const FriLayer &L);

@@ -1,6 +1,10 @@
 // prover.cu -- device-resident mk_r1cs_proof (r1cs-stark/src/prove.rs:14-378): the caller of the hot path,
 // so that only the traces go in and only roots / openings / the FRI proof come out.
 // Stage order and every formula follow the reference; citations are to r1cs-stark/src/prove.rs unless noted.
+#include <atomic>
+#include <memory>
+#include <thread>
+
 #include "internal.h"
 #include "pointwise.cuh"
 
@@ -652,69 +656,150 @@ extern "C" int sb_stark_proof_stage_ms(const sb_stark_proof *p, double ms[5]) {
     return SB_OK;
 }
 // serde_json::to_string(&StarkProof) (utils.rs:122-130 field order; run.rs:549 compact)
+// The proof is megabytes of decimal byte arrays.  The text is cut into pieces -- literals, and runs of at most JSON_RUN Merkle
+// branches of the main / linear-combination / FRI sections -- that are formatted independently on a few host threads into
+// their own buffers and then copied to their offsets in the result (round 1: one thread, 1.2 of poseidon3_test's 5 ms and
+// 3.5 of the 2^23 circuit's 54 ms; first threaded version: one thread per section, bounded by the largest section).
+namespace {
+struct JsonPiece {
+    std::string lit;                              // literal text, or
+    const uint8_t *leaves = nullptr, *nodes = nullptr;   // branches q0 .. q1 - 1 of an array of Proof{leaf,nodes}
+    size_t leaf_bytes = 0, depth = 0, q0 = 0, q1 = 0;
+    const uint8_t *digests = nullptr;             // or n_digests 32-byte arrays, comma separated (FRI last layer)
+    size_t n_digests = 0;
+    std::unique_ptr<char[]> buf;
+    size_t n = 0;
+    void make() {
+        if (leaves) {
+            buf.reset(new char[json_branches_bound(leaf_bytes, depth, q1 - q0)]);
+            n = (size_t)(json_branches_raw(buf.get(), leaves, leaf_bytes, nodes, depth, q0, q1) - buf.get());
+        } else if (digests) {
+            buf.reset(new char[n_digests * (4 * 32 + 3) + 8]);
+            char *w = buf.get();
+            for (size_t k = 0; k < n_digests; k++) {
+                if (k) *w++ = ',';
+                w = json_bytes_raw(w, digests + 32 * k, 32);
+            }
+            n = (size_t)(w - buf.get());
+        } else {
+            n = lit.size();
+        }
+    }
+    const char *data() const { return buf ? buf.get() : lit.data(); }
+};
+const size_t JSON_RUN = 48;       // branches per piece (~25-60 KB of text)
+
+void json_pieces_branches(std::vector<JsonPiece> &out, const uint8_t *leaves, size_t leaf_bytes, const uint8_t *nodes, size_t depth, size_t count) {
+    JsonPiece open;
+    open.lit = "[";
+    out.push_back(std::move(open));
+    for (size_t q0 = 0; q0 < count; q0 += JSON_RUN) {
+        if (q0) {
+            JsonPiece sep;
+            sep.lit = ",";
+            out.push_back(std::move(sep));
+        }
+        JsonPiece pc;
+        pc.leaves = leaves;
+        pc.nodes = nodes;
+        pc.leaf_bytes = leaf_bytes;
+        pc.depth = depth;
+        pc.q0 = q0;
+        pc.q1 = std::min(count, q0 + JSON_RUN);
+        out.push_back(std::move(pc));
+    }
+    JsonPiece close;
+    close.lit = "]";
+    out.push_back(std::move(close));
+}
+void json_lit(std::vector<JsonPiece> &out, const std::string &text) {
+    JsonPiece pc;
+    pc.lit = text;
+    out.push_back(std::move(pc));
+}
+}  // namespace
+
 extern "C" char *sb_stark_proof_json(const sb_stark_proof *p, size_t *len) {
     if (!p) return nullptr;
     try {
-        // The proof is megabytes of decimal byte arrays: the three big sections (main branches, linear-combination branches, FRI
-        // layers) are formatted on their own host threads and concatenated (JSON was 1.2 of poseidon3_test's 5 ms, 3.5 of the 2^23
-        // circuit's 54 ms when written by one thread).
-        std::string head, main_b, lc_b, fri_b;
-        head += "{\"m_root\":";
-        json_bytes(head, p->m_root, 32);
-        head += ",\"l_root\":";
-        json_bytes(head, p->l_root, 32);
-        head += ",\"a_root\":";
-        json_bytes(head, p->a_root, 32);
-        head += ",\"main_branches\":";
-        auto do_main = [&]() {
-            main_b.reserve(p->main_leaves.size() * 4 + p->main_nodes.size() * 4 + 4096);
-            json_branches(main_b, p->main_leaves.data(), 256, p->main_nodes.data(), p->depth, p->main_leaves.size() / 256);
-        };
-        auto do_lc = [&]() {
-            lc_b.reserve(p->lc_leaves.size() * 4 + p->lc_nodes.size() * 4 + 4096);
-            json_branches(lc_b, p->lc_leaves.data(), 32, p->lc_nodes.data(), p->depth, p->lc_leaves.size() / 32);
-        };
+        std::vector<JsonPiece> pcs;
+        {
+            std::string head = "{\"m_root\":";
+            json_bytes(head, p->m_root, 32);
+            head += ",\"l_root\":";
+            json_bytes(head, p->l_root, 32);
+            head += ",\"a_root\":";
+            json_bytes(head, p->a_root, 32);
+            head += ",\"main_branches\":";
+            json_lit(pcs, head);
+        }
+        json_pieces_branches(pcs, p->main_leaves.data(), 256, p->main_nodes.data(), p->depth, p->main_leaves.size() / 256);
+        json_lit(pcs, ",\"linear_comb_branches\":");
+        json_pieces_branches(pcs, p->lc_leaves.data(), 32, p->lc_nodes.data(), p->depth, p->lc_leaves.size() / 32);
+        json_lit(pcs, ",\"fri_proof\":[");
         const size_t n_layers = p->fri ? p->fri->layers.size() : 0;
-        std::vector<std::string> layer_s(n_layers);
-        auto do_layer = [&](size_t i) {
-            layer_s[i].reserve((size_t)1 << 19);
-            fri_layer_json_into(layer_s[i], p->fri->layers[i]);
+        for (size_t i = 0; i < n_layers; i++) {           // fri.rs:16-26, same text as fri_layer_json_into
+            const FriLayer &L = p->fri->layers[i];
+            if (i) json_lit(pcs, ",");
+            if (L.is_last) {
+                json_lit(pcs, "{\"Last\":{\"last\":[");
+                JsonPiece pc;
+                pc.digests = L.last.data();
+                pc.n_digests = L.last.size() / 32;
+                if (pc.n_digests) pcs.push_back(std::move(pc));
+                json_lit(pcs, "]}}");
+            } else {
+                std::string h = "{\"Middle\":{\"root2\":";
+                json_bytes(h, L.root2, 32);
+                h += ",\"column_branches\":";
+                json_lit(pcs, h);
+                json_pieces_branches(pcs, L.column_leaves.data(), 32, L.column_nodes.data(), L.depth_column, L.n_column);
+                json_lit(pcs, ",\"poly_branches\":");
+                json_pieces_branches(pcs, L.poly_leaves.data(), 32, L.poly_nodes.data(), L.depth_poly, L.n_poly);
+                json_lit(pcs, "}}");
+            }
+        }
+        json_lit(pcs, "]}");
+        // format the pieces: a few threads take them in turn (the calling thread included)
+        const size_t raw = p->main_leaves.size() + p->main_nodes.size() + p->lc_nodes.size();
+        unsigned T = std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency()));
+        if (raw < ((size_t)1 << 16)) T = 1;
+        std::atomic<size_t> next(0);
+        std::atomic<bool> failed(false);
+        auto work = [&]() {
+            try {
+                for (size_t i = next.fetch_add(1); i < pcs.size(); i = next.fetch_add(1)) pcs[i].make();
+            } catch (...) {
+                failed.store(true);
+            }
         };
-        if (p->main_nodes.size() >= ((size_t)1 << 16)) {
+        {
             std::vector<std::thread> th;
-            th.emplace_back(do_main);
-            th.emplace_back(do_lc);
-            for (size_t i = 1; i < n_layers; i++) th.emplace_back(do_layer, i);
-            if (n_layers) do_layer(0);
+            for (unsigned t = 1; t < T; t++) th.emplace_back(work);
+            work();
             for (auto &t : th) t.join();
-        } else {
-            do_main();
-            do_lc();
-            for (size_t i = 0; i < n_layers; i++) do_layer(i);
         }
-        fri_b.push_back('[');
-        for (size_t i = 0; i < n_layers; i++) {
-            if (i) fri_b.push_back(',');
-            fri_b += layer_s[i];
+        if (failed.load()) return nullptr;
+        size_t total = 0;
+        std::vector<size_t> off(pcs.size());
+        for (size_t i = 0; i < pcs.size(); i++) {
+            off[i] = total;
+            total += pcs[i].n;
         }
-        fri_b.push_back(']');
-        static const char k_lc[] = ",\"linear_comb_branches\":", k_fri[] = ",\"fri_proof\":";
-        const size_t total = head.size() + main_b.size() + (sizeof k_lc - 1) + lc_b.size() + (sizeof k_fri - 1) + fri_b.size() + 1;
         char *r = (char *)malloc(total + 1);
         if (!r) return nullptr;
-        char *w = r;
-        auto put = [&](const char *src, size_t n) {
-            memcpy(w, src, n);
-            w += n;
+        next.store(0);
+        auto gather = [&]() {
+            for (size_t i = next.fetch_add(1); i < pcs.size(); i = next.fetch_add(1)) memcpy(r + off[i], pcs[i].data(), pcs[i].n);
         };
-        put(head.data(), head.size());
-        put(main_b.data(), main_b.size());
-        put(k_lc, sizeof k_lc - 1);
-        put(lc_b.data(), lc_b.size());
-        put(k_fri, sizeof k_fri - 1);
-        put(fri_b.data(), fri_b.size());
-        put("}", 1);
-        *w = 0;
+        {
+            std::vector<std::thread> th;
+            if (total >= ((size_t)1 << 21))
+                for (unsigned t = 1; t < std::min(T, 4u); t++) th.emplace_back(gather);
+            gather();
+            for (auto &t : th) t.join();
+        }
+        r[total] = 0;
         if (len) *len = total;
         return r;
     } catch (...) {

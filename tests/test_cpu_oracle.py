@@ -272,18 +272,21 @@ def test_proof_json_reader_round_trip(oracle, tmp_path):
     from stark_pure_rust_b200 import _lib
     L = _lib.load()
     d = os.path.join(ROOT, "tests", "golden", "circuits")
-    path = str(tmp_path / "compute.json")
-    rc, _ = oracle.prove_files(os.path.join(d, "compute.r1cs"), os.path.join(d, "compute.wtns"), path)
-    assert rc == 0
-    text = open(path, "rb").read()
-    h = C.c_void_p()
-    assert L.sb_stark_proof_from_json(text, len(text), C.byref(h)) == 0
-    n = C.c_size_t()
-    s = L.sb_stark_proof_json(h, C.byref(n))
-    try:
-        assert C.string_at(s, n.value) == text
-    finally:
-        L.sb_free_string(s)
+    for name in ("compute", "poseidon3_test"):            # one thread; pieces formatted on several threads (2.5 MB)
+        path = str(tmp_path / (name + ".json"))
+        rc, _ = oracle.prove_files(os.path.join(d, name + ".r1cs"), os.path.join(d, name + ".wtns"), path)
+        assert rc == 0
+        text = open(path, "rb").read()
+        assert hashlib.sha256(text).hexdigest() == GOLD["proofs"][name]["proof_json_sha256"]
+        h = C.c_void_p()
+        assert L.sb_stark_proof_from_json(text, len(text), C.byref(h)) == 0
+        for _ in range(3):
+            n = C.c_size_t()
+            s = L.sb_stark_proof_json(h, C.byref(n))
+            try:
+                assert C.string_at(s, n.value) == text
+            finally:
+                L.sb_free_string(s)
         L.sb_stark_proof_free(h)
     for bad in (text[:-1], text.replace(b'"l_root"', b'"x_root"'), text.replace(b"[", b"[256,", 1), b"{}", b""):
         h = C.c_void_p()
