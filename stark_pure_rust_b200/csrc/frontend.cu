@@ -133,7 +133,16 @@ void parallel_for(size_t n, size_t min_grain, F body) {
         return;
     }
     std::vector<std::thread> th;
-    for (size_t i = 0; i < T; i++) th.emplace_back([=]() { body(n * i / T, n * (i + 1) / T); });
+    size_t started = 0;
+    for (; started + 1 < T; started++) {
+        const size_t i = started;
+        try {
+            th.emplace_back([=]() { body(n * i / T, n * (i + 1) / T); });
+        } catch (...) {
+            break;                  // no more threads to be had: this thread takes the rest
+        }
+    }
+    body(n * started / T, n);
     for (auto &t : th) t.join();
 }
 

@@ -775,7 +775,13 @@ extern "C" char *sb_stark_proof_json(const sb_stark_proof *p, size_t *len) {
         };
         {
             std::vector<std::thread> th;
-            for (unsigned t = 1; t < T; t++) th.emplace_back(work);
+            for (unsigned t = 1; t < T; t++) {
+                try {
+                    th.emplace_back(work);
+                } catch (...) {
+                    break;          // no more threads to be had: the ones running (and this one) take all pieces
+                }
+            }
             work();
             for (auto &t : th) t.join();
         }
@@ -795,7 +801,13 @@ extern "C" char *sb_stark_proof_json(const sb_stark_proof *p, size_t *len) {
         {
             std::vector<std::thread> th;
             if (total >= ((size_t)1 << 21))
-                for (unsigned t = 1; t < std::min(T, 4u); t++) th.emplace_back(gather);
+                for (unsigned t = 1; t < std::min(T, 4u); t++) {
+                    try {
+                        th.emplace_back(gather);
+                    } catch (...) {
+                        break;
+                    }
+                }
             gather();
             for (auto &t : th) t.join();
         }
