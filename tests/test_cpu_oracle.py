@@ -166,6 +166,14 @@ def test_library_exports_every_declared_symbol():
     assert set(L._proto) == set(syms)
 
 
+def test_public_header_is_plain_c():
+    """the drop-in boundary is a C ABI: include/stark_b200.h must compile as C (what a bindgen / cgo / ctypes user feeds it to)"""
+    hdr = os.path.join(ROOT, "include", "stark_b200.h")
+    for lang, cc in (("c", "gcc"), ("c++", "g++")):
+        r = subprocess.run([cc, "-fsyntax-only", "-Wall", "-Werror", "-x", lang, hdr], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+
+
 def test_host_blake_and_sampler_match_reference_kats():
     import stark_pure_rust_b200 as sb
     k = GOLD["reference_kats"]
